@@ -1,0 +1,103 @@
+// common.cuh -- shared helpers for libgcnmaxcut (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gcnmaxcut.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgcnmaxcut targets sm_100a (B200) only"
+#endif
+
+namespace gmc {
+
+constexpr int kWarp = 32;
+constexpr int kMaxClasses = 8;
+constexpr int kNumSMsB200 = 148;
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int sm_count();                      // cached cudaDevAttrMultiProcessorCount of the current device
+
+#define GMC_REQUIRE(cond, ...)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            gmc::set_error(__VA_ARGS__);               \
+            return GMC_ERR_INVALID_ARG;                \
+        }                                              \
+    } while (0)
+
+#define GMC_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            gmc::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                 \
+                           cudaGetErrorString(e__));                                    \
+            return (int)e__;                                                            \
+        }                                                                               \
+    } while (0)
+
+#define GMC_LAUNCH_CHECK() GMC_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+__host__ __device__ constexpr inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// ---- device helpers -------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_max(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// graph id of node v: largest g with graph_ptr[g] <= v   (graph_ptr has n_graphs+1 entries)
+__device__ __forceinline__ int find_graph(const int32_t* __restrict__ graph_ptr, int n_graphs, int64_t v) {
+    int lo = 0, hi = n_graphs;          // invariant: graph_ptr[lo] <= v < graph_ptr[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(graph_ptr + mid) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// streaming 128-bit load that does not pollute L1 (data touched once per CTA)
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& x) {
+    acc.x = fmaf(a, x.x, acc.x); acc.y = fmaf(a, x.y, acc.y);
+    acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace gmc

@@ -1,0 +1,254 @@
+// dense_small.cu -- the skinny (H -> n_classes) second layer and bias-gradient column sums.
+//
+// With n_out = 3 these are HBM-bound passes over H[N, n_in]; they run on CUDA cores by
+// design (padding K=3 to an MMA tile would waste >97% of the tensor pipe).
+//
+//   gmc_skinny_fwd_f32 : T = H * W                          (th.matmul inside conv2, TrainingNeural.py:83)
+//   gmc_skinny_bwd_f32 : dHpre = relu'(H) .* (dT * W^T),  dW = H^T dT,  dbias1 = colsum(dHpre)
+//                        in ONE pass over H (autograd of TrainingNeural.py:81-83)
+//   gmc_colsum_f32     : bias gradients
+// All reductions over nodes are two-stage with a fixed order -> bitwise reproducible.
+#include "common.cuh"
+
+namespace gmc {
+
+constexpr int kSkinnyMaxSmemFloats = 12288;   // 48 KB of W^T
+
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+skinny_fwd_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ W, float* __restrict__ T,
+                  int64_t ldt, int64_t n_rows, int n_in, int vec) {
+    extern __shared__ float Ws[];                         // Ws[k][j], row stride n_in_pad
+    const int n_in_pad = (n_in + 3) & ~3;
+    for (int i = threadIdx.x; i < n_in_pad * NOUT; i += blockDim.x) {
+        const int k = i / n_in_pad, j = i % n_in_pad;
+        Ws[i] = (j < n_in) ? W[(int64_t)j * NOUT + k] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
+         row += (int64_t)gridDim.x * warps_per_block) {
+        float acc[NOUT];
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) acc[k] = 0.f;
+        const float* h = H + row * ldh;
+        if (vec) {
+            for (int j = lane * 4; j < n_in; j += 128) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(h + j));
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) {
+                    const float4 w = *reinterpret_cast<const float4*>(&Ws[k * n_in_pad + j]);
+                    acc[k] = fmaf(x.x, w.x, acc[k]); acc[k] = fmaf(x.y, w.y, acc[k]);
+                    acc[k] = fmaf(x.z, w.z, acc[k]); acc[k] = fmaf(x.w, w.w, acc[k]);
+                }
+            }
+        } else {
+            for (int j = lane; j < n_in; j += 32) {
+                const float x = __ldg(h + j);
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) acc[k] = fmaf(x, Ws[k * n_in_pad + j], acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) T[row * ldt + k] = acc[k];
+        }
+    }
+}
+
+// ws layout: [n_ctas][n_in][NOUT + 1]   (last slot = dbias partial)
+template <int NOUT>
+__global__ void __launch_bounds__(128)
+skinny_bwd_kernel(const float* __restrict__ dT, int64_t lddt, const float* __restrict__ W, const float* __restrict__ H,
+                  int64_t ldh, float* __restrict__ dH, int64_t lddh, int64_t n_rows, int n_in, float* __restrict__ ws) {
+    const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per;
+    const int64_t r1 = min(n_rows, r0 + rows_per);
+    float* my_ws = ws + (int64_t)blockIdx.x * n_in * (NOUT + 1);
+    for (int j0 = threadIdx.x * 4; j0 < n_in; j0 += blockDim.x * 4) {
+        float w[4][NOUT], dw[4][NOUT], db[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            db[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) {
+                w[i][k] = (j0 + i < n_in) ? __ldg(W + (int64_t)(j0 + i) * NOUT + k) : 0.f;
+                dw[i][k] = 0.f;
+            }
+        }
+        for (int64_t v = r0; v < r1; ++v) {
+            float t[NOUT];
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) t[k] = __ldg(dT + v * lddt + k);
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(H + v * ldh + j0));
+            const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) { s = fmaf(t[k], w[i][k], s); dw[i][k] = fmaf(h[i], t[k], dw[i][k]); }
+                o[i] = h[i] > 0.f ? s : 0.f;
+                db[i] += o[i];
+            }
+            *reinterpret_cast<float4*>(dH + v * lddh + j0) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (j0 + i < n_in) {
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) my_ws[(int64_t)(j0 + i) * (NOUT + 1) + k] = dw[i][k];
+                my_ws[(int64_t)(j0 + i) * (NOUT + 1) + NOUT] = db[i];
+            }
+        }
+    }
+}
+
+__global__ void skinny_bwd_reduce_kernel(const float* __restrict__ ws, int n_ctas, int n_in, int nout,
+                                         float* __restrict__ dW, float* __restrict__ dbias) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over n_in * (nout + 1)
+    const int total = n_in * (nout + 1);
+    if (i >= total) return;
+    float s = 0.f;
+    for (int c = 0; c < n_ctas; ++c) s += ws[(int64_t)c * total + i];
+    const int j = i / (nout + 1), k = i % (nout + 1);
+    if (k < nout) dW[(int64_t)j * nout + k] = s;
+    else if (dbias) dbias[j] = s;
+}
+
+// ---- column sums ------------------------------------------------------------------------
+// stage 1: CTA b reduces rows [b*rows_per, ...) into ws[b][0..C)
+__global__ void __launch_bounds__(256)
+colsum_stage1(const float* __restrict__ X, int64_t ldx, int64_t n_rows, int n_cols, float* __restrict__ ws) {
+    __shared__ float red[256];
+    const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per;
+    const int64_t r1 = min(n_rows, r0 + rows_per);
+    float* out = ws + (int64_t)blockIdx.x * n_cols;
+    if (n_cols <= 8) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int64_t v = r0 + threadIdx.x; v < r1; v += blockDim.x)
+            for (int k = 0; k < n_cols; ++k) acc[k] += __ldg(X + v * ldx + k);
+        for (int k = 0; k < n_cols; ++k) {
+            red[threadIdx.x] = acc[k];
+            __syncthreads();
+            for (int s = 128; s > 0; s >>= 1) {
+                if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) out[k] = red[0];
+            __syncthreads();
+        }
+    } else {
+        for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+            float a = 0.f;
+            for (int64_t v = r0; v < r1; ++v) a += __ldg(X + v * ldx + c);
+            out[c] = a;
+        }
+    }
+}
+
+__global__ void colsum_stage2(const float* __restrict__ ws, int n_ctas, int n_cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    float s = 0.f;
+    for (int b = 0; b < n_ctas; ++b) s += ws[(int64_t)b * n_cols + c];
+    out[c] = s;
+}
+
+static int reduce_ctas() { return sm_count() * 4; }
+
+}  // namespace gmc
+
+extern "C" {
+
+int gmc_skinny_fwd_f32(const float* H, int64_t ldh, const float* W, float* T, int64_t ldt, int64_t n_rows,
+                       int32_t n_in, int32_t n_out, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(H && W && T, "gmc_skinny_fwd_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_in > 0 && n_out >= 1 && n_out <= kMaxClasses && ldh >= n_in && ldt >= n_out,
+                "gmc_skinny_fwd_f32: bad sizes (n_out must be 1..8)");
+    const int n_in_pad = (n_in + 3) & ~3;
+    GMC_REQUIRE(n_in_pad * n_out <= kSkinnyMaxSmemFloats, "gmc_skinny_fwd_f32: n_in*n_out too large (%d)", n_in * n_out);
+    if (n_rows == 0) return GMC_OK;
+    const int vec = (n_in % 4 == 0) && (ldh % 4 == 0) && aligned16(H);
+    const int threads = 256;
+    int64_t blocks = ceil_div<int64_t>(n_rows, threads / 32);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)n_in_pad * n_out * sizeof(float);
+    cudaStream_t s = as_stream(stream);
+#define GMC_CASE(K) case K: skinny_fwd_kernel<K><<<(unsigned)blocks, threads, smem, s>>>(H, ldh, W, T, ldt, n_rows, n_in, vec); break;
+    switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
+#undef GMC_CASE
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+size_t gmc_skinny_bwd_workspace_bytes(int32_t n_in, int32_t n_out) {
+    return (size_t)gmc::reduce_ctas() * 2 * (size_t)n_in * (size_t)(n_out + 1) * sizeof(float);
+}
+
+int gmc_skinny_bwd_f32(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh, float* dHpre,
+                       int64_t lddh, float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(dT && W && H && dHpre && dW, "gmc_skinny_bwd_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_in > 0 && n_out >= 1 && n_out <= kMaxClasses && ldh >= n_in && lddh >= n_in && lddt >= n_out,
+                "gmc_skinny_bwd_f32: bad sizes (n_out must be 1..8)");
+    GMC_REQUIRE(n_in % 4 == 0 && ldh % 4 == 0 && lddh % 4 == 0 && aligned16(H) && aligned16(dHpre),
+                "gmc_skinny_bwd_f32: n_in and leading dimensions must be multiples of 4 with 16-byte aligned bases");
+    int n_ctas = reduce_ctas() * 2;
+    if ((int64_t)n_ctas > n_rows) n_ctas = (int)(n_rows > 0 ? n_rows : 1);
+    const size_t need = (size_t)n_ctas * n_in * (n_out + 1) * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+        set_error("gmc_skinny_bwd_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GMC_ERR_WORKSPACE;
+    }
+    cudaStream_t s = as_stream(stream);
+    float* ws = reinterpret_cast<float*>(workspace);
+    if (n_rows == 0) {
+        GMC_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * n_in * n_out, s));
+        if (dbias) GMC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * n_in, s));
+        return GMC_OK;
+    }
+#define GMC_CASE(K) case K: skinny_bwd_kernel<K><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, dHpre, lddh, n_rows, n_in, ws); break;
+    switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
+#undef GMC_CASE
+    GMC_LAUNCH_CHECK();
+    const int total = n_in * (n_out + 1);
+    skinny_bwd_reduce_kernel<<<ceil_div(total, 256), 256, 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+size_t gmc_colsum_workspace_bytes(int32_t n_cols) { return (size_t)gmc::reduce_ctas() * (size_t)n_cols * sizeof(float); }
+
+int gmc_colsum_f32(const float* X, int64_t ldx, int64_t n_rows, int32_t n_cols, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(X && out, "gmc_colsum_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_cols > 0 && ldx >= n_cols, "gmc_colsum_f32: bad sizes");
+    int n_ctas = reduce_ctas();
+    if ((int64_t)n_ctas > n_rows) n_ctas = (int)(n_rows > 0 ? n_rows : 1);
+    const size_t need = (size_t)n_ctas * n_cols * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+        set_error("gmc_colsum_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GMC_ERR_WORKSPACE;
+    }
+    cudaStream_t s = as_stream(stream);
+    if (n_rows == 0) { GMC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, s)); return GMC_OK; }
+    float* ws = reinterpret_cast<float*>(workspace);
+    colsum_stage1<<<n_ctas, 256, 0, s>>>(X, ldx, n_rows, n_cols, ws);
+    GMC_LAUNCH_CHECK();
+    colsum_stage2<<<ceil_div(n_cols, 256), 256, 0, s>>>(ws, n_ctas, n_cols, out);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// gemm_api.cu -- C-ABI dispatch of the dense feature transforms (include/gcnmaxcut.h, section b).
+#include "common.cuh"
+
+namespace gmc {
+size_t simt_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int simt_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+              int64_t ldb, int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s);
+size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision);
+int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+            int64_t ldb, int64_t ldc, int accumulate, int precision, void* workspace, size_t workspace_bytes,
+            cudaStream_t s);
+
+static int gemm_dispatch(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                         int64_t lda, int64_t ldb, int64_t ldc, int accumulate, int precision, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    GMC_REQUIRE(A && B && C, "gmc_gemm: null pointer");
+    GMC_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gmc_gemm: negative dimension");
+    const int64_t a_min = (op == 2) ? M : K, b_min = (op == 1) ? K : N;
+    GMC_REQUIRE(lda >= a_min && ldb >= b_min && ldc >= N, "gmc_gemm: leading dimension too small (op %d)", op);
+    cudaStream_t s = as_stream(stream);
+    if (precision == GMC_GEMM_FP32)
+        return simt_gemm(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    if (precision == GMC_GEMM_TF32 || precision == GMC_GEMM_TF32X3)
+        return tc_gemm(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, precision, workspace, workspace_bytes, s);
+    set_error("gmc_gemm: unknown precision %d", precision);
+    return GMC_ERR_INVALID_ARG;
+}
+}  // namespace gmc
+
+extern "C" {
+
+size_t gmc_gemm_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t precision) {
+    if (precision == GMC_GEMM_FP32) return gmc::simt_workspace_bytes(M, N, K);
+    return gmc::tc_workspace_bytes(op, M, N, K, precision);
+}
+
+int gmc_gemm_nn(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                int64_t ldc, int32_t accumulate, int32_t precision, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    return gmc::gemm_dispatch(0, A, B, C, M, N, K, lda, ldb, ldc, accumulate, precision, workspace, workspace_bytes, stream);
+}
+int gmc_gemm_nt(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                int64_t ldc, int32_t accumulate, int32_t precision, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    return gmc::gemm_dispatch(1, A, B, C, M, N, K, lda, ldb, ldc, accumulate, precision, workspace, workspace_bytes, stream);
+}
+int gmc_gemm_tn(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                int64_t ldc, int32_t accumulate, int32_t precision, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    return gmc::gemm_dispatch(2, A, B, C, M, N, K, lda, ldb, ldc, accumulate, precision, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+/* gcnmaxcut.h -- C ABI of libgcnmaxcut.so: the B200 (sm_100a) hot path of GCN-max-cut.
+ *
+ * The reference (MJavaadAkhtar/GCN-max-cut) is pure Python with NO FFI of its own;
+ * every native instruction it executes lives in third-party wheels (dgl 2.0.0,
+ * torch).  Each entry point below therefore names the reference Python call site
+ * (file:line relative to the reference root) whose native work it replaces -- that
+ * call site is "the interface it binds".  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless a parameter
+ *     is documented as host; `stream` is a cudaStream_t passed as void*.
+ *   - return 0 on success, a negative GMC_ERR_* for argument errors, or a positive
+ *     cudaError_t; gmc_last_error() returns a thread-local description.
+ *   - no allocation and no host synchronisation inside (callers pass workspaces),
+ *     so every call is CUDA-graph capturable.
+ *   - graphs: in-edge CSR of an undirected graph with BOTH directions stored
+ *     (dgl.from_networkx semantics, graphExtender.py:102-103), int32 indices;
+ *     a batch is block-diagonal: graph g owns nodes [graph_ptr[g], graph_ptr[g+1]).
+ *   - matrices are row-major fp32 with an explicit leading dimension (elements).
+ */
+#ifndef GCNMAXCUT_H_
+#define GCNMAXCUT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMC_ABI_VERSION 1
+
+#define GMC_OK 0
+#define GMC_ERR_INVALID_ARG (-1)
+#define GMC_ERR_UNSUPPORTED (-2)
+#define GMC_ERR_WORKSPACE (-3)
+
+/* GEMM arithmetic */
+#define GMC_GEMM_FP32 0      /* CUDA-core FFMA, exact fp32 (parity path)                       */
+#define GMC_GEMM_TF32 1      /* tcgen05 kind::tf32, one pass, fp32 accumulate in TMEM          */
+#define GMC_GEMM_TF32X3 2    /* tcgen05, 3 split passes (hi*hi + hi*lo + lo*hi): fp32-grade    */
+
+/* loss modes */
+#define GMC_LOSS_STE 0       /* hard one-hot + straight-through (reference live path)          */
+#define GMC_LOSS_SOFT 1      /* soft objective sum w_ij p_i.p_j (north-star variant)           */
+
+int gmc_abi_version(void);
+const char* gmc_last_error(void);
+/* sm count / compute capability of the current device (host out-pointers). */
+int gmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- graph preparation ------------------------------------------------------------ */
+
+/* norm[v] = max(deg(v),1)^-1/2 ; *zero_degree_count (device int32, nullable) receives the
+ * number of rows with degree 0 (DGL raises on those: GraphConv allow_zero_in_degree=False).
+ * Replaces: dgl GraphConv degree normalisation, TrainingNeural.py:80,83. */
+int gmc_degree_norm_f32(const int32_t* rowptr, int64_t n_rows, float* norm,
+                        int32_t* zero_degree_count, void* stream);
+
+/* coef[e] = (vals ? vals[e] : 1) * norm_src[col[e]] * norm_dst[row(e)]  -- the values of
+ * A_hat = D^-1/2 A D^-1/2, computed once per (static) batch. */
+int gmc_edge_coef_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                      const float* norm_src, const float* norm_dst, int64_t n_rows,
+                      float* coef, void* stream);
+
+/* Dense padded adjacency rows X[v, u - graph_ptr[g]] = w_uv (zero elsewhere), X is
+ * [n_rows, n_cols] with leading dimension ldx.  Device-side replacement for
+ * commons.py:38-77 (gen_adj_matrix + qubo_dict_to_torch) + graphExtender.py:28-48. */
+int gmc_csr_densify_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                        const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows,
+                        int32_t n_cols, float* X, int64_t ldx, void* stream);
+
+/* ---- (a) symmetric-normalised CSR SpMM ---------------------------------------------- */
+
+/* Y[v,:] = act( nd[v] * sum_{e in row v} w_e * ns[col_e] * X[col_e,:] + bias )
+ * vals / norm_src / norm_dst / bias may be NULL (treated as 1 / 1 / 1 / 0); relu != 0
+ * applies max(.,0).  Passing the precomputed gmc_edge_coef_f32 array as `vals` with both
+ * norms NULL is the fast path.  A_hat is symmetric, so the backward SpMM is this call.
+ * Replaces: dgl update_all(copy_u,sum) + norms + bias inside GraphConv.forward
+ * (TrainingNeural.py:80 / :83) and F.relu (:81). */
+int gmc_spmm_symnorm_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                         const float* norm_src, const float* norm_dst, const float* X, float* Y,
+                         int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy,
+                         const float* bias, int32_t relu, void* stream);
+
+/* ---- (b) dense feature transforms --------------------------------------------------- */
+
+/* C[M,N] = op(A) * op(B) (+ C if accumulate != 0), row-major.
+ *   nn: A[M,K] lda, B[K,N] ldb      (X * W1,            TrainingNeural.py:80 th.matmul in GraphConv)
+ *   nt: A[M,K] lda, B[N,K] ldb      (dT1 * W1^T,        autograd of :80, only for trainable features)
+ *   tn: A[K,M] lda, B[K,N] ldb      (X^T * dT1 = dW1,   autograd of :80; K = all nodes -> split-K)
+ * `workspace` is required when the implementation splits K (tn); query the size first.
+ * precision: GMC_GEMM_*.  TF32 paths require sm_100a and 16-byte aligned rows. */
+size_t gmc_gemm_workspace_bytes(int32_t op /*0 nn,1 nt,2 tn*/, int64_t M, int64_t N, int64_t K,
+                                int32_t precision);
+int gmc_gemm_nn(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                int64_t lda, int64_t ldb, int64_t ldc, int32_t accumulate, int32_t precision,
+                void* workspace, size_t workspace_bytes, void* stream);
+int gmc_gemm_nt(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                int64_t lda, int64_t ldb, int64_t ldc, int32_t accumulate, int32_t precision,
+                void* workspace, size_t workspace_bytes, void* stream);
+int gmc_gemm_tn(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                int64_t lda, int64_t ldb, int64_t ldc, int32_t accumulate, int32_t precision,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Skinny second layer, forward: T[v,k] = sum_j H[v,j] * W[j,k], K_out <= 8.
+ * Replaces th.matmul inside conv2 (TrainingNeural.py:83). */
+int gmc_skinny_fwd_f32(const float* H, int64_t ldh, const float* W /*[n_in,n_out]*/, float* T,
+                       int64_t ldt, int64_t n_rows, int32_t n_in, int32_t n_out, void* stream);
+
+/* Skinny second layer, backward, one pass over H:
+ *   dHpre[v,j] = (H[v,j] > 0) * sum_k dT[v,k] W[j,k]     (ReLU mask = sign of the output)
+ *   dW[j,k]    = sum_v H[v,j] dT[v,k]
+ *   dbias[j]   = sum_v dHpre[v,j]                        (gradient of the FIRST layer's bias)
+ * Deterministic two-stage reduction through `workspace`
+ * (gmc_skinny_bwd_workspace_bytes).  Replaces autograd of TrainingNeural.py:81-83. */
+size_t gmc_skinny_bwd_workspace_bytes(int32_t n_in, int32_t n_out);
+int gmc_skinny_bwd_f32(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh,
+                       float* dHpre, int64_t lddh, float* dW, float* dbias, int64_t n_rows,
+                       int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* out[j] = sum_v X[v,j]   (bias gradients); deterministic; workspace >= gmc_colsum_workspace_bytes. */
+size_t gmc_colsum_workspace_bytes(int32_t n_cols);
+int gmc_colsum_f32(const float* X, int64_t ldx, int64_t n_rows, int32_t n_cols, float* out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (c) fused softmax + terminal override + max-cut loss + gradient ----------------- */
+
+/* One pass over the edge list.  Per node v of graph g (local index i = v - graph_ptr[g]):
+ *   P_v = softmax(Z_v);   s_v = onehot(argmax P_v) [STE] or P_v [SOFT];
+ *   if override_terminals and i < 3: s_v = e_i             (override_fixed_nodes)
+ *   loss_g = -C * 1/2 sum_{(u,v)} w_uv (1 - s_u . s_v)  (+ penalty * sum_{i<j<3} s_i . s_j)
+ *   dZ_v   = P_v * (g_v - <P_v, g_v>),  g_v = C * sum_u w_uv s_u (+ penalty term on terminals)
+ * P_out / dZ_out may be NULL.  loss_per_graph is float64 [n_graphs] (overwritten).
+ * n_classes <= 8; override needs n_classes >= 3.
+ * Replaces: F.softmax (TrainingNeural.py:84), override_fixed_nodes (:87-94),
+ * apply_max_to_one_hot (:96-106), calculate_HC_vectorized/compute_loss (:154-176, :291-309),
+ * terminal_independence_penalty (:178-195) and their autograd. */
+int gmc_softmax_cut_loss_fwd_bwd(const float* Z, int64_t ldz, const int32_t* rowptr,
+                                 const int32_t* colidx, const float* vals,
+                                 const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows,
+                                 int32_t n_classes, int32_t mode, int32_t override_terminals,
+                                 float penalty, float C, float* P_out, double* loss_per_graph,
+                                 float* dZ_out, void* stream);
+
+/* ---- (d) fused multi-tensor Adam ----------------------------------------------------- */
+
+/* torch.optim.Adam defaults (amsgrad=False, weight_decay=0): for each of n_tensors (<= 16)
+ *   m += (g-m)(1-b1); v = v*b2 + (1-b2) g*g; p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * The four pointer arrays and `sizes` are HOST arrays of length n_tensors (copied by value
+ * into the launch).  `step` is the 1-based step count t.  Replaces optimizer.step(),
+ * TrainingNeural.py:386 (optimizer built at :336-337). */
+int gmc_adam_multi(int32_t n_tensors, float* const* params, const float* const* grads,
+                   float* const* exp_avg, float* const* exp_avg_sq, const int64_t* sizes,
+                   double lr, double beta1, double beta2, double eps, int64_t step, void* stream);
+
+/* Same, but t is read from (and incremented in) device memory so that a captured CUDA graph
+ * can be replayed: *step_dev is the number of steps already taken. */
+int gmc_adam_multi_devstep(int32_t n_tensors, float* const* params, const float* const* grads,
+                           float* const* exp_avg, float* const* exp_avg_sq, const int64_t* sizes,
+                           double lr, double beta1, double beta2, double eps, int64_t* step_dev,
+                           void* stream);
+
+/* ---- (e) integer post-processing ------------------------------------------------------ */
+
+/* labels[v] = first argmax_k P[v,k]; the first min(3,n_g) nodes of each graph are forced to
+ * 0,1,2 when force_terminals != 0.  Replaces simple_partition_assignment,
+ * TestingNeuralNetwork.py:100-122. */
+int gmc_argmax_labels(const float* P, int64_t ldp, const int32_t* graph_ptr, int32_t n_graphs,
+                      int64_t n_rows, int32_t n_classes, int32_t force_terminals, int32_t* labels,
+                      void* stream);
+
+/* cut[g] = sum of w over undirected edges of graph g whose end points differ (int64, exact).
+ * wts: int32 per directed edge, NULL = 1.  Replaces calculate_cut_value,
+ * TestingNeuralNetwork.py:48-64 (== RandomizedMaxCut.py:48-60). */
+int gmc_cut_value_i32(const int32_t* labels, const int32_t* rowptr, const int32_t* colidx,
+                      const int32_t* wts, const int32_t* graph_ptr, int32_t n_graphs,
+                      int64_t n_rows, int64_t* cut, void* stream);
+
+/* P1: `iters` categorical samplings per graph, keep the FIRST iteration with the maximal cut.
+ * U: float64 uniforms, graph g uses U[u_ptr[g] + it*(n_g-3) + (i-3)] for local node i >= 3 --
+ * the host draws them with np.random.rand in the reference's call order.  compare_f32 selects
+ * `float32(r) < cumsum` (numpy >= 2) or `r < float64(cumsum)` (numpy 1.x).  cuts_ws: int64
+ * [n_graphs*iters].  Outputs: best_labels [n_rows], best_cut [n_graphs], best_iter [n_graphs].
+ * Replaces assign_partitions + post_processing_optimization, TestingNeuralNetwork.py:18-46, 66-98. */
+int gmc_sample_best_cut(const float* P, int64_t ldp, const double* U, const int64_t* u_ptr,
+                        const int32_t* rowptr, const int32_t* colidx, const int32_t* wts,
+                        const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows,
+                        int32_t n_classes, int32_t iters, int32_t compare_f32, int64_t* cuts_ws,
+                        int32_t* best_labels, int64_t* best_cut, int32_t* best_iter, void* stream);
+
+/* P2: greedy best-improvement node-move local search, <= iters moves per graph, nodes with
+ * local index < n_frozen never move; ties -> lowest node then lowest class; stops when no move
+ * has positive gain.  k-way generalisation of greedy_maxcut,
+ * "Other Algorithms/huerestics_multi-max.ipynb":L5817-5854. */
+int gmc_greedy_node_move(const int32_t* labels_in, const int32_t* rowptr, const int32_t* colidx,
+                         const int32_t* wts, const int32_t* graph_ptr, int32_t n_graphs,
+                         int64_t n_rows, int32_t n_classes, int32_t iters, int32_t n_frozen,
+                         int32_t* labels_out, int64_t* cut_out, int32_t* moves_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNMAXCUT_H_ */
