@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- GCN max-cut training throughput on B200 (BASELINE.json metric:
+"GCN train graph-epochs/s (n=1000,d=7,k=3) at 1/2/4/8 B200; SpMM HBM GB/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full training pass (forward, fused max-cut loss, backward, gradient all-reduce,
+Adam) over the rank's block-diagonal batch: 4 096 synthetic regular graphs, n=1000, F=1000 -> H=500
+-> K=3 (config 3 at N=1; with N ranks the job is config 4's 4 096*N graphs, d = 6 + g mod 3 --
+weak scaling).  Features are the zero-padded adjacency rows held DENSE in HBM ([N,1000] fp32,
+16.4 GB per GPU), i.e. exactly what the reference feeds its GraphConv (TrainingNeural.py:373), so
+the feature transforms are true dense GEMMs.
+
+Output: ONE JSON line on rank 0 (contract in the task statement) with `roofline`, `cpu_baseline`,
+`e2e`, `clocks`, `gpu_launches`.  `--impl reference` times the CPU port of the reference's own
+per-graph training step (oracle/ref_step.FaithfulPort; the Python reference cannot travel to the
+GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gcn-max-cut_b200")
+for _p in (ROOT, PKG, os.path.join(PKG, "python")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "GCN train graph-epochs/s (n=1000,d=7,k=3)"
+UNIT = "graph-epochs/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs-per-gpu", type=int, default=4096)
+    ap.add_argument("--nodes", type=int, default=1000)
+    ap.add_argument("--degree", type=int, default=7)
+    ap.add_argument("--features", type=int, default=1000)
+    ap.add_argument("--hidden", type=int, default=500)
+    ap.add_argument("--classes", type=int, default=3)
+    ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "fp32"),
+                    choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="time budget of the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="graphs per reference-arm step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback (B200_PROFILING.md)"
+    return d
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int, period: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=10)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU reference leg
+def cpu_reference_run(args, steps: int, warmup: int, sample: int, budget_s: float = 0.0):
+    """Times oracle.ref_step.FaithfulPort (the reference's per-graph training step restated on torch
+    CPU with the same cost structure) on `sample` synthetic graphs of the benchmark shape.  One step =
+    one pass over the sample (= `sample` sequential Adam steps, as the reference trains).  With
+    budget_s > 0 the number of timed steps is chosen so the leg ends within the budget."""
+    import numpy as np
+    import torch
+    from gmc_b200 import synth
+    from oracle import ref_step as rs
+
+    rowptr, colidx, gp = synth.regular_batch_arrays(sample, args.nodes, args.degree, seed=args.seed + 991)
+    items = []
+    for g in range(sample):
+        lo, hi = gp[g], gp[g + 1]
+        rp = (rowptr[lo: hi + 1] - rowptr[lo]).astype(np.int32)
+        ci = (colidx[rowptr[lo]: rowptr[hi]] - lo).astype(np.int32)
+        csr = rs.HostCSR(rp, ci, np.ones(len(ci), dtype=np.float32), args.nodes)
+        X = rs.dense_adjacency(csr, args.features)
+        items.append((csr, X))
+    threads = torch.get_num_threads()
+    port = rs.FaithfulPort(args.features, args.hidden, args.classes, lr=1e-3, seed=args.seed, pad=args.features)
+
+    def one_pass():
+        return sum(port.step(csr, X, X) for csr, X in items)
+
+    t0 = time.perf_counter()
+    for _ in range(max(1, warmup) if budget_s <= 0 else 1):
+        one_pass()
+    warm = time.perf_counter() - t0
+    if budget_s > 0:
+        per = warm
+        steps = max(1, int((budget_s - warm) / max(per, 1e-6)))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = time.perf_counter() - t0
+    value = sample * steps / dt
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample} graphs n={args.nodes} d={args.degree} F={args.features} H={args.hidden}, "
+                      f"{steps} passes ({sample * steps} sequential per-graph Adam steps) in {dt:.1f}s, "
+                      f"torch CPU {threads} threads, oracle/ref_step.FaithfulPort",
+            "ms_per_graph": 1000.0 * dt / (sample * steps), "steps": steps, "seconds": dt}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_run(args, args.steps, args.warmup, args.cpu_sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * res["seconds"] / res["steps"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bounded sample of config 3: {args.cpu_sample} of {args.graphs_per_gpu} synthetic "
+                               f"{args.degree}-regular graphs n={args.nodes}, F={args.features}, H={args.hidden}, "
+                               f"K={args.classes}, per-graph Adam steps (reference semantics)"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gmc_b200 import _lib, dist as gdist, ops, synth
+    from gmc_b200.engine import GCNEngine, OpTimer
+    from gmc_b200.graph import GraphBatch
+    from Training import TrainingNeural as T
+
+    rank, local_rank, world = gdist.init_from_env()
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"# warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    dev = _lib.require_cuda()
+    peaks = load_peaks()
+    B, n, F, H, K = args.graphs_per_gpu, args.nodes, args.features, args.hidden, args.classes
+
+    # ---- synthetic shard (host, pinned) -------------------------------------------------
+    if world == 1:
+        degs = args.degree
+    else:
+        g0 = rank * B
+        degs = [6 + ((g0 + g) % 3) for g in range(B)]
+    t_gen = time.perf_counter()
+    rowptr, colidx, graph_ptr = synth.regular_batch_arrays(B, n, degs, seed=args.seed + 1000 * rank)
+    t_gen = time.perf_counter() - t_gen
+    h_rowptr = torch.from_numpy(rowptr).pin_memory()
+    h_colidx = torch.from_numpy(colidx).pin_memory()
+    h_gptr = torch.from_numpy(graph_ptr).pin_memory()
+    batch = GraphBatch.from_arrays(rowptr, colidx, graph_ptr, device=dev)
+    N, nnz = batch.num_nodes, batch.nnz
+    X = ops.densify(batch, F)                           # dense padded adjacency rows, resident in HBM
+
+    torch.manual_seed(args.seed)                        # identical initial weights on every rank
+    cfg = T.TrainingConfig(n_nodes=n, dim_embedding=F, hidden_dim=H, number_classes=K, learning_rate=1e-3,
+                           gemm_precision=args.precision, batch_graphs=B)
+    net, embed, opt = T.setup_model_and_optimizer(cfg)
+    del embed
+    eng = GCNEngine(net, opt, precision=args.precision)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput --------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.train_step(batch, X)
+    sync_all()
+    eng.timer = OpTimer()
+    eng.launch_count = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = None
+    for _ in range(args.steps):
+        loss = eng.train_step(batch, X)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    sampler.stop()
+    eng.timer.collect()
+    timer = eng.timer
+    eng.timer = None
+    launches = eng.launch_count
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    gdist.all_reduce_max_(t)
+    ms_max = float(t.item())
+    total_graphs = B * world
+    value = total_graphs * args.steps / (ms_max / 1000.0)
+    last_loss = float(loss.sum().item())
+
+    # ---- end-to-end: host CSR buffers in, loss out, every step -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = args.e2e_steps or args.steps
+        d_rowptr = torch.empty_like(batch.rowptr)
+        d_colidx = torch.empty_like(batch.colidx)
+        d_gptr = torch.empty_like(batch.graph_ptr)
+
+        def e2e_step():
+            d_rowptr.copy_(h_rowptr, non_blocking=True)
+            d_colidx.copy_(h_colidx, non_blocking=True)
+            d_gptr.copy_(h_gptr, non_blocking=True)
+            b2 = GraphBatch.__new__(GraphBatch)
+            b2.device, b2.num_graphs, b2.sizes, b2.num_nodes, b2.nnz = dev, B, batch.sizes, N, nnz
+            b2.rowptr, b2.colidx, b2.graph_ptr = d_rowptr, d_colidx, d_gptr
+            b2.unit_weights, b2.wts_f32, b2.wts_i32, b2.integer_weights = True, None, None, True
+            b2.norm, _zero = ops.degree_norm(d_rowptr, N)            # includes the zero-degree check read-back
+            b2.coef = ops.edge_coef(d_rowptr, d_colidx, None, b2.norm, b2.norm, N)
+            ops.densify(b2, F, out=X)                                # device-side graphExtender
+            per_graph = eng.train_step(b2, X)
+            return per_graph.cpu()                                   # D2H of the step's result
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            host_loss = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        gdist.all_reduce_max_(t)
+        h2d = (h_rowptr.numel() + h_colidx.numel() + h_gptr.numel()) * 4
+        e2e = {"value": total_graphs * k_e2e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(B * 8 + 4), "steps": k_e2e,
+               "path": "pinned host CSR (rowptr, colidx, graph_ptr) -> H2D -> gmc_degree_norm/edge_coef/"
+                       "csr_densify (device-side graphExtender) -> GCNEngine.train_step -> per-graph loss D2H"}
+        del host_loss
+
+    # ---- rooflines ----------------------------------------------------------------------------
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0 if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"] / 2.0
+    spmm_bytes_h = 8.0 * N * H + 4.0 * nnz + 4.0 * (N + 1)
+    spmm_bytes_k = 8.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)
+    gemm_flops = 2.0 * N * F * H
+    algo = {
+        "gemm_nn_xw1": ("tensor", gemm_flops), "gemm_tn_dw1": ("tensor", gemm_flops),
+        "spmm_h": ("hbm", spmm_bytes_h), "spmm_k": ("hbm", spmm_bytes_k),
+        "skinny_fwd": ("hbm", 4.0 * N * H + 4.0 * N * K), "skinny_bwd": ("hbm", 8.0 * N * H + 4.0 * N * K),
+        "cut_loss": ("hbm", 12.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)), "colsum_db2": ("hbm", 4.0 * N * K),
+        "adam": ("hbm", 28.0 * (F * H + H + H * K + K)),
+    }
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic_db = json.load(open(tpath))
+        except Exception:
+            traffic_db = {}
+    ops_report = {}
+    for name, tot in timer.total_ms.items():
+        calls = timer.calls[name]
+        avg_ms = tot / calls
+        bound, work = algo.get(name, ("hbm", 0.0))
+        if bound == "hbm":
+            achieved, peak, unit = work / (avg_ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
+        else:
+            achieved, peak, unit = work / (avg_ms * 1e-3) / 1e12, tf32_peak, "TFLOP/s"
+        ops_report[name] = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                            "frac": achieved / peak if peak else None, "avg_ms": avg_ms, "calls": calls,
+                            "share_of_step": tot / ms, "traffic": traffic_db.get(name)}
+    dominant = max(timer.total_ms, key=lambda k: timer.total_ms[k]) if timer.total_ms else None
+    roofline = None
+    if dominant:
+        r = ops_report[dominant]
+        roofline = {"bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                    "frac": r["frac"], "traffic": r["traffic"], "kernel": dominant, "avg_ms": r["avg_ms"],
+                    "share_of_step": r["share_of_step"],
+                    "peak_source": peaks["_source"] + ("; tf32 peak taken as half of the sustained bf16 figure"
+                                                      if r["bound"] == "tensor" else ""),
+                    "precision": args.precision}
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = cpu_reference_run(args, 0, 1, min(4, args.cpu_sample), budget_s=args.cpu_seconds)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        clocks = sampler.summary()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
+            "config": {
+                "workload": (f"config 3: {B} synthetic {args.degree}-regular graphs n={n} as one block-diagonal CSR per GPU"
+                             if world == 1 else
+                             f"config 4: {total_graphs} synthetic regular graphs n={n}, d=6+(g mod 3), {B} per GPU"),
+                "features": f"dense zero-padded adjacency rows [{N},{F}] fp32 resident in HBM ({N * F * 4 / 1e9:.1f} GB/GPU)",
+                "model": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
+                "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",
+                "gemm_precision": args.precision, "parallelism": f"dp{world}",
+                "l2": f"inputs larger than L2 (X {N * F * 4 / 1e9:.1f} GB, activations {2 * N * H * 4 / 1e9:.1f} GB)",
+                "graph_generation_s": t_gen,
+            },
+            "roofline": roofline,
+            "spmm": ops_report.get("spmm_h"),
+            "ops": ops_report,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "loss_last_step": last_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

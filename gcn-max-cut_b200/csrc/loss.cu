@@ -163,7 +163,64 @@ cut_loss_kernel(const float* __restrict__ Z, int64_t ldz, const int32_t* __restr
     }
 }
 
+// standalone row softmax (inference / generic autograd use of GCNSoftmax.forward)
+template <int K>
+__global__ void softmax_fwd_kernel(const float* __restrict__ Z, int64_t ldz, int64_t n_rows, float* __restrict__ P) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_rows) return;
+    float z[K], p[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) z[k] = __ldg(Z + v * ldz + k);
+    softmax_row<K>(z, p);
+#pragma unroll
+    for (int k = 0; k < K; ++k) P[v * K + k] = p[k];
+}
+
+// dZ = P .* (dP - <P, dP>)
+template <int K>
+__global__ void softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ dP, int64_t n_rows,
+                                   float* __restrict__ dZ) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_rows) return;
+    float p[K], g[K], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { p[k] = __ldg(P + v * K + k); g[k] = __ldg(dP + v * K + k); dot = fmaf(p[k], g[k], dot); }
+#pragma unroll
+    for (int k = 0; k < K; ++k) dZ[v * K + k] = p[k] * (g[k] - dot);
+}
+
 }  // namespace gmc
+
+extern "C" int gmc_softmax_fwd_f32(const float* Z, int64_t ldz, int64_t n_rows, int32_t n_classes, float* P,
+                                   void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(Z && P, "gmc_softmax_fwd_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_classes >= 1 && n_classes <= kMaxClasses && ldz >= n_classes,
+                "gmc_softmax_fwd_f32: bad sizes (n_classes 1..8)");
+    if (n_rows == 0) return GMC_OK;
+    const unsigned blocks = (unsigned)ceil_div<int64_t>(n_rows, 256);
+    cudaStream_t s = as_stream(stream);
+#define GMC_CASE(K) case K: softmax_fwd_kernel<K><<<blocks, 256, 0, s>>>(Z, ldz, n_rows, P); break;
+    switch (n_classes) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
+#undef GMC_CASE
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+extern "C" int gmc_softmax_bwd_f32(const float* P, const float* dP, int64_t n_rows, int32_t n_classes, float* dZ,
+                                   void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(P && dP && dZ, "gmc_softmax_bwd_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_classes >= 1 && n_classes <= kMaxClasses, "gmc_softmax_bwd_f32: bad sizes");
+    if (n_rows == 0) return GMC_OK;
+    const unsigned blocks = (unsigned)ceil_div<int64_t>(n_rows, 256);
+    cudaStream_t s = as_stream(stream);
+#define GMC_CASE(K) case K: softmax_bwd_kernel<K><<<blocks, 256, 0, s>>>(P, dP, n_rows, dZ); break;
+    switch (n_classes) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
+#undef GMC_CASE
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
 
 extern "C" int gmc_softmax_cut_loss_fwd_bwd(const float* Z, int64_t ldz, const int32_t* rowptr, const int32_t* colidx,
                                             const float* vals, const int32_t* graph_ptr, int32_t n_graphs,

@@ -1,0 +1,218 @@
+"""GCNEngine -- the fused training / inference step of the B200 path.
+
+One explicit kernel sequence per step (no autograd, no torch operators):
+
+    fwd   T1 = X W1                       gmc_gemm_nn            (tensor / CUDA cores)
+          H1 = relu(A_hat T1 + b1)        gmc_spmm_symnorm_f32   (bias + ReLU fused)
+          T2 = H1 W2                      gmc_skinny_fwd_f32
+          Z  = A_hat T2 + b2              gmc_spmm_symnorm_f32
+    loss  P, loss_g, dZ                   gmc_softmax_cut_loss_fwd_bwd  (one pass over edges)
+    bwd   db2 = colsum(dZ)                gmc_colsum_f32
+          dT2 = A_hat dZ                  gmc_spmm_symnorm_f32   (A_hat symmetric)
+          dH1pre, dW2, db1                gmc_skinny_bwd_f32     (one pass over H1)
+          dT1 = A_hat dH1pre              gmc_spmm_symnorm_f32
+          dW1 = X^T dT1                   gmc_gemm_tn            (split-K over all nodes)
+         [dX  = dT1 W1^T                  gmc_gemm_nt            only if features are trainable]
+    dp    all-reduce(sum) of [dW1|db1|dW2|db2] over NCCL        (only when world_size > 1)
+    opt   Adam on W1,b1,W2,b2 [,X]        gmc_adam_multi
+
+It replaces the body of the reference's inner training loop,
+python/Training/TrainingNeural.py:371-388 (forward :373, override :374, STE :377, loss :380,
+backward :385, optimizer.step :386) and evaluate_model's body (:553-562).
+
+Buffers: two [N,H] activations are enough -- bufA holds T1 then dH1pre, bufB holds H1 then dT1.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from .graph import GraphBatch
+from .optim import FusedAdam
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+class OpTimer:
+    """CUDA-event stopwatch per engine op (events on torch's current stream, which is the stream
+    every gmc_* call is launched on).  Used by bench.py for the live roofline numbers."""
+
+    def __init__(self):
+        self.pending = []            # (name, start_event, stop_event)
+        self.total_ms: Dict[str, float] = {}
+        self.calls: Dict[str, int] = {}
+
+    def begin(self, name: str):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return (name, ev)
+
+    def end(self, token) -> None:
+        stop = torch.cuda.Event(enable_timing=True)
+        stop.record()
+        self.pending.append((token[0], token[1], stop))
+
+    def collect(self) -> None:
+        """Call after a synchronize: folds all finished intervals into the totals."""
+        for name, a, b in self.pending:
+            self.total_ms[name] = self.total_ms.get(name, 0.0) + a.elapsed_time(b)
+            self.calls[name] = self.calls.get(name, 0) + 1
+        self.pending = []
+
+    def reset(self) -> None:
+        self.pending, self.total_ms, self.calls = [], {}, {}
+
+
+class GCNEngine:
+    def __init__(self, net, optimizer: Optional[FusedAdam] = None, *, C: float = 1.0, loss_mode: str = "ste",
+                 override_terminals: bool = True, penalty: float = 0.0, precision: str = "fp32",
+                 process_group=None):
+        self.device = _lib.require_cuda()
+        self.net = net
+        self.optimizer = optimizer
+        self.C, self.loss_mode, self.override, self.penalty = float(C), loss_mode, bool(override_terminals), float(penalty)
+        if loss_mode not in _lib.LOSS_MODES:
+            raise ValueError(f"unknown loss_mode {loss_mode!r}")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"unknown precision {precision!r}")
+        self.precision = precision
+        self.pg = process_group
+        W1, b1, W2, b2 = self.params()
+        for p in (W1, b1, W2, b2):
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.GmcError("GCNEngine needs contiguous CUDA float32 parameters")
+        self.F, self.H = W1.shape
+        self.K = W2.shape[1]
+        if self.K > 8:
+            raise ValueError("number_classes > 8 is not supported by the fused kernels")
+        # flat gradient buffer [dW1 | db1 | dW2 | db2], segments 16-byte aligned
+        sizes = [W1.numel(), b1.numel(), W2.numel(), b2.numel()]
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot)
+            tot += _pad4(s)
+        self.grads_flat = torch.zeros(tot, dtype=torch.float32, device=self.device)
+        self.gW1 = self.grads_flat[offs[0]: offs[0] + sizes[0]].view_as(W1)
+        self.gb1 = self.grads_flat[offs[1]: offs[1] + sizes[1]]
+        self.gW2 = self.grads_flat[offs[2]: offs[2] + sizes[2]].view_as(W2)
+        self.gb2 = self.grads_flat[offs[3]: offs[3] + sizes[3]]
+        self.ws = ops.Workspace()
+        self._cap_nodes = 0
+        self._cap_graphs = 0
+        self.bufA = self.bufB = self.T2 = self.Z = self.P = self.dZ = self.dT2 = None
+        self.loss = None
+        self.timer: Optional[OpTimer] = None
+        self.launch_count = 0          # gmc_* kernels launched (bench.py's gpu_launches claim)
+
+    def _op(self, name: str, launches: int, fn, *args, **kwargs):
+        self.launch_count += launches
+        if self.timer is None:
+            return fn(*args, **kwargs)
+        tok = self.timer.begin(name)
+        out = fn(*args, **kwargs)
+        self.timer.end(tok)
+        return out
+
+    # ------------------------------------------------------------------ plumbing
+    def params(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        n = self.net
+        return n.conv1.weight, n.conv1.bias, n.conv2.weight, n.conv2.bias
+
+    def grads(self) -> List[torch.Tensor]:
+        return [self.gW1, self.gb1, self.gW2, self.gb2]
+
+    def _ensure(self, n_nodes: int, n_graphs: int) -> None:
+        if n_nodes > self._cap_nodes:
+            cap = n_nodes
+            dev, f32 = self.device, torch.float32
+            self.bufA = torch.empty((cap, self.H), dtype=f32, device=dev)
+            self.bufB = torch.empty((cap, self.H), dtype=f32, device=dev)
+            self.T2 = torch.empty((cap, self.K), dtype=f32, device=dev)
+            self.Z = torch.empty((cap, self.K), dtype=f32, device=dev)
+            self.P = torch.empty((cap, self.K), dtype=f32, device=dev)
+            self.dZ = torch.empty((cap, self.K), dtype=f32, device=dev)
+            self.dT2 = torch.empty((cap, self.K), dtype=f32, device=dev)
+            self._cap_nodes = cap
+        if n_graphs > self._cap_graphs:
+            self.loss = torch.empty(n_graphs, dtype=torch.float64, device=self.device)
+            self._cap_graphs = n_graphs
+
+    def _features(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        if X.dim() != 2 or X.shape[0] != batch.num_nodes or X.shape[1] != self.F:
+            raise ValueError(f"features must be [{batch.num_nodes}, {self.F}], got {tuple(X.shape)}")
+        if not X.is_cuda:
+            from .model import to_device_features
+            X = to_device_features(X, self.device)
+        return X
+
+    # ------------------------------------------------------------------ forward
+    def forward_logits(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        """Z (pre-softmax) for the batch; leaves H1 in bufB."""
+        X = self._features(batch, X)
+        N = batch.num_nodes
+        self._ensure(N, batch.num_graphs)
+        W1, b1, W2, b2 = self.params()
+        A, Bf = self.bufA[:N], self.bufB[:N]
+        self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, W1.data, out=A, precision=self.precision, workspace=self.ws)
+        self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf, bias=b1.data, relu=True)
+        self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
+        self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
+        return self.Z[:N]
+
+    def forward(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        """Softmax probabilities P [N,K] (a view into engine memory; clone to keep)."""
+        Z = self.forward_logits(batch, X)
+        N = batch.num_nodes
+        self._op("cut_loss", 1, ops.cut_loss, batch, Z, self.loss_mode, self.override, self.penalty, self.C,
+                 need_P=True, need_dZ=False, P=self.P[:N], loss=self.loss[: batch.num_graphs])
+        return self.P[:N]
+
+    def evaluate(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        """Per-graph loss (float64 [B], device) without gradients -- evaluate_model body (:553-562)."""
+        self.forward(batch, X)
+        return self.loss[: batch.num_graphs]
+
+    # ------------------------------------------------------------------ backward
+    def loss_and_grads(self, batch: GraphBatch, X: torch.Tensor, dX: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Forward + loss + full backward at the current weights.  Gradients land in
+        self.grads_flat (overwritten); returns per-graph loss (float64 [B], device view)."""
+        X = self._features(batch, X)
+        N, B = batch.num_nodes, batch.num_graphs
+        Z = self.forward_logits(batch, X)
+        W1, b1, W2, b2 = self.params()
+        A, Bf = self.bufA[:N], self.bufB[:N]
+        loss = self.loss[:B]
+        self._op("cut_loss", 1, ops.cut_loss, batch, Z, self.loss_mode, self.override, self.penalty, self.C,
+                 need_P=True, need_dZ=True, P=self.P[:N], dZ=self.dZ[:N], loss=loss)
+        self._op("colsum_db2", 2, ops.colsum, self.dZ[:N], out=self.gb2, workspace=self.ws)
+        self._op("spmm_k", 1, ops.spmm, batch, self.dZ[:N], out=self.dT2[:N])
+        self._op("skinny_bwd", 2, ops.skinny_bwd, self.dT2[:N], W2.data, Bf, dH=A, dW=self.gW2, dbias=self.gb1,
+                 workspace=self.ws)
+        self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf)                                   # dT1
+        self._op("gemm_tn_dw1", 2, ops.gemm, "tn", X, Bf, out=self.gW1, precision=self.precision, workspace=self.ws)
+        if dX is not None:
+            self._op("gemm_nt_dx", 1, ops.gemm, "nt", Bf, W1.data, out=dX, precision=self.precision,
+                     workspace=self.ws)
+        return loss
+
+    def allreduce_grads(self) -> None:
+        """Data-parallel exchange: ONE NCCL all-reduce of the 502 003-float gradient buffer."""
+        import torch.distributed as dist
+        if self.pg is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            dist.all_reduce(self.grads_flat, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def apply_adam(self) -> None:
+        if self.optimizer is None:
+            raise RuntimeError("GCNEngine was built without an optimizer")
+        self._op("adam", 1, self.optimizer.fused_step, list(self.params()), self.grads())
+
+    def train_step(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        """One optimiser step on the whole batch (loss = sum of per-graph losses)."""
+        loss = self.loss_and_grads(batch, X)
+        self.allreduce_grads()
+        self.apply_adam()
+        return loss

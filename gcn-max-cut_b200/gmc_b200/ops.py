@@ -1,0 +1,333 @@
+"""Thin torch-tensor wrappers over the C ABI (one gmc_* call each, on torch's current stream).
+
+torch is used for device memory and streams only; no torch operator computes anything on
+the hot path.  Every wrapper validates dtype/device/contiguity and raises -- nothing here
+falls back to a PyTorch implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+def _rowmajor(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """Accept 2-D tensors whose rows are contiguous (stride(1) == 1); return (tensor, ld)."""
+    _f32(t, name)
+    if t.dim() != 2:
+        raise ValueError(f"{name}: expected a 2-D tensor")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    if ld < t.shape[1]:
+        t = t.contiguous()
+        ld = t.shape[1]
+    return t, ld
+
+
+class Workspace:
+    """Grow-only device scratch (the C ABI never allocates)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> Tuple[Optional[int], int]:
+        if nbytes == 0:
+            return None, 0
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf.data_ptr(), self.buf.numel()
+
+
+_default_ws = Workspace()
+
+
+# ---------------------------------------------------------------- graph preparation
+def degree_norm(rowptr: torch.Tensor, n_rows: int) -> Tuple[torch.Tensor, int]:
+    norm = torch.empty(n_rows, dtype=torch.float32, device=rowptr.device)
+    zero = torch.zeros(1, dtype=torch.int32, device=rowptr.device)
+    check(lib().gmc_degree_norm_f32(rowptr.data_ptr(), n_rows, norm.data_ptr(), zero.data_ptr(), _stream()),
+          "gmc_degree_norm_f32")
+    return norm, int(zero.item())
+
+
+def edge_coef(rowptr, colidx, vals, norm_src, norm_dst, n_rows: int) -> torch.Tensor:
+    coef = torch.empty(colidx.numel(), dtype=torch.float32, device=colidx.device)
+    check(lib().gmc_edge_coef_f32(rowptr.data_ptr(), colidx.data_ptr(), _ptr(vals), _ptr(norm_src), _ptr(norm_dst),
+                                  n_rows, coef.data_ptr(), _stream()), "gmc_edge_coef_f32")
+    return coef
+
+
+def densify(batch, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Padded adjacency rows X[N, n_cols] of a GraphBatch (device-side graphExtender)."""
+    if out is None:
+        out = torch.empty((batch.num_nodes, n_cols), dtype=torch.float32, device=batch.device)
+    out, ld = _rowmajor(out, "out")
+    check(lib().gmc_csr_densify_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), _ptr(batch.wts_f32),
+                                    batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
+                                    out.data_ptr(), ld, _stream()), "gmc_csr_densify_f32")
+    return out
+
+
+# ---------------------------------------------------------------- (a) SpMM
+def spmm(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         relu: bool = False, use_coef: bool = True) -> torch.Tensor:
+    """Y = act(A_hat X + bias).  use_coef=False recomputes the norms per edge from batch.norm."""
+    X, ldx = _rowmajor(X, "X")
+    n, c = X.shape
+    if n != batch.num_nodes:
+        raise ValueError(f"X has {n} rows, batch has {batch.num_nodes} nodes")
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=X.device)
+    out, ldy = _rowmajor(out, "out")
+    if bias is not None:
+        _f32(bias, "bias")
+    if use_coef:
+        vals, ns, nd = batch.coef, None, None
+    else:
+        vals, ns, nd = None, batch.norm, batch.norm
+    check(lib().gmc_spmm_symnorm_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), _ptr(vals), _ptr(ns), _ptr(nd),
+                                     X.data_ptr(), out.data_ptr(), n, c, ldx, ldy, _ptr(bias), int(relu), _stream()),
+          "gmc_spmm_symnorm_f32")
+    return out
+
+
+# ---------------------------------------------------------------- (b) GEMM
+_OPS = {"nn": 0, "nt": 1, "tn": 2}
+
+
+def gemm(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+         precision: str = "fp32", workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """nn: A[M,K] B[K,N];  nt: A[M,K] B[N,K];  tn: A[K,M] B[K,N]  ->  C[M,N]"""
+    A, lda = _rowmajor(A, "A")
+    B, ldb = _rowmajor(B, "B")
+    if op == "nn":
+        M, K = A.shape; K2, N = B.shape
+    elif op == "nt":
+        M, K = A.shape; N, K2 = B.shape
+    elif op == "tn":
+        K, M = A.shape; K2, N = B.shape
+    else:
+        raise ValueError(f"unknown gemm op {op!r}")
+    if K != K2:
+        raise ValueError(f"gemm {op}: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs an output tensor")
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    out, ldc = _rowmajor(out, "out")
+    prec = _lib.PRECISIONS[precision]
+    ws = workspace or _default_ws
+    need = lib().gmc_gemm_workspace_bytes(_OPS[op], M, N, K, prec)
+    wptr, wbytes = ws.get(need, A.device)
+    fn = getattr(lib(), "gmc_gemm_" + op)
+    check(fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc, int(accumulate), prec, wptr, wbytes,
+             _stream()), "gmc_gemm_" + op)
+    return out
+
+
+def skinny_fwd(H: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    H, ldh = _rowmajor(H, "H")
+    W = _f32(W, "W").contiguous()
+    n, n_in = H.shape
+    n_out = W.shape[1]
+    if out is None:
+        out = torch.empty((n, n_out), dtype=torch.float32, device=H.device)
+    out, ldt = _rowmajor(out, "out")
+    check(lib().gmc_skinny_fwd_f32(H.data_ptr(), ldh, W.data_ptr(), out.data_ptr(), ldt, n, n_in, n_out, _stream()),
+          "gmc_skinny_fwd_f32")
+    return out
+
+
+def skinny_bwd(dT: torch.Tensor, W: torch.Tensor, H: torch.Tensor, dH: Optional[torch.Tensor] = None,
+               dW: Optional[torch.Tensor] = None, dbias: Optional[torch.Tensor] = None,
+               workspace: Optional[Workspace] = None):
+    dT, lddt = _rowmajor(dT, "dT")
+    H, ldh = _rowmajor(H, "H")
+    W = _f32(W, "W").contiguous()
+    n, n_in = H.shape
+    n_out = W.shape[1]
+    if dH is None:
+        dH = torch.empty((n, n_in), dtype=torch.float32, device=H.device)
+    dH, lddh = _rowmajor(dH, "dH")
+    if dW is None:
+        dW = torch.empty((n_in, n_out), dtype=torch.float32, device=H.device)
+    if dbias is None:
+        dbias = torch.empty(n_in, dtype=torch.float32, device=H.device)
+    ws = workspace or _default_ws
+    wptr, wbytes = ws.get(lib().gmc_skinny_bwd_workspace_bytes(n_in, n_out), H.device)
+    check(lib().gmc_skinny_bwd_f32(dT.data_ptr(), lddt, W.data_ptr(), H.data_ptr(), ldh, dH.data_ptr(), lddh,
+                                   dW.data_ptr(), dbias.data_ptr(), n, n_in, n_out, wptr, wbytes, _stream()),
+          "gmc_skinny_bwd_f32")
+    return dH, dW, dbias
+
+
+def colsum(X: torch.Tensor, out: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None) -> torch.Tensor:
+    X, ldx = _rowmajor(X, "X")
+    n, c = X.shape
+    if out is None:
+        out = torch.empty(c, dtype=torch.float32, device=X.device)
+    ws = workspace or _default_ws
+    wptr, wbytes = ws.get(lib().gmc_colsum_workspace_bytes(c), X.device)
+    check(lib().gmc_colsum_f32(X.data_ptr(), ldx, n, c, out.data_ptr(), wptr, wbytes, _stream()), "gmc_colsum_f32")
+    return out
+
+
+# ---------------------------------------------------------------- (c) fused loss
+def cut_loss(batch, Z: torch.Tensor, mode: str = "ste", override_terminals: bool = True, penalty: float = 0.0,
+             C: float = 1.0, need_P: bool = True, need_dZ: bool = True, P: Optional[torch.Tensor] = None,
+             dZ: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None):
+    """Returns (loss_per_graph float64 [B], P or None, dZ or None)."""
+    Z, ldz = _rowmajor(Z, "Z")
+    n, K = Z.shape
+    if need_P and P is None:
+        P = torch.empty((n, K), dtype=torch.float32, device=Z.device)
+    if need_dZ and dZ is None:
+        dZ = torch.empty((n, K), dtype=torch.float32, device=Z.device)
+    if loss is None:
+        loss = torch.empty(batch.num_graphs, dtype=torch.float64, device=Z.device)
+    for t, nm in ((P, "P"), (dZ, "dZ")):
+        if t is not None and not t.is_contiguous():
+            raise ValueError(f"{nm} must be contiguous [N, K]")
+    check(lib().gmc_softmax_cut_loss_fwd_bwd(Z.data_ptr(), ldz, batch.rowptr.data_ptr(), batch.colidx.data_ptr(),
+                                             _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(), batch.num_graphs, n, K,
+                                             _lib.LOSS_MODES[mode], int(override_terminals), float(penalty), float(C),
+                                             _ptr(P) if need_P else None, loss.data_ptr(),
+                                             _ptr(dZ) if need_dZ else None, _stream()),
+          "gmc_softmax_cut_loss_fwd_bwd")
+    return loss, (P if need_P else None), (dZ if need_dZ else None)
+
+
+def softmax_fwd(Z: torch.Tensor) -> torch.Tensor:
+    Z, ldz = _rowmajor(Z, "Z")
+    n, K = Z.shape
+    P = torch.empty((n, K), dtype=torch.float32, device=Z.device)
+    check(lib().gmc_softmax_fwd_f32(Z.data_ptr(), ldz, n, K, P.data_ptr(), _stream()), "gmc_softmax_fwd_f32")
+    return P
+
+
+def softmax_bwd(P: torch.Tensor, dP: torch.Tensor) -> torch.Tensor:
+    P = _f32(P, "P").contiguous()
+    dP = _f32(dP, "dP").contiguous()
+    dZ = torch.empty_like(P)
+    check(lib().gmc_softmax_bwd_f32(P.data_ptr(), dP.data_ptr(), P.shape[0], P.shape[1], dZ.data_ptr(), _stream()),
+          "gmc_softmax_bwd_f32")
+    return dZ
+
+
+# ---------------------------------------------------------------- (d) Adam
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def adam_multi(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], exp_avg: Sequence[torch.Tensor],
+               exp_avg_sq: Sequence[torch.Tensor], lr: float, beta1: float = 0.9, beta2: float = 0.999,
+               eps: float = 1e-8, step: Optional[int] = None, step_dev: Optional[torch.Tensor] = None) -> None:
+    """In-place Adam on up to 16 tensors per launch.  Pass either `step` (1-based host count) or
+    `step_dev` (int64 device scalar holding the number of steps taken; incremented on device)."""
+    n = len(params)
+    for group in (params, grads, exp_avg, exp_avg_sq):
+        if len(group) != n:
+            raise ValueError("adam_multi: list lengths differ")
+        for t in group:
+            _f32(t, "adam tensor")
+            if not t.is_contiguous():
+                raise ValueError("adam_multi: tensors must be contiguous")
+    for lo in range(0, n, 16):
+        hi = min(n, lo + 16)
+        sizes = (ctypes.c_int64 * (hi - lo))(*[p.numel() for p in params[lo:hi]])
+        args = (hi - lo, _ptr_array(params[lo:hi]), _ptr_array(grads[lo:hi]), _ptr_array(exp_avg[lo:hi]),
+                _ptr_array(exp_avg_sq[lo:hi]), sizes, float(lr), float(beta1), float(beta2), float(eps))
+        if step_dev is not None:
+            if hi < n:
+                raise ValueError("adam_multi with step_dev supports at most 16 tensors per call")
+            check(lib().gmc_adam_multi_devstep(*args, step_dev.data_ptr(), _stream()), "gmc_adam_multi_devstep")
+        else:
+            if step is None or step < 1:
+                raise ValueError("adam_multi: step must be >= 1")
+            check(lib().gmc_adam_multi(*args, int(step), _stream()), "gmc_adam_multi")
+
+
+# ---------------------------------------------------------------- (e) post-processing
+def argmax_labels(batch, P: torch.Tensor, force_terminals: bool = True) -> torch.Tensor:
+    P, ldp = _rowmajor(P, "P")
+    n, K = P.shape
+    labels = torch.empty(n, dtype=torch.int32, device=P.device)
+    check(lib().gmc_argmax_labels(P.data_ptr(), ldp, batch.graph_ptr.data_ptr(), batch.num_graphs, n, K,
+                                  int(force_terminals), labels.data_ptr(), _stream()), "gmc_argmax_labels")
+    return labels
+
+
+def _int_weights(batch) -> Optional[torch.Tensor]:
+    if batch.unit_weights:
+        return None
+    if batch.wts_i32 is None:
+        raise ValueError("integer cut kernels need integer edge weights (the reference writes weight=1, "
+                         "GraphCreator.py:88-90)")
+    return batch.wts_i32
+
+
+def cut_value(batch, labels: torch.Tensor) -> torch.Tensor:
+    if labels.dtype != torch.int32 or not labels.is_cuda or not labels.is_contiguous():
+        raise TypeError("labels: expected a contiguous CUDA int32 tensor")
+    out = torch.empty(batch.num_graphs, dtype=torch.int64, device=labels.device)
+    check(lib().gmc_cut_value_i32(labels.data_ptr(), batch.rowptr.data_ptr(), batch.colidx.data_ptr(),
+                                  _ptr(_int_weights(batch)), batch.graph_ptr.data_ptr(), batch.num_graphs,
+                                  batch.num_nodes, out.data_ptr(), _stream()), "gmc_cut_value_i32")
+    return out
+
+
+def sample_best_cut(batch, P: torch.Tensor, U: torch.Tensor, u_ptr: torch.Tensor, iters: int,
+                    compare_f32: bool):
+    """P1.  U float64 device uniforms, u_ptr int64 [B+1] offsets.  Returns (labels, cut, best_iter)."""
+    P, ldp = _rowmajor(P, "P")
+    n, K = P.shape
+    if U.dtype != torch.float64 or u_ptr.dtype != torch.int64:
+        raise TypeError("U must be float64 and u_ptr int64")
+    dev = P.device
+    cuts = torch.empty(batch.num_graphs * iters, dtype=torch.int64, device=dev)
+    labels = torch.empty(n, dtype=torch.int32, device=dev)
+    best = torch.empty(batch.num_graphs, dtype=torch.int64, device=dev)
+    best_it = torch.empty(batch.num_graphs, dtype=torch.int32, device=dev)
+    check(lib().gmc_sample_best_cut(P.data_ptr(), ldp, U.data_ptr(), u_ptr.data_ptr(), batch.rowptr.data_ptr(),
+                                    batch.colidx.data_ptr(), _ptr(_int_weights(batch)), batch.graph_ptr.data_ptr(),
+                                    batch.num_graphs, n, K, iters, int(compare_f32), cuts.data_ptr(),
+                                    labels.data_ptr(), best.data_ptr(), best_it.data_ptr(), _stream()),
+          "gmc_sample_best_cut")
+    return labels, best, best_it
+
+
+def greedy_node_move(batch, labels: torch.Tensor, n_classes: int = 3, iters: int = 200, n_frozen: int = 3):
+    """P2.  Returns (labels_out int32 [N], cut int64 [B], moves int32 [B])."""
+    if labels.dtype != torch.int32 or not labels.is_cuda or not labels.is_contiguous():
+        raise TypeError("labels: expected a contiguous CUDA int32 tensor")
+    dev = labels.device
+    out = torch.empty_like(labels)
+    cut = torch.empty(batch.num_graphs, dtype=torch.int64, device=dev)
+    moves = torch.empty(batch.num_graphs, dtype=torch.int32, device=dev)
+    check(lib().gmc_greedy_node_move(labels.data_ptr(), batch.rowptr.data_ptr(), batch.colidx.data_ptr(),
+                                     _ptr(_int_weights(batch)), batch.graph_ptr.data_ptr(), batch.num_graphs,
+                                     batch.num_nodes, n_classes, iters, n_frozen, out.data_ptr(), cut.data_ptr(),
+                                     moves.data_ptr(), _stream()), "gmc_greedy_node_move")
+    return out, cut, moves

@@ -1,0 +1,447 @@
+"""TrainingNeural -- B200 drop-in for the reference's python/Training/TrainingNeural.py.
+
+Same public surface (TrainingConfig, GCNSoftmax, setup_model_and_optimizer, train_single_epoch,
+train_model, train_from_pickle, train_multi_class, evaluate_model, load_neural_model,
+save_neural_model, the loss helpers and the legacy aliases), same prints, same checkpoint
+layout.  The arithmetic of the hot loop (reference :371-388) runs in gmc_b200.engine.GCNEngine
+on hand-written sm_100a kernels; there is no CPU fallback -- without a CUDA device every entry
+point that would compute raises gmc_b200._lib.GmcError.
+
+Opt-in extensions (defaults reproduce the reference exactly):
+    TrainingConfig.batch_graphs      graphs per optimiser step (1 = the reference's sequential
+                                     per-graph Adam steps; >1 = block-diagonal mini-batches with
+                                     loss = sum of per-graph losses)
+    TrainingConfig.gemm_precision    'fp32' (FFMA, parity) | 'tf32' | 'tf32x3' (tcgen05)
+    TrainingConfig.loss_mode         'ste' (reference live path) | 'soft' (north-star objective)
+    TrainingConfig.use_terminal_penalty   enable the penalty the reference left commented (:308)
+"""
+try:
+    from python.commons import *  # noqa: F401,F403  (reference spelling, :25)
+except ImportError:  # notebook spelling: <pkg>/python on sys.path
+    from commons import *  # noqa: F401,F403
+
+import random  # noqa: F401
+import weakref
+from dataclasses import dataclass
+from itertools import permutations
+from time import time
+from typing import Callable, Dict, List, Optional, Tuple  # noqa: F401
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F  # noqa: F401
+
+from gmc_b200 import _lib as _gmc_lib
+from gmc_b200.engine import GCNEngine
+from gmc_b200.graph import CSRGraph, GraphBatch
+from gmc_b200.model import GCNSoftmax, to_device_features
+from gmc_b200.optim import FusedAdam
+
+TORCH_DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+TORCH_DTYPE = torch.float32
+
+
+@dataclass
+class TrainingConfig:
+    """Hyper-parameter record; field-for-field the reference's (:36-60) plus opt-in extensions."""
+    n_nodes: int = 1000
+    dim_embedding: Optional[int] = None      # defaults to n_nodes
+    hidden_dim: Optional[int] = None         # defaults to dim_embedding // 2
+    dropout: float = 0.0
+    number_classes: int = 3
+
+    learning_rate: float = 0.001
+    number_epochs: int = 1000
+    tolerance: float = 1e-4
+    patience: int = 20
+    prob_threshold: float = 0.5
+
+    A: float = 0.0
+    C: float = 1.0
+    penalty: float = 1000.0
+
+    save_directory: Optional[str] = None
+    save_frequency: int = 100
+
+    # ---- extensions (not in the reference; defaults keep its behaviour) ----
+    batch_graphs: int = 1
+    gemm_precision: str = "fp32"
+    loss_mode: str = "ste"
+    use_terminal_penalty: bool = False
+
+    def __post_init__(self):
+        if self.dim_embedding is None:
+            self.dim_embedding = self.n_nodes
+        if self.hidden_dim is None:
+            self.hidden_dim = self.dim_embedding // 2
+
+
+# --------------------------------------------------------------------------------------------
+# loss helpers kept for API compatibility (device-agnostic torch; the training loop does not
+# call them -- the fused kernel computes the same quantities in closed form)
+# --------------------------------------------------------------------------------------------
+def override_fixed_nodes(h):
+    """Rows 0,1,2 -> e0,e1,e2 in value, identity in gradient (reference :87-94)."""
+    k = min(3, h.shape[0])
+    eye = torch.eye(h.shape[1], dtype=h.dtype, device=h.device)[:k]
+    head = eye + h[:k] - h[:k].detach()
+    return torch.cat([head, h[k:]], dim=0)
+
+
+def max_to_one_hot(tensor):
+    """one_hot(argmax) with a straight-through gradient (reference :96-102)."""
+    hot = torch.zeros_like(tensor)
+    hot[torch.argmax(tensor)] = 1.0
+    return hot + tensor - tensor.detach()
+
+
+def apply_max_to_one_hot(output):
+    """Row-wise max_to_one_hot (reference :104-106), vectorised."""
+    idx = torch.argmax(output, dim=1, keepdim=True)
+    hot = torch.zeros_like(output).scatter_(1, idx, 1.0)
+    return hot + output - output.detach()
+
+
+def extend_matrix_torch_training(matrix, N):
+    size = matrix.shape[0]
+    if N <= size:
+        return matrix
+    out = torch.zeros((N, N), dtype=matrix.dtype, device=matrix.device)
+    out[:size, :size] = matrix
+    return out
+
+
+def extend_matrix_torch(matrix, N, torch_dtype=None, torch_device=None):
+    """Zero-pad the columns of a square matrix to N (reference :137-152)."""
+    size = matrix.shape[0]
+    if N < size:
+        raise ValueError("N should be greater than or equal to the original matrix size.")
+    out = torch.zeros(size, N, dtype=matrix.dtype, device=matrix.device)
+    out[:, :size] = matrix
+    if torch_dtype is not None:
+        out = out.type(torch_dtype)
+    if torch_device is not None:
+        out = out.to(torch_device)
+    return out
+
+
+def calculate_HC_vectorized(s, adjacency_matrix):
+    """sum(A * (1 - pad(s s^T))) / 2 (reference :154-176).  The reference pads to a hard-coded
+    1000 columns (:171); padding to A's own width is identical whenever the reference runs."""
+    same = s @ s.T
+    padded = extend_matrix_torch(same, adjacency_matrix.shape[1])
+    return torch.sum(adjacency_matrix.to(s.device) * (1 - padded)) / 2
+
+
+def terminal_independence_penalty(s, terminal_nodes: List[int]):
+    """sum_{i<j in T} s_i . s_j (reference :178-195)."""
+    total = 0
+    for a in range(len(terminal_nodes)):
+        for b in range(a + 1, len(terminal_nodes)):
+            total = total + torch.dot(s[terminal_nodes[a]], s[terminal_nodes[b]])
+    return total
+
+
+def find_ac_parameters(graph):
+    """(max_degree + 1, max_degree / 2) (reference :197-210)."""
+    top = max(d for _, d in graph.degree())
+    return top + 1, top / 2
+
+
+def generate_terminal_permutations(terminal_dict: Dict):
+    keys = list(terminal_dict.keys())
+    return [dict(zip(keys, perm)) for perm in permutations(terminal_dict.values())]
+
+
+def calculate_all_cut_legacy(q_torch, s):
+    """Legacy per-column cut (reference :227-251)."""
+    if len(s) == 0:
+        return 0
+    total = 0
+    for i in range(s.shape[1]):
+        col = s[:, i].unsqueeze(0)
+        total = total + (q_torch * (col != col.t()).float()).sum() / 2
+    return total / 2
+
+
+def evaluate_optimal_partitioning(net, dgl_graph, inputs, adjacency_matrix, terminal_dict: Dict):
+    """Legacy helper (reference :253-289): best thresholded cut over terminal permutations."""
+    net.eval()
+    best = float("inf")
+    if dgl_graph.number_of_nodes() < 30:
+        inputs = torch.ones((dgl_graph.number_of_nodes(), 30))
+    with torch.no_grad():
+        for _ in generate_terminal_permutations(terminal_dict):
+            probs = override_fixed_nodes(net(dgl_graph, inputs))
+            hard = (probs >= 0.5).float()
+            value = calculate_all_cut_legacy(adjacency_matrix.to(hard.device), hard)
+            if value < best:
+                best = value
+    return best
+
+
+def compute_loss(s, adjacency_matrix, A: float = 0, C: float = 1, penalty: float = 1000):
+    """C * (-HC); A and penalty are accepted and ignored exactly like the reference (:291-309)."""
+    return C * (-1 * calculate_HC_vectorized(s, adjacency_matrix))
+
+
+# --------------------------------------------------------------------------------------------
+# model / optimiser
+# --------------------------------------------------------------------------------------------
+def setup_model_and_optimizer(config: TrainingConfig):
+    """(net, embed, optimizer) as the reference (:311-339).  `embed` is created, registered with
+    the optimiser and never receives a gradient -- it only travels into checkpoints as 'inputs'."""
+    device = _gmc_lib.require_cuda()
+    net = GCNSoftmax(in_feats=config.dim_embedding, hidden_size=config.hidden_dim,
+                     num_classes=config.number_classes, dropout=config.dropout, device=device)
+    net = net.type(TORCH_DTYPE).to(device)
+    net.set_gemm_precision(getattr(config, "gemm_precision", "fp32"))
+    embed = nn.Embedding(config.n_nodes, config.dim_embedding)
+    embed = embed.type(TORCH_DTYPE).to(device)
+    optimizer = FusedAdam(chain(net.parameters(), embed.parameters()), lr=config.learning_rate)
+    return net, embed, optimizer
+
+
+def _engine_for(net, optimizer, config: TrainingConfig) -> GCNEngine:
+    key = (id(optimizer), float(config.C), getattr(config, "loss_mode", "ste"),
+           bool(getattr(config, "use_terminal_penalty", False)), float(config.penalty),
+           getattr(config, "gemm_precision", "fp32"))
+    cached = _ENGINES.get(net)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    if optimizer is not None and not isinstance(optimizer, FusedAdam):
+        raise TypeError("the B200 training loop needs the FusedAdam returned by setup_model_and_optimizer")
+    engine = GCNEngine(net, optimizer, C=config.C, loss_mode=key[2], override_terminals=True,
+                       penalty=config.penalty if key[3] else 0.0, precision=key[5])
+    _ENGINES[net] = (key, engine)
+    return engine
+
+
+_ENGINES = weakref.WeakKeyDictionary()     # net -> (settings key, GCNEngine); never pickled with the model
+
+
+class _PreparedItem:
+    __slots__ = ("batch", "X")
+
+    def __init__(self, batch, X):
+        self.batch, self.X = batch, X
+
+
+def _graph_handle(item) -> CSRGraph:
+    handle, _, nx_graph, _ = item
+    if isinstance(handle, CSRGraph):
+        return handle
+    if isinstance(handle, GraphBatch):
+        raise TypeError("dataset items hold single graphs; pass GraphBatch objects to GCNEngine directly")
+    return from_networkx(nx_graph)  # foreign handle (e.g. legacy DGL object): rebuild from networkx
+
+
+def _check_features_are_adjacency(batch: GraphBatch, X: torch.Tensor) -> None:
+    """The reference's loss reads its weights from `adjacency_matrix` (= the features, :380).  The
+    fused kernel reads them from the graph instead, which is the same thing for every dataset
+    graphExtender produces; refuse anything else rather than silently diverge."""
+    from gmc_b200 import ops
+    want = ops.densify(batch, X.shape[1])
+    if not torch.equal(want, X):
+        raise NotImplementedError("dataset features are not the zero-padded adjacency rows of the graph; "
+                                  "the fused max-cut loss takes its edge weights from the graph structure")
+
+
+def _prepare(dataset: Dict, batch_graphs: int, device) -> List[_PreparedItem]:
+    """Device-resident (GraphBatch, X) per optimiser step, cached on the dataset dict's identity."""
+    cache = _PREPARED.get(id(dataset))
+    keys = list(dataset.keys())
+    if cache is not None and cache[0] is dataset and cache[1] == (keys, batch_graphs):
+        return cache[2]
+    items = [dataset[k] for k in keys]
+    steps: List[_PreparedItem] = []
+    for lo in range(0, len(items), max(1, batch_graphs)):
+        chunk = items[lo: lo + max(1, batch_graphs)]
+        handles = [_graph_handle(it) for it in chunk]
+        batch = GraphBatch(handles, device=device)
+        feats = [to_device_features(it[1], device) for it in chunk]
+        X = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+        _check_features_are_adjacency(batch, X)
+        steps.append(_PreparedItem(batch, X))
+    if len(_PREPARED) > 8:
+        _PREPARED.clear()
+    _PREPARED[id(dataset)] = (dataset, (keys, batch_graphs), steps)
+    return steps
+
+
+_PREPARED: Dict[int, tuple] = {}
+
+
+def train_single_epoch(dataset: Dict, net, optimizer, embed, config: TrainingConfig,
+                       dataset_files: Optional[List[str]] = None) -> float:
+    """One pass over the dataset: forward, override, STE, loss, backward, Adam per graph, in dict
+    order (reference :341-390).  Returns the summed loss.  The per-graph `.item()` host sync of the
+    reference (:388) is replaced by one device-side accumulation read back once per epoch."""
+    device = _gmc_lib.require_cuda()
+    net.train()
+    engine = _engine_for(net, optimizer, config)
+    if dataset_files is None:
+        dataset_files = ["./nx_test_generated_graph_n200_300_d8_12_t500.pkl"]
+    total = torch.zeros((), dtype=torch.float64, device=device)
+    for dataset_file in dataset_files:
+        current = dataset if isinstance(dataset, dict) else open_file(dataset_file)
+        for step in _prepare(current, int(getattr(config, "batch_graphs", 1)), device):
+            losses = engine.train_step(step.batch, step.X)
+            total += losses.sum()
+    return float(total.item())
+
+
+def _early_stop_update(epoch: int, loss: float, prev_loss: float, counter: int, config: TrainingConfig):
+    """Patience bookkeeping of the reference (:430-437): returns (counter, stop)."""
+    if epoch > 0 and (loss > prev_loss or abs(prev_loss - loss) <= config.tolerance):
+        counter += 1
+        return counter, counter >= config.patience
+    return 0, False
+
+
+def _run_training_loop(config: TrainingConfig, epoch_fn: Callable[[], float], net, optimizer, embed,
+                       saver=torch.save) -> Tuple:
+    """Epoch loop, early stopping, best-loss tracking, periodic + final checkpoints (reference
+    :412-484).  Split out so the host logic is testable without a GPU."""
+    best_loss = float("inf")
+    best_model_state = None
+    loss_history: List[float] = []
+    patience_counter = 0
+    prev_loss = float("inf")
+    start_time = time()
+    epoch = -1
+    for epoch in range(config.number_epochs):
+        cumulative_loss = epoch_fn()
+        loss_history.append(cumulative_loss)
+        patience_counter, stop = _early_stop_update(epoch, cumulative_loss, prev_loss, patience_counter, config)
+        if stop:
+            print(f"Early stopping at epoch {epoch}")
+            break
+        if cumulative_loss < best_loss:
+            best_loss = cumulative_loss
+            best_model_state = net.state_dict()      # aliases live tensors, as in the reference (:442)
+        prev_loss = cumulative_loss
+        if epoch % config.save_frequency == 0:
+            print(f"Epoch: {epoch}, Cumulative Loss: {cumulative_loss:.6f}")
+            if config.save_directory:
+                saver(_checkpoint(net, optimizer, embed, epoch, loss_history, config),
+                      f"./epoch_{epoch}_loss_{cumulative_loss:.4f}_{config.save_directory}")
+    if best_model_state is not None:
+        net.load_state_dict(best_model_state)        # no-op by aliasing: the last weights are returned
+    training_time = time() - start_time
+    print(f"Training completed in {training_time:.2f} seconds")
+    print(f"Best loss: {best_loss:.6f}")
+    if config.save_directory:
+        final_filename = f"./final_{config.save_directory}"
+        saver(_checkpoint(net, optimizer, embed, epoch, loss_history, config), final_filename)
+        print(f"Final model saved to {final_filename}")
+    return net, best_loss, epoch, embed.weight, loss_history
+
+
+def _checkpoint(net, optimizer, embed, epoch, loss_history, config) -> Dict:
+    return {"epoch": epoch, "model": net.state_dict(), "optimizer": optimizer.state_dict(),
+            "loss_history": loss_history, "inputs": embed.weight, "config": config}
+
+
+def train_model(dataset: Dict, config: TrainingConfig, dataset_files: Optional[List[str]] = None) -> Tuple:
+    """Main training function (reference :392-484); returns
+    (net, best_loss, final_epoch, embed.weight, loss_history)."""
+    print(f"Starting training with {config.number_epochs} epochs")
+    print(f"Model: {config.n_nodes} nodes, {config.number_classes} classes")
+    print(f"Device: {TORCH_DEVICE}")
+    net, embed, optimizer = setup_model_and_optimizer(config)
+    return _run_training_loop(
+        config, lambda: train_single_epoch(dataset, net, optimizer, embed, config, dataset_files),
+        net, optimizer, embed)
+
+
+def train_from_pickle(dataset_filename: str, model_name: str, n_nodes: int = 1000, **kwargs) -> Tuple:
+    """Train from a graphExtender pickle (reference :486-513)."""
+    config = TrainingConfig(**{"n_nodes": n_nodes, "save_directory": f"{model_name}.pth", **kwargs})
+    print(f"Loading dataset from {dataset_filename}")
+    dataset = open_file(dataset_filename)
+    return train_model(dataset, config)
+
+
+def train_multi_class(dataset_filename: str, model_name: str, num_classes: int = 3, **kwargs) -> Tuple:
+    """reference :515-535"""
+    params = {"number_classes": num_classes, "save_directory": f"{model_name}.pth", **kwargs}
+    return train_from_pickle(dataset_filename, model_name, **params)
+
+
+def evaluate_model(model, dataset: Dict, config: TrainingConfig) -> Dict:
+    """No-grad forward + override + STE + loss per graph (reference :537-570)."""
+    device = _gmc_lib.require_cuda()
+    model.eval()
+    cached = _ENGINES.get(model)
+    engine = cached[1] if cached is not None else _engine_for(model, None, config)
+    total = torch.zeros((), dtype=torch.float64, device=device)
+    num_samples = 0
+    for step in _prepare(dataset, 1, device):
+        total += engine.evaluate(step.batch, step.X).sum()
+        num_samples += step.batch.num_graphs
+    total_loss = float(total.item())
+    return {"average_loss": total_loss / num_samples if num_samples > 0 else 0,
+            "total_loss": total_loss, "num_samples": num_samples}
+
+
+def load_neural_model(model_path: str, config: TrainingConfig):
+    """(net, inputs, loaded_config) from a checkpoint (reference :572-609).  Reference-written
+    files pickle their config as `python.Training.TrainingNeural.TrainingConfig` or
+    `Training.TrainingNeural.TrainingConfig`; both resolve to this module's dataclass."""
+    import torch.serialization
+    device = _gmc_lib.require_cuda()
+    try:
+        torch.serialization.add_safe_globals([TrainingConfig])
+        checkpoint = torch.load(model_path, map_location=device)
+    except Exception:
+        checkpoint = torch.load(model_path, map_location=device, weights_only=False)
+    net, embed, _ = setup_model_and_optimizer(config)
+    net.load_state_dict(checkpoint["model"])
+    return net, checkpoint.get("inputs", embed.weight), checkpoint.get("config", config)
+
+
+def save_neural_model(model, optimizer, embed, epoch: int, loss_history: List, config: TrainingConfig,
+                      model_path: str):
+    """reference :611-634"""
+    torch.save(_checkpoint(model, optimizer, embed, epoch, loss_history, config), model_path)
+    print(f"Model saved to {model_path}")
+
+
+# --------------------------------------------------------------------------------------------
+# legacy compatibility (reference :636-733)
+# --------------------------------------------------------------------------------------------
+def get_gnn_legacy(n_nodes: int, gnn_hypers: Dict, opt_params: Dict, torch_device, torch_dtype):
+    config = TrainingConfig(n_nodes=n_nodes, dim_embedding=gnn_hypers["dim_embedding"],
+                            hidden_dim=gnn_hypers["hidden_dim"], dropout=gnn_hypers["dropout"],
+                            number_classes=gnn_hypers["number_classes"], learning_rate=opt_params["lr"])
+    return setup_model_and_optimizer(config)
+
+
+def hyperparameters_legacy(n: int = 80, d: int = 3, p=None, graph_type: str = "reg", number_epochs: int = int(1e5),
+                           learning_rate: float = 1e-4, prob_threshold: float = 0.5, tol: float = 1e-4,
+                           patience: int = 100):
+    dim_embedding = n
+    return (n, d, p, graph_type, number_epochs, learning_rate, prob_threshold, tol, patience, dim_embedding,
+            int(dim_embedding / 2))
+
+
+def train_legacy_wrapper(model_name: str, filename: str = "./testData/nx_generated_graph_n80_d3_t200.pkl",
+                         n: int = 80):
+    return train_from_pickle(filename, model_name, n_nodes=n, learning_rate=0.001, patience=20)
+
+
+def train_2way_neural_legacy(model_name: str, filename: str = "./testData/prepareDS.pkl"):
+    return train_multi_class(filename, model_name, num_classes=2, n_nodes=4096, learning_rate=0.001, patience=20,
+                             number_epochs=500)
+
+
+get_gnn = get_gnn_legacy
+hyperParameters = hyperparameters_legacy
+train1 = train_legacy_wrapper
+train_2wayNeural = train_2way_neural_legacy
+FIndAC = find_ac_parameters
+GetOptimalNetValue = evaluate_optimal_partitioning
+calculateAllCut = calculate_all_cut_legacy
+LoadNeuralModel = load_neural_model

@@ -145,6 +145,14 @@ int gmc_softmax_cut_loss_fwd_bwd(const float* Z, int64_t ldz, const int32_t* row
                                  float penalty, float C, float* P_out, double* loss_per_graph,
                                  float* dZ_out, void* stream);
 
+/* Stand-alone row softmax P = softmax(Z) (dense [n_rows, n_classes] output) and its backward
+ * dZ = P .* (dP - <P,dP>); used by GCNSoftmax.forward outside the fused training step
+ * (inference: TestingNeuralNetwork.py:142-143; F.softmax TrainingNeural.py:84). */
+int gmc_softmax_fwd_f32(const float* Z, int64_t ldz, int64_t n_rows, int32_t n_classes, float* P,
+                        void* stream);
+int gmc_softmax_bwd_f32(const float* P, const float* dP, int64_t n_rows, int32_t n_classes, float* dZ,
+                        void* stream);
+
 /* ---- (d) fused multi-tensor Adam ----------------------------------------------------- */
 
 /* torch.optim.Adam defaults (amsgrad=False, weight_decay=0): for each of n_tensors (<= 16)

@@ -1,0 +1,354 @@
+"""GPU parity tests (`-m gpu`): every kernel, called through the C ABI (gmc_b200.ops -> ctypes),
+against the CPU oracle (oracle/ref_step.py, oracle/postproc.c) on the same seeded inputs.
+Tolerances: fp32 paths rel 1e-4 (north_star), usually far tighter; integer paths bit-exact."""
+import math
+import os
+
+import networkx as nx
+import numpy as np
+import pytest
+import torch
+
+from gmc_b200 import _lib, ops, synth
+from gmc_b200.graph import CSRGraph, GraphBatch, ZeroDegreeError
+from oracle import postproc as pp
+from oracle import ref_step as rs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def nx_regular(n, d, seed, weights=None):
+    g = nx.random_regular_graph(d=d, n=n, seed=seed)
+    rng = np.random.default_rng(seed)
+    for u, v in g.edges():
+        g[u][v]["weight"] = int(rng.integers(1, 5)) if weights else 1
+    return g
+
+
+def make_batch(specs, weights=False):
+    graphs = [nx_regular(n, d, s, weights) for n, d, s in specs]
+    csrs = [rs.csr_from_networkx(g) for g in graphs]
+    batch = GraphBatch([CSRGraph.from_networkx(g) for g in graphs])
+    return graphs, csrs, batch
+
+
+def ahat_dense(csr, dtype=torch.float64):
+    A = (rs.dense_adjacency(csr, dtype=dtype) != 0).to(dtype)
+    dinv = torch.diag(A.sum(1).clamp(min=1).pow(-0.5))
+    return dinv @ A @ dinv
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+# ------------------------------------------------------------------ SpMM
+@pytest.mark.parametrize("C", [3, 1, 4, 16, 20, 64, 100, 500, 1000, 37])
+@pytest.mark.parametrize("use_coef", [True, False])
+def test_spmm_matches_dense_ahat(C, use_coef):
+    graphs, csrs, batch = make_batch([(40, 5, 1), (64, 7, 2), (30, 6, 3), (50, 8, 4)], weights=True)
+    torch.manual_seed(C)
+    X = torch.randn(batch.num_nodes, C)
+    bias = torch.randn(C)
+    want = torch.cat([ahat_dense(c) @ X[s:e].double() for c, (s, e) in
+                      zip(csrs, zip(batch.graph_ptr_host[:-1], batch.graph_ptr_host[1:]))])
+    got = ops.spmm(batch, X.to(DEV), use_coef=use_coef)
+    assert relerr(got.cpu(), want) < 2e-6
+    got2 = ops.spmm(batch, X.to(DEV), bias=bias.to(DEV), relu=True, use_coef=use_coef)
+    assert relerr(got2.cpu(), torch.relu(want + bias.double())) < 2e-6
+
+
+def test_spmm_strided_rows_and_symmetry():
+    _, csrs, batch = make_batch([(100, 7, 9)])
+    torch.manual_seed(0)
+    big = torch.randn(100, 96, device=DEV)
+    X = big[:, 16:80]                                   # ld = 96, 64 columns, 16-byte aligned offset
+    out_big = torch.zeros(100, 128, device=DEV)
+    ops.spmm(batch, X, out=out_big[:, :64])
+    want = ahat_dense(csrs[0]) @ X.cpu().double()
+    assert relerr(out_big[:, :64].cpu(), want) < 2e-6 and float(out_big[:, 64:].abs().sum()) == 0.0
+    # <Y, A X> == <A Y, X>: the backward SpMM is the forward SpMM
+    Y = torch.randn(100, 64, device=DEV)
+    lhs = (Y * ops.spmm(batch, X.contiguous())).sum().item()
+    rhs = (ops.spmm(batch, Y) * X).sum().item()
+    assert abs(lhs - rhs) <= 1e-4 * abs(lhs)
+
+
+def test_zero_degree_raises_like_dgl():
+    g = nx.Graph()
+    g.add_nodes_from(range(5))
+    g.add_edge(0, 1, weight=1)
+    with pytest.raises(ZeroDegreeError):
+        GraphBatch([CSRGraph.from_networkx(g)])
+    b = GraphBatch([CSRGraph.from_networkx(g)], check_degrees=False)       # norms clamp to 1
+    assert torch.allclose(b.norm.cpu(), torch.tensor([1.0, 1.0, 1.0, 1.0, 1.0]))
+
+
+def test_densify_equals_extender_features():
+    graphs, csrs, batch = make_batch([(20, 3, 1), (36, 5, 2)], weights=True)
+    X = ops.densify(batch, 48).cpu()
+    want = torch.cat([rs.dense_adjacency(c, 48) for c in csrs])
+    assert torch.equal(X, want)
+
+
+# ------------------------------------------------------------------ GEMM (fp32 parity path)
+@pytest.mark.parametrize("op,M,N,K", [
+    ("nn", 300, 500, 1000), ("nn", 129, 7, 33), ("nn", 1, 1, 1), ("nn", 257, 130, 8),
+    ("nt", 200, 96, 500), ("nt", 65, 33, 17),
+    ("tn", 1000, 500, 3000), ("tn", 100, 64, 70000), ("tn", 37, 5, 9),
+])
+def test_gemm_fp32_matches_float64(op, M, N, K):
+    torch.manual_seed(M + N + K)
+    if op == "nn":
+        A, B = torch.randn(M, K), torch.randn(K, N)
+        want = A.double() @ B.double()
+    elif op == "nt":
+        A, B = torch.randn(M, K), torch.randn(N, K)
+        want = A.double() @ B.double().t()
+    else:
+        A, B = torch.randn(K, M), torch.randn(K, N)
+        want = A.double().t() @ B.double()
+    got = ops.gemm(op, A.to(DEV), B.to(DEV))
+    assert relerr(got.cpu(), want) < 5e-6 * max(1.0, math.sqrt(K) / 30)
+    acc = torch.ones(M, N, device=DEV)
+    ops.gemm(op, A.to(DEV), B.to(DEV), out=acc, accumulate=True)
+    assert relerr(acc.cpu(), want + 1.0) < 5e-6 * max(1.0, math.sqrt(K) / 30)
+
+
+def test_gemm_unaligned_leading_dimensions():
+    torch.manual_seed(3)
+    A = torch.randn(50, 45, device=DEV)[:, 1:44]          # ld 45, offset 1 -> scalar path
+    B = torch.randn(43, 21, device=DEV)
+    got = ops.gemm("nn", A, B)
+    assert relerr(got.cpu(), A.cpu().double() @ B.cpu().double()) < 5e-6
+
+
+def test_gemm_tn_is_deterministic():
+    torch.manual_seed(1)
+    A, B = torch.randn(50000, 64, device=DEV), torch.randn(50000, 48, device=DEV)
+    a = ops.gemm("tn", A, B)
+    b = ops.gemm("tn", A, B)
+    assert torch.equal(a, b)
+
+
+def test_gemm_rejects_bad_arguments():
+    A = torch.randn(4, 5, device=DEV)
+    with pytest.raises(ValueError):
+        ops.gemm("nn", A, torch.randn(6, 3, device=DEV))
+    with pytest.raises(TypeError):
+        ops.gemm("nn", A.double(), torch.randn(5, 3, device=DEV))
+    with pytest.raises(TypeError):
+        ops.gemm("nn", A.cpu(), torch.randn(5, 3))
+
+
+# ------------------------------------------------------------------ skinny layer / colsum
+@pytest.mark.parametrize("n_in,n_out", [(500, 3), (16, 3), (24, 2), (128, 8), (50, 3)])
+def test_skinny_forward_backward(n_in, n_out):
+    torch.manual_seed(n_in)
+    n = 777
+    H = torch.relu(torch.randn(n, n_in))
+    W = torch.randn(n_in, n_out)
+    dT = torch.randn(n, n_out)
+    got = ops.skinny_fwd(H.to(DEV), W.to(DEV))
+    assert relerr(got.cpu(), H.double() @ W.double()) < 3e-6
+    if n_in % 4 == 0:
+        dH, dW, db = ops.skinny_bwd(dT.to(DEV), W.to(DEV), H.to(DEV))
+        want_dH = (dT.double() @ W.double().t()) * (H > 0)
+        assert relerr(dH.cpu(), want_dH) < 3e-6
+        assert relerr(dW.cpu(), H.double().t() @ dT.double()) < 3e-6
+        assert relerr(db.cpu(), want_dH.sum(0)) < 3e-6
+        dH2, dW2, db2 = ops.skinny_bwd(dT.to(DEV), W.to(DEV), H.to(DEV))
+        assert torch.equal(dW, dW2) and torch.equal(db, db2)             # deterministic reduction
+
+
+@pytest.mark.parametrize("n,c", [(1000, 3), (5, 3), (70000, 3), (3000, 500), (17, 33)])
+def test_colsum(n, c):
+    torch.manual_seed(n)
+    X = torch.randn(n, c)
+    got = ops.colsum(X.to(DEV))
+    assert np.abs(got.cpu().numpy() - X.double().sum(0).numpy()).max() < 1e-4 * math.sqrt(n)
+
+
+# ------------------------------------------------------------------ fused loss
+@pytest.mark.parametrize("mode,override,penalty", [("ste", True, 0.0), ("ste", False, 0.0), ("soft", True, 0.0),
+                                                   ("soft", False, 7.0), ("ste", True, 5.0), ("soft", True, 3.0)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_cut_loss_matches_oracle(mode, override, penalty, weighted):
+    specs = [(40, 5, 1), (64, 7, 2), (50, 8, 4)] if weighted else [(40, 5, 1), (64, 7, 2), (30, 6, 3), (34, 8, 4)]
+    graphs, csrs, batch = make_batch(specs, weights=weighted)
+    torch.manual_seed(5)
+    Z = torch.randn(batch.num_nodes, 3) * 2
+    loss, P, dZ = ops.cut_loss(batch, Z.to(DEV), mode=mode, override_terminals=override, penalty=penalty, C=1.5)
+    gp = batch.graph_ptr_host
+    for i, csr in enumerate(csrs):
+        Zi = Z[gp[i]: gp[i + 1]]
+        Pi = torch.softmax(Zi.double(), dim=1)
+        want = rs.ste_loss_and_grads(csr, Pi, C=1.5, override_terminals=override, mode=mode, penalty=penalty)
+        assert abs(loss[i].item() - float(want["loss"])) <= 1e-5 * max(1.0, abs(float(want["loss"])))
+        assert relerr(P[gp[i]: gp[i + 1]].cpu(), Pi) < 1e-6
+        assert np.abs(dZ[gp[i]: gp[i + 1]].cpu().numpy() - want["dZ"].numpy()).max() < 2e-5 * (1 + penalty)
+    if mode == "ste" and penalty == 0.0:
+        # integrality: loss == -C * integer cut of the hard labels
+        labels = ops.argmax_labels(batch, P, force_terminals=override)
+        if not weighted or batch.wts_i32 is not None:
+            cuts = ops.cut_value(batch, labels)
+            assert torch.equal((loss / -1.5).round().long().cpu(), cuts.cpu())
+
+
+def test_cut_loss_two_class_and_eight_class():
+    _, csrs, batch = make_batch([(30, 4, 1)])
+    for K in (2, 8):
+        torch.manual_seed(K)
+        Z = torch.randn(30, K)
+        loss, P, dZ = ops.cut_loss(batch, Z.to(DEV), mode="ste", override_terminals=K >= 3)
+        want = rs.ste_loss_and_grads(csrs[0], torch.softmax(Z.double(), 1), override_terminals=K >= 3)
+        assert abs(loss[0].item() - float(want["loss"])) < 1e-6
+        assert np.abs(dZ.cpu().numpy() - want["dZ"].numpy()).max() < 2e-5
+    with pytest.raises(_lib.GmcError):
+        ops.cut_loss(batch, torch.randn(30, 2, device=DEV), override_terminals=True)
+
+
+def test_softmax_fwd_bwd():
+    torch.manual_seed(0)
+    Z = (torch.randn(1000, 3) * 5).requires_grad_()
+    P = torch.softmax(Z, 1)
+    dP = torch.randn(1000, 3)
+    P.backward(dP)
+    got = ops.softmax_fwd(Z.detach().to(DEV))
+    assert relerr(got.cpu(), P.detach()) < 1e-6
+    assert np.abs(ops.softmax_bwd(got, dP.to(DEV)).cpu().numpy() - Z.grad.numpy()).max() < 1e-6
+
+
+# ------------------------------------------------------------------ Adam
+def test_adam_matches_torch_adam_over_steps():
+    torch.manual_seed(0)
+    shapes = [(1000, 500), (500,), (500, 3), (3,), (7, 5)]
+    ref = [torch.nn.Parameter(torch.randn(*s)) for s in shapes]
+    mine = [p.detach().clone().to(DEV) for p in ref]
+    m = [torch.zeros_like(p) for p in mine]
+    v = [torch.zeros_like(p) for p in mine]
+    opt = torch.optim.Adam(ref, lr=1e-3)
+    step_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    mine2 = [p.clone() for p in mine]
+    m2 = [torch.zeros_like(p) for p in mine]
+    v2 = [torch.zeros_like(p) for p in mine]
+    for t in range(1, 8):
+        grads = [torch.randn(*s) * (10.0 if t % 2 else 0.01) for s in shapes]
+        for p, g in zip(ref, grads):
+            p.grad = g.clone()
+        opt.step()
+        gd = [g.to(DEV) for g in grads]
+        ops.adam_multi(mine, gd, m, v, lr=1e-3, step=t)
+        ops.adam_multi(mine2, gd, m2, v2, lr=1e-3, step_dev=step_dev)
+        for a, b, c in zip(mine, ref, mine2):
+            assert relerr(a.cpu(), b.detach()) < 2e-6
+            assert relerr(c.cpu(), b.detach()) < 2e-6
+    assert int(step_dev.item()) == 7
+
+
+# ------------------------------------------------------------------ integer post-processing
+def test_postproc_fixture_bit_exact():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "postproc.npz"))
+    f32 = int(str(z["numpy_version"]).split(".")[0]) >= 2
+    for tag in ("s", "m", "l", "w"):
+        n = int(z[f"{tag}_n"])
+        g = nx.Graph()
+        g.add_nodes_from(range(n))
+        for (u, v), w in zip(z[f"{tag}_edges"], z[f"{tag}_w"]):
+            g.add_edge(int(u), int(v), weight=int(w))
+        batch = GraphBatch([CSRGraph.from_networkx(g)])
+        P = torch.from_numpy(z[f"{tag}_P"]).to(DEV)
+        labels = ops.argmax_labels(batch, P)
+        assert labels.cpu().tolist() == z[f"{tag}_simple"].tolist()
+        assert int(ops.cut_value(batch, labels).item()) == int(z[f"{tag}_simple_cut"])
+        np.random.seed(int(z[f"{tag}_post_seed"]))
+        U = torch.from_numpy(np.random.rand(200 * (n - 3))).to(DEV)
+        u_ptr = torch.tensor([0, U.numel()], dtype=torch.int64, device=DEV)
+        best_labels, best, best_it = ops.sample_best_cut(batch, P, U, u_ptr, 200, compare_f32=f32)
+        assert int(best.item()) == int(z[f"{tag}_post_cut"])
+        assert best_labels.cpu().tolist() == z[f"{tag}_post_labels"].tolist()
+
+
+@pytest.mark.parametrize("compare_f32", [True, False])
+def test_sample_best_cut_batched_vs_oracle(compare_f32):
+    specs = [(50, 6, 1), (3, 2, 2), (120, 7, 3), (77, 8, 4), (4, 3, 5)]
+    graphs, csrs, batch = make_batch(specs, weights=True)
+    rng = np.random.default_rng(0)
+    P = torch.softmax(torch.from_numpy(rng.normal(0, 1.5, size=(batch.num_nodes, 3)).astype(np.float32)), 1)
+    iters = 37
+    counts = [iters * max(n - 3, 0) for n, _, _ in specs]
+    u_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    U = rng.random(int(u_ptr[-1]))
+    # adversarial uniforms: exactly on float32 cumulative boundaries
+    Pn = P.numpy()
+    U[5] = float(Pn[3 + 5 % 47, 0])
+    U[6] = float(np.float32(Pn[9, 0]) + np.float32(Pn[9, 1]))
+    labels, best, best_it = ops.sample_best_cut(batch, P.to(DEV), torch.from_numpy(U).to(DEV),
+                                                torch.from_numpy(u_ptr).to(DEV), iters, compare_f32=compare_f32)
+    gp = batch.graph_ptr_host
+    for i, csr in enumerate(csrs):
+        wl, wc, wi = pp.sample_best_cut(csr.rowptr, csr.colidx, Pn[gp[i]: gp[i + 1]], U[u_ptr[i]: u_ptr[i + 1]], iters,
+                                        csr.weights.astype(np.int32), compare_f32=compare_f32)
+        assert int(best[i].item()) == wc and int(best_it[i].item()) == wi
+        assert labels[gp[i]: gp[i + 1]].cpu().tolist() == wl.tolist()
+
+
+@pytest.mark.parametrize("K,n_frozen", [(3, 3), (2, 0), (5, 3), (8, 1)])
+def test_greedy_node_move_bit_exact(K, n_frozen):
+    specs = [(60, 6, 1), (200, 7, 2), (31 * 2, 5, 3), (8, 3, 4)]
+    graphs, csrs, batch = make_batch(specs, weights=True)
+    rng = np.random.default_rng(K)
+    start = rng.integers(0, K, size=batch.num_nodes).astype(np.int32)
+    for iters in (0, 1, 7, 200):
+        out, cut, moves = ops.greedy_node_move(batch, torch.from_numpy(start).to(DEV), K, iters, n_frozen)
+        gp = batch.graph_ptr_host
+        for i, csr in enumerate(csrs):
+            wl, wc, wm = pp.greedy_node_move(csr.rowptr, csr.colidx, start[gp[i]: gp[i + 1]], K, iters, n_frozen,
+                                             csr.weights.astype(np.int32))
+            assert int(cut[i].item()) == wc and int(moves[i].item()) == wm
+            assert out[gp[i]: gp[i + 1]].cpu().tolist() == wl.tolist()
+
+
+def test_known_answer_cut_values_on_device():
+    # the reference's seeded randomized-maxcut answers (randomizedAlgo.ipynb:L113,L186) through the GPU evaluator
+    for n, seed, kw, expected in ((500, 42, dict(max_iterations=1000, threshold=1, patience=50), 1393),
+                                  (1000, 42, dict(max_iterations=2000, threshold=1, patience=100), 2741)):
+        g = nx.random_regular_graph(d=8, n=n, seed=seed)
+        cut, part = pp.py_randomized_k_way_maxcut(g, k=3, random_seed=seed, **kw)
+        batch = GraphBatch([CSRGraph.from_networkx(g)])
+        labels = torch.tensor([part[i] for i in range(n)], dtype=torch.int32, device=DEV)
+        assert int(ops.cut_value(batch, labels).item()) == expected == cut
+
+
+# ------------------------------------------------------------------ full-size properties (config 3 shape)
+def test_full_size_properties_n1000_d7():
+    B, n, d = 64, 1000, 7
+    batch = synth.regular_batch(B, n, d, seed=11)
+    assert batch.num_nodes == B * n and batch.nnz == B * n * d
+    # A_hat 1 = 1 for a regular graph (row sums of D^-1/2 A D^-1/2)
+    ones = torch.ones(B * n, 500, device=DEV)
+    Y = ops.spmm(batch, ones)
+    assert float((Y - 1).abs().max()) < 1e-5
+    # linearity
+    torch.manual_seed(0)
+    X1, X2 = torch.randn(B * n, 500, device=DEV), torch.randn(B * n, 500, device=DEV)
+    lin = ops.spmm(batch, X1 + 2 * X2) - (ops.spmm(batch, X1) + 2 * ops.spmm(batch, X2))
+    assert float(lin.abs().max()) < 1e-4
+    # cut of a uniform random labelling: 0 <= cut <= |E| and a checksum of checksums against the oracle evaluator
+    rng = np.random.default_rng(1)
+    labels = rng.integers(0, 3, size=B * n).astype(np.int32)
+    cuts = ops.cut_value(batch, torch.from_numpy(labels).to(DEV)).cpu().numpy()
+    assert (cuts >= 0).all() and (cuts <= n * d // 2).all()
+    rp, ci = batch.rowptr.cpu().numpy(), batch.colidx.cpu().numpy()
+    assert int(cuts.sum()) == pp.cut_value(rp, ci, labels)
+    # greedy never decreases the cut, keeps terminals, and is idempotent at its fixed point
+    start = torch.from_numpy(labels).to(DEV)
+    out, cut2, moves = ops.greedy_node_move(batch, start, 3, 200, 3)
+    assert (cut2.cpu().numpy() >= cuts).all()
+    gp = batch.graph_ptr_host[:-1]
+    assert torch.equal(out.cpu()[gp], start.cpu()[gp]) and torch.equal(out.cpu()[gp + 2], start.cpu()[gp + 2])
+    out3, cut3, moves3 = ops.greedy_node_move(batch, out, 3, 10**4, 3)
+    out4, cut4, moves4 = ops.greedy_node_move(batch, out3, 3, 200, 3)
+    assert int(moves4.sum()) == 0 and torch.equal(out3, out4) and torch.equal(cut3, cut4)
