@@ -1,15 +1,432 @@
-// gemm_tcgen05.cu -- tensor-core path of the dense feature transforms (placeholder until the
-// tcgen05/TMA kernel lands: reports GMC_ERR_UNSUPPORTED, never silently falls back).
+// gemm_tcgen05.cu -- (b) dense feature transforms on the 5th-generation tensor cores.
+//
+//   C[M,N] (+)= op(A) * op(B),  fp32 in HBM, kind::tf32 MMA, fp32 accumulation in TMEM.
+//     nn  X[M,K] * W1[K,N]          A K-major,  B MN-major      (GraphConv th.matmul, TrainingNeural.py:80)
+//     tn  X[K,M]^T * dT1[K,N]       A MN-major, B MN-major      (dW1; K = all nodes of the batch -> split-K)
+//     nt  dT1[M,K] * W1[N,K]^T      A K-major,  B K-major       (dX; only for trainable features)
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) into a 4-stage smem ring,
+//               completion counted on mbarriers (expect_tx)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer: 128x256x8 TF32 MMAs, smem operands via
+//               UMMA descriptors, tcgen05.commit releases smem stages / publishes accumulators
+//   warps 2..5  epilogue: tcgen05.ld (32x32b.x32) TMEM -> registers -> global; two 256-column TMEM
+//               accumulators so the epilogue of tile i overlaps the MMAs of tile i+1
+//
+// Tiles: BLOCK_M=128, BLOCK_N=256, BLOCK_K=32 fp32 (= one 128-byte swizzle row); 48 KB per stage.
+// Out-of-range rows/columns/k are zero-filled by TMA and masked in the epilogue, so M, N, K are arbitrary
+// (leading dimensions must be multiples of 4 floats: TMA needs 16-byte strides).
+//
+// Precision: GMC_GEMM_TF32 is one pass (operands truncated to 10 mantissa bits by the MMA).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gmc {
+namespace tc {
 
-size_t tc_workspace_bytes(int, int64_t, int64_t, int64_t, int) { return 0; }
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 32, UMMA_K = 8;
+constexpr int STAGES = 4, ACC_STAGES = 2, TMEM_COLS = 512;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;              // 16 KB
+constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;              // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CHUNK_BYTES = BLOCK_K * 128;                  // one MN-major box: 32 k-rows x 128 B
+constexpr int THREADS = 192;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-int tc_gemm(int, const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int,
-            void*, size_t, cudaStream_t) {
-    set_error("gmc_gemm: tcgen05 TF32 path not built in this library version");
-    return GMC_ERR_UNSUPPORTED;
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (error returned to the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("gmc tcgen05 gemm: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), version 1.
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B -- the only layout the
+// hardware accepts for MN-major 32-bit (tf32) operands (4 k-rows x 128 B atoms, 32-byte swizzle chunks;
+// the matching TMA mode is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+    return (1u << 4)                              // D format  : F32
+         | (2u << 7) | (2u << 10)                 // A/B format: TF32
+         | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+         | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+struct Params {
+    float* C;                // output (or split-K workspace)
+    int64_t M, N, K, ldc;
+    int64_t split_stride;    // elements between split-K partials (0 when k_splits == 1)
+    int64_t k_per_split;     // multiple of BLOCK_K
+    int m_tiles, n_tiles, k_splits;
+    int accumulate;
+    int vec_ok;              // 16-byte aligned C rows
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
+    const uint32_t bars = tiles + STAGES * STAGE_BYTES;
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+    const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 8 * ACC_STAGES;
+    const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_map(&tmA);
+        prefetch_map(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int64_t tiles_mn = (int64_t)p.m_tiles * p.n_tiles;
+    const int64_t n_work = tiles_mn * p.k_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = (int)(w / tiles_mn);
+                const int64_t rem = w - (int64_t)split * tiles_mn;
+                const int m0 = (int)(rem / p.n_tiles) * BLOCK_M, n0 = (int)(rem % p.n_tiles) * BLOCK_N;
+                const int64_t kb = (int64_t)split * p.k_per_split;
+                const int64_t ke = min(p.K, kb + p.k_per_split);
+                for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint32_t fb = full_bar + 8 * stage;
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb);
+                    } else {
+                        tma_load_2d(sa, &tmA, (int)k0, m0, fb);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb);
+                    } else {
+                        tma_load_2d(sb, &tmB, (int)k0, n0, fb);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+        // K-major : SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1 = CUTLASS convention)
+        // MN-major: SWIZZLE_128B_BASE32B, 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart (SBO)
+        const uint32_t a_lbo = A_MN ? CHUNK_BYTES : 16, b_lbo = B_MN ? CHUNK_BYTES : 16;
+        const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+        const uint32_t a_lay = A_MN ? 1 : 2, b_lay = B_MN ? 1 : 2;
+        const uint32_t a_step = A_MN ? 1024 : UMMA_K * 4, b_step = B_MN ? 1024 : UMMA_K * 4;
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = (int)(w / tiles_mn);
+            const int64_t kb = (int64_t)split * p.k_per_split;
+            const int64_t ke = min(p.K, kb + p.k_per_split);
+            mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            uint32_t first = 1;
+            for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+                mbar_wait(full_bar + 8 * stage, phase);
+                tc_fence_after();
+                __syncwarp();
+                if (elect_one()) {
+                    const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t ad = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
+                        const uint64_t bd = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
+                        umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                    umma_commit(empty_bar + 8 * stage);            // smem stage reusable once these MMAs retire
+                    if (k0 + BLOCK_K >= ke) umma_commit(tfull_bar + 8 * acc);
+                }
+                __syncwarp();
+                first = 0;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = (int)(w / tiles_mn);
+            const int64_t rem = w - (int64_t)split * tiles_mn;
+            const int64_t m0 = (rem / p.n_tiles) * BLOCK_M;
+            const int n0 = (int)(rem % p.n_tiles) * BLOCK_N;
+            float* Cs = p.C + (int64_t)split * p.split_stride;
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int64_t m = m0 + 32 * q + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                const int n = n0 + 32 * c;
+                if (n >= p.N) break;                               // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(t_row + 32 * c, r);
+                if (m < p.M) {
+                    float* dst = Cs + m * p.ldc + n;
+                    if (p.vec_ok && n + 32 <= p.N) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                            float4* d4 = reinterpret_cast<float4*>(dst) + i;
+                            if (p.accumulate) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                            *d4 = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (n + i < p.N) dst[i] = p.accumulate ? dst[i] + __uint_as_float(r[i]) : __uint_as_float(r[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t MN, int64_t N,
+                                        float* __restrict__ C, int64_t ldc, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= MN) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * MN + i];
+    float* c = C + (i / N) * ldc + (i % N);
+    *c = accumulate ? *c + s : s;
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [outer rows, inner cols] with row pitch ld (elements); box = [box_outer, box_inner]
+static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer, bool mn_major) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error("gmc_gemm(tf32): cuTensorMapEncodeTiled entry point not available"); return GMC_ERR_UNSUPPORTED; }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gmc_gemm(tf32): cuTensorMapEncodeTiled failed (%d)", (int)r); return GMC_ERR_INVALID_ARG; }
+    return GMC_OK;
+}
+
+static int pick_splits(int64_t tiles, int64_t K) {
+    const int sms = sm_count();
+    if (tiles >= sms || K < 8 * BLOCK_K) return 1;
+    int64_t s = sms / tiles;
+    const int64_t max_by_k = K / (4 * BLOCK_K);
+    if (s > max_by_k) s = max_by_k;
+    return (int)(s < 1 ? 1 : s);
+}
+
+template <bool A_MN, bool B_MN>
+static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                  int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GMC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BLOCK_K, true);       // A[K rows, M cols]
+    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M, false);  // A[M rows, K cols]
+    if (rc) return rc;
+    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BLOCK_K, true);       // B[K rows, N cols]
+    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, BLOCK_N, false);  // B[N rows, K cols]
+    if (rc) return rc;
+
+    Params p;
+    p.M = M; p.N = N; p.K = K;
+    p.m_tiles = (int)ceil_div<int64_t>(M, BLOCK_M);
+    p.n_tiles = (int)ceil_div<int64_t>(N, BLOCK_N);
+    const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+    int splits = pick_splits(tiles, K);
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
+        splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
+        if (splits < 1) splits = 1;
+    }
+    int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(K, splits), BLOCK_K) * BLOCK_K;
+    splits = (int)ceil_div<int64_t>(K, k_per);
+    p.k_splits = splits;
+    p.k_per_split = k_per;
+    if (splits == 1) {
+        p.C = C; p.ldc = ldc; p.split_stride = 0; p.accumulate = accumulate;
+        p.vec_ok = (ldc % 4 == 0) && aligned16(C);
+    } else {
+        p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
+        p.vec_ok = (N % 4 == 0) && aligned16(workspace);
+    }
+    const int64_t n_work = tiles * splits;
+    const int grid = (int)(n_work < sm_count() ? n_work : sm_count());
+    gemm_tf32_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
+    GMC_LAUNCH_CHECK();
+    if (splits > 1) {
+        const int64_t MN = M * N;
+        tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
+        GMC_LAUNCH_CHECK();
+    }
+    return GMC_OK;
+}
+
+}  // namespace tc
+
+size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision) {
+    (void)op; (void)precision;
+    const int64_t tiles = ceil_div<int64_t>(M, tc::BLOCK_M) * ceil_div<int64_t>(N, tc::BLOCK_N);
+    const int splits = tc::pick_splits(tiles, K);
+    return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+}
+
+int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+            int64_t ldb, int64_t ldc, int accumulate, int precision, void* workspace, size_t workspace_bytes,
+            cudaStream_t s) {
+    if (precision != GMC_GEMM_TF32) {
+        set_error("gmc_gemm: precision %d is not implemented on the tcgen05 path yet (use GMC_GEMM_TF32 or GMC_GEMM_FP32)", precision);
+        return GMC_ERR_UNSUPPORTED;
+    }
+    GMC_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B),
+                "gmc_gemm(tf32): TMA needs 16-byte aligned bases and leading dimensions that are multiples of 4");
+    GMC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gmc_gemm(tf32): dimension exceeds int32 TMA coordinates");
+    if (M == 0 || N == 0) return GMC_OK;
+    if (K == 0) {
+        if (!accumulate) GMC_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, s));
+        return GMC_OK;
+    }
+    switch (op) {
+        case 0: return tc::launch<false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 1: return tc::launch<false, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 2: return tc::launch<true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    }
+    set_error("gmc_gemm: bad op %d", op);
+    return GMC_ERR_INVALID_ARG;
 }
 
 }  // namespace gmc
