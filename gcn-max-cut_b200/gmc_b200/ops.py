@@ -101,12 +101,15 @@ def spmm(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optio
     if bias is not None:
         _f32(bias, "bias")
     if use_coef:
-        vals, ns, nd = batch.coef, None, None
-    else:
-        vals, ns, nd = None, batch.norm, batch.norm
-    check(lib().gmc_spmm_symnorm_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), _ptr(vals), _ptr(ns), _ptr(nd),
-                                     X.data_ptr(), out.data_ptr(), n, c, ldx, ldy, _ptr(bias), int(relu), _stream()),
-          "gmc_spmm_symnorm_f32")
+        # block-diagonal fast path: shared-memory staged slabs when the graphs fit, else warp-per-row
+        check(lib().gmc_spmm_batched_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(),
+                                         batch.graph_ptr.data_ptr(), batch.num_graphs, batch.max_nodes, X.data_ptr(),
+                                         out.data_ptr(), n, c, ldx, ldy, _ptr(bias), int(relu), _stream()),
+              "gmc_spmm_batched_f32")
+        return out
+    check(lib().gmc_spmm_symnorm_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), None, batch.norm.data_ptr(),
+                                     batch.norm.data_ptr(), X.data_ptr(), out.data_ptr(), n, c, ldx, ldy, _ptr(bias),
+                                     int(relu), _stream()), "gmc_spmm_symnorm_f32")
     return out
 
 

@@ -60,6 +60,55 @@ def test_spmm_matches_dense_ahat(C, use_coef):
     assert relerr(got2.cpu(), torch.relu(want + bias.double())) < 2e-6
 
 
+@pytest.mark.parametrize("C", [500, 64, 100, 128, 28, 36, 1000])
+@pytest.mark.parametrize("specs", [[(1000, 7, 1), (1000, 6, 2)], [(200, 5, 3), (128, 7, 4), (1000, 8, 5), (300, 6, 6)],
+                                   [(1800, 3, 7), (130, 4, 8)], [(3000, 4, 9)]])
+def test_spmm_slab_kernel_matches_row_kernel_and_dense(C, specs):
+    """Graphs with >= 128 nodes take the shared-memory slab kernel (W4 = 7, 4 or 2 by size)."""
+    graphs, csrs, batch = make_batch(specs)
+    torch.manual_seed(C)
+    X = torch.randn(batch.num_nodes, C, device=DEV)
+    bias = torch.randn(C, device=DEV)
+    slab = ops.spmm(batch, X, bias=bias, relu=True)                      # gmc_spmm_batched_f32
+    rowk = ops.spmm(batch, X, bias=bias, relu=True, use_coef=False)      # warp-per-row kernel
+    assert relerr(slab.cpu(), rowk.cpu()) < 2e-6
+    gp = batch.graph_ptr_host
+    i = len(csrs) - 1
+    want = torch.relu(ahat_dense(csrs[i]) @ X[gp[i]: gp[i + 1]].cpu().double() + bias.cpu().double())
+    assert relerr(slab[gp[i]: gp[i + 1]].cpu(), want) < 2e-6
+    plain = ops.spmm(batch, X)
+    assert relerr(plain.cpu(), ops.spmm(batch, X, use_coef=False).cpu()) < 2e-6
+
+
+def test_spmm_slab_irregular_degrees_and_nonfinite_isolation():
+    # irregular degrees inside one warp (different trip counts per row group) and a NaN in one graph must
+    # not leak into rows that do not reference it
+    g1 = nx.gnm_random_graph(400, 2400, seed=1)
+    g1.remove_nodes_from([n for n, d in g1.degree() if d == 0])
+    g1 = nx.convert_node_labels_to_integers(g1)
+    g2 = nx.random_regular_graph(d=3, n=256, seed=2)
+    for g in (g1, g2):
+        nx.set_edge_attributes(g, 1, "weight")
+    csrs = [rs.csr_from_networkx(g) for g in (g1, g2)]
+    batch = GraphBatch([CSRGraph.from_networkx(g) for g in (g1, g2)])
+    torch.manual_seed(0)
+    X = torch.randn(batch.num_nodes, 96, device=DEV)
+    got = ops.spmm(batch, X)
+    want = torch.cat([ahat_dense(c) @ X[s:e].cpu().double() for c, (s, e) in
+                      zip(csrs, zip(batch.graph_ptr_host[:-1], batch.graph_ptr_host[1:]))])
+    assert relerr(got.cpu(), want) < 2e-6
+    n1 = csrs[0].n
+    X2 = X.clone()
+    X2[0, :] = float("nan")                                # node 0 of graph 1
+    got2 = ops.spmm(batch, X2)
+    nbrs = set(csrs[0].colidx[csrs[0].rowptr[0]: csrs[0].rowptr[1]].tolist())
+    touched = torch.isnan(got2).any(dim=1).cpu().numpy()
+    expect = np.zeros(batch.num_nodes, dtype=bool)
+    rows = np.repeat(np.arange(n1), np.diff(csrs[0].rowptr))
+    expect[rows[csrs[0].colidx == 0]] = True
+    assert (touched == expect).all()
+
+
 def test_spmm_strided_rows_and_symmetry():
     _, csrs, batch = make_batch([(100, 7, 9)])
     torch.manual_seed(0)
