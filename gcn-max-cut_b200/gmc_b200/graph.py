@@ -13,6 +13,7 @@ order, undirected edges stored in both directions (nnz = 2|E|).
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -197,6 +198,20 @@ class GraphBatch:
                 f"({zero} nodes; DGL GraphConv raises the same with allow_zero_in_degree=False)")
         self.coef = ops.edge_coef(self.rowptr, self.colidx, None, self.norm, self.norm, self.num_nodes)
         self.max_nodes = int(self.sizes.max()) if self.num_graphs else 0
+        # ELL plan for the shared-memory slab SpMM.  Measured on B200 (profiles/r01_spmm_slab_notes.md) the slab
+        # kernel is instruction-issue bound at 5.7 ms where the warp-per-row kernel is L2-bound at 5.0 ms for
+        # config 3, so it is opt-in (GMC_SPMM_SLAB=1 or build_plan()) until it wins.
+        self.plan = None
+        if os.environ.get("GMC_SPMM_SLAB", "0") == "1":
+            self.build_plan()
+
+    def build_plan(self) -> bool:
+        """Build the ELL plan that lets ops.spmm take the shared-memory slab kernel (needs max degree <= 8)."""
+        from . import ops
+        if self.max_nodes >= 128 and self.num_nodes > 0:
+            self.plan = ops.spmm_plan(self.rowptr, self.colidx, self.coef, self.graph_ptr, self.num_graphs,
+                                      self.num_nodes)
+        return self.plan is not None
 
     # per-graph views --------------------------------------------------------------------
     def node_slice(self, g: int) -> slice:

@@ -76,6 +76,17 @@ def edge_coef(rowptr, colidx, vals, norm_src, norm_dst, n_rows: int) -> torch.Te
     return coef
 
 
+def spmm_plan(rowptr, colidx, coef, graph_ptr, n_graphs: int, n_rows: int) -> Optional[torch.Tensor]:
+    """ELL plan for the slab SpMM (None when some row has more than 8 neighbours)."""
+    nbytes = lib().gmc_spmm_plan_bytes(n_rows)
+    plan = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=colidx.device)
+    over = torch.zeros(1, dtype=torch.int32, device=colidx.device)
+    check(lib().gmc_spmm_plan_build(rowptr.data_ptr(), colidx.data_ptr(), coef.data_ptr(), graph_ptr.data_ptr(),
+                                    n_graphs, n_rows, plan.data_ptr(), over.data_ptr(), _stream()),
+          "gmc_spmm_plan_build")
+    return None if int(over.item()) else plan
+
+
 def densify(batch, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Padded adjacency rows X[N, n_cols] of a GraphBatch (device-side graphExtender)."""
     if out is None:
@@ -103,8 +114,9 @@ def spmm(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optio
     if use_coef:
         # block-diagonal fast path: shared-memory staged slabs when the graphs fit, else warp-per-row
         check(lib().gmc_spmm_batched_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(),
-                                         batch.graph_ptr.data_ptr(), batch.num_graphs, batch.max_nodes, X.data_ptr(),
-                                         out.data_ptr(), n, c, ldx, ldy, _ptr(bias), int(relu), _stream()),
+                                         batch.graph_ptr.data_ptr(), batch.num_graphs, batch.max_nodes,
+                                         _ptr(getattr(batch, "plan", None)), X.data_ptr(), out.data_ptr(), n, c,
+                                         ldx, ldy, _ptr(bias), int(relu), _stream()),
               "gmc_spmm_batched_f32")
         return out
     check(lib().gmc_spmm_symnorm_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), None, batch.norm.data_ptr(),

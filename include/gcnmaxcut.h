@@ -85,14 +85,20 @@ int gmc_spmm_symnorm_f32(const int32_t* rowptr, const int32_t* colidx, const flo
                          const float* bias, int32_t relu, void* stream);
 
 /* Same product for a BLOCK-DIAGONAL batch whose A_hat values were precomputed (`coef` from
- * gmc_edge_coef_f32): when every graph fits the on-chip slab buffers (max_nodes x 112 B x 2),
- * source rows are staged once into shared memory (cp.async, double buffered) and gathered from
- * there, cutting L2 traffic from (d+1)x to ~2x; otherwise it runs the warp-per-row kernel.
- * Results are identical to gmc_spmm_symnorm_f32(rowptr, colidx, coef, NULL, NULL, ...). */
+ * gmc_edge_coef_f32).  With an ELL `plan` of the batch (8 padded (local col, coef) slots per row,
+ * built once by gmc_spmm_plan_build; needs max degree <= 8) and graphs that fit the on-chip slab
+ * buffers (max_nodes x 112 B x 2), source rows are staged once into shared memory (cp.async, double
+ * buffered) and gathered from there, cutting L2 traffic from (d+1)x to ~2x; otherwise (plan NULL,
+ * large graphs, narrow matrices) it runs the warp-per-row kernel.  Results are identical to
+ * gmc_spmm_symnorm_f32(rowptr, colidx, coef, NULL, NULL, ...). */
+size_t gmc_spmm_plan_bytes(int64_t n_rows);
+int gmc_spmm_plan_build(const int32_t* rowptr, const int32_t* colidx, const float* coef,
+                        const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, void* plan,
+                        int32_t* overflow /* device, set to 1 if some degree > 8 */, void* stream);
 int gmc_spmm_batched_f32(const int32_t* rowptr, const int32_t* colidx, const float* coef,
                          const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes,
-                         const float* X, float* Y, int64_t n_rows, int32_t n_cols, int64_t ldx,
-                         int64_t ldy, const float* bias, int32_t relu, void* stream);
+                         const void* plan, const float* X, float* Y, int64_t n_rows, int32_t n_cols,
+                         int64_t ldx, int64_t ldy, const float* bias, int32_t relu, void* stream);
 
 /* ---- (b) dense feature transforms --------------------------------------------------- */
 

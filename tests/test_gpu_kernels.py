@@ -66,6 +66,7 @@ def test_spmm_matches_dense_ahat(C, use_coef):
 def test_spmm_slab_kernel_matches_row_kernel_and_dense(C, specs):
     """Graphs with >= 128 nodes take the shared-memory slab kernel (W4 = 7, 4 or 2 by size)."""
     graphs, csrs, batch = make_batch(specs)
+    assert batch.build_plan()                                            # opt in to the slab kernel
     torch.manual_seed(C)
     X = torch.randn(batch.num_nodes, C, device=DEV)
     bias = torch.randn(C, device=DEV)
@@ -91,6 +92,7 @@ def test_spmm_slab_irregular_degrees_and_nonfinite_isolation():
         nx.set_edge_attributes(g, 1, "weight")
     csrs = [rs.csr_from_networkx(g) for g in (g1, g2)]
     batch = GraphBatch([CSRGraph.from_networkx(g) for g in (g1, g2)])
+    assert not batch.build_plan()                          # degrees > 8: no ELL plan, warp-per-row kernel
     torch.manual_seed(0)
     X = torch.randn(batch.num_nodes, 96, device=DEV)
     got = ops.spmm(batch, X)
