@@ -109,14 +109,23 @@ skinny_bwd_kernel(const float* __restrict__ dT, int64_t lddt, const float* __res
 
 __global__ void skinny_bwd_reduce_kernel(const float* __restrict__ ws, int n_ctas, int n_in, int nout,
                                          float* __restrict__ dW, float* __restrict__ dbias) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over n_in * (nout + 1)
+    // block = 32 outputs (x) x 32 partial-groups (y): coalesced 128-byte reads, fixed summation order
+    __shared__ float red[32][33];
     const int total = n_in * (nout + 1);
-    if (i >= total) return;
+    const int i = blockIdx.x * 32 + threadIdx.x;               // over n_in * (nout + 1)
     float s = 0.f;
-    for (int c = 0; c < n_ctas; ++c) s += ws[(int64_t)c * total + i];
-    const int j = i / (nout + 1), k = i % (nout + 1);
-    if (k < nout) dW[(int64_t)j * nout + k] = s;
-    else if (dbias) dbias[j] = s;
+    if (i < total)
+        for (int c = threadIdx.y; c < n_ctas; c += 32) s += ws[(int64_t)c * total + i];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < total) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += red[y][threadIdx.x];
+        const int j = i / (nout + 1), k = i % (nout + 1);
+        if (k < nout) dW[(int64_t)j * nout + k] = t;
+        else if (dbias) dbias[j] = t;
+    }
 }
 
 // ---- column sums ------------------------------------------------------------------------
@@ -222,7 +231,7 @@ int gmc_skinny_bwd_f32(const float* dT, int64_t lddt, const float* W, const floa
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();
     const int total = n_in * (n_out + 1);
-    skinny_bwd_reduce_kernel<<<ceil_div(total, 256), 256, 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
+    skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
 }

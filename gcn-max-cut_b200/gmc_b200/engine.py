@@ -158,8 +158,13 @@ class GCNEngine:
         W1, b1, W2, b2 = self.params()
         A, Bf = self.bufA[:N], self.bufB[:N]
         self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, W1.data, out=A, precision=self.precision, workspace=self.ws)
-        self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf, bias=b1.data, relu=True)
-        self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
+        if 16 <= self.H <= 512 and self.H % 4 == 0 and getattr(batch, "plan", None) is None:
+            # aggregation + bias + ReLU + the skinny projection H1 W2 in one pass over the row
+            self._op("spmm_h_fused", 1, ops.spmm_fused_skinny, batch, A, W2.data, out=Bf, proj=self.T2[:N],
+                     bias=b1.data, relu=True)
+        else:
+            self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf, bias=b1.data, relu=True)
+            self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
         self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
         return self.Z[:N]
 

@@ -125,6 +125,26 @@ def spmm(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optio
     return out
 
 
+def spmm_fused_skinny(batch, X: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      proj: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, relu: bool = True):
+    """(Y, T) with Y = act(A_hat X + bias) and T = Y W in one pass (n_cols <= 512, W [n_cols, n_out<=8])."""
+    X, ldx = _rowmajor(X, "X")
+    W = _f32(W, "W").contiguous()
+    n, c = X.shape
+    n_out = W.shape[1]
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=X.device)
+    out, ldy = _rowmajor(out, "out")
+    if proj is None:
+        proj = torch.empty((n, n_out), dtype=torch.float32, device=X.device)
+    proj, ldt = _rowmajor(proj, "proj")
+    check(lib().gmc_spmm_fused_skinny_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(), None,
+                                          None, X.data_ptr(), out.data_ptr(), n, c, ldx, ldy, _ptr(bias), int(relu),
+                                          W.data_ptr(), n_out, proj.data_ptr(), ldt, _stream()),
+          "gmc_spmm_fused_skinny_f32")
+    return out, proj
+
+
 # ---------------------------------------------------------------- (b) GEMM
 _OPS = {"nn": 0, "nt": 1, "tn": 2}
 

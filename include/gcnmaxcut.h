@@ -100,6 +100,17 @@ int gmc_spmm_batched_f32(const int32_t* rowptr, const int32_t* colidx, const flo
                          const void* plan, const float* X, float* Y, int64_t n_rows, int32_t n_cols,
                          int64_t ldx, int64_t ldy, const float* bias, int32_t relu, void* stream);
 
+/* gmc_spmm_symnorm_f32 with the skinny second-layer projection fused into its epilogue:
+ *   Y[v,:] = act(A_hat X + bias)[v,:]  and  T[v,k] = sum_j Y[v,j] W[j,k]   (W [n_cols, n_out], n_out <= 8)
+ * One warp owns a whole row, so n_cols must be <= 512 (GMC_ERR_UNSUPPORTED otherwise).
+ * Replaces GraphConv aggregation + bias (TrainingNeural.py:80), F.relu (:81) and conv2's th.matmul (:83)
+ * in ONE pass: the separate read of H by gmc_skinny_fwd_f32 disappears. */
+int gmc_spmm_fused_skinny_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                              const float* norm_src, const float* norm_dst, const float* X, float* Y,
+                              int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy,
+                              const float* bias, int32_t relu, const float* W, int32_t n_out, float* T,
+                              int64_t ldt, void* stream);
+
 /* ---- (b) dense feature transforms --------------------------------------------------- */
 
 /* C[M,N] = op(A) * op(B) (+ C if accumulate != 0), row-major.

@@ -111,6 +111,21 @@ def test_spmm_slab_irregular_degrees_and_nonfinite_isolation():
     assert (touched == expect).all()
 
 
+@pytest.mark.parametrize("C,K", [(500, 3), (64, 2), (128, 8), (20, 3), (512, 5)])
+def test_spmm_fused_skinny_projection(C, K):
+    graphs, csrs, batch = make_batch([(70, 6, 1), (33 * 2, 7, 2), (1000, 7, 3), (9, 2, 4)])
+    torch.manual_seed(C + K)
+    X = torch.randn(batch.num_nodes, C, device=DEV)
+    W = torch.randn(C, K, device=DEV)
+    bias = torch.randn(C, device=DEV)
+    Y, T = ops.spmm_fused_skinny(batch, X, W, bias=bias, relu=True)
+    want_Y = ops.spmm(batch, X, bias=bias, relu=True, use_coef=False)
+    assert torch.equal(Y, want_Y) or relerr(Y.cpu(), want_Y.cpu()) < 1e-6
+    assert relerr(T.cpu(), want_Y.cpu().double() @ W.cpu().double()) < 3e-6
+    with pytest.raises(_lib.GmcError):
+        ops.spmm_fused_skinny(batch, torch.randn(batch.num_nodes, 516, device=DEV), torch.randn(516, 3, device=DEV))
+
+
 def test_spmm_strided_rows_and_symmetry():
     _, csrs, batch = make_batch([(100, 7, 9)])
     torch.manual_seed(0)
