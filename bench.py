@@ -213,7 +213,7 @@ def run_b200_arm(args):
     h_gptr = torch.from_numpy(graph_ptr).pin_memory()
     batch = GraphBatch.from_arrays(rowptr, colidx, graph_ptr, device=dev)
     N, nnz = batch.num_nodes, batch.nnz
-    X = ops.densify(batch, F)                           # dense padded adjacency rows, resident in HBM
+    X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
 
     torch.manual_seed(args.seed)                        # identical initial weights on every rank
     cfg = T.TrainingConfig(n_nodes=n, dim_embedding=F, hidden_dim=H, number_classes=K, learning_rate=1e-3,

@@ -97,4 +97,15 @@ int gmc_csr_densify_f32(const int32_t* rowptr, const int32_t* colidx, const floa
     return GMC_OK;
 }
 
+int gmc_copy2d_f32(float* dst, int64_t lddst, const float* src, int64_t ldsrc, int64_t n_rows, int32_t n_cols,
+                   void* stream) {
+    GMC_REQUIRE(dst && src, "gmc_copy2d_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_cols >= 0 && lddst >= n_cols && ldsrc >= n_cols, "gmc_copy2d_f32: bad sizes");
+    if (n_rows == 0 || n_cols == 0) return GMC_OK;
+    GMC_CUDA(cudaMemcpy2DAsync(dst, (size_t)lddst * sizeof(float), src, (size_t)ldsrc * sizeof(float),
+                               (size_t)n_cols * sizeof(float), (size_t)n_rows, cudaMemcpyDeviceToDevice,
+                               gmc::as_stream(stream)));
+    return GMC_OK;
+}
+
 }  // extern "C"

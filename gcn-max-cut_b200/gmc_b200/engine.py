@@ -101,6 +101,7 @@ class GCNEngine:
         self.gW2 = self.grads_flat[offs[2]: offs[2] + sizes[2]].view_as(W2)
         self.gb2 = self.grads_flat[offs[3]: offs[3] + sizes[3]]
         self.ws = ops.Workspace()
+        self.W1p = ops.padded_empty(self.F, self.H, self.device, zero=True)   # 128-byte pitched copy of W1 per step
         self._cap_nodes = 0
         self._cap_graphs = 0
         self.bufA = self.bufB = self.T2 = self.Z = self.P = self.dZ = self.dT2 = None
@@ -129,8 +130,9 @@ class GCNEngine:
         if n_nodes > self._cap_nodes:
             cap = n_nodes
             dev, f32 = self.device, torch.float32
-            self.bufA = torch.empty((cap, self.H), dtype=f32, device=dev)
-            self.bufB = torch.empty((cap, self.H), dtype=f32, device=dev)
+            # row pitch padded to 128 B: TMA boxes / 128-bit gathers never straddle cache lines
+            self.bufA = ops.padded_empty(cap, self.H, dev)
+            self.bufB = ops.padded_empty(cap, self.H, dev)
             self.T2 = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.Z = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.P = torch.empty((cap, self.K), dtype=f32, device=dev)
@@ -157,7 +159,8 @@ class GCNEngine:
         self._ensure(N, batch.num_graphs)
         W1, b1, W2, b2 = self.params()
         A, Bf = self.bufA[:N], self.bufB[:N]
-        self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, W1.data, out=A, precision=self.precision, workspace=self.ws)
+        ops.copy2d(self.W1p, W1.data)
+        self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, self.W1p, out=A, precision=self.precision, workspace=self.ws)
         if 16 <= self.H <= 512 and self.H % 4 == 0 and getattr(batch, "plan", None) is None:
             # aggregation + bias + ReLU + the skinny projection H1 W2 in one pass over the row
             self._op("spmm_h_fused", 1, ops.spmm_fused_skinny, batch, A, W2.data, out=Bf, proj=self.T2[:N],
@@ -200,7 +203,7 @@ class GCNEngine:
         self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf)                                   # dT1
         self._op("gemm_tn_dw1", 2, ops.gemm, "tn", X, Bf, out=self.gW1, precision=self.precision, workspace=self.ws)
         if dX is not None:
-            self._op("gemm_nt_dx", 1, ops.gemm, "nt", Bf, W1.data, out=dX, precision=self.precision,
+            self._op("gemm_nt_dx", 1, ops.gemm, "nt", Bf, self.W1p, out=dX, precision=self.precision,
                      workspace=self.ws)
         return loss
 

@@ -98,6 +98,27 @@ def densify(batch, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
+def pad_cols(n: int, multiple: int = 32) -> int:
+    """Leading dimension (floats) padded to 128 bytes."""
+    return (n + multiple - 1) // multiple * multiple
+
+
+def padded_empty(rows: int, cols: int, device, zero: bool = False) -> torch.Tensor:
+    """[rows, cols] fp32 view whose row pitch is a multiple of 128 bytes."""
+    make = torch.zeros if zero else torch.empty
+    return make((rows, pad_cols(cols)), dtype=torch.float32, device=device)[:, :cols]
+
+
+def copy2d(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    dst, lddst = _rowmajor(dst, "dst")
+    src, ldsrc = _rowmajor(src, "src")
+    if dst.shape != src.shape:
+        raise ValueError("copy2d: shape mismatch")
+    check(lib().gmc_copy2d_f32(dst.data_ptr(), lddst, src.data_ptr(), ldsrc, src.shape[0], src.shape[1], _stream()),
+          "gmc_copy2d_f32")
+    return dst
+
+
 # ---------------------------------------------------------------- (a) SpMM
 def spmm(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          relu: bool = False, use_coef: bool = True) -> torch.Tensor:
