@@ -291,6 +291,218 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+// =================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x 256 tile.  Each CTA stages its own
+// 128 rows of A and its own 128 columns of B (32 KB per stage instead of 48 KB for the same MMA work), the
+// leader CTA issues M=256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.  The single-CTA
+// kernel is L2->SM bandwidth bound (48 KB per 512 MMA cycles = the ~42 B/clk/SM LTS limit); pairing cuts the
+// operand traffic per SM by a third.
+// =================================================================================================
+constexpr int STAGES2 = 6;
+constexpr int HALF = 128;                                   // rows of A / columns of B staged per CTA
+constexpr int A2_BYTES = HALF * BLOCK_K * 4, B2_BYTES = HALF * BLOCK_K * 4, STAGE2_BYTES = A2_BYTES + B2_BYTES;
+constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+         | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);          // N = 256, M = 256 (pair)
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    const uint32_t bars = tiles + STAGES2 * STAGE2_BYTES;
+    const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES2;
+    const uint32_t tfull_bar = bars + 16 * STAGES2, tempty_bar = tfull_bar + 8 * ACC_STAGES;
+    const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_map(&tmA);
+        prefetch_map(&tmB);
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int64_t tiles_mn = (int64_t)p.m_tiles * p.n_tiles;       // tiles of 256 x 256
+    const int64_t n_work = tiles_mn * p.k_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs, own halves) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t w = pair; w < n_work; w += n_pairs) {
+                const int split = (int)(w / tiles_mn);
+                const int64_t rem = w - (int64_t)split * tiles_mn;
+                const int m0 = (int)(rem / p.n_tiles) * 256 + HALF * (int)rank;
+                const int n0 = (int)(rem % p.n_tiles) * 256 + HALF * (int)rank;
+                const int64_t kb = (int64_t)split * p.k_per_split;
+                const int64_t ke = min(p.K, kb + p.k_per_split);
+                for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A2_BYTES;
+                    const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);          // the LEADER's full barrier
+                    if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * STAGE2_BYTES);
+                    else mbar_arrive_cluster(fb);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < HALF / 32; ++j) tma_load_2d_2sm(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb);
+                    } else {
+                        tma_load_2d_2sm(sa, &tmA, (int)k0, m0, fb);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < HALF / 32; ++j) tma_load_2d_2sm(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb);
+                    } else {
+                        tma_load_2d_2sm(sb, &tmB, (int)k0, n0, fb);
+                    }
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc2(A_MN, B_MN);
+            const uint32_t a_lbo = A_MN ? CHUNK_BYTES : 16, b_lbo = B_MN ? CHUNK_BYTES : 16;
+            const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+            const uint32_t a_lay = A_MN ? 1 : 2, b_lay = B_MN ? 1 : 2;
+            const uint32_t a_step = A_MN ? 1024 : UMMA_K * 4, b_step = B_MN ? 1024 : UMMA_K * 4;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t w = pair; w < n_work; w += n_pairs) {
+                const int split = (int)(w / tiles_mn);
+                const int64_t kb = (int64_t)split * p.k_per_split;
+                const int64_t ke = min(p.K, kb + p.k_per_split);
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                uint32_t first = 1;
+                for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    __syncwarp();
+                    if (elect_one()) {
+                        const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A2_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t ad = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
+                            const uint64_t bd = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
+                            umma_tf32_2sm(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        umma_commit_2sm(empty_bar + 8 * stage, 3);      // frees the stage in BOTH CTAs
+                        if (k0 + BLOCK_K >= ke) umma_commit_2sm(tfull_bar + 8 * acc, 3);
+                    }
+                    __syncwarp();
+                    first = 0;
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5, both CTAs: own 128 rows) =====================
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t w = pair; w < n_work; w += n_pairs) {
+            const int split = (int)(w / tiles_mn);
+            const int64_t rem = w - (int64_t)split * tiles_mn;
+            const int64_t m0 = (rem / p.n_tiles) * 256 + HALF * (int64_t)rank;
+            const int n0 = (int)(rem % p.n_tiles) * 256;
+            float* Cs = p.C + (int64_t)split * p.split_stride;
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int64_t m = m0 + 32 * q + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
+#pragma unroll 1
+            for (int c = 0; c < 256 / 32; ++c) {
+                const int n = n0 + 32 * c;
+                if (n >= p.N) break;                               // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(t_row + 32 * c, r);
+                if (m < p.M) {
+                    float* dst = Cs + m * p.ldc + n;
+                    if (p.vec_ok && n + 32 <= p.N) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                            float4* d4 = reinterpret_cast<float4*>(dst) + i;
+                            if (p.accumulate) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                            *d4 = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (n + i < p.N) dst[i] = p.accumulate ? dst[i] + __uint_as_float(r[i]) : __uint_as_float(r[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty_bar + 8 * acc, 0));   // leader's barrier, 8 arrivals
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    __syncwarp();                                                 // reconverge before the .aligned cluster barrier
+    tc_fence_before();
+    cluster_sync_all();                                           // nobody leaves while the peer may still touch us
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t MN, int64_t N,
                                         float* __restrict__ C, int64_t ldc, int accumulate) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,12 +608,88 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
     return GMC_OK;
 }
 
+static bool use_two_cta() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GMC_GEMM_1CTA");
+        cached = (e && e[0] == '1') ? 0 : 1;
+    }
+    return cached == 1;
+}
+
+static int pick_splits2(int64_t tiles, int64_t K) {
+    const int pairs = sm_count() / 2;
+    if (tiles >= pairs || K < 8 * BLOCK_K) return 1;
+    int64_t s = pairs / tiles;
+    const int64_t max_by_k = K / (4 * BLOCK_K);
+    if (s > max_by_k) s = max_by_k;
+    return (int)(s < 1 ? 1 : s);
+}
+
+template <bool A_MN, bool B_MN>
+static int launch2(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GMC_CUDA(cudaFuncSetAttribute(gemm_tf32_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SMEM2_BYTES));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BLOCK_K, true);
+    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, HALF, false);
+    if (rc) return rc;
+    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BLOCK_K, true);
+    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, HALF, false);
+    if (rc) return rc;
+
+    Params p;
+    p.M = M; p.N = N; p.K = K;
+    p.m_tiles = (int)ceil_div<int64_t>(M, 256);
+    p.n_tiles = (int)ceil_div<int64_t>(N, 256);
+    const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+    int splits = pick_splits2(tiles, K);
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
+        splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
+        if (splits < 1) splits = 1;
+    }
+    int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(K, splits), BLOCK_K) * BLOCK_K;
+    splits = (int)ceil_div<int64_t>(K, k_per);
+    p.k_splits = splits;
+    p.k_per_split = k_per;
+    if (splits == 1) {
+        p.C = C; p.ldc = ldc; p.split_stride = 0; p.accumulate = accumulate;
+        p.vec_ok = (ldc % 4 == 0) && aligned16(C);
+    } else {
+        p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
+        p.vec_ok = (N % 4 == 0) && aligned16(workspace);
+    }
+    const int64_t n_work = tiles * splits;
+    const int pairs = sm_count() / 2;
+    const int grid = 2 * (int)(n_work < pairs ? n_work : pairs);
+    gemm_tf32_2cta_kernel<A_MN, B_MN><<<grid, THREADS, SMEM2_BYTES, s>>>(tmA, tmB, p);
+    GMC_LAUNCH_CHECK();
+    if (splits > 1) {
+        const int64_t MN = M * N;
+        tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
+        GMC_LAUNCH_CHECK();
+    }
+    return GMC_OK;
+}
+
 }  // namespace tc
 
 size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision) {
     (void)op; (void)precision;
-    const int64_t tiles = ceil_div<int64_t>(M, tc::BLOCK_M) * ceil_div<int64_t>(N, tc::BLOCK_N);
-    const int splits = tc::pick_splits(tiles, K);
+    int splits;
+    if (tc::use_two_cta()) {
+        const int64_t tiles = ceil_div<int64_t>(M, 256) * ceil_div<int64_t>(N, 256);
+        splits = tc::pick_splits2(tiles, K);
+    } else {
+        const int64_t tiles = ceil_div<int64_t>(M, tc::BLOCK_M) * ceil_div<int64_t>(N, tc::BLOCK_N);
+        splits = tc::pick_splits(tiles, K);
+    }
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
 }
 
@@ -419,6 +707,13 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
     if (K == 0) {
         if (!accumulate) GMC_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, s));
         return GMC_OK;
+    }
+    if (tc::use_two_cta()) {
+        switch (op) {
+            case 0: return tc::launch2<false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+            case 1: return tc::launch2<false, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+            case 2: return tc::launch2<true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        }
     }
     switch (op) {
         case 0: return tc::launch<false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
