@@ -610,9 +610,11 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
 
 static bool use_two_cta() {
     static int cached = -1;
+    // Measured on B200 (profiles/r01_gemm_notes.md): the pair kernel moves 1.5x fewer bytes from L2 but its tensor
+    // pipe is only 26 % active (1-CTA: 48 %), so it is opt-in (GMC_GEMM_2CTA=1) until the stall is understood.
     if (cached < 0) {
-        const char* e = getenv("GMC_GEMM_1CTA");
-        cached = (e && e[0] == '1') ? 0 : 1;
+        const char* e = getenv("GMC_GEMM_2CTA");
+        cached = (e && e[0] == '1') ? 1 : 0;
     }
     return cached == 1;
 }
