@@ -328,7 +328,9 @@ def run_b200_arm(args):
             achieved, peak, unit = work / (avg_ms * 1e-3) / 1e12, tf32_peak, "TFLOP/s"
         ops_report[name] = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                             "frac": achieved / peak if peak else None, "avg_ms": avg_ms, "calls": calls,
-                            "share_of_step": tot / ms, "traffic": traffic_db.get(name)}
+                            "share_of_step": tot / ms,
+                            # DRAM bytes per launch from the committed ncu --set full capture (per graph x graphs/GPU)
+                            "traffic": (traffic_db.get("per_graph_bytes", {}).get(name) or 0.0) * B or None}
     dominant = max(timer.total_ms, key=lambda k: timer.total_ms[k]) if timer.total_ms else None
     roofline = None
     if dominant:

@@ -10,6 +10,8 @@
 
 namespace gmc {
 
+// rows per warp (measured at config 3): 8 -> 5.8 ms (5.64 MB/graph of DRAM traffic, algorithmic 4.04: ~47 graphs of
+// rows in flight exceed L2), 2 -> 6.2 ms (W^T staging + epilogue latency dominate), 1 via L1 -> 7.1 ms
 constexpr int kFusedRowsPerWarp = 8;
 
 template <int NV, int NOUT>
