@@ -21,7 +21,7 @@
 
 namespace gmc {
 
-constexpr int kSlabThreads = 1024;
+constexpr int kSlabThreads = 768;
 constexpr int kEll = 8;                                   // padded neighbour slots per row
 constexpr size_t kSlabSmemMax = 227 * 1024;
 
@@ -101,14 +101,18 @@ spmm_slab_kernel(const int4* __restrict__ ell_col, const float4* __restrict__ el
         const int col0 = s * W4;
         const int nv = min(W4, c4 - col0);
         const bool active = lg < nv;
-        // this row group's first neighbour list: issue before waiting on the slab
-        int r = gidx;
-        int4 c_lo, c_hi; float4 a_lo, a_hi;
-        if (r < n_g) {
-            const int64_t slot = ((int64_t)base + r) * 2;
-            c_lo = __ldg(ell_col + slot); c_hi = __ldg(ell_col + slot + 1);
-            a_lo = __ldg(ell_coef + slot); a_hi = __ldg(ell_coef + slot + 1);
-        }
+        // neighbour lists of this row group's first TWO rows: issued before waiting on the slab; every list is
+        // re-loaded one full (two-row) iteration ahead of its use, which covers the L2 latency with 24 warps/SM
+        struct Slots { int4 c_lo, c_hi; float4 a_lo, a_hi; };
+        auto load_slots = [&](Slots& S, int row) {
+            const int64_t slot = ((int64_t)base + row) * 2;
+            S.c_lo = __ldg(ell_col + slot); S.c_hi = __ldg(ell_col + slot + 1);
+            S.a_lo = __ldg(ell_coef + slot); S.a_hi = __ldg(ell_coef + slot + 1);
+        };
+        Slots S0, S1;
+        const int r0 = gidx;
+        if (r0 < n_g) load_slots(S0, r0);
+        if (r0 + GROUPS < n_g) load_slots(S1, r0 + GROUPS);
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias && active) b4 = __ldg(bias + col0 + lg);
 
@@ -119,28 +123,26 @@ spmm_slab_kernel(const int4* __restrict__ ell_col, const float4* __restrict__ el
         __syncthreads();
 
         const float4* src = sbuf + (size_t)buf * rows_cap * W4 + lg;
-        for (; r < n_g; r += GROUPS) {
-            // prefetch the next row's slots while this row is accumulated
-            const int rn = r + GROUPS;
-            int4 n_lo = c_lo, n_hi = c_hi; float4 m_lo = a_lo, m_hi = a_hi;
-            if (rn < n_g) {
-                const int64_t slot = ((int64_t)base + rn) * 2;
-                n_lo = __ldg(ell_col + slot); n_hi = __ldg(ell_col + slot + 1);
-                m_lo = __ldg(ell_coef + slot); m_hi = __ldg(ell_coef + slot + 1);
+        // padded slots carry coef 0 and point at the all-zero row, so they add exactly 0 and a non-finite
+        // source row can only reach rows that really reference it
+        auto row_out = [&](const Slots& S, int row) {
+            if (!active) return;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v0 = src[S.c_lo.x * W4], v1 = src[S.c_lo.y * W4], v2 = src[S.c_lo.z * W4], v3 = src[S.c_lo.w * W4];
+            const float4 v4 = src[S.c_hi.x * W4], v5 = src[S.c_hi.y * W4], v6 = src[S.c_hi.z * W4], v7 = src[S.c_hi.w * W4];
+            fma4(acc, S.a_lo.x, v0); fma4(acc, S.a_lo.y, v1); fma4(acc, S.a_lo.z, v2); fma4(acc, S.a_lo.w, v3);
+            fma4(acc, S.a_hi.x, v4); fma4(acc, S.a_hi.y, v5); fma4(acc, S.a_hi.z, v6); fma4(acc, S.a_hi.w, v7);
+            acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+            if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+            Y[(int64_t)(base + row) * ldy4 + col0 + lg] = acc;
+        };
+        for (int r = r0; r < n_g; r += 2 * GROUPS) {
+            row_out(S0, r);
+            if (r + 2 * GROUPS < n_g) load_slots(S0, r + 2 * GROUPS);
+            if (r + GROUPS < n_g) {
+                row_out(S1, r + GROUPS);
+                if (r + 3 * GROUPS < n_g) load_slots(S1, r + 3 * GROUPS);
             }
-            if (active) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                // padded slots carry coef 0 and point at the all-zero row, so they add exactly 0 and a
-                // non-finite source row can only reach rows that really reference it
-                const float4 v0 = src[c_lo.x * W4], v1 = src[c_lo.y * W4], v2 = src[c_lo.z * W4], v3 = src[c_lo.w * W4];
-                const float4 v4 = src[c_hi.x * W4], v5 = src[c_hi.y * W4], v6 = src[c_hi.z * W4], v7 = src[c_hi.w * W4];
-                fma4(acc, a_lo.x, v0); fma4(acc, a_lo.y, v1); fma4(acc, a_lo.z, v2); fma4(acc, a_lo.w, v3);
-                fma4(acc, a_hi.x, v4); fma4(acc, a_hi.y, v5); fma4(acc, a_hi.z, v6); fma4(acc, a_hi.w, v7);
-                acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-                if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-                Y[(int64_t)(base + r) * ldy4 + col0 + lg] = acc;
-            }
-            c_lo = n_lo; c_hi = n_hi; a_lo = m_lo; a_hi = m_hi;
         }
         __syncthreads();                                  // buffer `buf` may be overwritten by the next issue
         buf ^= 1;
