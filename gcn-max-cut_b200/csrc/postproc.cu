@@ -65,6 +65,31 @@ __global__ void halve_kernel(int64_t* __restrict__ x, int n) {
     if (i < n) x[i] = x[i] / 2;
 }
 
+// ---- many labelings of ONE graph (randomized baseline, RandomizedMaxCut.py:63-122) ------------------------
+// grid = T labelings; labels uint8 [T][n]; cut[t] = exact integer cut of labeling t
+__global__ void __launch_bounds__(256)
+cut_value_multi_kernel(const uint8_t* __restrict__ labels, const int32_t* __restrict__ rowptr,
+                       const int32_t* __restrict__ colidx, const int32_t* __restrict__ wts, int n,
+                       int64_t* __restrict__ cut) {
+    __shared__ long long red[8];
+    const uint8_t* lab = labels + (int64_t)blockIdx.x * n;
+    long long c = 0;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        const int lv = lab[v];
+        const int e0 = __ldg(rowptr + v), e1 = __ldg(rowptr + v + 1);
+        for (int e = e0; e < e1; ++e)
+            if (lab[__ldg(colidx + e)] != lv) c += wts ? __ldg(wts + e) : 1;
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        cut[blockIdx.x] = s / 2;
+    }
+}
+
 // ---- P1: categorical sampling ------------------------------------------------------------
 // label of local node i (global v) in iteration `it` -- assign_partitions (:18-46)
 __device__ __forceinline__ int sampled_label(const float* __restrict__ P, int64_t ldp, int64_t v, int i, int K,
@@ -269,6 +294,17 @@ int gmc_cut_value_i32(const int32_t* labels, const int32_t* rowptr, const int32_
         labels, rowptr, colidx, wts, graph_ptr, n_graphs, n_rows, reinterpret_cast<unsigned long long*>(cut));
     GMC_LAUNCH_CHECK();
     halve_kernel<<<ceil_div(n_graphs, 256), 256, 0, s>>>(cut, n_graphs);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+int gmc_cut_value_multi_u8(const uint8_t* labels, const int32_t* rowptr, const int32_t* colidx, const int32_t* wts,
+                           int32_t n_nodes, int32_t n_labelings, int64_t* cut, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(labels && rowptr && colidx && cut, "gmc_cut_value_multi_u8: null pointer");
+    GMC_REQUIRE(n_nodes >= 0 && n_labelings >= 0, "gmc_cut_value_multi_u8: bad sizes");
+    if (n_labelings == 0) return GMC_OK;
+    cut_value_multi_kernel<<<n_labelings, 256, 0, as_stream(stream)>>>(labels, rowptr, colidx, wts, n_nodes, cut);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
 }

@@ -61,6 +61,7 @@ SIGNATURES: Dict[str, tuple] = {
                                        P, P]),
     "gmc_argmax_labels": (c_int, [P, c_int64, P, c_int32, c_int64, c_int32, c_int32, P, P]),
     "gmc_cut_value_i32": (c_int, [P, P, P, P, P, c_int32, c_int64, P, P]),
+    "gmc_cut_value_multi_u8": (c_int, [P, P, P, P, c_int32, c_int32, P, P]),
     "gmc_sample_best_cut": (c_int, [P, c_int64, P, P, P, P, P, P, c_int32, c_int64, c_int32, c_int32, c_int32, P, P,
                                     P, P, P]),
     "gmc_greedy_node_move": (c_int, [P, P, P, P, P, c_int32, c_int64, c_int32, c_int32, c_int32, P, P, P, P]),

@@ -354,6 +354,22 @@ def cut_value(batch, labels: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def cut_value_multi(batch, labels_u8: torch.Tensor) -> torch.Tensor:
+    """Cuts of T labelings (uint8 [T, n]) of a ONE-graph batch; returns int64 [T]."""
+    if batch.num_graphs != 1:
+        raise ValueError("cut_value_multi evaluates many labelings of a single graph")
+    if labels_u8.dtype != torch.uint8 or not labels_u8.is_cuda or not labels_u8.is_contiguous() or labels_u8.dim() != 2:
+        raise TypeError("labels: expected a contiguous CUDA uint8 tensor [T, n]")
+    T, n = labels_u8.shape
+    if n != batch.num_nodes:
+        raise ValueError("labels have the wrong number of nodes")
+    out = torch.empty(T, dtype=torch.int64, device=labels_u8.device)
+    check(lib().gmc_cut_value_multi_u8(labels_u8.data_ptr(), batch.rowptr.data_ptr(), batch.colidx.data_ptr(),
+                                       _ptr(_int_weights(batch)), n, T, out.data_ptr(), _stream()),
+          "gmc_cut_value_multi_u8")
+    return out
+
+
 def sample_best_cut(batch, P: torch.Tensor, U: torch.Tensor, u_ptr: torch.Tensor, iters: int,
                     compare_f32: bool):
     """P1.  U float64 device uniforms, u_ptr int64 [B+1] offsets.  Returns (labels, cut, best_iter)."""

@@ -256,6 +256,87 @@ def test_multiple_graphs(model, processed_graphs: Dict, graph_sizes: List[int], 
     return test_results, results_by_size
 
 
+def test_multiple_graphs_batched(model, processed_graphs: Dict, graph_sizes: List[int],
+                                 post_processing_iterations: int = 200, verbose: bool = False,
+                                 greedy_iterations: int = 0) -> Tuple[List[Dict], Dict]:
+    """Same results as test_multiple_graphs (identical cuts, assignments and final numpy RNG state), computed
+    for ALL selected graphs at once: one block-diagonal forward pass, one argmax + integer-cut launch, one
+    best-of-N sampling launch (uniforms drawn per graph in dataset order, as the per-graph loop would).
+    The per-graph `simple_time` / `post_time` fields hold the batch time divided by the number of graphs.
+    With greedy_iterations > 0 each result also carries `greedy_cut` / `greedy_assignment`: the north-star
+    node-move local search started from the post-processed assignment."""
+    from gmc_b200.engine import GCNEngine
+    from gmc_b200.model import to_device_features
+    dev = _gmc_lib.require_cuda()
+    results_by_size = {size: {"simple": {"cut_values": [], "times": []},
+                              "post_processed": {"cut_values": [], "times": []}} for size in graph_sizes}
+    chosen = []
+    for key, (handle, X, nx_graph, terminals) in processed_graphs.items():
+        name, size = _size_bucket(key, nx_graph, graph_sizes)
+        if size in graph_sizes:
+            chosen.append((name, size, handle, X, nx_graph, terminals))
+        elif verbose:
+            print(f"  Skipping {name}: graph size {size} not in test configuration")
+    if not chosen:
+        return [], results_by_size
+    handles = [h if isinstance(h, CSRGraph) else CSRGraph.from_networkx(g) for _, _, h, _, g, _ in chosen]
+    batch = GraphBatch(handles, device=dev)
+    feats = [to_device_features(X, dev) for _, _, _, X, _, _ in chosen]
+    X_all = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+    engine = GCNEngine(model, None, precision=getattr(model.conv1, "gemm_precision", "fp32"))
+    with torch.no_grad():
+        probs = engine.forward(batch, X_all).clone()
+
+    t0 = time()
+    labels = _ops.argmax_labels(batch, probs, force_terminals=True)
+    simple_cuts = _ops.cut_value(batch, labels).cpu().numpy()
+    simple_labels = labels.cpu().numpy()
+    simple_time = (time() - t0) / len(chosen)
+
+    t0 = time()
+    if post_processing_iterations > 0:
+        best_labels, best = _sample_best(batch, probs, post_processing_iterations)
+        post_cuts, post_labels = best.cpu().numpy(), best_labels.cpu().numpy()
+    else:
+        post_cuts, post_labels = None, None
+    post_time = (time() - t0) / len(chosen)
+    greedy = None
+    if greedy_iterations > 0 and post_labels is not None:
+        g_labels, g_cut, _ = _ops.greedy_node_move(batch, best_labels, probs.shape[1], greedy_iterations, 3)
+        greedy = (g_labels.cpu().numpy(), g_cut.cpu().numpy())
+
+    probs_host = probs.cpu().numpy()
+    gp = batch.graph_ptr_host
+    test_results: List[Dict] = []
+    for i, (name, size, _h, _X, nx_graph, terminals) in enumerate(chosen):
+        lo, hi = int(gp[i]), int(gp[i + 1])
+        s_cut = int(simple_cuts[i])
+        p_cut = int(post_cuts[i]) if post_cuts is not None else -float("inf")
+        improvement = p_cut - s_cut
+        result = {
+            "success": True, "nodes": len(nx_graph.nodes()), "edges": len(nx_graph.edges()),
+            "simple_cut": s_cut, "simple_time": simple_time, "simple_assignment": simple_labels[lo:hi].tolist(),
+            "post_cut": p_cut, "post_time": post_time,
+            "post_assignment": post_labels[lo:hi].tolist() if post_labels is not None else None,
+            "improvement": improvement,
+            "improvement_percent": (improvement / s_cut * 100) if s_cut > 0 else 0,
+            "terminals": terminals, "node_probabilities": probs_host[lo:hi].copy(),
+            "graph_name": name, "graph_size": size,
+        }
+        if greedy is not None:
+            result["greedy_cut"] = int(greedy[1][i])
+            result["greedy_assignment"] = greedy[0][lo:hi].tolist()
+        test_results.append(result)
+        bucket = results_by_size[size]
+        bucket["simple"]["cut_values"].append(s_cut)
+        bucket["simple"]["times"].append(simple_time)
+        bucket["post_processed"]["cut_values"].append(p_cut)
+        bucket["post_processed"]["times"].append(post_time)
+        if verbose:
+            print(f"  {name}: simple {s_cut}, post-processed {p_cut} ({improvement:+d})")
+    return test_results, results_by_size
+
+
 def analyze_results(test_results: List[Dict], results_by_size: Dict, graph_sizes: List[int]) -> Dict[str, Any]:
     """Aggregate statistics over test results (subset of reference :297-382: the numeric summary;
     report/plot helpers are presentation code and out of scope)."""

@@ -220,6 +220,12 @@ int gmc_cut_value_i32(const int32_t* labels, const int32_t* rowptr, const int32_
                       const int32_t* wts, const int32_t* graph_ptr, int32_t n_graphs,
                       int64_t n_rows, int64_t* cut, void* stream);
 
+/* cut[t] for T labelings (uint8 [T][n_nodes]) of ONE graph -- the evaluation loop of the randomized k-way
+ * baseline, RandomAlgorithm/RandomizedMaxCut.py:63-122 (one call evaluates a whole chunk of iterations). */
+int gmc_cut_value_multi_u8(const uint8_t* labels, const int32_t* rowptr, const int32_t* colidx,
+                           const int32_t* wts, int32_t n_nodes, int32_t n_labelings, int64_t* cut,
+                           void* stream);
+
 /* P1: `iters` categorical samplings per graph, keep the FIRST iteration with the maximal cut.
  * U: float64 uniforms, graph g uses U[u_ptr[g] + it*(n_g-3) + (i-3)] for local node i >= 3 --
  * the host draws them with np.random.rand in the reference's call order.  compare_f32 selects
