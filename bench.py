@@ -274,7 +274,8 @@ def run_b200_arm(args):
             b2.unit_weights, b2.wts_f32, b2.wts_i32, b2.integer_weights = True, None, None, True
             b2.norm, _zero = ops.degree_norm(d_rowptr, N)            # includes the zero-degree check read-back
             b2.coef = ops.edge_coef(d_rowptr, d_colidx, None, b2.norm, b2.norm, N)
-            b2.plan = None
+            b2.plan = (ops.spmm_plan(d_rowptr, d_colidx, b2.norm, b2.norm, d_gptr, B, N)
+                       if batch.plan is not None else None)   # slab-SpMM plan: a function of the graph, rebuilt per step
             ops.densify(b2, F, out=X)                                # device-side graphExtender
             per_graph = eng.train_step(b2, X)
             return per_graph.cpu()                                   # D2H of the step's result

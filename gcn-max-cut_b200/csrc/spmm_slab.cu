@@ -5,25 +5,35 @@
 // profiles/r01_v1_*).  Here one persistent CTA owns a (graph, column-slab) work item:
 //
 //   * the graph's source rows, restricted to a slab of W4 float4 columns, are staged ONCE into
-//     shared memory with cp.async (16-byte LDGSTS, L1 bypass), double-buffered so the loads of the
-//     next item overlap the gathers of the current one;
-//   * a group of GROUP lanes owns one output row and gathers its neighbours' slab rows from shared
-//     memory (LDS.128, one row group per 128-bit phase -> conflict-free);
-//   * neighbour lists come from an ELL "plan" (8 padded (local col, coef) slots per row, built once per
-//     static batch by gmc_spmm_plan_build): no rowptr->colidx dependent load chain, and the next row's
-//     slots are prefetched while the current row is accumulated;
-//   * the output slab is written with 128-bit stores (bias + ReLU fused).
+//     shared memory: full 128-row boxes by TMA (cp.async.bulk.tensor.2d issued by one thread, mbarrier
+//     completion -- no LSU wavefronts, no per-thread issue cost), the tail rows by cp.async.  The
+//     default keeps TWO CTAs per SM (W4 = 7, 112 KB each) so one CTA's staging overlaps the other's
+//     gathers; GMC_SLAB_VARIANT selects the other schedules that were measured (one CTA per SM with
+//     224-byte slabs, or one CTA with two 112-byte buffers);
+//   * LANES lanes own one output row and gather its neighbours' slab rows from shared memory with
+//     LDS.128 -- every quarter-warp phase reads one contiguous row segment, so the gathers are
+//     bank-conflict free;
+//   * neighbour lists come from an ELL "plan" built once per static batch (gmc_spmm_plan_build):
+//     8 uint16 LOCAL node ids (one 16-byte load) + ONE coefficient per row, padded slots point at an
+//     all-zero shared-memory row; the next rows' slots are prefetched while the current row is
+//     accumulated (also across work items);
+//   * the output slab is written with 128-bit stores (row coefficient, bias and ReLU fused).
 //
-// L2->SM traffic drops from (d+1) x to ~2 x the matrix; HBM traffic stays the algorithmic
-// 8*N*C + 4*nnz + 4*(N+1) bytes.  Used when every graph of the batch fits the slab buffers and has
-// max degree <= 8; otherwise gmc_spmm_batched_f32 runs the warp-per-row kernel (same results).
+// L2->SM traffic drops from (d+1) x to ~1 x the matrix; HBM traffic stays the algorithmic
+// 8*N*C + 4*nnz + 4*(N+1) bytes.  Used when every graph of the batch fits the slab buffer, has max
+// degree <= 8 and uniform neighbour norms (regular graphs); otherwise gmc_spmm_batched_f32 runs the
+// warp-per-row kernel.  The two kernels differ only in rounding order (sum-then-scale vs fused coef).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace gmc {
 
-constexpr int kSlabThreads = 768;
 constexpr int kEll = 8;                                   // padded neighbour slots per row
 constexpr size_t kSlabSmemMax = 227 * 1024;
+constexpr size_t kPlanHeader = 16;                        // int32 max_degree + padding
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -34,161 +44,330 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- plan: ELL packing of a block-diagonal CSR -----------------------------------------------
-// plan layout: int32 col[n_rows][8] (LOCAL node ids, padded with n_g = the kernel's all-zero row) followed by
-//              float coef[n_rows][8] (padded with 0).  One warp per 4 rows.
+// plan layout: [16-byte header: int32 max degree] [uint16 col[n_rows][8]] [float coef[n_rows]]
+// col = LOCAL node ids, padded with n_g (the kernel's all-zero row).  A_hat[v,u] = nd[v] * ns[u] (GraphConv's
+// norm='both'); the plan keeps ONE coefficient per row, coef[v] = nd[v] * ns[u], which requires every neighbour of
+// v to carry the same ns -- true for the regular graphs the reference generates (GraphCreator 'reg') and for
+// any graph whose neighbours of a node share a degree.  Other batches flag `overflow` and use the row kernel.
 __global__ void ell_pack_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                const float* __restrict__ coef, const int32_t* __restrict__ graph_ptr, int n_graphs,
-                                int64_t n_rows, int32_t* __restrict__ ell_col, float* __restrict__ ell_coef,
+                                const float* __restrict__ norm_src, const float* __restrict__ norm_dst,
+                                const int32_t* __restrict__ graph_ptr, int n_graphs, int64_t n_rows,
+                                int32_t* __restrict__ header, uint4* __restrict__ ell_col, float* __restrict__ coef,
                                 int* __restrict__ overflow) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // slot index
-    if (i >= n_rows * kEll) return;
-    const int64_t v = i / kEll;
-    const int j = (int)(i % kEll);
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_rows) return;
     const int g = find_graph(graph_ptr, n_graphs, v);
     const int base = __ldg(graph_ptr + g);
+    const int n_g = __ldg(graph_ptr + g + 1) - base;
     const int e0 = __ldg(rowptr + v), deg = __ldg(rowptr + v + 1) - e0;
-    if (deg > kEll && j == 0) *overflow = 1;
-    if (j < deg) {
-        ell_col[i] = __ldg(colidx + e0 + j) - base;
-        ell_coef[i] = __ldg(coef + e0 + j);
-    } else {
-        ell_col[i] = __ldg(graph_ptr + g + 1) - base;     // the slab buffers keep an all-zero row at index n_g
-        ell_coef[i] = 0.f;
+    if (deg > kEll || n_g > 65534) { *overflow = 1; return; }
+    atomicMax(header, deg);
+    uint32_t c[kEll];
+    float ns0 = 0.f;
+    bool uniform = true;
+#pragma unroll
+    for (int j = 0; j < kEll; ++j) {
+        c[j] = (uint32_t)n_g;
+        if (j < deg) {
+            const int u = __ldg(colidx + e0 + j);
+            const float ns = __ldg(norm_src + u);
+            if (j == 0) ns0 = ns;
+            uniform = uniform && (ns == ns0);
+            c[j] = (uint32_t)(u - base);
+        }
     }
+    if (!uniform) { *overflow = 1; return; }
+    ell_col[v] = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
+    coef[v] = __ldg(norm_dst + v) * ns0;
 }
 
-// W4: float4 columns per slab, GROUP: lanes per output row (power of two >= W4, <= 8)
-template <int W4, int GROUP>
-__global__ void __launch_bounds__(kSlabThreads, 1)
-spmm_slab_kernel(const int4* __restrict__ ell_col, const float4* __restrict__ ell_coef,
+// ---- TMA / mbarrier wrappers (staging path) ----------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) { printf("gmc spmm slab: mbarrier timeout (block %d)\n", (int)blockIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+constexpr int kBoxRows = 128;                             // rows per TMA box
+
+// W4: float4 columns per slab; LANES: lanes per output row (power of two >= W4); MINB: CTAs per SM;
+// DEPTH: rows whose neighbour lists are prefetched ahead per row group; TMA: stage full 128-row boxes with
+// cp.async.bulk.tensor (one elected thread, mbarrier completion) and only the tail rows with cp.async
+template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF>
+__global__ void __launch_bounds__(THREADS, MINB)
+spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restrict__ header,
+                 const uint4* __restrict__ ell_col, const float* __restrict__ plan_nd,
                  const int32_t* __restrict__ graph_ptr, const float4* __restrict__ X, float4* __restrict__ Y,
                  int n_graphs, int c4, int64_t ldx4, int64_t ldy4, const float4* __restrict__ bias, int relu,
                  int n_slabs, int rows_cap) {
-    extern __shared__ float4 sbuf[];                      // [2][rows_cap][W4]
+    extern __shared__ __align__(128) float4 sbuf_all[];   // NBUF x [rows_cap][W4]: rows, the all-zero row, one pad row; mbarriers
+    constexpr int GROUPS = THREADS / LANES;
+    constexpr uint32_t BOX_BYTES = kBoxRows * W4 * 16;
     const int tid = threadIdx.x;
-    const int lg = tid & (GROUP - 1);                     // lane within the row group
-    constexpr int GROUPS = kSlabThreads / GROUP;
-    const int gidx = tid / GROUP;
+    const int lg = tid & (LANES - 1);                     // lane within the row group
+    const int gidx = tid / LANES;
     const int64_t n_items = (int64_t)n_graphs * n_slabs;
-
-    auto issue = [&](int64_t w, int buf) {
-        const int g = (int)(w / n_slabs), s = (int)(w % n_slabs);
-        const int base = __ldg(graph_ptr + g);
-        const int n_g = __ldg(graph_ptr + g + 1) - base;
-        const int col0 = s * W4;
-        const int nv = min(W4, c4 - col0);
-        float4* dst = sbuf + (size_t)buf * rows_cap * W4;
-        const float4* src = X + (int64_t)base * ldx4 + col0;
-        // thread -> (row, float4) with the float4 index fastest, no integer division in the loop
-        int r = tid / nv, q = tid - r * nv;
-        const int dr = kSlabThreads / nv, dq = kSlabThreads - dr * nv;
-        while (r < n_g) {
+    const bool slot7 = __ldg(header) > 7;
+    const uint32_t BUF_BYTES = (uint32_t)rows_cap * W4 * 16;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sbuf_all);
+    const uint32_t bar0 = sbase + NBUF * BUF_BYTES;
+    uint32_t parity = 0;                                  // bit b = phase of buffer b's mbarrier
+    if (TMA) {
+        if (tid == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+            for (int b = 0; b < NBUF; ++b) mbar_init(bar0 + 8 * b, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // stage one (graph, slab) item into buffer b.  Full 128-row boxes go
+    // through TMA (one thread), the tail rows (all rows without TMA) through cp.async: thread -> (row, float4)
+    auto issue = [&](int64_t wi, int b0, int ng, int b) {
+        const int col = (int)(wi % n_slabs) * W4;
+        const int nvi = min(W4, c4 - col);
+        const int n_box = TMA ? ng / kBoxRows : 0;
+        if (TMA && tid == 0 && n_box > 0) {
+            mbar_expect_tx(bar0 + 8 * b, (uint32_t)n_box * BOX_BYTES);
+            for (int k = 0; k < n_box; ++k)
+                tma_load_2d(sbase + b * BUF_BYTES + (uint32_t)k * BOX_BYTES, &tmX, col * 4, b0 + k * kBoxRows, bar0 + 8 * b);
+        }
+        const int rt = n_box * kBoxRows;
+        const float4* src = X + (int64_t)(b0 + rt) * ldx4 + col;
+        float4* buf = sbuf_all + (size_t)b * rows_cap * W4;
+        float4* dst = buf + rt * W4;
+        const int n_t = ng - rt;
+        int r = tid / nvi, q = tid - r * nvi;
+        const int dr = THREADS / nvi, dq = THREADS - dr * nvi;
+        while (r < n_t) {
             cp_async16(dst + r * W4 + q, src + (int64_t)r * ldx4 + q);
             r += dr; q += dq;
-            if (q >= nv) { q -= nv; ++r; }
+            if (q >= nvi) { q -= nvi; ++r; }
         }
-        if (tid < W4) dst[n_g * W4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero row for padded slots
+        if (tid < W4) buf[ng * W4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // target of padded slots
+        cp_async_commit();
     };
 
-    int buf = 0;
+    struct Slots { uint4 c; float d; };
+    Slots S[DEPTH];
+    bool pre[DEPTH];
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) pre[k] = false;
+
     int64_t w = blockIdx.x;
-    if (w < n_items) issue(w, 0);
-    cp_async_commit();
+    int base = 0, n_g = 0, cur = 0;
+    if (w < n_items) {
+        const int g = (int)(w / n_slabs);
+        base = __ldg(graph_ptr + g);
+        n_g = __ldg(graph_ptr + g + 1) - base;
+        if (NBUF == 2) issue(w, base, n_g, 0);
+    }
     for (; w < n_items; w += gridDim.x) {
-        const int g = (int)(w / n_slabs), s = (int)(w % n_slabs);
-        const int base = __ldg(graph_ptr + g);
-        const int n_g = __ldg(graph_ptr + g + 1) - base;
+        const int s = (int)(w % n_slabs);
         const int col0 = s * W4;
         const int nv = min(W4, c4 - col0);
+        float4* sbuf = sbuf_all + (size_t)cur * rows_cap * W4;
+        if (NBUF == 1) issue(w, base, n_g, 0);
+        // the next item's extent, fetched now so that its latency hides behind this item
+        const int64_t wn = w + gridDim.x;
+        int base_n = 0, n_g_n = 0;
+        if (wn < n_items) {
+            const int gn = (int)(wn / n_slabs);
+            base_n = __ldg(graph_ptr + gn);
+            n_g_n = __ldg(graph_ptr + gn + 1) - base_n;
+        }
+        if (NBUF == 2) {
+            if (wn < n_items) issue(wn, base_n, n_g_n, cur ^ 1);
+            else cp_async_commit();
+        }
         const bool active = lg < nv;
-        // neighbour lists of this row group's first TWO rows: issued before waiting on the slab; every list is
-        // re-loaded one full (two-row) iteration ahead of its use, which covers the L2 latency with 24 warps/SM
-        struct Slots { int4 c_lo, c_hi; float4 a_lo, a_hi; };
-        auto load_slots = [&](Slots& S, int row) {
-            const int64_t slot = ((int64_t)base + row) * 2;
-            S.c_lo = __ldg(ell_col + slot); S.c_hi = __ldg(ell_col + slot + 1);
-            S.a_lo = __ldg(ell_coef + slot); S.a_hi = __ldg(ell_coef + slot + 1);
+        auto load_slots = [&](Slots& S, int b0, int row) {
+            const int64_t v = (int64_t)b0 + row;
+            S.c = __ldg(ell_col + v);
+            S.d = __ldg(plan_nd + v);
         };
-        Slots S0, S1;
+        // neighbour lists of this row group's first DEPTH rows: normally already in flight (issued after the last
+        // use of each slot in the previous item), so that no item starts on a cold L2 round trip
         const int r0 = gidx;
-        if (r0 < n_g) load_slots(S0, r0);
-        if (r0 + GROUPS < n_g) load_slots(S1, r0 + GROUPS);
+#pragma unroll
+        for (int k = 0; k < DEPTH; ++k)
+            if (!pre[k] && r0 + k * GROUPS < n_g) load_slots(S[k], base, r0 + k * GROUPS);
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias && active) b4 = __ldg(bias + col0 + lg);
 
-        const int64_t wn = w + gridDim.x;
-        if (wn < n_items) issue(wn, buf ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();                               // everything but the newest group has landed
+        if (NBUF == 2) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (TMA && n_g >= kBoxRows) { mbar_wait(bar0 + 8 * cur, (parity >> cur) & 1u); parity ^= 1u << cur; }
         __syncthreads();
 
-        const float4* src = sbuf + (size_t)buf * rows_cap * W4 + lg;
-        // padded slots carry coef 0 and point at the all-zero row, so they add exactly 0 and a non-finite
-        // source row can only reach rows that really reference it
+        // padded slots point at the all-zero row, so they add exactly 0 and a non-finite source row can only reach
+        // rows that really reference it.  Lanes >= nv read past their row (the pad row keeps that in bounds, and
+        // those banks are free in the same LDS phase) and never store.
+        const float4* sl = sbuf + lg;
+        auto gather = [&](uint32_t u) { return sl[u * W4]; };
+        auto add4 = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
         auto row_out = [&](const Slots& S, int row) {
-            if (!active) return;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 v0 = src[S.c_lo.x * W4], v1 = src[S.c_lo.y * W4], v2 = src[S.c_lo.z * W4], v3 = src[S.c_lo.w * W4];
-            const float4 v4 = src[S.c_hi.x * W4], v5 = src[S.c_hi.y * W4], v6 = src[S.c_hi.z * W4], v7 = src[S.c_hi.w * W4];
-            fma4(acc, S.a_lo.x, v0); fma4(acc, S.a_lo.y, v1); fma4(acc, S.a_lo.z, v2); fma4(acc, S.a_lo.w, v3);
-            fma4(acc, S.a_hi.x, v4); fma4(acc, S.a_hi.y, v5); fma4(acc, S.a_hi.z, v6); fma4(acc, S.a_hi.w, v7);
-            acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+            float4 acc = gather(S.c.x & 0xffffu);
+            {
+                const float4 v1 = gather(S.c.x >> 16), v2 = gather(S.c.y & 0xffffu), v3 = gather(S.c.y >> 16);
+                add4(acc, v1); add4(acc, v2); add4(acc, v3);
+            }
+            {
+                const float4 v4 = gather(S.c.z & 0xffffu), v5 = gather(S.c.z >> 16), v6 = gather(S.c.w & 0xffffu);
+                add4(acc, v4); add4(acc, v5); add4(acc, v6);
+            }
+            if (slot7) add4(acc, gather(S.c.w >> 16));
+            acc.x = fmaf(acc.x, S.d, b4.x); acc.y = fmaf(acc.y, S.d, b4.y);
+            acc.z = fmaf(acc.z, S.d, b4.z); acc.w = fmaf(acc.w, S.d, b4.w);
             if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-            Y[(int64_t)(base + row) * ldy4 + col0 + lg] = acc;
+            if (active) Y[(int64_t)(base + row) * ldy4 + col0 + lg] = acc;
         };
-        for (int r = r0; r < n_g; r += 2 * GROUPS) {
-            row_out(S0, r);
-            if (r + 2 * GROUPS < n_g) load_slots(S0, r + 2 * GROUPS);
-            if (r + GROUPS < n_g) {
-                row_out(S1, r + GROUPS);
-                if (r + 3 * GROUPS < n_g) load_slots(S1, r + 3 * GROUPS);
+        for (int r = r0; r < n_g; r += DEPTH * GROUPS) {
+#pragma unroll
+            for (int k = 0; k < DEPTH; ++k) {
+                const int rk = r + k * GROUPS;
+                if (rk < n_g) {
+                    row_out(S[k], rk);
+                    if (rk + DEPTH * GROUPS < n_g) {
+                        load_slots(S[k], base, rk + DEPTH * GROUPS);
+                    } else {                              // last use in this item: fetch the next item's row for this slot
+                        pre[k] = r0 + k * GROUPS < n_g_n;
+                        if (pre[k]) load_slots(S[k], base_n, r0 + k * GROUPS);
+                    }
+                } else if (r == r0) {
+                    pre[k] = false;                       // slot unused in this item
+                }
             }
         }
-        __syncthreads();                                  // buffer `buf` may be overwritten by the next issue
-        buf ^= 1;
+        __syncthreads();                                  // the buffer may be overwritten by the next item
+        base = base_n; n_g = n_g_n;
+        if (NBUF == 2) cur ^= 1;
     }
     cp_async_wait<0>();
 }
 
-static size_t plan_bytes(int64_t n_rows) { return (size_t)n_rows * kEll * (sizeof(int32_t) + sizeof(float)); }
+static size_t plan_bytes(int64_t n_rows) { return kPlanHeader + (size_t)n_rows * (kEll * sizeof(uint16_t) + sizeof(float)); }
+
+// GMC_SLAB_VARIANT (tuning aid): B (default) = two CTAs of 512 threads per SM, 112-byte slabs, TMA staging;
+// A = one CTA per SM, 224-byte slabs, TMA; C = B with cp.async staging; D = B with prefetch depth 3; E = A with cp.async
+static int slab_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GMC_SLAB_VARIANT");
+        v = 1;
+        if (e && e[0] >= 'A' && e[0] <= 'E') v = e[0] - 'A';
+    }
+    return v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn slab_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF>
+static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_graphs, int max_nodes, const float4* X4,
+                           float4* Y4, int64_t n_rows, int c4, int64_t ldx4, int64_t ldy4, const float4* b4, int relu,
+                           cudaStream_t s, int* launched) {
+    const int rows_cap = (max_nodes + 2 + 7) & ~7;         // buffers stay 128-byte aligned (TMA destination)
+    const size_t smem = (size_t)NBUF * rows_cap * W4 * sizeof(float4) + 16;
+    if (smem + 1024 > (228 * 1024) / MINB || smem > kSlabSmemMax) return GMC_OK;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (TMA) {
+        EncodeTiledFn enc = slab_encode_fn();
+        if (!enc) return GMC_OK;                          // no driver entry point: let the caller take another kernel
+        cuuint64_t dims[2] = {(cuuint64_t)c4 * 4, (cuuint64_t)n_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)ldx4 * 16};
+        cuuint32_t box[2] = {W4 * 4, kBoxRows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float4*>(X4), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("gmc_spmm_batched_f32: cuTensorMapEncodeTiled failed (%d)", (int)r); return GMC_ERR_INVALID_ARG; }
+    }
+    static bool attr = false;
+    if (!attr) {
+        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabSmemMax));
+        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF>,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
+    }
+    const int32_t* header = reinterpret_cast<const int32_t*>(plan);
+    const uint4* ecol = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(plan) + kPlanHeader);
+    const float* pnd = reinterpret_cast<const float*>(ecol + n_rows);
+    const int n_slabs = ceil_div(c4, W4);
+    const int64_t items = (int64_t)n_graphs * n_slabs;
+    const int64_t slots = (int64_t)sm_count() * MINB;
+    const int grid = (int)(items < slots ? items : slots);
+    spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF><<<grid, THREADS, smem, s>>>(
+        tm, header, ecol, pnd, graph_ptr, X4, Y4, n_graphs, c4, ldx4, ldy4, b4, relu, n_slabs, rows_cap);
+    GMC_LAUNCH_CHECK();
+    *launched = 1;
+    return GMC_OK;
+}
 
 static int slab_launch(const void* plan, const int32_t* graph_ptr, int n_graphs, int max_nodes, const float* X, float* Y,
                        int64_t n_rows, int n_cols, int64_t ldx, int64_t ldy, const float* bias, int relu,
                        cudaStream_t s, int* launched) {
     *launched = 0;
-    if (!plan || !graph_ptr || n_graphs <= 0 || max_nodes < 128 || n_cols < 64 || n_cols % 4 || ldx % 4 || ldy % 4)
+    if (!plan || !graph_ptr || n_graphs <= 0 || max_nodes < 128 || n_cols < 16 || n_cols % 4 || ldx % 4 || ldy % 4)
         return GMC_OK;
     if (!aligned16(X) || !aligned16(Y) || (bias && !aligned16(bias)) || !aligned16(plan)) return GMC_OK;
     const int c4 = n_cols / 4;
-    const int4* ecol = reinterpret_cast<const int4*>(plan);
-    const float4* ecoef = reinterpret_cast<const float4*>(reinterpret_cast<const int32_t*>(plan) + n_rows * kEll);
     const float4* X4 = reinterpret_cast<const float4*>(X);
     float4* Y4 = reinterpret_cast<float4*>(Y);
     const float4* b4 = reinterpret_cast<const float4*>(bias);
-#define GMC_SLAB(W4, GROUP)                                                                                     \
-    {                                                                                                           \
-        const size_t smem = (size_t)2 * (max_nodes + 1) * (W4) * sizeof(float4);                                      \
-        if (smem <= kSlabSmemMax) {                                                                             \
-            static bool attr = false;                                                                           \
-            if (!attr) {                                                                                        \
-                GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, GROUP>,                                      \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabSmemMax)); \
-                attr = true;                                                                                    \
-            }                                                                                                   \
-            const int n_slabs = ceil_div(c4, (W4));                                                             \
-            const int64_t items = (int64_t)n_graphs * n_slabs;                                                  \
-            const int grid = (int)(items < sm_count() ? items : sm_count());                                    \
-            spmm_slab_kernel<W4, GROUP><<<grid, kSlabThreads, smem, s>>>(ecol, ecoef, graph_ptr, X4, Y4,        \
-                                                                         n_graphs, c4, ldx / 4, ldy / 4, b4,    \
-                                                                         relu, n_slabs, max_nodes + 1);        \
-            GMC_LAUNCH_CHECK();                                                                                 \
-            *launched = 1;                                                                                      \
-            return GMC_OK;                                                                                      \
-        }                                                                                                       \
+#define GMC_SLAB(W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF)                                                             \
+    {                                                                                                              \
+        const int rc = slab_launch_one<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF>(plan, graph_ptr, n_graphs,      \
+                                                                             max_nodes, X4, Y4, n_rows, c4,       \
+                                                                             ldx / 4, ldy / 4, b4, relu, s,       \
+                                                                             launched);                            \
+        if (rc != GMC_OK || *launched) return rc;                                                                  \
     }
-    GMC_SLAB(7, 8)
-    GMC_SLAB(4, 4)
-    GMC_SLAB(2, 2)
+    switch (slab_variant()) {
+        case 0: GMC_SLAB(14, 16, 1024, 1, 2, true, 1) break;
+        case 2: GMC_SLAB(7, 8, 1024, 1, 2, true, 2) break;
+        case 3: GMC_SLAB(7, 8, 768, 1, 4, true, 2) break;
+        case 4: GMC_SLAB(7, 8, 512, 2, 2, false, 1) break;
+        default: break;
+    }
+    GMC_SLAB(7, 8, 512, 2, 2, true, 1)
+    GMC_SLAB(14, 16, 1024, 1, 2, true, 1)
+    GMC_SLAB(7, 8, 1024, 1, 2, true, 1)
+    GMC_SLAB(4, 4, 1024, 1, 2, true, 1)
 #undef GMC_SLAB
     return GMC_OK;
 }
@@ -201,19 +380,24 @@ size_t gmc_spmm_plan_bytes(int64_t n_rows) { return gmc::plan_bytes(n_rows); }
 
 // Builds the ELL plan of a block-diagonal batch.  *overflow (device int32) is set to 1 when some row has more
 // than 8 neighbours, in which case the plan must not be used (pass plan = NULL to gmc_spmm_batched_f32).
-int gmc_spmm_plan_build(const int32_t* rowptr, const int32_t* colidx, const float* coef, const int32_t* graph_ptr,
-                        int32_t n_graphs, int64_t n_rows, void* plan, int32_t* overflow, void* stream) {
+int gmc_spmm_plan_build(const int32_t* rowptr, const int32_t* colidx, const float* norm_src, const float* norm_dst,
+                        const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, void* plan, int32_t* overflow,
+                        void* stream) {
     using namespace gmc;
-    GMC_REQUIRE(rowptr && colidx && coef && graph_ptr && plan && overflow, "gmc_spmm_plan_build: null pointer");
+    GMC_REQUIRE(rowptr && colidx && norm_src && norm_dst && graph_ptr && plan && overflow,
+                "gmc_spmm_plan_build: null pointer");
     GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0, "gmc_spmm_plan_build: bad sizes");
+    GMC_REQUIRE(aligned16(plan), "gmc_spmm_plan_build: plan must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
     GMC_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int32_t), s));
+    GMC_CUDA(cudaMemsetAsync(plan, 0, kPlanHeader, s));
     if (n_rows == 0) return GMC_OK;
-    int32_t* ecol = reinterpret_cast<int32_t*>(plan);
-    float* ecoef = reinterpret_cast<float*>(ecol + n_rows * kEll);
-    const int64_t total = n_rows * kEll;
-    ell_pack_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, s>>>(rowptr, colidx, coef, graph_ptr, n_graphs,
-                                                                           n_rows, ecol, ecoef, overflow);
+    int32_t* header = reinterpret_cast<int32_t*>(plan);
+    uint4* ecol = reinterpret_cast<uint4*>(reinterpret_cast<char*>(plan) + kPlanHeader);
+    float* pcoef = reinterpret_cast<float*>(ecol + n_rows);
+    ell_pack_kernel<<<(unsigned)ceil_div<int64_t>(n_rows, 256), 256, 0, s>>>(rowptr, colidx, norm_src, norm_dst,
+                                                                            graph_ptr, n_graphs, n_rows, header, ecol,
+                                                                            pcoef, overflow);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
 }

@@ -37,7 +37,7 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_copy2d_f32": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P]),
     "gmc_spmm_symnorm_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P]),
     "gmc_spmm_plan_bytes": (c_size_t, [c_int64]),
-    "gmc_spmm_plan_build": (c_int, [P, P, P, P, c_int32, c_int64, P, P, P]),
+    "gmc_spmm_plan_build": (c_int, [P, P, P, P, P, c_int32, c_int64, P, P, P]),
     "gmc_spmm_batched_f32": (c_int, [P, P, P, P, c_int32, c_int32, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P]),
     "gmc_spmm_fused_skinny_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P, c_int32,
                                           P, c_int64, P]),

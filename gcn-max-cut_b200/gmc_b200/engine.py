@@ -24,6 +24,7 @@ Buffers: two [N,H] activations are enough -- bufA holds T1 then dH1pre, bufB hol
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -31,6 +32,11 @@ import torch
 from . import _lib, ops
 from .graph import GraphBatch
 from .optim import FusedAdam
+
+
+# forward aggregation: the fused row kernel (aggregate + bias + ReLU + H1 W2 in one pass) unless GMC_FWD_SLAB=1 asks
+# for the slab SpMM followed by the separate skinny projection
+_FWD_SLAB = os.environ.get("GMC_FWD_SLAB", "0") == "1"
 
 
 def _pad4(n: int) -> int:
@@ -161,7 +167,7 @@ class GCNEngine:
         A, Bf = self.bufA[:N], self.bufB[:N]
         ops.copy2d(self.W1p, W1.data)
         self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, self.W1p, out=A, precision=self.precision, workspace=self.ws)
-        if 16 <= self.H <= 512 and self.H % 4 == 0 and getattr(batch, "plan", None) is None:
+        if 16 <= self.H <= 512 and self.H % 4 == 0 and not (_FWD_SLAB and getattr(batch, "plan", None) is not None):
             # aggregation + bias + ReLU + the skinny projection H1 W2 in one pass over the row
             self._op("spmm_h_fused", 1, ops.spmm_fused_skinny, batch, A, W2.data, out=Bf, proj=self.T2[:N],
                      bias=b1.data, relu=True)

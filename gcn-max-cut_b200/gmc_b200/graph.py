@@ -198,18 +198,21 @@ class GraphBatch:
                 f"({zero} nodes; DGL GraphConv raises the same with allow_zero_in_degree=False)")
         self.coef = ops.edge_coef(self.rowptr, self.colidx, None, self.norm, self.norm, self.num_nodes)
         self.max_nodes = int(self.sizes.max()) if self.num_graphs else 0
-        # ELL plan for the shared-memory slab SpMM.  Measured on B200 (profiles/r01_spmm_slab_notes.md) the slab
-        # kernel is instruction-issue bound at 5.7 ms where the warp-per-row kernel is L2-bound at 5.0 ms for
-        # config 3, so it is opt-in (GMC_SPMM_SLAB=1 or build_plan()) until it wins.
+        # ELL plan for the shared-memory slab SpMM (TMA-staged, 0.60 of the HBM roofline at config 3 vs 0.50-0.54
+        # for the L2-bound warp-per-row kernel, profiles/r01_spmm_slab_notes.md).  One CTA owns a (graph, slab)
+        # item, so it only pays off when the batch has enough graphs to fill the GPU: built automatically for
+        # batches of >= 32 graphs; GMC_SPMM_SLAB=0 disables it, =1 forces it for any batch.
         self.plan = None
-        if os.environ.get("GMC_SPMM_SLAB", "0") == "1":
+        mode = os.environ.get("GMC_SPMM_SLAB", "auto")
+        if mode == "1" or (mode != "0" and self.num_graphs >= 32):
             self.build_plan()
 
     def build_plan(self) -> bool:
-        """Build the ELL plan that lets ops.spmm take the shared-memory slab kernel (needs max degree <= 8)."""
+        """Build the ELL plan that lets ops.spmm take the shared-memory slab kernel (needs max degree <= 8 and,
+        per node, neighbours of equal degree -- regular graphs)."""
         from . import ops
         if self.max_nodes >= 128 and self.num_nodes > 0:
-            self.plan = ops.spmm_plan(self.rowptr, self.colidx, self.coef, self.graph_ptr, self.num_graphs,
+            self.plan = ops.spmm_plan(self.rowptr, self.colidx, self.norm, self.norm, self.graph_ptr, self.num_graphs,
                                       self.num_nodes)
         return self.plan is not None
 

@@ -76,12 +76,15 @@ def edge_coef(rowptr, colidx, vals, norm_src, norm_dst, n_rows: int) -> torch.Te
     return coef
 
 
-def spmm_plan(rowptr, colidx, coef, graph_ptr, n_graphs: int, n_rows: int) -> Optional[torch.Tensor]:
-    """ELL plan for the slab SpMM (None when some row has more than 8 neighbours)."""
+def spmm_plan(rowptr, colidx, norm_src, norm_dst, graph_ptr, n_graphs: int, n_rows: int) -> Optional[torch.Tensor]:
+    """ELL plan for the slab SpMM of A_hat = diag(norm_dst) A diag(norm_src) (None when some row has more
+    than 8 neighbours, a graph has more than 65534 nodes, or a node's neighbours do not share one norm_src
+    value -- i.e. the plan serves regular graphs)."""
     nbytes = lib().gmc_spmm_plan_bytes(n_rows)
     plan = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=colidx.device)
     over = torch.zeros(1, dtype=torch.int32, device=colidx.device)
-    check(lib().gmc_spmm_plan_build(rowptr.data_ptr(), colidx.data_ptr(), coef.data_ptr(), graph_ptr.data_ptr(),
+    check(lib().gmc_spmm_plan_build(rowptr.data_ptr(), colidx.data_ptr(), norm_src.data_ptr(), norm_dst.data_ptr(),
+                                    graph_ptr.data_ptr(),
                                     n_graphs, n_rows, plan.data_ptr(), over.data_ptr(), _stream()),
           "gmc_spmm_plan_build")
     return None if int(over.item()) else plan

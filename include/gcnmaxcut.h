@@ -91,16 +91,20 @@ int gmc_spmm_symnorm_f32(const int32_t* rowptr, const int32_t* colidx, const flo
                          const float* bias, int32_t relu, void* stream);
 
 /* Same product for a BLOCK-DIAGONAL batch whose A_hat values were precomputed (`coef` from
- * gmc_edge_coef_f32).  With an ELL `plan` of the batch (8 padded (local col, coef) slots per row,
- * built once by gmc_spmm_plan_build; needs max degree <= 8) and graphs that fit the on-chip slab
- * buffers (max_nodes x 112 B x 2), source rows are staged once into shared memory (cp.async, double
- * buffered) and gathered from there, cutting L2 traffic from (d+1)x to ~2x; otherwise (plan NULL,
- * large graphs, narrow matrices) it runs the warp-per-row kernel.  Results are identical to
- * gmc_spmm_symnorm_f32(rowptr, colidx, coef, NULL, NULL, ...). */
+ * gmc_edge_coef_f32, coef_e = norm_dst[v] * norm_src[u] as in GraphConv norm='both').  With an ELL `plan`
+ * of the batch (8 uint16 local neighbour ids + one coefficient per row, built once by
+ * gmc_spmm_plan_build; needs max degree <= 8, graphs of < 65535 nodes and, per row, neighbours that
+ * share one norm_src value -- regular graphs) and graphs that fit the on-chip slab buffer
+ * ((max_nodes + 2) x 112 B, two CTAs per SM), the source rows of one (graph, 28-column slab) are staged
+ * once into shared memory by TMA, gathered from there with conflict-free LDS.128 and scaled by the row
+ * coefficient on the way out -- L2 traffic drops from (d+1)x to ~1x the matrix.  Otherwise (plan NULL,
+ * large graphs, narrow matrices) it runs the warp-per-row kernel.  Both paths compute the same product;
+ * they differ only in rounding order (sum-then-scale vs fused per-edge coef, 1e-7 relative). */
 size_t gmc_spmm_plan_bytes(int64_t n_rows);
-int gmc_spmm_plan_build(const int32_t* rowptr, const int32_t* colidx, const float* coef,
-                        const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, void* plan,
-                        int32_t* overflow /* device, set to 1 if some degree > 8 */, void* stream);
+int gmc_spmm_plan_build(const int32_t* rowptr, const int32_t* colidx, const float* norm_src,
+                        const float* norm_dst, const int32_t* graph_ptr, int32_t n_graphs,
+                        int64_t n_rows, void* plan,
+                        int32_t* overflow /* device, set to 1 if the plan cannot be used */, void* stream);
 int gmc_spmm_batched_f32(const int32_t* rowptr, const int32_t* colidx, const float* coef,
                          const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes,
                          const void* plan, const float* X, float* Y, int64_t n_rows, int32_t n_cols,
