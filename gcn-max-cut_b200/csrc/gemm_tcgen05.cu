@@ -70,6 +70,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask`, and each of those
+// CTAs' mbarriers (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -82,6 +91,18 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -129,11 +150,18 @@ struct Params {
     int64_t split_stride;    // elements between split-K partials (0 when k_splits == 1)
     int64_t k_per_split;     // multiple of BLOCK_K
     int m_tiles, n_tiles, k_splits;
+    int mg_tiles;            // m-tile groups of CL (cluster size) tiles: ceil(m_tiles / CL)
     int accumulate;
     int vec_ok;              // 16-byte aligned C rows
 };
 
-template <bool A_MN, bool B_MN>
+// CL = thread-block cluster size (1, 2 or 4).  With CL > 1 the CTAs of a cluster own CL consecutive m-tiles of
+// the SAME n-tile and k-range: each CTA loads its own A tile and 1/CL of the shared B tile, multicast into every
+// CTA's shared memory.  The single-CTA kernel is bound by the L2->SM request rate (48 KB per k-block and SM
+// against the ~42 B/clk/SM LTS limit); sharing B cuts that to 16 + 32/CL KB.  A stage may be refilled only when
+// ALL CTAs of the cluster have consumed it, so the MMA warps multicast their tcgen05.commit to every CTA's
+// empty barrier (arrival count CL).
+template <bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -146,11 +174,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
 
     if (warp == 0 && lane == 0) {
         prefetch_map(&tmA);
         prefetch_map(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, CL); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -159,21 +189,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();          // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int64_t tiles_mn = (int64_t)p.m_tiles * p.n_tiles;
-    const int64_t n_work = tiles_mn * p.k_splits;
+    // cluster-level work items: (split, m-group, n-tile); every CTA of a cluster walks the same list
+    const int64_t tiles_gn = (int64_t)p.mg_tiles * p.n_tiles;
+    const int64_t n_work = tiles_gn * p.k_splits;
+    const int64_t cw0 = blockIdx.x / CL, cw_step = gridDim.x / CL;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int split = (int)(w / tiles_mn);
-                const int64_t rem = w - (int64_t)split * tiles_mn;
-                const int m0 = (int)(rem / p.n_tiles) * BLOCK_M, n0 = (int)(rem % p.n_tiles) * BLOCK_N;
+            for (int64_t w = cw0; w < n_work; w += cw_step) {
+                const int split = (int)(w / tiles_gn);
+                const int64_t rem = w - (int64_t)split * tiles_gn;
+                const int m0 = ((int)(rem / p.n_tiles) * CL + (int)rank) * BLOCK_M, n0 = (int)(rem % p.n_tiles) * BLOCK_N;
                 const int64_t kb = (int64_t)split * p.k_per_split;
                 const int64_t ke = min(p.K, kb + p.k_per_split);
                 for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
@@ -187,11 +219,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     } else {
                         tma_load_2d(sa, &tmA, (int)k0, m0, fb);
                     }
-                    if (B_MN) {
+                    if (CL == 1) {
+                        if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb);
-                    } else {
-                        tma_load_2d(sb, &tmB, (int)k0, n0, fb);
+                            for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb);
+                        } else {
+                            tma_load_2d(sb, &tmB, (int)k0, n0, fb);
+                        }
+                    } else if (B_MN) {                             // this CTA's share of the 8 column chunks, to everyone
+                        constexpr int PER = BLOCK_N / 32 / CL;
+#pragma unroll
+                        for (int jj = 0; jj < PER; ++jj) {
+                            const int j = (int)rank * PER + jj;
+                            tma_load_2d_mc(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb, MASK);
+                        }
+                    } else {                                       // K-major B: this CTA's BLOCK_N / CL rows, to everyone
+                        constexpr int ROWS = BLOCK_N / CL;
+                        tma_load_2d_mc(sb + rank * (ROWS * BLOCK_K * 4), &tmB, (int)k0, n0 + (int)rank * ROWS, fb, MASK);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -208,8 +252,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t a_step = A_MN ? 1024 : UMMA_K * 4, b_step = B_MN ? 1024 : UMMA_K * 4;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int split = (int)(w / tiles_mn);
+        for (int64_t w = cw0; w < n_work; w += cw_step) {
+            const int split = (int)(w / tiles_gn);
             const int64_t kb = (int64_t)split * p.k_per_split;
             const int64_t ke = min(p.K, kb + p.k_per_split);
             mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
@@ -229,7 +273,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
                         first = 0;
                     }
-                    umma_commit(empty_bar + 8 * stage);            // smem stage reusable once these MMAs retire
+                    // smem stage reusable once these MMAs retire -- in every CTA of the cluster
+                    if (CL == 1) umma_commit(empty_bar + 8 * stage); else umma_commit_mc(empty_bar + 8 * stage, MASK);
                     if (k0 + BLOCK_K >= ke) umma_commit(tfull_bar + 8 * acc);
                 }
                 __syncwarp();
@@ -242,10 +287,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                                    // TMEM lane quarter this warp may access
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int split = (int)(w / tiles_mn);
-            const int64_t rem = w - (int64_t)split * tiles_mn;
-            const int64_t m0 = (rem / p.n_tiles) * BLOCK_M;
+        for (int64_t w = cw0; w < n_work; w += cw_step) {
+            const int split = (int)(w / tiles_gn);
+            const int64_t rem = w - (int64_t)split * tiles_gn;
+            const int64_t m0 = ((rem / p.n_tiles) * CL + rank) * BLOCK_M;
             const int n0 = (int)(rem % p.n_tiles) * BLOCK_N;
             float* Cs = p.C + (int64_t)split * p.split_stride;
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
@@ -255,7 +300,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 const int n = n0 + 32 * c;
-                if (n >= p.N) break;                               // warp-uniform
+                if (n >= p.N || m0 >= p.M) break;                  // warp-uniform
                 uint32_t r[32];
                 tmem_ld32(t_row + 32 * c, r);
                 if (m < p.M) {
@@ -283,8 +328,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
 
+    __syncwarp();                                                  // reconverge before the aligned barriers
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();          // nobody leaves while a peer may still multicast to us
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -303,14 +349,6 @@ constexpr int HALF = 128;                                   // rows of A / colum
 constexpr int A2_BYTES = HALF * BLOCK_K * 4, B2_BYTES = HALF * BLOCK_K * 4, STAGE2_BYTES = A2_BYTES + B2_BYTES;
 constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + 1024 + 256;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -548,21 +586,67 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_
     return GMC_OK;
 }
 
-static int pick_splits(int64_t tiles, int64_t K) {
-    const int sms = sm_count();
-    if (tiles >= sms || K < 8 * BLOCK_K) return 1;
-    int64_t s = sms / tiles;
+// cluster size of the multicast kernel: GMC_GEMM_CLUSTER = 1 | 2 | 4 | 8.  Default 4: on B200 33 clusters of 4 are
+// co-resident (132 of 148 SMs) yet config 3 runs 8.3 / 7.9 ms (nn / tn) against 8.8 / 9.3 ms with pairs and
+// 10.7 / 10.1 ms without multicast (profiles/r01_gemm_notes.md)
+static int cluster_size() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GMC_GEMM_CLUSTER");
+        cached = 4;
+        if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8')) cached = e[0] - '0';
+    }
+    return cached;
+}
+
+static int pick_splits_cl(int64_t cluster_tiles, int64_t K, int slots) {
+    if (cluster_tiles >= slots || K < 8 * BLOCK_K) return 1;
+    int64_t s = slots / cluster_tiles;
     const int64_t max_by_k = K / (4 * BLOCK_K);
     if (s > max_by_k) s = max_by_k;
     return (int)(s < 1 ? 1 : s);
 }
 
-template <bool A_MN, bool B_MN>
+// co-resident clusters of the kernel on this device: the GPC geometry may admit fewer than SMs / CL
+template <bool A_MN, bool B_MN, int CL>
+static int cluster_slots(cudaLaunchConfig_t* cfg) {
+    static int cached = -1;
+    if (cached < 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+            attr_set = true;
+        }
+        cached = sm_count() / CL;
+        if (CL > 1) {
+            cudaLaunchConfig_t probe = {};
+            probe.blockDim = dim3(THREADS);
+            probe.dynamicSmemBytes = SMEM_BYTES;
+            probe.gridDim = dim3((sm_count() / CL) * CL);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            probe.attrs = attr;
+            probe.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<A_MN, B_MN, CL>, &probe) == cudaSuccess && n > 0) {
+                if (n < cached) cached = n;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (getenv("GMC_GEMM_DEBUG")) fprintf(stderr, "gmc gemm: cluster size %d -> %d co-resident clusters\n", CL, cached);
+    }
+    (void)cfg;
+    return cached;
+}
+
+template <bool A_MN, bool B_MN, int CL>
 static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        GMC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GMC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM_BYTES));
         attr_set = true;
     }
@@ -572,15 +656,27 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
     else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M, false);  // A[M rows, K cols]
     if (rc) return rc;
     if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BLOCK_K, true);       // B[K rows, N cols]
-    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, BLOCK_N, false);  // B[N rows, K cols]
+    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, BLOCK_N / CL, false);  // B[N rows, K cols]
     if (rc) return rc;
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int slots = cluster_slots<A_MN, B_MN, CL>(&cfg);        // co-resident clusters (GPC geometry), <= SMs / CL
 
     Params p;
     p.M = M; p.N = N; p.K = K;
     p.m_tiles = (int)ceil_div<int64_t>(M, BLOCK_M);
     p.n_tiles = (int)ceil_div<int64_t>(N, BLOCK_N);
-    const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-    int splits = pick_splits(tiles, K);
+    p.mg_tiles = ceil_div(p.m_tiles, CL);
+    const int64_t ctiles = (int64_t)p.mg_tiles * p.n_tiles;
+    int splits = pick_splits_cl(ctiles, K, slots);
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
         if (splits < 1) splits = 1;
@@ -596,16 +692,27 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
         p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
         p.vec_ok = (N % 4 == 0) && aligned16(workspace);
     }
-    const int64_t n_work = tiles * splits;
-    const int grid = (int)(n_work < sm_count() ? n_work : sm_count());
-    gemm_tf32_kernel<A_MN, B_MN><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
-    GMC_LAUNCH_CHECK();
+    const int64_t n_work = ctiles * splits;
+    const int grid = (int)(n_work < slots ? n_work : slots) * CL;
+    cfg.gridDim = dim3(grid);
+    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN, CL>, tmA, tmB, p));
     if (splits > 1) {
         const int64_t MN = M * N;
         tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
         GMC_LAUNCH_CHECK();
     }
     return GMC_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_cl(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                     int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    switch (cluster_size()) {
+        case 1: return launch<A_MN, B_MN, 1>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 8: return launch<A_MN, B_MN, 8>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 2: return launch<A_MN, B_MN, 2>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        default: return launch<A_MN, B_MN, 4>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    }
 }
 
 static bool use_two_cta() {
@@ -689,8 +796,9 @@ size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision
         const int64_t tiles = ceil_div<int64_t>(M, 256) * ceil_div<int64_t>(N, 256);
         splits = tc::pick_splits2(tiles, K);
     } else {
-        const int64_t tiles = ceil_div<int64_t>(M, tc::BLOCK_M) * ceil_div<int64_t>(N, tc::BLOCK_N);
-        splits = tc::pick_splits(tiles, K);
+        const int cl = tc::cluster_size();
+        const int64_t ctiles = ceil_div<int64_t>(ceil_div<int64_t>(M, tc::BLOCK_M), cl) * ceil_div<int64_t>(N, tc::BLOCK_N);
+        splits = tc::pick_splits_cl(ctiles, K, sm_count() / cl);      // upper bound of what launch() picks
     }
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
 }
@@ -718,9 +826,9 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
         }
     }
     switch (op) {
-        case 0: return tc::launch<false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-        case 1: return tc::launch<false, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-        case 2: return tc::launch<true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 0: return tc::launch_cl<false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 1: return tc::launch_cl<false, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 2: return tc::launch_cl<true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
     }
     set_error("gmc_gemm: bad op %d", op);
     return GMC_ERR_INVALID_ARG;
