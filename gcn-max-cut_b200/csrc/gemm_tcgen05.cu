@@ -19,6 +19,8 @@
 //
 // Precision: GMC_GEMM_TF32 is one pass (operands truncated to 10 mantissa bits by the MMA).
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -32,7 +34,9 @@ constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;              // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int CHUNK_BYTES = BLOCK_K * 128;                  // one MN-major box: 32 k-rows x 128 B
 constexpr int THREADS = 192;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_BUF_BYTES = 32 * 32 * 4;                  // one 32-row x 32-column output block per epilogue warp
+constexpr int EPI_BYTES = 4 /*warps*/ * 2 /*buffers*/ * EPI_BUF_BYTES;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,6 +83,15 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
         " [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -153,6 +166,7 @@ struct Params {
     int mg_tiles;            // m-tile groups of CL (cluster size) tiles: ceil(m_tiles / CL)
     int accumulate;
     int vec_ok;              // 16-byte aligned C rows
+    int tma_store;           // epilogue through shared memory + cp.async.bulk.tensor stores (tmC valid)
 };
 
 // CL = thread-block cluster size (1, 2 or 4).  With CL > 1 the CTAs of a cluster own CL consecutive m-tiles of
@@ -163,11 +177,13 @@ struct Params {
 // empty barrier (arrival count CL).
 template <bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
-    const uint32_t bars = tiles + STAGES * STAGE_BYTES;
+    const uint32_t epi = tiles + STAGES * STAGE_BYTES;             // epilogue staging: 4 warps x 2 x 4 KB, 1024-aligned
+    const uint32_t bars = epi + EPI_BYTES;
     const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
     const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 8 * ACC_STAGES;
     const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
@@ -287,6 +303,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                                    // TMEM lane quarter this warp may access
         int acc = 0; uint32_t acc_phase = 0;
+        int ebuf = 0;
         for (int64_t w = cw0; w < n_work; w += cw_step) {
             const int split = (int)(w / tiles_gn);
             const int64_t rem = w - (int64_t)split * tiles_gn;
@@ -303,7 +320,26 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (n >= p.N || m0 >= p.M) break;                  // warp-uniform
                 uint32_t r[32];
                 tmem_ld32(t_row + 32 * c, r);
-                if (m < p.M) {
+                if (p.tma_store) {
+                    // registers -> 128B-swizzled staging block (lane = row, 16-byte chunk i at i ^ (row & 7): conflict-free
+                    // STS.128) -> one TMA store of 32 full 128-byte row segments; rows / columns beyond M / N are clipped
+                    const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
+                    if (lane == 0) bulk_wait_read<1>();            // the store that last read this buffer has drained it
+                    __syncwarp();
+                    const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((i ^ (lane & 7)) << 4)),
+                                     "r"(r[4 * i]), "r"(r[4 * i + 1]), "r"(r[4 * i + 2]), "r"(r[4 * i + 3]) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, buf, n, (int)(m0 + 32 * q));
+                        bulk_commit();
+                    }
+                    ebuf ^= 1;
+                } else if (m < p.M) {
                     float* dst = Cs + m * p.ldc + n;
                     if (p.vec_ok && n + 32 <= p.N) {
 #pragma unroll
@@ -326,6 +362,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait_all();                            // outstanding TMA stores complete before the CTA exits
     }
 
     __syncwarp();                                                  // reconverge before the aligned barriers
@@ -599,6 +636,12 @@ static int cluster_size() {
     return cached;
 }
 
+static bool no_tma_store() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("GMC_GEMM_NO_TMA_STORE"); cached = (e && e[0] == '1') ? 1 : 0; }
+    return cached == 1;
+}
+
 static int pick_splits_cl(int64_t cluster_tiles, int64_t K, int slots) {
     if (cluster_tiles >= slots || K < 8 * BLOCK_K) return 1;
     int64_t s = slots / cluster_tiles;
@@ -692,10 +735,19 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
         p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
         p.vec_ok = (N % 4 == 0) && aligned16(workspace);
     }
+    // direct (non split-K, non accumulating) outputs leave through a 128B-swizzled staging block and TMA stores
+    CUtensorMap tmC;
+    memset(&tmC, 0, sizeof(tmC));
+    p.tma_store = 0;
+    if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
+        rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
+        if (rc) return rc;
+        p.tma_store = 1;
+    }
     const int64_t n_work = ctiles * splits;
     const int grid = (int)(n_work < slots ? n_work : slots) * CL;
     cfg.gridDim = dim3(grid);
-    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN, CL>, tmA, tmB, p));
+    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN, CL>, tmA, tmB, tmC, p));
     if (splits > 1) {
         const int64_t MN = M * N;
         tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
