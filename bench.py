@@ -54,13 +54,25 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "tf32"),
                     choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--workload", default="config3", choices=["config3", "config5", "config2"],
+                    help="config3 (default, the headline): 4096 graphs n=1000 per GPU; config5: one 7-regular graph "
+                         "n=1M, F=256, H=128, learned embeddings (SpMM/GEMM roofline stress); config2: inference + "
+                         "200-iteration post-processing on test graphs n=50..500")
+    ap.add_argument("--feature-source", default="adjacency", choices=["adjacency", "embedding"],
+                    help="adjacency: dense zero-padded adjacency rows (the reference's live path); embedding: learned "
+                         "dense node embeddings X~N(0,1) with dL/dX and their own Adam update (north-star mode)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="time budget of the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=8, help="graphs per reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(--steps, 10)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.workload == "config5":
+        args.graphs_per_gpu, args.nodes, args.degree, args.features, args.hidden = 1, 1000000, 7, 256, 128
+        args.feature_source = "embedding"
+        args.no_cpu_baseline = True          # the per-graph reference step at n = 1M is not a bounded sample
+    return args
 
 
 def load_peaks():
@@ -213,14 +225,31 @@ def run_b200_arm(args):
     h_gptr = torch.from_numpy(graph_ptr).pin_memory()
     batch = GraphBatch.from_arrays(rowptr, colidx, graph_ptr, device=dev)
     N, nnz = batch.num_nodes, batch.nnz
-    X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
-
+    embedding = args.feature_source == "embedding"
     torch.manual_seed(args.seed)                        # identical initial weights on every rank
     cfg = T.TrainingConfig(n_nodes=n, dim_embedding=F, hidden_dim=H, number_classes=K, learning_rate=1e-3,
                            gemm_precision=args.precision, batch_graphs=B)
     net, embed, opt = T.setup_model_and_optimizer(cfg)
     del embed
+    x_param = x_grad = None
+    if embedding:
+        # learned node embeddings: one [N, F] table per GPU (rows never leave the rank), 128-byte row pitch;
+        # parameter + gradient + Adam moments = 4 x N x ld x 4 bytes
+        from gmc_b200.optim import FusedAdam
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(args.seed + 17 + rank)
+        x_param = torch.nn.Parameter(torch.zeros((N, ops.pad_cols(F)), dtype=torch.float32, device=dev),
+                                     requires_grad=False)
+        x_param.data[:, :F].normal_(generator=gen)
+        x_grad = torch.zeros_like(x_param.data)
+        X = x_param.data[:, :F]
+        opt = FusedAdam(list(net.parameters()) + [x_param], lr=1e-3)
+    else:
+        X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
     eng = GCNEngine(net, opt, precision=args.precision)
+
+    def train_step(b):
+        return eng.train_step(b, X, feature_param=x_param, feature_grad=x_grad)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -230,7 +259,7 @@ def run_b200_arm(args):
 
     # ---- device-resident throughput --------------------------------------------------------
     for _ in range(args.warmup):
-        eng.train_step(batch, X)
+        train_step(batch)
     sync_all()
     eng.timer = OpTimer()
     eng.launch_count = 0
@@ -240,7 +269,7 @@ def run_b200_arm(args):
     e0.record()
     loss = None
     for _ in range(args.steps):
-        loss = eng.train_step(batch, X)
+        loss = train_step(batch)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -276,8 +305,9 @@ def run_b200_arm(args):
             b2.coef = ops.edge_coef(d_rowptr, d_colidx, None, b2.norm, b2.norm, N)
             b2.plan = (ops.spmm_plan(d_rowptr, d_colidx, b2.norm, b2.norm, d_gptr, B, N)
                        if batch.plan is not None else None)   # slab-SpMM plan: a function of the graph, rebuilt per step
-            ops.densify(b2, F, out=X)                                # device-side graphExtender
-            per_graph = eng.train_step(b2, X)
+            if not embedding:
+                ops.densify(b2, F, out=X)                            # device-side graphExtender
+            per_graph = train_step(b2)
             return per_graph.cpu()                                   # D2H of the step's result
 
         e2e_step()
@@ -295,13 +325,20 @@ def run_b200_arm(args):
         e2e = {"value": total_graphs * k_e2e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(B * 8 + 4), "steps": k_e2e,
                "path": "pinned host CSR (rowptr, colidx, graph_ptr) -> H2D -> gmc_degree_norm/edge_coef/"
-                       "csr_densify (device-side graphExtender) -> GCNEngine.train_step -> per-graph loss D2H"}
+                       + ("spmm_plan (embeddings are resident parameters)" if embedding else
+                          "csr_densify (device-side graphExtender)")
+                       + " -> GCNEngine.train_step -> per-graph loss D2H"}
         del host_loss
 
     # ---- rooflines ----------------------------------------------------------------------------
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0 if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"] / 2.0
-    spmm_bytes_h = 8.0 * N * H + 4.0 * nnz + 4.0 * (N + 1)
-    spmm_bytes_k = 8.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)
+    # compulsory form while one graph's source rows stay L2-resident (n*C*4 <= 32 MiB), else gather form
+    def spmm_bytes(C):
+        if n * C * 4 <= 32 * 2 ** 20:
+            return 8.0 * N * C + 4.0 * nnz + 4.0 * (N + 1)
+        return 4.0 * nnz * C + 4.0 * N * C + 4.0 * nnz + 4.0 * (N + 1)
+    spmm_bytes_h, spmm_bytes_k = spmm_bytes(H), spmm_bytes(K)
+    ldx = ops.pad_cols(F)
     gemm_flops = 2.0 * N * F * H
     algo = {
         "gemm_nn_xw1": ("tensor", gemm_flops), "gemm_tn_dw1": ("tensor", gemm_flops),
@@ -310,6 +347,7 @@ def run_b200_arm(args):
         "skinny_fwd": ("hbm", 4.0 * N * H + 4.0 * N * K), "skinny_bwd": ("hbm", 8.0 * N * H + 4.0 * N * K),
         "cut_loss": ("hbm", 12.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)), "colsum_db2": ("hbm", 4.0 * N * K),
         "adam": ("hbm", 28.0 * (F * H + H + H * K + K)),
+        "gemm_nt_dx": ("tensor", gemm_flops), "adam_features": ("hbm", 28.0 * N * ldx),
     }
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -327,7 +365,15 @@ def run_b200_arm(args):
             achieved, peak, unit = work / (avg_ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
         else:
             achieved, peak, unit = work / (avg_ms * 1e-3) / 1e12, tf32_peak, "TFLOP/s"
-        ops_report[name] = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+        extra = {}
+        if name.startswith("spmm") and n * H * 4 > 32 * 2 ** 20:
+            # gather-form bytes count every neighbour row as an HBM read; L2 still catches part of them, so the
+            # compulsory-form figure (each row once) is reported beside it: real DRAM traffic lies in between
+            Cw = K if name == "spmm_k" else H
+            comp = 8.0 * N * Cw + 4.0 * nnz + 4.0 * (N + 1) + (4.0 * N * K if name == "spmm_h_fused" else 0.0)
+            extra = {"achieved_compulsory": comp / (avg_ms * 1e-3) / 1e9,
+                     "frac_compulsory": comp / (avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        ops_report[name] = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, **extra,
                             "frac": achieved / peak if peak else None, "avg_ms": avg_ms, "calls": calls,
                             "share_of_step": tot / ms,
                             # DRAM bytes per launch from the committed ncu --set full capture (per graph x graphs/GPU)
@@ -356,10 +402,16 @@ def run_b200_arm(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
             "config": {
-                "workload": (f"config 3: {B} synthetic {args.degree}-regular graphs n={n} as one block-diagonal CSR per GPU"
+                "workload": (f"config 5: one synthetic {args.degree}-regular graph n={n}, F={F}, H={H}, K={K}"
+                             if args.workload == "config5" else
+                             f"config 3: {B} synthetic {args.degree}-regular graphs n={n} as one block-diagonal CSR per GPU"
                              if world == 1 else
                              f"config 4: {total_graphs} synthetic regular graphs n={n}, d=6+(g mod 3), {B} per GPU"),
-                "features": f"dense zero-padded adjacency rows [{N},{F}] fp32 resident in HBM ({N * F * 4 / 1e9:.1f} GB/GPU)",
+                "features": (f"learned node embeddings [{N},{F}] fp32 (parameter + gradient + Adam moments "
+                             f"{4 * N * ldx * 4 / 1e9:.1f} GB/GPU), dL/dX = dT1 W1^T, own fused Adam update"
+                             if embedding else
+                             f"dense zero-padded adjacency rows [{N},{F}] fp32 resident in HBM ({N * F * 4 / 1e9:.1f} GB/GPU)"),
+                "spmm_bytes_form": "compulsory" if n * H * 4 <= 32 * 2 ** 20 else "gather",
                 "model": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
                 "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",
                 "gemm_precision": args.precision, "parallelism": f"dp{world}",
@@ -372,6 +424,7 @@ def run_b200_arm(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,
+            "node_epochs_per_s": value * n,
             "clocks": clocks,
             "loss_last_step": last_loss,
         }
@@ -379,6 +432,112 @@ def run_b200_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- config 2
+def run_config2(args):
+    """BASELINE.json configs[1]: inference + 200-iteration post-processing on test graphs n=50/100/200/300/500
+    (10 each, d in 6..8, 3 terminals), single B200.  One step = one pass over the 50 graphs through the
+    reference-facing API: forward, argmax assignment + integer cut, best-of-200 categorical sampling (the
+    reference's post_processing_optimization) and the north-star greedy node-move search (200 iterations).
+    value = device-resident dataset; e2e = host feature tensors uploaded every pass."""
+    import contextlib
+    import random
+
+    import networkx as nx
+    import numpy as np
+    import torch
+
+    from DataGenerator import graphExtender as E
+    from Testing import TestingNeuralNetwork as Te
+    from Training import TrainingNeural as T
+    from gmc_b200 import _lib, model as gmodel
+
+    dev = _lib.require_cuda()
+    sizes, per_size, iters = [50, 100, 200, 300, 500], 10, 200
+    random.seed(0)
+    graphs, terms = {}, {}
+    for size in sizes:
+        for i in range(per_size):
+            name = f"test_n{size}_{i}"
+            g = nx.random_regular_graph(d=random.randint(6, 8), n=size, seed=size * 1000 + i)
+            nx.set_edge_attributes(g, 1, "weight")
+            graphs[name], terms[name] = g, random.sample(range(3, size), 3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds = E.process_graphs_from_folder(graphs, terms, max_nodes=1000)
+    n_graphs = len(ds)
+    cfg = T.TrainingConfig(n_nodes=1000, dim_embedding=1000, hidden_dim=500, gemm_precision="fp32")
+    torch.manual_seed(args.seed)
+    net, _, _ = T.setup_model_and_optimizer(cfg)
+    net.eval()
+
+    def one_pass(batched: bool):
+        np.random.seed(1)
+        if batched:
+            return Te.test_multiple_graphs_batched(net, ds, sizes, iters, greedy_iterations=iters)
+        return Te.test_multiple_graphs(net, ds, sizes, iters, verbose=False)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps, out
+
+    steps, warmup = max(1, min(args.steps, 20)), max(3, args.warmup)
+    sampler = ClockSampler(0)
+    sampler.start()
+    dt_batched, (res_b, _) = timed(lambda: one_pass(True), steps, warmup)
+    sampler.stop()
+    dt_loop, (res_l, _) = timed(lambda: one_pass(False), max(1, steps // 4), 1)
+
+    def e2e_pass():
+        gmodel._FEATURE_CACHE.clear()                    # host feature tensors are uploaded again every pass
+        return one_pass(True)
+    dt_e2e, _ = timed(e2e_pass, steps, 1)
+    same = all(a["simple_cut"] == b["simple_cut"] and a["post_cut"] == b["post_cut"] for a, b in zip(res_l, res_b))
+    h2d = sum(int(v[1].numel()) * 4 for v in ds.values())
+
+    # CPU baseline: the reference's test_single_graph cost structure on one graph per size
+    from oracle import postproc as pp, ref_step as rs
+    port = rs.FaithfulPort(1000, 500, 3, seed=args.seed, pad=1000)
+    sample = [ds[k] for k in list(ds.keys())[::per_size]]
+    t0 = time.perf_counter()
+    for _, X, g, _t in sample:
+        csr = rs.csr_from_networkx(g)
+        with torch.no_grad():
+            P = port.forward(csr, X).numpy()
+        pp.py_cut_value(pp.simple_assignment(P).tolist(), g)
+        best = -1
+        for _ in range(iters):
+            best = max(best, pp.py_cut_value(pp.py_assign_partitions(P), g))
+    dt_cpu = time.perf_counter() - t0
+    cpu = {"value": len(sample) / dt_cpu, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"{len(sample)} graphs (one per size {sizes}), forward + argmax cut + {iters} samplings each, "
+                     f"pure-Python loops as the reference, {dt_cpu:.1f}s"}
+    line = {
+        "metric": "inference + 200-iteration post-processing graphs/s (n=50..500, d=6-8, k=3)",
+        "value": n_graphs / dt_batched, "unit": "graphs/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1000.0 * dt_batched, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"config 2: {n_graphs} test graphs n in {sizes} x {per_size}, d in 6..8, 3 terminals, "
+                               "model 1000->500->3 (random init), best-of-200 sampling + 200-iteration greedy node moves",
+                   "api": "Testing.TestingNeuralNetwork.test_multiple_graphs_batched (one block-diagonal batch)"},
+        "per_graph_loop": {"value": n_graphs / dt_loop, "unit": "graphs/s",
+                           "api": "test_multiple_graphs (reference-shaped per-graph loop)", "same_cuts_as_batched": same},
+        "roofline": None,
+        "cpu_baseline": cpu,
+        "e2e": {"value": n_graphs / dt_e2e, "unit": "graphs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": int(sum(len(r["simple_assignment"]) for r in res_b) * (8 * 3 + 4 * 3))},
+        "clocks": sampler.summary(),
+        "avg_cut": {"simple": float(np.mean([r["simple_cut"] for r in res_b])),
+                    "sampled": float(np.mean([r["post_cut"] for r in res_b])),
+                    "greedy": float(np.mean([r["greedy_cut"] for r in res_b]))},
+    }
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -391,6 +550,8 @@ def main():
     with contextlib.redirect_stdout(out):
         if args.impl == "reference":
             run_reference_arm(args)
+        elif args.workload == "config2":
+            run_config2(args)
         else:
             run_b200_arm(args)
     sys.stdout.flush()

@@ -219,14 +219,33 @@ class GCNEngine:
         if self.pg is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             dist.all_reduce(self.grads_flat, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def apply_adam(self) -> None:
+    def apply_adam(self, feature_param: Optional[torch.Tensor] = None,
+                   feature_grad: Optional[torch.Tensor] = None) -> None:
         if self.optimizer is None:
             raise RuntimeError("GCNEngine was built without an optimizer")
         self._op("adam", 1, self.optimizer.fused_step, list(self.params()), self.grads())
+        if feature_param is not None:
+            # per-graph / per-node embeddings never leave the rank: no all-reduce, their own Adam launch
+            self._op("adam_features", 1, self.optimizer.fused_step, [feature_param], [feature_grad])
 
-    def train_step(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
-        """One optimiser step on the whole batch (loss = sum of per-graph losses)."""
-        loss = self.loss_and_grads(batch, X)
+    def train_step(self, batch: GraphBatch, X: torch.Tensor, feature_param: Optional[torch.Tensor] = None,
+                   feature_grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimiser step on the whole batch (loss = sum of per-graph losses).
+
+        Learned node-embedding input (the north-star's feature mode; reference precedent python/utils.py:184,
+        `inputs = embed.weight`): pass the parameter that X is a view of (`feature_param`, registered with the
+        optimiser) and a same-shaped gradient buffer (`feature_grad`).  dL/dX = dT1 W1^T is written into the
+        rows/columns of `feature_grad` that X covers (everything else must be zero) and the parameter takes its
+        own fused Adam update."""
+        dX = None
+        if feature_param is not None:
+            if feature_grad is None or feature_grad.shape != feature_param.shape or not feature_grad.is_contiguous():
+                raise ValueError("feature_grad must be a contiguous buffer shaped like feature_param")
+            if X.data_ptr() != feature_param.data_ptr() or X.shape[0] > feature_param.shape[0] \
+                    or X.stride(0) != feature_param.stride(0):
+                raise ValueError("X must be a leading-rows / leading-columns view of feature_param")
+            dX = feature_grad[: X.shape[0], : X.shape[1]]
+        loss = self.loss_and_grads(batch, X, dX=dX)
         self.allreduce_grads()
-        self.apply_adam()
+        self.apply_adam(feature_param, feature_grad)
         return loss

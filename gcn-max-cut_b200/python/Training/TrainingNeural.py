@@ -14,6 +14,10 @@ Opt-in extensions (defaults reproduce the reference exactly):
     TrainingConfig.gemm_precision    'fp32' (FFMA, parity) | 'tf32' | 'tf32x3' (tcgen05)
     TrainingConfig.loss_mode         'ste' (reference live path) | 'soft' (north-star objective)
     TrainingConfig.use_terminal_penalty   enable the penalty the reference left commented (:308)
+    TrainingConfig.feature_source    'adjacency' (reference live path: zero-padded adjacency rows are the
+                                     features, :373) | 'embedding' (north-star: the learned nn.Embedding is the
+                                     input, `inputs = embed.weight[:n]`, as in the legacy trainer
+                                     python/utils.py:184; it then receives gradients and Adam updates)
 """
 try:
     from python.commons import *  # noqa: F401,F403  (reference spelling, :25)
@@ -69,8 +73,11 @@ class TrainingConfig:
     gemm_precision: str = "fp32"
     loss_mode: str = "ste"
     use_terminal_penalty: bool = False
+    feature_source: str = "adjacency"
 
     def __post_init__(self):
+        if self.feature_source not in ("adjacency", "embedding"):
+            raise ValueError(f"feature_source must be 'adjacency' or 'embedding', got {self.feature_source!r}")
         if self.dim_embedding is None:
             self.dim_embedding = self.n_nodes
         if self.hidden_dim is None:
@@ -286,10 +293,44 @@ def train_single_epoch(dataset: Dict, net, optimizer, embed, config: TrainingCon
     total = torch.zeros((), dtype=torch.float64, device=device)
     for dataset_file in dataset_files:
         current = dataset if isinstance(dataset, dict) else open_file(dataset_file)
+        embedding_mode = getattr(config, "feature_source", "adjacency") == "embedding"
         for step in _prepare(current, int(getattr(config, "batch_graphs", 1)), device):
-            losses = engine.train_step(step.batch, step.X)
+            if embedding_mode:
+                losses = _embedding_step(engine, step, embed)
+            else:
+                losses = engine.train_step(step.batch, step.X)
             total += losses.sum()
     return float(total.item())
+
+
+def _embedding_features(batch: GraphBatch, embed) -> torch.Tensor:
+    """inputs = embed.weight[:n] (python/utils.py:184 generalised to the multi-graph loop): one graph per step, its
+    node i reads embedding row i."""
+    if batch.num_graphs != 1:
+        raise NotImplementedError("feature_source='embedding' trains one graph per step (batch_graphs=1): the "
+                                  "embedding table is indexed by node id, which a block-diagonal batch would alias")
+    weight = embed.weight
+    if batch.num_nodes > weight.shape[0]:
+        raise ValueError(f"graph has {batch.num_nodes} nodes but the embedding table has {weight.shape[0]} rows")
+    return weight.data[: batch.num_nodes]
+
+
+def _embedding_step(engine: GCNEngine, step, embed) -> torch.Tensor:
+    weight = embed.weight
+    state = _EMBED_STATE.get(embed)                   # keyed by the module (tensors do not hash/compare as keys)
+    if state is None or state[0].shape != weight.shape or state[0].device != weight.device:
+        state = [torch.zeros_like(weight.data), 0]
+        _EMBED_STATE[embed] = state
+    grad, prev_rows = state
+    n = step.batch.num_nodes
+    if prev_rows > n:
+        grad[n: prev_rows].zero_()                    # rows a larger previous graph wrote
+    state[1] = n
+    return engine.train_step(step.batch, _embedding_features(step.batch, embed), feature_param=weight,
+                             feature_grad=grad)
+
+
+_EMBED_STATE = weakref.WeakKeyDictionary()            # nn.Embedding -> [gradient buffer, rows written last step]
 
 
 def _early_stop_update(epoch: int, loss: float, prev_loss: float, counter: int, config: TrainingConfig):
