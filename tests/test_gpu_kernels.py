@@ -111,6 +111,27 @@ def test_spmm_slab_irregular_degrees_and_nonfinite_isolation():
     assert (touched == expect).all()
 
 
+def test_spmm_plan_needs_uniform_neighbour_norms():
+    """The slab plan keeps ONE coefficient per row (nd[v] * ns[u]), so a graph whose neighbours of some node have
+    different degrees must be refused (-> warp-per-row kernel), even when its max degree is <= 8."""
+    g = nx.random_regular_graph(d=4, n=200, seed=5)
+    g.remove_edge(*next(iter(g.edges())))                   # two nodes of degree 3 among degree-4 nodes
+    nx.set_edge_attributes(g, 1, "weight")
+    csr = rs.csr_from_networkx(g)
+    batch = GraphBatch([CSRGraph.from_networkx(g)])
+    assert batch.plan is None and not batch.build_plan()
+    torch.manual_seed(0)
+    X = torch.randn(200, 64, device=DEV)
+    assert relerr(ops.spmm(batch, X).cpu(), ahat_dense(csr) @ X.cpu().double()) < 2e-6
+    # a batch of >= 32 regular graphs gets its plan automatically, and mixing degrees ACROSS graphs is fine
+    graphs, csrs, big = make_batch([(128 + 2 * (i % 3), 5 + i % 3, i) for i in range(32)])
+    assert big.plan is not None
+    X = torch.randn(big.num_nodes, 100, device=DEV)
+    want = torch.cat([ahat_dense(c) @ X[s:e].cpu().double() for c, (s, e) in
+                      zip(csrs, zip(big.graph_ptr_host[:-1], big.graph_ptr_host[1:]))])
+    assert relerr(ops.spmm(big, X).cpu(), want) < 2e-6
+
+
 @pytest.mark.parametrize("C,K", [(500, 3), (64, 2), (128, 8), (20, 3), (512, 5)])
 def test_spmm_fused_skinny_projection(C, K):
     graphs, csrs, batch = make_batch([(70, 6, 1), (33 * 2, 7, 2), (1000, 7, 3), (9, 2, 4)])
