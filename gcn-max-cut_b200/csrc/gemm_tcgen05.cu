@@ -839,10 +839,41 @@ static int launch2(const float* A, const float* B, float* C, int64_t M, int64_t 
     return GMC_OK;
 }
 
+// ---- 3xTF32: low-order operand parts ------------------------------------------------------------
+// The MMA reads the upper 19 bits of each fp32 operand (truncation), so feeding x itself IS feeding hi(x).
+// lo(x) = x - hi(x) is exact in fp32; its own truncation to TF32 costs 2^-21 |x| at most.
+__global__ void __launch_bounds__(256)
+tf32_lo_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ L, int64_t ldl, int64_t rows, int cols) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // one float4 of the (padded) output row
+    const int c4 = (int)(ldl >> 2);
+    const int64_t r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    if (r >= rows) return;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cols) {                                                      // cols % 4 == 0 is required by the TMA path
+        const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + c);
+        out.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        out.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        out.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        out.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+    }
+    *reinterpret_cast<float4*>(L + r * ldl + c) = out;
+}
+
+static int64_t lo_ld(int64_t cols) { return (cols + 31) / 32 * 32; }     // 128-byte row pitch for the TMA boxes
+
+static int make_lo(const float* X, int64_t ldx, float* L, int64_t rows, int64_t cols, cudaStream_t s) {
+    const int64_t ldl = lo_ld(cols);
+    const int64_t n4 = rows * (ldl / 4);
+    if (n4 == 0) return GMC_OK;
+    tf32_lo_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, s>>>(X, ldx, L, ldl, rows, (int)cols);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
 }  // namespace tc
 
-size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision) {
-    (void)op; (void)precision;
+static size_t tc_splitk_bytes(int64_t M, int64_t N, int64_t K) {
     int splits;
     if (tc::use_two_cta()) {
         const int64_t tiles = ceil_div<int64_t>(M, 256) * ceil_div<int64_t>(N, 256);
@@ -855,13 +886,27 @@ size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
 }
 
-int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
-            int64_t ldb, int64_t ldc, int accumulate, int precision, void* workspace, size_t workspace_bytes,
-            cudaStream_t s) {
-    if (precision != GMC_GEMM_TF32) {
-        set_error("gmc_gemm: precision %d is not implemented on the tcgen05 path yet (use GMC_GEMM_TF32 or GMC_GEMM_FP32)", precision);
-        return GMC_ERR_UNSUPPORTED;
+// operand shapes as stored: nn A[M,K] B[K,N]; nt A[M,K] B[N,K]; tn A[K,M] B[K,N]
+static void operand_shapes(int op, int64_t M, int64_t N, int64_t K, int64_t* ra, int64_t* ca, int64_t* rb, int64_t* cb) {
+    *ra = op == 2 ? K : M; *ca = op == 2 ? M : K;
+    *rb = op == 1 ? N : K; *cb = op == 1 ? K : N;
+}
+
+size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision) {
+    size_t need = (tc_splitk_bytes(M, N, K) + 255) & ~(size_t)255;
+    if (precision == GMC_GEMM_TF32X3) {
+        int64_t ra, ca, rb, cb;
+        operand_shapes(op, M, N, K, &ra, &ca, &rb, &cb);
+        need += ((size_t)ra * tc::lo_ld(ca) * sizeof(float) + 255) & ~(size_t)255;
+        need += ((size_t)rb * tc::lo_ld(cb) * sizeof(float) + 255) & ~(size_t)255;
     }
+    return need;
+}
+
+
+static int tc_gemm_pass(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                        int64_t ldb, int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes,
+                        cudaStream_t s) {
     GMC_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B),
                 "gmc_gemm(tf32): TMA needs 16-byte aligned bases and leading dimensions that are multiples of 4");
     GMC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gmc_gemm(tf32): dimension exceeds int32 TMA coordinates");
@@ -884,6 +929,44 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
     }
     set_error("gmc_gemm: bad op %d", op);
     return GMC_ERR_INVALID_ARG;
+}
+
+int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+            int64_t ldb, int64_t ldc, int accumulate, int precision, void* workspace, size_t workspace_bytes,
+            cudaStream_t s) {
+    if (precision == GMC_GEMM_TF32)
+        return tc_gemm_pass(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    if (precision != GMC_GEMM_TF32X3) {
+        set_error("gmc_gemm: unknown tensor-core precision %d", precision);
+        return GMC_ERR_INVALID_ARG;
+    }
+    // 3xTF32 (fp32-grade): C = hi(A) hi(B) + lo(A) hi(B) + hi(A) lo(B); the lo*lo term (2^-22 relative) is dropped.
+    // Three passes of the TF32 kernel, the low parts materialised in the caller's workspace.
+    if (M == 0 || N == 0) return GMC_OK;
+    if (K == 0) return tc_gemm_pass(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    GMC_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B),
+                "gmc_gemm(tf32x3): TMA needs 16-byte aligned bases and leading dimensions that are multiples of 4");
+    int64_t ra, ca, rb, cb;
+    operand_shapes(op, M, N, K, &ra, &ca, &rb, &cb);
+    GMC_REQUIRE(ca % 4 == 0 && cb % 4 == 0, "gmc_gemm(tf32x3): operand row lengths must be multiples of 4 floats");
+    const size_t split_bytes = (tc_splitk_bytes(M, N, K) + 255) & ~(size_t)255;
+    const size_t a_bytes = ((size_t)ra * tc::lo_ld(ca) * sizeof(float) + 255) & ~(size_t)255;
+    const size_t b_bytes = ((size_t)rb * tc::lo_ld(cb) * sizeof(float) + 255) & ~(size_t)255;
+    GMC_REQUIRE(workspace && workspace_bytes >= split_bytes + a_bytes + b_bytes,
+                "gmc_gemm(tf32x3): workspace too small (gmc_gemm_workspace_bytes reports the need)");
+    GMC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "gmc_gemm(tf32x3): workspace must be 256-byte aligned");
+    char* wsb = reinterpret_cast<char*>(workspace);
+    float* A_lo = reinterpret_cast<float*>(wsb + split_bytes);
+    float* B_lo = reinterpret_cast<float*>(wsb + split_bytes + a_bytes);
+    int rc = tc::make_lo(A, lda, A_lo, ra, ca, s);
+    if (rc) return rc;
+    rc = tc::make_lo(B, ldb, B_lo, rb, cb, s);
+    if (rc) return rc;
+    rc = tc_gemm_pass(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, split_bytes, s);
+    if (rc) return rc;
+    rc = tc_gemm_pass(op, A_lo, B, C, M, N, K, tc::lo_ld(ca), ldb, ldc, 1, workspace, split_bytes, s);
+    if (rc) return rc;
+    return tc_gemm_pass(op, A, B_lo, C, M, N, K, lda, tc::lo_ld(cb), ldc, 1, workspace, split_bytes, s);
 }
 
 }  // namespace gmc

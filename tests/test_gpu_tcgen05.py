@@ -85,6 +85,32 @@ def test_tf32_exact_on_adjacency_features():
     assert relerr(got.cpu(), X.double() @ W.double()) < 1.5e-3
 
 
+@pytest.mark.parametrize("op,M,N,K", [("nn", 1000, 500, 1000), ("nn", 132, 260, 40), ("nt", 200, 96, 500),
+                                      ("tn", 1000, 500, 3000), ("tn", 1000, 500, 200000)])
+def test_tf32x3_is_fp32_grade(op, M, N, K):
+    """3xTF32 (hi*hi + lo*hi + hi*lo on the tensor cores): agrees with the float64 product of the UNtruncated
+    operands to fp32 accumulation error, i.e. ~1000x closer than one TF32 pass."""
+    torch.manual_seed(M + N + K)
+    if op == "nn":
+        A, B = torch.randn(M, K), torch.randn(K, N)
+        exact = A.double() @ B.double()
+    elif op == "nt":
+        A, B = torch.randn(M, K), torch.randn(N, K)
+        exact = A.double() @ B.double().t()
+    else:
+        A, B = torch.randn(K, M), torch.randn(K, N)
+        exact = A.double().t() @ B.double()
+    got = ops.gemm(op, A.to(DEV), B.to(DEV), precision="tf32x3")
+    one_pass = ops.gemm(op, A.to(DEV), B.to(DEV), precision="tf32")
+    tol = 3e-6 * max(1.0, math.sqrt(K) / 8)
+    assert relerr(got.cpu(), exact) < tol
+    # (for very long K the fp32 accumulation of the split-K partials, common to both, narrows the gap)
+    assert relerr(one_pass.cpu(), exact) > (20 if K <= 4096 else 5) * relerr(got.cpu(), exact)
+    acc = torch.full((M, N), -1.0, device=DEV)
+    ops.gemm(op, A.to(DEV), B.to(DEV), out=acc, accumulate=True, precision="tf32x3")
+    assert relerr(acc.cpu(), exact - 1.0) < tol
+
+
 def test_tf32_rejects_unaligned():
     A = torch.randn(64, 33, device=DEV)
     with pytest.raises(_lib.GmcError):
