@@ -391,8 +391,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// remote arrive with the DEFAULT (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive(cta_id) does.  The
+// explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR per call; issued once per k-block by the peer
+// producer it cost ~1750 cycles per k-block (ncu source page, profiles/r01_gemm_notes.md) -- the 2-CTA "stall".
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
     asm volatile(
@@ -434,7 +437,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_map(&tmA);
         prefetch_map(&tmB);
-        for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+        // full: ONE arrival (the leader's expect_tx for both CTAs' bytes); the peer's TMA only adds complete_tx
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -466,7 +470,6 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A2_BYTES;
                     const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);          // the LEADER's full barrier
                     if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * STAGE2_BYTES);
-                    else mbar_arrive_cluster(fb);
                     if (A_MN) {
 #pragma unroll
                         for (int j = 0; j < HALF / 32; ++j) tma_load_2d_2sm(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb);
