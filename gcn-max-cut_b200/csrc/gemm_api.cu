@@ -20,8 +20,14 @@ static int gemm_dispatch(int op, const float* A, const float* B, float* C, int64
     cudaStream_t s = as_stream(stream);
     if (precision == GMC_GEMM_FP32)
         return simt_gemm(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-    if (precision == GMC_GEMM_TF32 || precision == GMC_GEMM_TF32X3)
+    if (precision == GMC_GEMM_TF32 || precision == GMC_GEMM_TF32X3) {
+        // Skinny problems (the 3-class layer: a dimension below one 16-byte row) cannot be described to TMA; they take
+        // the exact CUDA-core kernel -- never a lower precision than asked for.  Anything else that TMA cannot address
+        // (unaligned base / leading dimension) is still rejected by the tensor-core path with an error.
+        if (N < 4 || M < 4 || K < 4)
+            return simt_gemm(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
         return tc_gemm(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, precision, workspace, workspace_bytes, s);
+    }
     set_error("gmc_gemm: unknown precision %d", precision);
     return GMC_ERR_INVALID_ARG;
 }
@@ -30,8 +36,10 @@ static int gemm_dispatch(int op, const float* A, const float* B, float* C, int64
 extern "C" {
 
 size_t gmc_gemm_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t precision) {
-    if (precision == GMC_GEMM_FP32) return gmc::simt_workspace_bytes(M, N, K);
-    return gmc::tc_workspace_bytes(op, M, N, K, precision);
+    const size_t simt = gmc::simt_workspace_bytes(M, N, K);
+    if (precision == GMC_GEMM_FP32) return simt;
+    const size_t tc = gmc::tc_workspace_bytes(op, M, N, K, precision);
+    return tc > simt ? tc : simt;            // skinny shapes are routed to the CUDA-core kernel (gemm_dispatch)
 }
 
 int gmc_gemm_nn(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,

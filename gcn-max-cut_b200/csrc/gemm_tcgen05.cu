@@ -163,22 +163,26 @@ struct Params {
     int64_t split_stride;    // elements between split-K partials (0 when k_splits == 1)
     int64_t k_per_split;     // multiple of BLOCK_K
     int m_tiles, n_tiles, k_splits;
-    int mg_tiles;            // m-tile groups of CL (cluster size) tiles: ceil(m_tiles / CL)
+    int mg_tiles;            // m-tile groups of CLM tiles: ceil(m_tiles / CLM)
+    int ng_tiles;            // n-tile groups of CLN tiles: ceil(n_tiles / CLN)
     int accumulate;
     int vec_ok;              // 16-byte aligned C rows
     int tma_store;           // epilogue through shared memory + cp.async.bulk.tensor stores (tmC valid)
 };
 
-// CL = thread-block cluster size (1, 2 or 4).  With CL > 1 the CTAs of a cluster own CL consecutive m-tiles of
-// the SAME n-tile and k-range: each CTA loads its own A tile and 1/CL of the shared B tile, multicast into every
-// CTA's shared memory.  The single-CTA kernel is bound by the L2->SM request rate (48 KB per k-block and SM
-// against the ~42 B/clk/SM LTS limit); sharing B cuts that to 16 + 32/CL KB.  A stage may be refilled only when
-// ALL CTAs of the cluster have consumed it, so the MMA warps multicast their tcgen05.commit to every CTA's
-// empty barrier (arrival count CL).
-template <bool A_MN, bool B_MN, int CL>
+// Thread-block cluster of CLM x CLN CTAs (rank = rm + CLM * rn) that owns CLM consecutive m-tiles x CLN consecutive
+// n-tiles of one k-range.  The A tile of m-tile rm is needed by the CLN CTAs of that row: each loads 1/CLN of it and
+// multicasts it to the row; the B tile of n-tile rn is needed by the CLM CTAs of that column: each loads 1/CLM and
+// multicasts it to the column.  Why: the kernel is bound by L2 (LTS) throughput -- SM reads, DRAM fills and
+// write-backs all count (config 3 nn, single CTA: 97.6 GB of SM reads in 9.7 ms; an L2 prefetch experiment made it
+// slower).  SM reads per output scale with 1/(256 CLN) + 1/(128 CLM).  A stage may be refilled only when every CTA
+// that receives one of this CTA's multicasts has consumed it, and symmetrically, so each MMA warp multicasts its
+// tcgen05.commit to its row and column (arrival count CLM + CLN - 1).
+template <bool A_MN, bool B_MN, int CLM, int CLN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const Params p) {
+    constexpr int CL = CLM * CLN;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
@@ -191,12 +195,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
-    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+    const uint32_t rm = rank % CLM, rn = rank / CLM;
+    // row = the CLN CTAs that share my A tile, column = the CLM CTAs that share my B tile
+    uint32_t row_mask = 0, col_mask = 0;
+#pragma unroll
+    for (int j = 0; j < CLN; ++j) row_mask |= 1u << (rm + CLM * j);
+#pragma unroll
+    for (int i = 0; i < CLM; ++i) col_mask |= 1u << (i + CLM * rn);
+    const uint16_t MASK_A = (uint16_t)row_mask, MASK_B = (uint16_t)col_mask, MASK_ALL = (uint16_t)(row_mask | col_mask);
 
     if (warp == 0 && lane == 0) {
         prefetch_map(&tmA);
         prefetch_map(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, CL); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, CLM + CLN - 1); }
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -209,8 +220,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    // cluster-level work items: (split, m-group, n-tile); every CTA of a cluster walks the same list
-    const int64_t tiles_gn = (int64_t)p.mg_tiles * p.n_tiles;
+    // cluster-level work items: (split, m-group, n-group); every CTA of a cluster walks the same list
+    const int64_t tiles_gn = (int64_t)p.mg_tiles * p.ng_tiles;
     const int64_t n_work = tiles_gn * p.k_splits;
     const int64_t cw0 = blockIdx.x / CL, cw_step = gridDim.x / CL;
 
@@ -221,7 +232,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int64_t w = cw0; w < n_work; w += cw_step) {
                 const int split = (int)(w / tiles_gn);
                 const int64_t rem = w - (int64_t)split * tiles_gn;
-                const int m0 = ((int)(rem / p.n_tiles) * CL + (int)rank) * BLOCK_M, n0 = (int)(rem % p.n_tiles) * BLOCK_N;
+                const int m0 = ((int)(rem / p.ng_tiles) * CLM + (int)rm) * BLOCK_M;
+                const int n0 = ((int)(rem % p.ng_tiles) * CLN + (int)rn) * BLOCK_N;
                 const int64_t kb = (int64_t)split * p.k_per_split;
                 const int64_t ke = min(p.K, kb + p.k_per_split);
                 for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
@@ -229,29 +241,41 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint32_t fb = full_bar + 8 * stage;
                     mbar_expect_tx(fb, STAGE_BYTES);
-                    if (A_MN) {
+                    if (CLN == 1) {
+                        if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb);
-                    } else {
-                        tma_load_2d(sa, &tmA, (int)k0, m0, fb);
+                            for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb);
+                        } else {
+                            tma_load_2d(sa, &tmA, (int)k0, m0, fb);
+                        }
+                    } else if (A_MN) {                             // my share of the 4 row chunks, to my cluster row
+                        constexpr int PER = BLOCK_M / 32 / CLN;
+#pragma unroll
+                        for (int jj = 0; jj < PER; ++jj) {
+                            const int j = (int)rn * PER + jj;
+                            tma_load_2d_mc(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb, MASK_A);
+                        }
+                    } else {                                       // K-major A: my BLOCK_M / CLN rows, to my cluster row
+                        constexpr int ROWS = BLOCK_M / CLN;
+                        tma_load_2d_mc(sa + rn * (ROWS * BLOCK_K * 4), &tmA, (int)k0, m0 + (int)rn * ROWS, fb, MASK_A);
                     }
-                    if (CL == 1) {
+                    if (CLM == 1) {
                         if (B_MN) {
 #pragma unroll
                             for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb);
                         } else {
                             tma_load_2d(sb, &tmB, (int)k0, n0, fb);
                         }
-                    } else if (B_MN) {                             // this CTA's share of the 8 column chunks, to everyone
-                        constexpr int PER = BLOCK_N / 32 / CL;
+                    } else if (B_MN) {                             // my share of the 8 column chunks, to my cluster column
+                        constexpr int PER = BLOCK_N / 32 / CLM;
 #pragma unroll
                         for (int jj = 0; jj < PER; ++jj) {
-                            const int j = (int)rank * PER + jj;
-                            tma_load_2d_mc(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb, MASK);
+                            const int j = (int)rm * PER + jj;
+                            tma_load_2d_mc(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb, MASK_B);
                         }
-                    } else {                                       // K-major B: this CTA's BLOCK_N / CL rows, to everyone
-                        constexpr int ROWS = BLOCK_N / CL;
-                        tma_load_2d_mc(sb + rank * (ROWS * BLOCK_K * 4), &tmB, (int)k0, n0 + (int)rank * ROWS, fb, MASK);
+                    } else {                                       // K-major B: my BLOCK_N / CLM rows, to my cluster column
+                        constexpr int ROWS = BLOCK_N / CLM;
+                        tma_load_2d_mc(sb + rm * (ROWS * BLOCK_K * 4), &tmB, (int)k0, n0 + (int)rm * ROWS, fb, MASK_B);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -290,7 +314,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         first = 0;
                     }
                     // smem stage reusable once these MMAs retire -- in every CTA of the cluster
-                    if (CL == 1) umma_commit(empty_bar + 8 * stage); else umma_commit_mc(empty_bar + 8 * stage, MASK);
+                    if (CL == 1) umma_commit(empty_bar + 8 * stage); else umma_commit_mc(empty_bar + 8 * stage, MASK_ALL);
                     if (k0 + BLOCK_K >= ke) umma_commit(tfull_bar + 8 * acc);
                 }
                 __syncwarp();
@@ -307,8 +331,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int64_t w = cw0; w < n_work; w += cw_step) {
             const int split = (int)(w / tiles_gn);
             const int64_t rem = w - (int64_t)split * tiles_gn;
-            const int64_t m0 = ((rem / p.n_tiles) * CL + rank) * BLOCK_M;
-            const int n0 = (int)(rem % p.n_tiles) * BLOCK_N;
+            const int64_t m0 = ((rem / p.ng_tiles) * CLM + rm) * BLOCK_M;
+            const int n0 = ((int)(rem % p.ng_tiles) * CLN + (int)rn) * BLOCK_N;
             float* Cs = p.C + (int64_t)split * p.split_stride;
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
@@ -626,23 +650,25 @@ static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_
     return GMC_OK;
 }
 
-// cluster size of the multicast kernel: GMC_GEMM_CLUSTER = 1 | 2 | 4 | 8.  Default 4: on B200 33 clusters of 4 are
-// co-resident (132 of 148 SMs) yet config 3 runs 8.3 / 7.9 ms (nn / tn) against 8.8 / 9.3 ms with pairs and
-// 10.7 / 10.1 ms without multicast (profiles/r01_gemm_notes.md)
-static int cluster_size() {
-    static int cached = -1;
-    if (cached < 0) {
+// cluster shape of the multicast kernel: GMC_GEMM_CLUSTER = "1" | "2" | "4" | "8" (CLM x 1) | "2x2" | "4x2" (CLM x CLN).
+// Default: 2x2 for tn (both operands streamed from HBM) when the problem has at least two n-tiles, else 4x1 --
+// the best shapes measured at config 3 (profiles/r01_gemm_notes.md: nn 7.5 ms with 4x1, tn 7.0 ms with 2x2).
+static void cluster_shape(bool a_mn, int64_t n_tiles, int* clm, int* cln) {
+    static int cm = -1, cn = -1;
+    if (cm < 0) {
         const char* e = getenv("GMC_GEMM_CLUSTER");
-        cached = 4;
-        if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8')) cached = e[0] - '0';
+        cm = 0; cn = 0;                                            // 0 = automatic
+        if (e && e[0] >= '1' && e[0] <= '8') {
+            cm = e[0] - '0';
+            cn = (e[1] == 'x' && e[2] == '2') ? 2 : 1;
+            const bool ok = (cn == 1 && (cm == 1 || cm == 2 || cm == 4 || cm == 8)) || (cn == 2 && (cm == 2 || cm == 4));
+            if (!ok) { cm = 0; cn = 0; }
+        }
     }
-    return cached;
-}
-
-static bool no_tma_store() {
-    static int cached = -1;
-    if (cached < 0) { const char* e = getenv("GMC_GEMM_NO_TMA_STORE"); cached = (e && e[0] == '1') ? 1 : 0; }
-    return cached == 1;
+    if (cm > 0) { *clm = cm; *cln = cn; return; }
+    if (a_mn && n_tiles >= 2) { *clm = 2; *cln = 2; return; }
+    *clm = 4;
+    *cln = 1;
 }
 
 static int pick_splits_cl(int64_t cluster_tiles, int64_t K, int slots) {
@@ -653,16 +679,19 @@ static int pick_splits_cl(int64_t cluster_tiles, int64_t K, int slots) {
     return (int)(s < 1 ? 1 : s);
 }
 
+static bool no_tma_store() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("GMC_GEMM_NO_TMA_STORE"); cached = (e && e[0] == '1') ? 1 : 0; }
+    return cached == 1;
+}
+
 // co-resident clusters of the kernel on this device: the GPC geometry may admit fewer than SMs / CL
-template <bool A_MN, bool B_MN, int CL>
-static int cluster_slots(cudaLaunchConfig_t* cfg) {
+template <bool A_MN, bool B_MN, int CLM, int CLN>
+static int cluster_slots() {
+    constexpr int CL = CLM * CLN;
     static int cached = -1;
     if (cached < 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-            attr_set = true;
-        }
+        cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, CLM, CLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         cached = sm_count() / CL;
         if (CL > 1) {
             cudaLaunchConfig_t probe = {};
@@ -675,34 +704,28 @@ static int cluster_slots(cudaLaunchConfig_t* cfg) {
             probe.attrs = attr;
             probe.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<A_MN, B_MN, CL>, &probe) == cudaSuccess && n > 0) {
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<A_MN, B_MN, CLM, CLN>, &probe) == cudaSuccess && n > 0) {
                 if (n < cached) cached = n;
             } else {
                 cudaGetLastError();
             }
         }
-        if (getenv("GMC_GEMM_DEBUG")) fprintf(stderr, "gmc gemm: cluster size %d -> %d co-resident clusters\n", CL, cached);
+        if (getenv("GMC_GEMM_DEBUG")) fprintf(stderr, "gmc gemm: cluster %dx%d -> %d co-resident clusters\n", CLM, CLN, cached);
     }
-    (void)cfg;
     return cached;
 }
 
-template <bool A_MN, bool B_MN, int CL>
+template <bool A_MN, bool B_MN, int CLM, int CLN>
 static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GMC_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)SMEM_BYTES));
-        attr_set = true;
-    }
+    constexpr int CL = CLM * CLN;
     CUtensorMap tmA, tmB;
     int rc;
     if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BLOCK_K, true);       // A[K rows, M cols]
-    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M, false);  // A[M rows, K cols]
+    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M / CLN, false);  // A[M rows, K cols]
     if (rc) return rc;
     if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BLOCK_K, true);       // B[K rows, N cols]
-    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, BLOCK_N / CL, false);  // B[N rows, K cols]
+    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, BLOCK_N / CLM, false);  // B[N rows, K cols]
     if (rc) return rc;
 
     cudaLaunchConfig_t cfg = {};
@@ -714,14 +737,15 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const int slots = cluster_slots<A_MN, B_MN, CL>(&cfg);        // co-resident clusters (GPC geometry), <= SMs / CL
+    const int slots = cluster_slots<A_MN, B_MN, CLM, CLN>();      // co-resident clusters (GPC geometry), <= SMs / CL
 
-    Params p;
+    Params p = {};
     p.M = M; p.N = N; p.K = K;
     p.m_tiles = (int)ceil_div<int64_t>(M, BLOCK_M);
     p.n_tiles = (int)ceil_div<int64_t>(N, BLOCK_N);
-    p.mg_tiles = ceil_div(p.m_tiles, CL);
-    const int64_t ctiles = (int64_t)p.mg_tiles * p.n_tiles;
+    p.mg_tiles = ceil_div(p.m_tiles, CLM);
+    p.ng_tiles = ceil_div(p.n_tiles, CLN);
+    const int64_t ctiles = (int64_t)p.mg_tiles * p.ng_tiles;
     int splits = pick_splits_cl(ctiles, K, slots);
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
@@ -750,7 +774,7 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
     const int64_t n_work = ctiles * splits;
     const int grid = (int)(n_work < slots ? n_work : slots) * CL;
     cfg.gridDim = dim3(grid);
-    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN, CL>, tmA, tmB, tmC, p));
+    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN, CLM, CLN>, tmA, tmB, tmC, p));
     if (splits > 1) {
         const int64_t MN = M * N;
         tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
@@ -762,12 +786,14 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
 template <bool A_MN, bool B_MN>
 static int launch_cl(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
-    switch (cluster_size()) {
-        case 1: return launch<A_MN, B_MN, 1>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-        case 8: return launch<A_MN, B_MN, 8>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-        case 2: return launch<A_MN, B_MN, 2>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-        default: return launch<A_MN, B_MN, 4>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-    }
+    int clm, cln;
+    cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln);
+#define GMC_GEMM_CASE(CM, CN)                                                                                       \
+    if (clm == CM && cln == CN)                                                                                     \
+        return launch<A_MN, B_MN, CM, CN>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    GMC_GEMM_CASE(1, 1) GMC_GEMM_CASE(2, 1) GMC_GEMM_CASE(4, 1) GMC_GEMM_CASE(8, 1) GMC_GEMM_CASE(2, 2) GMC_GEMM_CASE(4, 2)
+#undef GMC_GEMM_CASE
+    return launch<A_MN, B_MN, 4, 1>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
 }
 
 static bool use_two_cta() {
@@ -876,15 +902,17 @@ static int make_lo(const float* X, int64_t ldx, float* L, int64_t rows, int64_t 
 
 }  // namespace tc
 
-static size_t tc_splitk_bytes(int64_t M, int64_t N, int64_t K) {
+static size_t tc_splitk_bytes(int op, int64_t M, int64_t N, int64_t K) {
     int splits;
     if (tc::use_two_cta()) {
         const int64_t tiles = ceil_div<int64_t>(M, 256) * ceil_div<int64_t>(N, 256);
         splits = tc::pick_splits2(tiles, K);
     } else {
-        const int cl = tc::cluster_size();
-        const int64_t ctiles = ceil_div<int64_t>(ceil_div<int64_t>(M, tc::BLOCK_M), cl) * ceil_div<int64_t>(N, tc::BLOCK_N);
-        splits = tc::pick_splits_cl(ctiles, K, sm_count() / cl);      // upper bound of what launch() picks
+        int clm, cln;
+        tc::cluster_shape(op == 2, ceil_div<int64_t>(N, tc::BLOCK_N), &clm, &cln);
+        const int64_t ctiles = ceil_div<int64_t>(ceil_div<int64_t>(M, tc::BLOCK_M), clm) *
+                               ceil_div<int64_t>(ceil_div<int64_t>(N, tc::BLOCK_N), cln);
+        splits = tc::pick_splits_cl(ctiles, K, sm_count() / (clm * cln));   // upper bound of what launch() picks
     }
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
 }
@@ -896,7 +924,7 @@ static void operand_shapes(int op, int64_t M, int64_t N, int64_t K, int64_t* ra,
 }
 
 size_t tc_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int precision) {
-    size_t need = (tc_splitk_bytes(M, N, K) + 255) & ~(size_t)255;
+    size_t need = (tc_splitk_bytes(op, M, N, K) + 255) & ~(size_t)255;
     if (precision == GMC_GEMM_TF32X3) {
         int64_t ra, ca, rb, cb;
         operand_shapes(op, M, N, K, &ra, &ca, &rb, &cb);
@@ -952,7 +980,7 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
     int64_t ra, ca, rb, cb;
     operand_shapes(op, M, N, K, &ra, &ca, &rb, &cb);
     GMC_REQUIRE(ca % 4 == 0 && cb % 4 == 0, "gmc_gemm(tf32x3): operand row lengths must be multiples of 4 floats");
-    const size_t split_bytes = (tc_splitk_bytes(M, N, K) + 255) & ~(size_t)255;
+    const size_t split_bytes = (tc_splitk_bytes(op, M, N, K) + 255) & ~(size_t)255;
     const size_t a_bytes = ((size_t)ra * tc::lo_ld(ca) * sizeof(float) + 255) & ~(size_t)255;
     const size_t b_bytes = ((size_t)rb * tc::lo_ld(cb) * sizeof(float) + 255) & ~(size_t)255;
     GMC_REQUIRE(workspace && workspace_bytes >= split_bytes + a_bytes + b_bytes,

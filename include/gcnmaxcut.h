@@ -40,6 +40,8 @@ extern "C" {
 #define GMC_GEMM_FP32 0      /* CUDA-core FFMA, exact fp32 (parity path)                       */
 #define GMC_GEMM_TF32 1      /* tcgen05 kind::tf32, one pass, fp32 accumulate in TMEM          */
 #define GMC_GEMM_TF32X3 2    /* tcgen05, 3 split passes (hi*hi + hi*lo + lo*hi): fp32-grade    */
+/* With either tensor-core precision, problems with a dimension < 4 (the 3-class layer) run on the exact
+ * CUDA-core kernel; other operands TMA cannot address (unaligned base / ld % 4 != 0) return an error. */
 
 /* loss modes */
 #define GMC_LOSS_STE 0       /* hard one-hot + straight-through (reference live path)          */
