@@ -54,10 +54,11 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "tf32"),
                     choices=["fp32", "tf32", "tf32x3"])
-    ap.add_argument("--workload", default="config3", choices=["config3", "config5", "config2"],
+    ap.add_argument("--workload", default="config3", choices=["config3", "config5", "config2", "config1"],
                     help="config3 (default, the headline): 4096 graphs n=1000 per GPU; config5: one 7-regular graph "
                          "n=1M, F=256, H=128, learned embeddings (SpMM/GEMM roofline stress); config2: inference + "
-                         "200-iteration post-processing on test graphs n=50..500")
+                         "200-iteration post-processing on test graphs n=50..500; config1: the reference pipeline itself "
+                         "(20 graphs n=500, one Adam step per graph) through train_single_epoch")
     ap.add_argument("--feature-source", default="adjacency", choices=["adjacency", "embedding"],
                     help="adjacency: dense zero-padded adjacency rows (the reference's live path); embedding: learned "
                          "dense node embeddings X~N(0,1) with dL/dX and their own Adam update (north-star mode)")
@@ -454,6 +455,81 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- config 1
+def run_config1(args):
+    """BASELINE.json configs[0]: the reference pipeline -- 20 random regular graphs n=500 (d in 6..8), 3 terminals,
+    extended to n_nodes=1000, dim_embedding=1000, hidden_dim=500, Adam lr=1e-3, ONE optimiser step per graph in dict
+    order (reference semantics), through the drop-in API (process_graphs_from_folder -> train_single_epoch).
+    One step = one epoch = 20 sequential per-graph steps, replayed from captured CUDA graphs."""
+    import contextlib
+    import random
+
+    import torch
+
+    from DataGenerator import GraphCreator as C, graphExtender as E
+    from Training import TrainingNeural as T
+    from gmc_b200 import _lib
+
+    _lib.require_cuda()
+    random.seed(0)
+    n_graphs = 20
+    graphs = {i: C.generate_graph(n=500, d=random.randint(6, 8), graph_type="reg", random_seed=1000 + i)
+              for i in range(n_graphs)}
+    terms = {i: C.generate_unique_terminals(500, 3) for i in range(n_graphs)}
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds = E.process_graphs_from_folder(graphs, terms, max_nodes=1000)
+    t_extend = time.perf_counter() - t0
+    precision = "fp32" if args.precision == "fp32" else args.precision
+    cfg = T.TrainingConfig(n_nodes=1000, dim_embedding=1000, hidden_dim=500, learning_rate=1e-3, gemm_precision=precision)
+    torch.manual_seed(args.seed)
+    net, embed, opt = T.setup_model_and_optimizer(cfg)
+    for _ in range(max(3, args.warmup)):
+        T.train_single_epoch(ds, net, opt, embed, cfg)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = T.train_single_epoch(ds, net, opt, embed, cfg)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sampler.stop()
+    eng = T._engine_for(net, opt, cfg)
+
+    from oracle import ref_step as rs
+    port = rs.FaithfulPort(1000, 500, 3, lr=1e-3, seed=args.seed, pad=1000)
+    items = [(rs.csr_from_networkx(ds[k][2]), ds[k][1]) for k in list(ds.keys())[:8]]
+    for csr, X in items[:2]:
+        port.step(csr, X, X)
+    t0 = time.perf_counter()
+    for csr, X in items:
+        port.step(csr, X, X)
+    dt_cpu = time.perf_counter() - t0
+    line = {
+        "metric": "GCN train graph-epochs/s, reference pipeline (n=500, one Adam step per graph)",
+        "value": n_graphs * steps / dt, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
+        "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if precision == "fp32" else precision, "data": "synthetic",
+        "config": {"workload": "config 1: 20 random regular graphs n=500 (d in 6..8), 3 terminals, extended to 1000 "
+                               "features, hidden 500, 3 classes, Adam lr=1e-3, sequential per-graph steps",
+                   "api": "DataGenerator.graphExtender.process_graphs_from_folder -> Training.TrainingNeural.train_single_epoch",
+                   "cuda_graph_replays": eng.graph_replays, "graph_extender_s": t_extend},
+        "ms_per_graph_step": 1000.0 * dt / (steps * n_graphs),
+        "roofline": None,
+        "cpu_baseline": {"value": len(items) / dt_cpu, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{len(items)} of the 20 graphs, one sequential Adam step each, "
+                                   f"oracle/ref_step.FaithfulPort, {dt_cpu:.1f}s"},
+        "e2e": {"value": n_graphs * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                "note": "the dataset is uploaded once by the first epoch, as the reference keeps it in host memory"},
+        "gpu_launches": eng.launch_count,
+        "clocks": sampler.summary(),
+        "loss_last_epoch": loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------- config 2
 def run_config2(args):
     """BASELINE.json configs[1]: inference + 200-iteration post-processing on test graphs n=50/100/200/300/500
@@ -572,6 +648,8 @@ def main():
             run_reference_arm(args)
         elif args.workload == "config2":
             run_config2(args)
+        elif args.workload == "config1":
+            run_config1(args)
         else:
             run_b200_arm(args)
     sys.stdout.flush()

@@ -114,6 +114,11 @@ class GCNEngine:
         self.loss = None
         self.timer: Optional[OpTimer] = None
         self.launch_count = 0          # gmc_* kernels launched (bench.py's gpu_launches claim)
+        # CUDA-graph replay of whole training steps (train_step_graphed): one captured graph per (batch, features)
+        self._graphs: Dict[tuple, dict] = {}
+        self._step_dev: Optional[torch.Tensor] = None      # device-side Adam step counter shared by all graphs
+        self._step_dev_value = 0                           # what that counter holds, mirrored on the host
+        self.graph_replays = 0
 
     def _op(self, name: str, launches: int, fn, *args, **kwargs):
         self.launch_count += launches
@@ -227,6 +232,74 @@ class GCNEngine:
         if feature_param is not None:
             # per-graph / per-node embeddings never leave the rank: no all-reduce, their own Adam launch
             self._op("adam_features", 1, self.optimizer.fused_step, [feature_param], [feature_grad])
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _adam_state(self):
+        opt = self.optimizer
+        params = list(self.params())
+        group = None
+        for g in opt.param_groups:
+            if any(p is q for q in g["params"] for p in params[:1]):
+                group = g
+        if group is None:
+            raise RuntimeError("the model parameters are not registered with the optimiser")
+        states = [opt._state_for(p) for p in params]
+        return params, group, states
+
+    def _train_step_capturable(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        """train_step with nothing host-dependent baked in: Adam reads its step count from device memory."""
+        loss = self.loss_and_grads(batch, X)
+        params, group, states = self._adam_state()
+        b1, b2 = group["betas"]
+        ops.adam_multi([p.data for p in params], self.grads(), [s["exp_avg"] for s in states],
+                       [s["exp_avg_sq"] for s in states], lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
+                       step_dev=self._step_dev)
+        self.launch_count += 1
+        return loss
+
+    def train_step_graphed(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        """train_step replayed from a captured CUDA graph.  The reference trains one small graph per optimiser step
+        (TrainingNeural.py:371-388): ~15 kernels of a few microseconds each, so the loop is launch-bound; every
+        (batch, features) pair of a dataset is visited once per epoch, which makes it a natural unit to capture.
+        First visit: eager step (sizes buffers, primes the kernels' one-time attribute calls).  Second visit: capture
+        + replay.  Later visits: one cudaGraphLaunch.  Bit-identical to train_step (same kernels, same order);
+        falls back to the eager step under data parallelism or while a timer is attached."""
+        import torch.distributed as dist
+        if self.timer is not None or self.pg is not None or (dist.is_available() and dist.is_initialized()
+                                                             and dist.get_world_size() > 1):
+            return self.train_step(batch, X)
+        params, group, states = self._adam_state()
+        key = (id(batch), X.data_ptr(), tuple(X.shape), group["lr"], tuple(group["betas"]), group["eps"])
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 4096:
+                self._graphs.clear()
+            self._graphs[key] = {"batch": batch, "X": X, "graph": None, "loss": None}   # keeps both alive
+            return self.train_step(batch, X)
+        if entry["graph"] is None:
+            steps = {int(s["step"].item()) for s in states}
+            if len(steps) != 1:
+                return self.train_step(batch, X)             # parameters with different histories: stay eager
+            if self._step_dev is None:
+                self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+                self._step_dev_value = 0
+            launches = self.launch_count
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                entry["loss"] = self._train_step_capturable(batch, X)
+            entry["graph"], entry["launches"] = graph, self.launch_count - launches
+            self.launch_count = launches
+        # eager steps (first visits of other items) advance only the host counters: resynchronise the device one
+        host_step = int(states[0]["step"].item())
+        if host_step != self._step_dev_value:
+            self._step_dev.fill_(host_step)
+        entry["graph"].replay()
+        self._step_dev_value = host_step + 1
+        self.graph_replays += 1
+        self.launch_count += entry["launches"]
+        for st in states:
+            st["step"] += 1
+        return entry["loss"]
 
     def train_step(self, batch: GraphBatch, X: torch.Tensor, feature_param: Optional[torch.Tensor] = None,
                    feature_grad: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -42,6 +42,12 @@ from gmc_b200.graph import CSRGraph, GraphBatch
 from gmc_b200.model import GCNSoftmax, to_device_features
 from gmc_b200.optim import FusedAdam
 
+import os as _os
+
+# per-graph optimiser steps are replayed from captured CUDA graphs (GCNEngine.train_step_graphed); GMC_CUDA_GRAPHS=0
+# keeps the eager launch sequence
+_USE_CUDA_GRAPHS = _os.environ.get("GMC_CUDA_GRAPHS", "1") != "0"
+
 TORCH_DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 TORCH_DTYPE = torch.float32
 
@@ -297,6 +303,8 @@ def train_single_epoch(dataset: Dict, net, optimizer, embed, config: TrainingCon
         for step in _prepare(current, int(getattr(config, "batch_graphs", 1)), device):
             if embedding_mode:
                 losses = _embedding_step(engine, step, embed)
+            elif _USE_CUDA_GRAPHS:
+                losses = engine.train_step_graphed(step.batch, step.X)   # launch-bound per-graph steps: graph replay
             else:
                 losses = engine.train_step(step.batch, step.X)
             total += losses.sum()
