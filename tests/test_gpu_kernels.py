@@ -297,6 +297,60 @@ def test_cut_loss_two_class_and_eight_class():
         ops.cut_loss(batch, torch.randn(30, 2, device=DEV), override_terminals=True)
 
 
+def test_ragged_tiny_graphs_and_empty_calls():
+    """Edge cases the reference exercises implicitly: the smallest graphs that can carry three terminals (a triangle,
+    K4) next to full-size ones in ONE batch, and empty inputs straight through the C ABI (every entry point must
+    return GMC_OK without launching)."""
+    import ctypes
+    tri = nx.complete_graph(3)
+    k4 = nx.complete_graph(4)
+    big = nx.random_regular_graph(d=7, n=1000, seed=3)
+    mid = nx.random_regular_graph(d=6, n=129, seed=4)
+    graphs = [tri, big, k4, mid]
+    for g in graphs:
+        nx.set_edge_attributes(g, 1, "weight")
+    csrs = [rs.csr_from_networkx(g) for g in graphs]
+    batch = GraphBatch([CSRGraph.from_networkx(g) for g in graphs])
+    gp = batch.graph_ptr_host
+    torch.manual_seed(0)
+    X = torch.randn(batch.num_nodes, 64, device=DEV)
+    want = torch.cat([ahat_dense(c) @ X[s:e].cpu().double() for c, (s, e) in zip(csrs, zip(gp[:-1], gp[1:]))])
+    assert relerr(ops.spmm(batch, X).cpu(), want) < 2e-6
+    batch.build_plan()                                         # graphs below 128 nodes ride along in the slab kernel
+    assert relerr(ops.spmm(batch, X).cpu(), want) < 2e-6
+    Z = torch.randn(batch.num_nodes, 3) * 2
+    loss, P, dZ = ops.cut_loss(batch, Z.to(DEV), mode="ste", override_terminals=True)
+    labels = ops.argmax_labels(batch, P, force_terminals=True)
+    cuts = ops.cut_value(batch, labels).cpu()
+    for i, csr in enumerate(csrs):
+        Pi = torch.softmax(Z[gp[i]: gp[i + 1]].double(), dim=1)
+        w = rs.ste_loss_and_grads(csr, Pi, override_terminals=True)
+        assert abs(loss[i].item() - float(w["loss"])) < 1e-6 and int(cuts[i]) == int(round(-float(w["loss"])))
+        assert np.abs(dZ[gp[i]: gp[i + 1]].cpu().numpy() - w["dZ"].numpy()).max() < 2e-5
+    assert int(cuts[0]) == 3 and int(cuts[2]) >= 5               # triangle: all three edges cut; K4: 3 terminals apart
+    g_labels, g_cut, _ = ops.greedy_node_move(batch, labels, 3, 200, 3)
+    for i, csr in enumerate(csrs):
+        wl, wc = pp.greedy_node_move(csr.rowptr, csr.colidx, labels[gp[i]: gp[i + 1]].cpu().numpy(), 3, 200, 3)[:2]
+        assert int(g_cut[i]) == int(wc) and (g_labels[gp[i]: gp[i + 1]].cpu().numpy() == wl).all()
+
+    # ---- empty inputs through the raw ABI
+    L = _lib.lib()
+    z = ctypes.c_void_p(0)
+    one = torch.zeros(8, device=DEV)
+    i32 = torch.zeros(8, dtype=torch.int32, device=DEV)
+    i64 = torch.zeros(8, dtype=torch.int64, device=DEV)
+    f64 = torch.zeros(8, dtype=torch.float64, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert L.gmc_spmm_symnorm_f32(p(i32), p(i32), z, z, z, p(one), p(one[4:]), 0, 4, 4, 4, z, 0, z) == 0
+    assert L.gmc_gemm_nn(p(one), p(one), p(one), 0, 4, 4, 4, 4, 4, 0, 1, z, 0, z) == 0
+    assert L.gmc_gemm_nn(p(one), p(one), p(one), 0, 4, 4, 4, 4, 4, 0, 0, z, 0, z) == 0
+    assert L.gmc_cut_value_i32(p(i32), p(i32), p(i32), z, p(i32), 0, 0, p(i64), z) == 0
+    assert L.gmc_argmax_labels(p(one), 3, p(i32), 0, 0, 3, 1, p(i32), z) == 0
+    assert L.gmc_softmax_cut_loss_fwd_bwd(p(one), 3, p(i32), p(i32), z, p(i32), 0, 0, 3, 0, 1, ctypes.c_float(0.0),
+                                          ctypes.c_float(1.0), p(one), p(f64), p(one), z) == 0
+    torch.cuda.synchronize()
+
+
 def test_softmax_fwd_bwd():
     torch.manual_seed(0)
     Z = (torch.randn(1000, 3) * 5).requires_grad_()
