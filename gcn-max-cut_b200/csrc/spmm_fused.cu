@@ -14,7 +14,8 @@ namespace gmc {
 // the whole grid works on ONE contiguous window of gridDim x 8 rows (~5 graphs at config 3 = 10 MB of source rows,
 // L2-resident).  The earlier blocked schedule (8 consecutive rows per warp, one CTA per 64 rows) kept ~47 graphs of
 // rows in flight, overflowed L2 and re-read 40 % of the source rows from DRAM (5.64 MB/graph against 4.04 algorithmic).
-constexpr int kFusedCtasPerSm = 4;
+template <int NV, int NOUT>
+static int fused_ctas_per_sm(size_t smem);
 
 template <int NV, int NOUT>
 __global__ void __launch_bounds__(256)
@@ -113,6 +114,21 @@ spmm_fused_skinny_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     }
 }
 
+// resident CTAs per SM of one instantiation (registers and the W^T staging decide): queried once
+template <int NV, int NOUT>
+static int fused_ctas_per_sm(size_t smem) {
+    static int cached = 0;
+    if (cached == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_fused_skinny_kernel<NV, NOUT>, 256, smem) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            n = 4;
+        }
+        cached = n;
+    }
+    return cached;
+}
+
 }  // namespace gmc
 
 extern "C" int gmc_spmm_fused_skinny_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
@@ -138,18 +154,21 @@ extern "C" int gmc_spmm_fused_skinny_f32(const int32_t* rowptr, const int32_t* c
     const int c4 = n_cols / 4;
     const int warps = 8;
     const int64_t blocks = ceil_div<int64_t>(n_rows, warps);
-    const int64_t resident = (int64_t)sm_count() * kFusedCtasPerSm;
-    const unsigned grid = (unsigned)(blocks < resident ? blocks : resident);
     const size_t smem = (size_t)n_cols * n_out * sizeof(float);
     const float4* X4 = reinterpret_cast<const float4*>(X);
     float4* Y4 = reinterpret_cast<float4*>(Y);
     const float4* b4 = reinterpret_cast<const float4*>(bias);
 #define GMC_LAUNCH(NV, K)                                                                                           \
-    spmm_fused_skinny_kernel<NV, K><<<grid, warps * 32, smem, s>>>(rowptr, colidx, vals, norm_src, norm_dst, X4, Y4, \
-                                                                   n_rows, c4, ldx / 4, ldy / 4, b4, relu, W, T, ldt)
+    {                                                                                                               \
+        const int64_t resident = (int64_t)sm_count() * fused_ctas_per_sm<NV, K>(smem);                              \
+        const unsigned grid = (unsigned)(blocks < resident ? blocks : resident);                                    \
+        spmm_fused_skinny_kernel<NV, K><<<grid, warps * 32, smem, s>>>(rowptr, colidx, vals, norm_src, norm_dst,    \
+                                                                       X4, Y4, n_rows, c4, ldx / 4, ldy / 4, b4,   \
+                                                                       relu, W, T, ldt);                            \
+    }
 #define GMC_NV(K)                                      \
-    if (c4 <= 32) GMC_LAUNCH(1, K);                    \
-    else if (c4 <= 64) GMC_LAUNCH(2, K);               \
+    if (c4 <= 32) GMC_LAUNCH(1, K)                     \
+    else if (c4 <= 64) GMC_LAUNCH(2, K)                \
     else GMC_LAUNCH(4, K)
     switch (n_out) {
         case 1: GMC_NV(1); break;
