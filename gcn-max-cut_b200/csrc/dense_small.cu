@@ -79,11 +79,7 @@ skinny_bwd_kernel(const float* __restrict__ dT, int64_t lddt, const float* __res
                 dw[i][k] = 0.f;
             }
         }
-        for (int64_t v = r0; v < r1; ++v) {
-            float t[NOUT];
-#pragma unroll
-            for (int k = 0; k < NOUT; ++k) t[k] = __ldg(dT + v * lddt + k);
-            const float4 h4 = __ldg(reinterpret_cast<const float4*>(H + v * ldh + j0));
+        auto row = [&](const float (&t)[NOUT], const float4 h4, int64_t v) {
             const float h[4] = {h4.x, h4.y, h4.z, h4.w};
             float o[4];
 #pragma unroll
@@ -95,6 +91,23 @@ skinny_bwd_kernel(const float* __restrict__ dT, int64_t lddt, const float* __res
                 db[i] += o[i];
             }
             *reinterpret_cast<float4*>(dH + v * lddh + j0) = make_float4(o[0], o[1], o[2], o[3]);
+        };
+        // two rows per iteration, both loads issued before the first use (more bytes in flight per thread)
+        int64_t v = r0;
+        for (; v + 2 <= r1; v += 2) {
+            float t0[NOUT], t1[NOUT];
+            const float4 ha = __ldg(reinterpret_cast<const float4*>(H + v * ldh + j0));
+            const float4 hb = __ldg(reinterpret_cast<const float4*>(H + (v + 1) * ldh + j0));
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) { t0[k] = __ldg(dT + v * lddt + k); t1[k] = __ldg(dT + (v + 1) * lddt + k); }
+            row(t0, ha, v);
+            row(t1, hb, v + 1);
+        }
+        for (; v < r1; ++v) {
+            float t[NOUT];
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) t[k] = __ldg(dT + v * lddt + k);
+            row(t, __ldg(reinterpret_cast<const float4*>(H + v * ldh + j0)), v);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
