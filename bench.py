@@ -59,9 +59,11 @@ def parse_args():
                          "n=1M, F=256, H=128, learned embeddings (SpMM/GEMM roofline stress); config2: inference + "
                          "200-iteration post-processing on test graphs n=50..500; config1: the reference pipeline itself "
                          "(20 graphs n=500, one Adam step per graph) through train_single_epoch")
-    ap.add_argument("--feature-source", default="adjacency", choices=["adjacency", "embedding"],
-                    help="adjacency: dense zero-padded adjacency rows (the reference's live path); embedding: learned "
-                         "dense node embeddings X~N(0,1) with dL/dX and their own Adam update (north-star mode)")
+    ap.add_argument("--feature-source", default="adjacency", choices=["adjacency", "adjacency-sparse", "embedding"],
+                    help="adjacency: dense zero-padded adjacency rows (the reference's live path) through the tensor-core "
+                         "GEMMs; adjacency-sparse: the same features, but X W1 / X^T dT1 computed as aggregations over "
+                         "the graph (csrc/spmm_adj.cu), X never formed; embedding: learned dense node embeddings "
+                         "X~N(0,1) with dL/dX and their own Adam update (north-star mode)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="time budget of the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=8, help="graphs per reference-arm step")
@@ -227,6 +229,7 @@ def run_b200_arm(args):
     batch = GraphBatch.from_arrays(rowptr, colidx, graph_ptr, device=dev)
     N, nnz = batch.num_nodes, batch.nnz
     embedding = args.feature_source == "embedding"
+    sparse_adj = args.feature_source == "adjacency-sparse"
     torch.manual_seed(args.seed)                        # identical initial weights on every rank
     cfg = T.TrainingConfig(n_nodes=n, dim_embedding=F, hidden_dim=H, number_classes=K, learning_rate=1e-3,
                            gemm_precision=args.precision, batch_graphs=B)
@@ -245,9 +248,14 @@ def run_b200_arm(args):
         x_grad = torch.zeros_like(x_param.data)
         X = x_param.data[:, :F]
         opt = FusedAdam(list(net.parameters()) + [x_param], lr=1e-3)
+    elif sparse_adj:
+        X = None                                         # the features are implied by the graph; no dense X anywhere
+        if not ops.adjacency_kernels_apply(batch, F):
+            raise SystemExit("--feature-source adjacency-sparse needs a batch with an ELL plan (regular graphs, "
+                             ">= 32 graphs, n <= 1024 <= features + 24)")
     else:
         X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
-    eng = GCNEngine(net, opt, precision=args.precision)
+    eng = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=sparse_adj)
 
     def train_step(b):
         return eng.train_step(b, X, feature_param=x_param, feature_grad=x_grad)
@@ -320,7 +328,7 @@ def run_b200_arm(args):
             b2.coef = ops.edge_coef(d_rowptr, d_colidx, None, b2.norm, b2.norm, N)
             b2.plan = (ops.spmm_plan(d_rowptr, d_colidx, b2.norm, b2.norm, d_gptr, B, N)
                        if batch.plan is not None else None)   # slab-SpMM plan: a function of the graph, rebuilt per step
-            if not embedding:
+            if not embedding and not sparse_adj:
                 ops.densify(b2, F, out=X)                            # device-side graphExtender
             per_graph = train_step(b2)
             consumed[slot].record()
@@ -351,6 +359,30 @@ def run_b200_arm(args):
                        + " -> GCNEngine.train_step -> per-graph loss D2H"}
         del host_loss
 
+    # ---- the same workload with layer 1 in aggregation form (reported beside the headline, never instead of it) ----
+    alt = None
+    if not embedding and not sparse_adj and ops.adjacency_kernels_apply(batch, F):
+        eng_s = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=True)
+        for _ in range(3):
+            eng_s.train_step(batch, None)
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_alt = min(args.steps, 10)
+        a0.record()
+        for _ in range(k_alt):
+            eng_s.train_step(batch, None)
+        a1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        gdist.all_reduce_max_(t)
+        alt = {"adjacency_sparse": {"value": total_graphs * k_alt / (float(t.item()) / 1000.0), "unit": UNIT,
+                                    "ms_per_step": float(t.item()) / k_alt, "steps": k_alt, "dtype": "f32",
+                                    "what": "identical model and inputs; X W1 and X^T dT1 computed as aggregations over "
+                                            "the graph (csrc/spmm_adj.cu) instead of dense tensor-core GEMMs -- valid "
+                                            "because the features are the zero-padded adjacency rows; "
+                                            "bench.py --feature-source adjacency-sparse gives the full line"}}
+        del eng_s
+
     # ---- rooflines ----------------------------------------------------------------------------
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0 if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"] / 2.0
     # compulsory form while one graph's source rows stay L2-resident (n*C*4 <= 32 MiB), else gather form
@@ -369,6 +401,8 @@ def run_b200_arm(args):
         "cut_loss": ("hbm", 12.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)), "colsum_db2": ("hbm", 4.0 * N * K),
         "adam": ("hbm", 28.0 * (F * H + H + H * K + K)),
         "gemm_nt_dx": ("tensor", gemm_flops), "adam_features": ("hbm", 28.0 * N * ldx),
+        # aggregation form of layer 1: write T1 / read dT1 once + the 16-byte neighbour-id row per node
+        "adj_fwd_xw1": ("hbm", 4.0 * N * H + 16.0 * N), "adj_bwd_dw1": ("hbm", 4.0 * N * H + 16.0 * N),
     }
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -421,7 +455,7 @@ def run_b200_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if (args.precision == "fp32" or sparse_adj) else args.precision, "data": "synthetic",
             "config": {
                 "workload": (f"config 5: one synthetic {args.degree}-regular graph n={n}, F={F}, H={H}, K={K}"
                              if args.workload == "config5" else
@@ -431,12 +465,16 @@ def run_b200_arm(args):
                 "features": (f"learned node embeddings [{N},{F}] fp32 (parameter + gradient + Adam moments "
                              f"{4 * N * ldx * 4 / 1e9:.1f} GB/GPU), dL/dX = dT1 W1^T, own fused Adam update"
                              if embedding else
+                             f"zero-padded adjacency rows [{N},{F}] (implied by the graph, never formed): X W1 and "
+                             "X^T dT1 run as aggregations over the ELL plan (spmm_adj.cu), no tensor-core work"
+                             if sparse_adj else
                              f"dense zero-padded adjacency rows [{N},{F}] fp32 resident in HBM ({N * F * 4 / 1e9:.1f} GB/GPU)"),
                 "spmm_bytes_form": "compulsory" if n * H * 4 <= 32 * 2 ** 20 else "gather",
                 "model": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
                 "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",
                 "gemm_precision": args.precision, "parallelism": f"dp{world}",
-                "l2": f"inputs larger than L2 (X {N * F * 4 / 1e9:.1f} GB, activations {2 * N * H * 4 / 1e9:.1f} GB)",
+                "l2": (f"inputs larger than L2 (activations {2 * N * H * 4 / 1e9:.1f} GB)" if sparse_adj else
+                       f"inputs larger than L2 (X {N * F * 4 / 1e9:.1f} GB, activations {2 * N * H * 4 / 1e9:.1f} GB)"),
                 "graph_generation_s": t_gen,
             },
             "roofline": roofline,
@@ -445,6 +483,7 @@ def run_b200_arm(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,
+            "alt_paths": alt,
             "node_epochs_per_s": value * n,
             "clocks": clocks,
             "loss_last_step": last_loss,

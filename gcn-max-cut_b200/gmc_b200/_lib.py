@@ -41,6 +41,10 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_spmm_batched_f32": (c_int, [P, P, P, P, c_int32, c_int32, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P]),
     "gmc_spmm_fused_skinny_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P, c_int32,
                                           P, c_int64, P]),
+    "gmc_adj_features_fwd_f32": (c_int, [P, P, c_int32, c_int32, P, c_int64, c_int32, P, c_int64, c_int64, c_int32, P]),
+    "gmc_adj_features_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "gmc_adj_features_bwd_f32": (c_int, [P, P, c_int32, c_int32, P, c_int64, c_int64, c_int32, P, c_int64, c_int32, P,
+                                         c_size_t, P]),
     "gmc_gemm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int32]),
     "gmc_gemm_nn": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_size_t, P]),
     "gmc_gemm_nt": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_size_t, P]),

@@ -76,7 +76,7 @@ class OpTimer:
 class GCNEngine:
     def __init__(self, net, optimizer: Optional[FusedAdam] = None, *, C: float = 1.0, loss_mode: str = "ste",
                  override_terminals: bool = True, penalty: float = 0.0, precision: str = "fp32",
-                 process_group=None):
+                 process_group=None, adjacency_kernels: bool = False):
         self.device = _lib.require_cuda()
         self.net = net
         self.optimizer = optimizer
@@ -86,6 +86,10 @@ class GCNEngine:
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"unknown precision {precision!r}")
         self.precision = precision
+        # adjacency_kernels: the caller guarantees that the features ARE the zero-padded unit-weight adjacency rows of
+        # the batch (the reference's live input, TrainingNeural.py:373).  X W1 and X^T dT1 then run as aggregations
+        # over the batch's ELL plan (csrc/spmm_adj.cu) whenever the batch qualifies, and X itself is never read.
+        self.adjacency_kernels = bool(adjacency_kernels)
         self.pg = process_group
         W1, b1, W2, b2 = self.params()
         for p in (W1, b1, W2, b2):
@@ -154,7 +158,14 @@ class GCNEngine:
             self.loss = torch.empty(n_graphs, dtype=torch.float64, device=self.device)
             self._cap_graphs = n_graphs
 
-    def _features(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+    def _sparse_layer1(self, batch: GraphBatch) -> bool:
+        return self.adjacency_kernels and ops.adjacency_kernels_apply(batch, self.F)
+
+    def _features(self, batch: GraphBatch, X: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if X is None:
+            if not self._sparse_layer1(batch):
+                raise ValueError("features may only be omitted when the adjacency kernels apply to the batch")
+            return None
         if X.dim() != 2 or X.shape[0] != batch.num_nodes or X.shape[1] != self.F:
             raise ValueError(f"features must be [{batch.num_nodes}, {self.F}], got {tuple(X.shape)}")
         if not X.is_cuda:
@@ -171,7 +182,10 @@ class GCNEngine:
         W1, b1, W2, b2 = self.params()
         A, Bf = self.bufA[:N], self.bufB[:N]
         ops.copy2d(self.W1p, W1.data)
-        self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, self.W1p, out=A, precision=self.precision, workspace=self.ws)
+        if self._sparse_layer1(batch):
+            self._op("adj_fwd_xw1", 1, ops.adj_features_fwd, batch, self.W1p, out=A)
+        else:
+            self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, self.W1p, out=A, precision=self.precision, workspace=self.ws)
         if 16 <= self.H <= 512 and self.H % 4 == 0 and not (_FWD_SLAB and getattr(batch, "plan", None) is not None):
             # aggregation + bias + ReLU + the skinny projection H1 W2 in one pass over the row
             self._op("spmm_h_fused", 1, ops.spmm_fused_skinny, batch, A, W2.data, out=Bf, proj=self.T2[:N],
@@ -200,6 +214,8 @@ class GCNEngine:
         """Forward + loss + full backward at the current weights.  Gradients land in
         self.grads_flat (overwritten); returns per-graph loss (float64 [B], device view)."""
         X = self._features(batch, X)
+        if dX is not None and self._sparse_layer1(batch):
+            raise ValueError("adjacency_kernels promises fixed adjacency features; trainable features need the dense path")
         N, B = batch.num_nodes, batch.num_graphs
         Z = self.forward_logits(batch, X)
         W1, b1, W2, b2 = self.params()
@@ -212,7 +228,10 @@ class GCNEngine:
         self._op("skinny_bwd", 2, ops.skinny_bwd, self.dT2[:N], W2.data, Bf, dH=A, dW=self.gW2, dbias=self.gb1,
                  workspace=self.ws)
         self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf)                                   # dT1
-        self._op("gemm_tn_dw1", 2, ops.gemm, "tn", X, Bf, out=self.gW1, precision=self.precision, workspace=self.ws)
+        if self._sparse_layer1(batch):
+            self._op("adj_bwd_dw1", 2, ops.adj_features_bwd, batch, Bf, out=self.gW1, workspace=self.ws)
+        else:
+            self._op("gemm_tn_dw1", 2, ops.gemm, "tn", X, Bf, out=self.gW1, precision=self.precision, workspace=self.ws)
         if dX is not None:
             self._op("gemm_nt_dx", 1, ops.gemm, "nt", Bf, self.W1p, out=dX, precision=self.precision,
                      workspace=self.ws)

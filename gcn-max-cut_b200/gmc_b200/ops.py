@@ -203,6 +203,40 @@ def gemm(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] 
     return out
 
 
+def adjacency_kernels_apply(batch, n_w_rows: int) -> bool:
+    """Can X W / X^T dT for X = zero-padded unit-weight adjacency rows be computed as aggregations for this batch?"""
+    return (getattr(batch, "plan", None) is not None and bool(getattr(batch, "unit_weights", False))
+            and batch.max_nodes <= min(n_w_rows, 1024) and n_w_rows <= 1030)
+
+
+def adj_features_fwd(batch, W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """T = X W for X = the batch's zero-padded adjacency rows [N, W.shape[0]], without forming X (row gather of W)."""
+    W, ldw = _rowmajor(W, "W")
+    n_w_rows, c = W.shape
+    if out is None:
+        out = torch.empty((batch.num_nodes, c), dtype=torch.float32, device=W.device)
+    out, ldt = _rowmajor(out, "out")
+    check(lib().gmc_adj_features_fwd_f32(batch.plan.data_ptr(), batch.graph_ptr.data_ptr(), batch.num_graphs,
+                                         batch.max_nodes, W.data_ptr(), ldw, n_w_rows, out.data_ptr(), ldt,
+                                         batch.num_nodes, c, _stream()), "gmc_adj_features_fwd_f32")
+    return out
+
+
+def adj_features_bwd(batch, dT: torch.Tensor, out: torch.Tensor, workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """out = X^T dT for the same X ([out.shape[0], dT.shape[1]]); deterministic."""
+    dT, lddt = _rowmajor(dT, "dT")
+    out, lddw = _rowmajor(out, "out")
+    n_w_rows, c = out.shape
+    if dT.shape != (batch.num_nodes, c):
+        raise ValueError("adj_features_bwd: dT must be [num_nodes, out.shape[1]]")
+    ws = workspace or _default_ws
+    wptr, wbytes = ws.get(lib().gmc_adj_features_bwd_workspace_bytes(n_w_rows, c), dT.device)
+    check(lib().gmc_adj_features_bwd_f32(batch.plan.data_ptr(), batch.graph_ptr.data_ptr(), batch.num_graphs,
+                                         batch.max_nodes, dT.data_ptr(), lddt, batch.num_nodes, c, out.data_ptr(), lddw,
+                                         n_w_rows, wptr, wbytes, _stream()), "gmc_adj_features_bwd_f32")
+    return out
+
+
 def skinny_fwd(H: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     H, ldh = _rowmajor(H, "H")
     W = _f32(W, "W").contiguous()

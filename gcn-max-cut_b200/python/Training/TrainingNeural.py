@@ -14,6 +14,10 @@ Opt-in extensions (defaults reproduce the reference exactly):
     TrainingConfig.gemm_precision    'fp32' (FFMA, parity) | 'tf32' | 'tf32x3' (tcgen05)
     TrainingConfig.loss_mode         'ste' (reference live path) | 'soft' (north-star objective)
     TrainingConfig.use_terminal_penalty   enable the penalty the reference left commented (:308)
+    TrainingConfig.adjacency_kernels  with feature_source='adjacency' and batch_graphs >= 32: the dataset features are
+                                     verified to be the zero-padded adjacency rows (they always are for graphExtender
+                                     output), so layer 1's X W1 and X^T dT1 run as aggregations over the graph
+                                     structure instead of dense GEMMs -- same results up to fp32 summation order
     TrainingConfig.feature_source    'adjacency' (reference live path: zero-padded adjacency rows are the
                                      features, :373) | 'embedding' (north-star: the learned nn.Embedding is the
                                      input, `inputs = embed.weight[:n]`, as in the legacy trainer
@@ -80,6 +84,7 @@ class TrainingConfig:
     loss_mode: str = "ste"
     use_terminal_penalty: bool = False
     feature_source: str = "adjacency"
+    adjacency_kernels: bool = False          # batched steps only: X W1 / X^T dT1 as aggregations (csrc/spmm_adj.cu)
 
     def __post_init__(self):
         if self.feature_source not in ("adjacency", "embedding"):
@@ -219,14 +224,16 @@ def setup_model_and_optimizer(config: TrainingConfig):
 def _engine_for(net, optimizer, config: TrainingConfig) -> GCNEngine:
     key = (id(optimizer), float(config.C), getattr(config, "loss_mode", "ste"),
            bool(getattr(config, "use_terminal_penalty", False)), float(config.penalty),
-           getattr(config, "gemm_precision", "fp32"))
+           getattr(config, "gemm_precision", "fp32"),
+           bool(getattr(config, "adjacency_kernels", False))
+           and getattr(config, "feature_source", "adjacency") == "adjacency")
     cached = _ENGINES.get(net)
     if cached is not None and cached[0] == key:
         return cached[1]
     if optimizer is not None and not isinstance(optimizer, FusedAdam):
         raise TypeError("the B200 training loop needs the FusedAdam returned by setup_model_and_optimizer")
     engine = GCNEngine(net, optimizer, C=config.C, loss_mode=key[2], override_terminals=True,
-                       penalty=config.penalty if key[3] else 0.0, precision=key[5])
+                       penalty=config.penalty if key[3] else 0.0, precision=key[5], adjacency_kernels=key[6])
     _ENGINES[net] = (key, engine)
     return engine
 

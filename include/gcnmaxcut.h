@@ -210,6 +210,24 @@ int gmc_adam_multi_devstep(int32_t n_tensors, float* const* params, const float*
                            double lr, double beta1, double beta2, double eps, int64_t* step_dev,
                            void* stream);
 
+/* ---- (b') layer-1 feature transform when the features ARE the zero-padded adjacency rows ----------------
+ * The reference feeds `adjacency_matrix` [n, 1000] as input features (TrainingNeural.py:373; built by
+ * DataGenerator/graphExtender.py:106-111).  For unit edge weights X W1 is a row gather of W1 and X^T dT1 a
+ * per-local-node aggregation of dT1, so both dense GEMMs (and the dense X itself) can be skipped:
+ *   fwd: T[v,:]  = sum_{u in N(v)} W[local(u),:]                      == gmc_gemm_nn(X, W)
+ *   bwd: dW[j,:] = sum_graphs sum_{v in N_g(j)} dT[v,:], 0 for j >= n  == gmc_gemm_tn(X, dT)
+ * `plan` is the batch's ELL plan (gmc_spmm_plan_build; only its neighbour ids are used).  Both return
+ * GMC_ERR_UNSUPPORTED for shapes outside their reach (n_cols % 4, max_nodes > n_w_rows, n_w_rows > 1030,
+ * max_nodes > 1024): the caller then keeps the dense tensor-core path.  bwd is deterministic. */
+int gmc_adj_features_fwd_f32(const void* plan, const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes,
+                             const float* W, int64_t ldw, int32_t n_w_rows, float* T, int64_t ldt,
+                             int64_t n_rows, int32_t n_cols, void* stream);
+size_t gmc_adj_features_bwd_workspace_bytes(int32_t n_w_rows, int32_t n_cols);
+int gmc_adj_features_bwd_f32(const void* plan, const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes,
+                             const float* dT, int64_t lddt, int64_t n_rows, int32_t n_cols, float* dW,
+                             int64_t lddw, int32_t n_w_rows, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* ---- (e) integer post-processing ------------------------------------------------------ */
 
 /* labels[v] = first argmax_k P[v,k]; the first min(3,n_g) nodes of each graph are forced to

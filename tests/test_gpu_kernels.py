@@ -297,6 +297,31 @@ def test_cut_loss_two_class_and_eight_class():
         ops.cut_loss(batch, torch.randn(30, 2, device=DEV), override_terminals=True)
 
 
+@pytest.mark.parametrize("C", [500, 64, 28, 100])
+def test_adjacency_feature_kernels_equal_dense_gemms(C):
+    """X W and X^T dT for X = zero-padded adjacency rows, computed as aggregations over the ELL plan (spmm_adj.cu),
+    equal the dense products exactly up to fp32 summation order; graphs smaller than the feature width, mixed
+    degrees (padded ELL slots) and rows of dW beyond the largest graph (must be 0) included."""
+    specs = [(1000, 7, 1), (200, 5, 2), (130, 8, 3), (1000, 6, 4), (400, 3, 5)] + [(128 + 2 * i, 4 + i % 5, 10 + i) for i in range(30)]
+    graphs, csrs, batch = make_batch(specs)
+    assert batch.plan is not None and ops.adjacency_kernels_apply(batch, 1000)
+    F = 1000
+    torch.manual_seed(C)
+    W = ops.padded_empty(F, C, DEV); W.normal_()
+    X = ops.densify(batch, F)
+    T = ops.adj_features_fwd(batch, W)
+    assert relerr(T.cpu(), X.cpu().double() @ W.cpu().double()) < 2e-6
+    dT = torch.randn(batch.num_nodes, C, device=DEV)
+    dW = torch.full((F, C), 7.0, device=DEV)
+    ops.adj_features_bwd(batch, dT, out=dW)
+    want = X.cpu().double().t() @ dT.cpu().double()
+    assert relerr(dW.cpu(), want) < 2e-5
+    assert float(dW[batch.max_nodes:].abs().sum()) == 0.0 or batch.max_nodes == F
+    dW2 = torch.empty_like(dW)
+    ops.adj_features_bwd(batch, dT, out=dW2)
+    assert torch.equal(dW, dW2)                                              # deterministic
+
+
 def test_ragged_tiny_graphs_and_empty_calls():
     """Edge cases the reference exercises implicitly: the smallest graphs that can carry three terminals (a triangle,
     K4) next to full-size ones in ONE batch, and empty inputs straight through the C ABI (every entry point must
