@@ -61,7 +61,8 @@ __device__ __forceinline__ void add4(float4& a, const float4& v) { a.x += v.x; a
 // ---- forward: T1[v, slab] = sum over neighbours of W[local id, slab] -------------------------------------------
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-adj_fwd_kernel(const uint4* __restrict__ ell_col, const int32_t* __restrict__ graph_ptr, int n_graphs,
+adj_fwd_kernel(const int32_t* __restrict__ header, const uint4* __restrict__ ell_col,
+               const int32_t* __restrict__ graph_ptr, int n_graphs,
                const float4* __restrict__ W, int64_t ldw4, int n_w_rows, float4* __restrict__ T, int64_t ldt4, int c4,
                int n_slabs, int parts) {
     constexpr int W4 = kAdjW4, LANES = 8, GROUPS = THREADS / LANES;
@@ -85,6 +86,7 @@ adj_fwd_kernel(const uint4* __restrict__ ell_col, const int32_t* __restrict__ gr
     }
     __syncthreads();
     const bool active = lg < nv;
+    const bool slot7 = __ldg(header) > 7;                 // max degree of the batch: 7-regular graphs skip the 8th slot
     const float4* sl = wbuf + lg;
     const uint32_t zero_row = (uint32_t)n_w_rows;
     for (int g = part; g < n_graphs; g += parts) {
@@ -102,9 +104,10 @@ adj_fwd_kernel(const uint4* __restrict__ ell_col, const int32_t* __restrict__ gr
                 add4(acc, v1); add4(acc, v2); add4(acc, v3);
             }
             {
-                const float4 v4 = src(c.z & 0xffffu), v5 = src(c.z >> 16), v6 = src(c.w & 0xffffu), v7 = src(c.w >> 16);
-                add4(acc, v4); add4(acc, v5); add4(acc, v6); add4(acc, v7);
+                const float4 v4 = src(c.z & 0xffffu), v5 = src(c.z >> 16), v6 = src(c.w & 0xffffu);
+                add4(acc, v4); add4(acc, v5); add4(acc, v6);
             }
+            if (slot7) add4(acc, src(c.w >> 16));
             if (active) T[(int64_t)(base + r) * ldt4 + col0 + lg] = acc;
             c = cn;
         }
@@ -116,7 +119,8 @@ constexpr int kAdjBwdThreads = 1024;
 constexpr int kAdjBwdRpg = 8;                             // output rows per row group: graphs of <= 1024 nodes
 
 __global__ void __launch_bounds__(kAdjBwdThreads, 1)
-adj_bwd_kernel(const __grid_constant__ CUtensorMap tmD, const uint4* __restrict__ ell_col,
+adj_bwd_kernel(const __grid_constant__ CUtensorMap tmD, const int32_t* __restrict__ header,
+               const uint4* __restrict__ ell_col,
                const int32_t* __restrict__ graph_ptr, int n_graphs, const float4* __restrict__ dT, int64_t lddt4, int c4,
                int n_slabs, int parts, int rows_cap, int n_w_rows, float4* __restrict__ ws, int64_t ldws4) {
     constexpr int W4 = kAdjW4, LANES = 8, THREADS = kAdjBwdThreads, GROUPS = THREADS / LANES, RPG = kAdjBwdRpg;
@@ -168,6 +172,7 @@ adj_bwd_kernel(const __grid_constant__ CUtensorMap tmD, const uint4* __restrict_
     float4 acc[RPG];
 #pragma unroll
     for (int k = 0; k < RPG; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool slot7 = __ldg(header) > 7;
 
     int cur = 0;
     uint32_t parity = 0;
@@ -195,8 +200,9 @@ adj_bwd_kernel(const __grid_constant__ CUtensorMap tmD, const uint4* __restrict_
                 const float4 v2 = sl[(cc.y & 0xffffu) * W4], v3 = sl[(cc.y >> 16) * W4];
                 add4(acc[k], v0); add4(acc[k], v1); add4(acc[k], v2); add4(acc[k], v3);
                 const float4 v4 = sl[(cc.z & 0xffffu) * W4], v5 = sl[(cc.z >> 16) * W4];
-                const float4 v6 = sl[(cc.w & 0xffffu) * W4], v7 = sl[(cc.w >> 16) * W4];
-                add4(acc[k], v4); add4(acc[k], v5); add4(acc[k], v6); add4(acc[k], v7);
+                const float4 v6 = sl[(cc.w & 0xffffu) * W4];
+                add4(acc[k], v4); add4(acc[k], v5); add4(acc[k], v6);
+                if (slot7) add4(acc[k], sl[(cc.w >> 16) * W4]);
             }
             cc = cn;
         }
@@ -275,7 +281,7 @@ int gmc_adj_features_fwd_f32(const void* plan, const int32_t* graph_ptr, int32_t
     if (parts > n_graphs) parts = n_graphs;
     const uint4* ecol = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(plan) + kAdjPlanHeader);
     adj_fwd_kernel<512, 2><<<n_slabs * parts, 512, smem, as_stream(stream)>>>(
-        ecol, graph_ptr, n_graphs, reinterpret_cast<const float4*>(W), ldw / 4, n_w_rows, reinterpret_cast<float4*>(T),
+        reinterpret_cast<const int32_t*>(plan), ecol, graph_ptr, n_graphs, reinterpret_cast<const float4*>(W), ldw / 4, n_w_rows, reinterpret_cast<float4*>(T),
         ldt / 4, c4, n_slabs, parts);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
@@ -331,7 +337,8 @@ int gmc_adj_features_bwd_f32(const void* plan, const int32_t* graph_ptr, int32_t
     }
     const int64_t ldws4 = (n_cols + 3) / 4;
     const uint4* ecol = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(plan) + kAdjPlanHeader);
-    adj_bwd_kernel<<<n_slabs * parts, kAdjBwdThreads, smem, s>>>(tm, ecol, graph_ptr, n_graphs,
+    adj_bwd_kernel<<<n_slabs * parts, kAdjBwdThreads, smem, s>>>(tm, reinterpret_cast<const int32_t*>(plan), ecol,
+                                                                graph_ptr, n_graphs,
                                                                 reinterpret_cast<const float4*>(dT), lddt / 4, c4, n_slabs,
                                                                 parts, rows_cap, n_w_rows,
                                                                 reinterpret_cast<float4*>(workspace), ldws4);
