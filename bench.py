@@ -8,9 +8,14 @@
 One "step" = one full training pass (forward, fused max-cut loss, backward, gradient all-reduce,
 Adam) over the rank's block-diagonal batch: 4 096 synthetic regular graphs, n=1000, F=1000 -> H=500
 -> K=3 (config 3 at N=1; with N ranks the job is config 4's 4 096*N graphs, d = 6 + g mod 3 --
-weak scaling).  Features are the zero-padded adjacency rows held DENSE in HBM ([N,1000] fp32,
-16.4 GB per GPU), i.e. exactly what the reference feeds its GraphConv (TrainingNeural.py:373), so
-the feature transforms are true dense GEMMs.
+weak scaling).  Features are the zero-padded adjacency rows held DENSE in HBM ([N,1000]), i.e. exactly
+what the reference feeds its GraphConv (TrainingNeural.py:373), so the feature transforms are true
+dense GEMMs on the tensor cores.  --precision picks their operand type: bf16 (default; the north-star's
+"TF32/bf16 with fp32 accumulation": 0/1 features are exact in bf16, W1 and dT1 are rounded to bf16,
+master weights / activations / loss / Adam stay fp32), tf32 (fp32 operands, one TF32 pass), tf32x3 and
+fp32 (fp32-grade parity paths).  The default line also carries `alt_paths`: the same step with TF32
+GEMMs and with layer 1 in aggregation form (--feature-source adjacency-sparse).
+Other workloads: --workload config1 | config2 | config5, --feature-source embedding.
 
 Output: ONE JSON line on rank 0 (contract in the task statement) with `roofline`, `cpu_baseline`,
 `e2e`, `clocks`, `gpu_launches`.  `--impl reference` times the CPU port of the reference's own
@@ -52,8 +57,8 @@ def parse_args():
     ap.add_argument("--features", type=int, default=1000)
     ap.add_argument("--hidden", type=int, default=500)
     ap.add_argument("--classes", type=int, default=3)
-    ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "tf32"),
-                    choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "bf16"),
+                    choices=["fp32", "tf32", "tf32x3", "bf16"])
     ap.add_argument("--workload", default="config3", choices=["config3", "config5", "config2", "config1"],
                     help="config3 (default, the headline): 4096 graphs n=1000 per GPU; config5: one 7-regular graph "
                          "n=1M, F=256, H=128, learned embeddings (SpMM/GEMM roofline stress); config2: inference + "
@@ -253,6 +258,8 @@ def run_b200_arm(args):
         if not ops.adjacency_kernels_apply(batch, F):
             raise SystemExit("--feature-source adjacency-sparse needs a batch with an ELL plan (regular graphs, "
                              ">= 32 graphs, n <= 1024 <= features + 24)")
+    elif args.precision == "bf16":
+        X = ops.densify_bf16(batch, F)                   # dense padded adjacency rows in bf16 (0/1: exact), 128-byte pitch
     else:
         X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
     eng = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=sparse_adj)
@@ -328,8 +335,8 @@ def run_b200_arm(args):
             b2.coef = ops.edge_coef(d_rowptr, d_colidx, None, b2.norm, b2.norm, N)
             b2.plan = (ops.spmm_plan(d_rowptr, d_colidx, b2.norm, b2.norm, d_gptr, B, N)
                        if batch.plan is not None else None)   # slab-SpMM plan: a function of the graph, rebuilt per step
-            if not embedding and not sparse_adj:
-                ops.densify(b2, F, out=X)                            # device-side graphExtender
+            if not embedding and not sparse_adj:                     # device-side graphExtender
+                (ops.densify_bf16 if X.dtype == torch.bfloat16 else ops.densify)(b2, F, out=X)
             per_graph = train_step(b2)
             consumed[slot].record()
             return per_graph.cpu()                                   # D2H of the step's result
@@ -359,43 +366,61 @@ def run_b200_arm(args):
                        + " -> GCNEngine.train_step -> per-graph loss D2H"}
         del host_loss
 
-    # ---- the same workload with layer 1 in aggregation form (reported beside the headline, never instead of it) ----
-    alt = None
-    if not embedding and not sparse_adj and ops.adjacency_kernels_apply(batch, F):
-        eng_s = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=True)
+    # ---- the same workload on the other paths (reported beside the headline, never instead of it) ----------------
+    def timed_alt(engine, feats, k):
         for _ in range(3):
-            eng_s.train_step(batch, None)
+            engine.train_step(batch, feats)
         sync_all()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k_alt = min(args.steps, 10)
         a0.record()
-        for _ in range(k_alt):
-            eng_s.train_step(batch, None)
+        for _ in range(k):
+            engine.train_step(batch, feats)
         a1.record()
         torch.cuda.synchronize()
         t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
         gdist.all_reduce_max_(t)
-        alt = {"adjacency_sparse": {"value": total_graphs * k_alt / (float(t.item()) / 1000.0), "unit": UNIT,
-                                    "ms_per_step": float(t.item()) / k_alt, "steps": k_alt, "dtype": "f32",
-                                    "what": "identical model and inputs; X W1 and X^T dT1 computed as aggregations over "
-                                            "the graph (csrc/spmm_adj.cu) instead of dense tensor-core GEMMs -- valid "
-                                            "because the features are the zero-padded adjacency rows; "
-                                            "bench.py --feature-source adjacency-sparse gives the full line"}}
-        del eng_s
+        return {"value": total_graphs * k / (float(t.item()) / 1000.0), "unit": UNIT, "ms_per_step": float(t.item()) / k,
+                "steps": k}
+
+    alt = None
+    if args.workload == "config3" and not embedding and not sparse_adj:
+        alt = {}
+        k_alt = min(args.steps, 10)
+        if ops.adjacency_kernels_apply(batch, F):
+            eng_s = GCNEngine(net, opt, precision="fp32", adjacency_kernels=True)
+            alt["adjacency_sparse"] = dict(timed_alt(eng_s, None, k_alt), dtype="f32",
+                what="identical model and inputs; X W1 and X^T dT1 computed as aggregations over the graph "
+                     "(csrc/spmm_adj.cu) instead of dense tensor-core GEMMs -- valid because the features are the "
+                     "zero-padded adjacency rows; bench.py --feature-source adjacency-sparse gives the full line")
+            del eng_s
+            torch.cuda.empty_cache()
+        if args.precision == "bf16":
+            X32 = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))
+            eng_t = GCNEngine(net, opt, precision="tf32")
+            alt["tf32"] = dict(timed_alt(eng_t, X32, k_alt), dtype="tf32",
+                what="the same dense step with fp32 features and one-pass TF32 GEMMs (bench.py --precision tf32); "
+                     "--precision tf32x3 / fp32 are the fp32-grade parity paths (profiles/)")
+            del eng_t, X32
+            torch.cuda.empty_cache()
 
     # ---- rooflines ----------------------------------------------------------------------------
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0 if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"] / 2.0
+    if args.precision == "bf16":                         # bf16 operands: the measured bf16 figure itself
+        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     # compulsory form while one graph's source rows stay L2-resident (n*C*4 <= 32 MiB), else gather form
     def spmm_bytes(C):
         if n * C * 4 <= 32 * 2 ** 20:
             return 8.0 * N * C + 4.0 * nnz + 4.0 * (N + 1)
         return 4.0 * nnz * C + 4.0 * N * C + 4.0 * nnz + 4.0 * (N + 1)
     spmm_bytes_h, spmm_bytes_k = spmm_bytes(H), spmm_bytes(K)
+    spmm_bytes_h_bwd = spmm_bytes_h
+    if args.precision == "bf16" and not sparse_adj and not embedding:
+        spmm_bytes_h_bwd -= 2.0 * N * H                  # dT1 leaves the backward slab SpMM as bf16
     ldx = ops.pad_cols(F)
     gemm_flops = 2.0 * N * F * H
     algo = {
         "gemm_nn_xw1": ("tensor", gemm_flops), "gemm_tn_dw1": ("tensor", gemm_flops),
-        "spmm_h": ("hbm", spmm_bytes_h), "spmm_k": ("hbm", spmm_bytes_k),
+        "spmm_h": ("hbm", spmm_bytes_h_bwd), "spmm_k": ("hbm", spmm_bytes_k),
         "spmm_h_fused": ("hbm", spmm_bytes_h + 4.0 * N * K),
         "skinny_fwd": ("hbm", 4.0 * N * H + 4.0 * N * K), "skinny_bwd": ("hbm", 8.0 * N * H + 4.0 * N * K),
         "cut_loss": ("hbm", 12.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)), "colsum_db2": ("hbm", 4.0 * N * K),
@@ -440,8 +465,9 @@ def run_b200_arm(args):
         roofline = {"bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
                     "frac": r["frac"], "traffic": r["traffic"], "kernel": dominant, "avg_ms": r["avg_ms"],
                     "share_of_step": r["share_of_step"],
-                    "peak_source": peaks["_source"] + ("; tf32 peak taken as half of the sustained bf16 figure"
-                                                      if r["bound"] == "tensor" else ""),
+                    "peak_source": peaks["_source"] + (("; sustained bf16 figure" if args.precision == "bf16" else
+                                                        "; tf32 peak taken as half of the sustained bf16 figure")
+                                                       if r["bound"] == "tensor" else ""),
                     "precision": args.precision}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
@@ -468,7 +494,8 @@ def run_b200_arm(args):
                              f"zero-padded adjacency rows [{N},{F}] (implied by the graph, never formed): X W1 and "
                              "X^T dT1 run as aggregations over the ELL plan (spmm_adj.cu), no tensor-core work"
                              if sparse_adj else
-                             f"dense zero-padded adjacency rows [{N},{F}] fp32 resident in HBM ({N * F * 4 / 1e9:.1f} GB/GPU)"),
+                             f"dense zero-padded adjacency rows [{N},{F}] {'bf16' if args.precision == 'bf16' else 'fp32'} "
+                             f"resident in HBM ({N * F * (2 if args.precision == 'bf16' else 4) / 1e9:.1f} GB/GPU)"),
                 "spmm_bytes_form": "compulsory" if n * H * 4 <= 32 * 2 ** 20 else "gather",
                 "model": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
                 "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",

@@ -10,6 +10,10 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
             int64_t ldb, int64_t ldc, int accumulate, int precision, void* workspace, size_t workspace_bytes,
             cudaStream_t s);
 
+size_t tc_bf16_workspace_bytes(int op, int64_t M, int64_t N, int64_t K);
+int tc_gemm_bf16(int op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                 int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
 static int gemm_dispatch(int op, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                          int64_t lda, int64_t ldb, int64_t ldc, int accumulate, int precision, void* workspace,
                          size_t workspace_bytes, void* stream) {
@@ -56,6 +60,21 @@ int gmc_gemm_tn(const float* A, const float* B, float* C, int64_t M, int64_t N, 
                 int64_t ldc, int32_t accumulate, int32_t precision, void* workspace, size_t workspace_bytes,
                 void* stream) {
     return gmc::gemm_dispatch(2, A, B, C, M, N, K, lda, ldb, ldc, accumulate, precision, workspace, workspace_bytes, stream);
+}
+
+size_t gmc_gemm_bf16_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K) {
+    return gmc::tc_bf16_workspace_bytes(op, M, N, K);
+}
+
+// C[M,N] (+)= op(A) op(B) with bf16 operands in device memory (op: 0 nn, 1 nt, 2 tn as gmc_gemm_*), fp32 out.
+int gmc_gemm_bf16(int32_t op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                  int64_t ldb, int64_t ldc, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(A && B && C, "gmc_gemm_bf16: null pointer");
+    GMC_REQUIRE(op >= 0 && op <= 2 && M >= 0 && N >= 0 && K >= 0, "gmc_gemm_bf16: bad op or negative dimension");
+    const int64_t a_min = (op == 2) ? M : K, b_min = (op == 1) ? K : N;
+    GMC_REQUIRE(lda >= a_min && ldb >= b_min && ldc >= N, "gmc_gemm_bf16: leading dimension too small (op %d)", op);
+    return tc_gemm_bf16(op, A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, as_stream(stream));
 }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 // gemm_tcgen05.cu -- (b) dense feature transforms on the 5th-generation tensor cores.
 //
-//   C[M,N] (+)= op(A) * op(B),  fp32 in HBM, kind::tf32 MMA, fp32 accumulation in TMEM.
+//   C[M,N] (+)= op(A) * op(B),  fp32 or bf16 operands in HBM, kind::tf32 / kind::f16 MMA, fp32 accumulation in TMEM,
+//   fp32 output.
 //     nn  X[M,K] * W1[K,N]          A K-major,  B MN-major      (GraphConv th.matmul, TrainingNeural.py:80)
 //     tn  X[K,M]^T * dT1[K,N]       A MN-major, B MN-major      (dW1; K = all nodes of the batch -> split-K)
 //     nt  dT1[M,K] * W1[N,K]^T      A K-major,  B K-major       (dX; only for trainable features)
@@ -17,7 +18,9 @@
 // Out-of-range rows/columns/k are zero-filled by TMA and masked in the epilogue, so M, N, K are arbitrary
 // (leading dimensions must be multiples of 4 floats: TMA needs 16-byte strides).
 //
-// Precision: GMC_GEMM_TF32 is one pass (operands truncated to 10 mantissa bits by the MMA).
+// Precision: GMC_GEMM_TF32 is one pass (operands truncated to 10 mantissa bits by the MMA); GMC_GEMM_TF32X3 three
+// passes with materialised low-order parts (fp32-grade); gmc_gemm_bf16 takes bf16 operands (64-element stages, the same
+// byte geometry: half the operand traffic per flop, twice the MMA rate).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -150,9 +153,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, bool bf16 = false) {
     return (1u << 4)                              // D format  : F32
-         | (2u << 7) | (2u << 10)                 // A/B format: TF32
+         | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10)   // A/B format: TF32 = 2 (kind::tf32), BF16 = 1 (kind::f16)
          | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
          | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
@@ -178,11 +188,18 @@ struct Params {
 // slower).  SM reads per output scale with 1/(256 CLN) + 1/(128 CLM).  A stage may be refilled only when every CTA
 // that receives one of this CTA's multicasts has consumed it, and symmetrically, so each MMA warp multicasts its
 // tcgen05.commit to its row and column (arrival count CLM + CLN - 1).
-template <bool A_MN, bool B_MN, int CLM, int CLN>
+template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const Params p) {
     constexpr int CL = CLM * CLN;
+    // element-size dependent geometry; everything in BYTES is the same for fp32 (tf32) and bf16 operands: a stage row
+    // is 128 B = 32 fp32 or 64 bf16 along k (K-major) or along m/n (MN-major chunk), one MMA eats 32 B of k
+    constexpr int ELT = BF16 ? 2 : 4;
+    constexpr int BK = 128 / ELT;                                  // k elements per stage
+    constexpr int MNC = 128 / ELT;                                 // m/n elements per MN-major chunk
+    constexpr int UK = 32 / ELT;                                   // k elements per MMA
+    constexpr int CHUNK = BK * 128;                                // bytes of one MN-major chunk (BK k-rows x 128 B)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
@@ -236,7 +253,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int n0 = ((int)(rem % p.ng_tiles) * CLN + (int)rn) * BLOCK_N;
                 const int64_t kb = (int64_t)split * p.k_per_split;
                 const int64_t ke = min(p.K, kb + p.k_per_split);
-                for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+                for (int64_t k0 = kb; k0 < ke; k0 += BK) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint32_t fb = full_bar + 8 * stage;
@@ -244,38 +261,38 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (CLN == 1) {
                         if (A_MN) {
 #pragma unroll
-                            for (int j = 0; j < BLOCK_M / 32; ++j) tma_load_2d(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb);
+                            for (int j = 0; j < BLOCK_M / MNC; ++j) tma_load_2d(sa + j * CHUNK, &tmA, m0 + MNC * j, (int)k0, fb);
                         } else {
                             tma_load_2d(sa, &tmA, (int)k0, m0, fb);
                         }
                     } else if (A_MN) {                             // my share of the 4 row chunks, to my cluster row
-                        constexpr int PER = BLOCK_M / 32 / CLN;
+                        constexpr int PER = BLOCK_M / MNC / CLN;
 #pragma unroll
                         for (int jj = 0; jj < PER; ++jj) {
                             const int j = (int)rn * PER + jj;
-                            tma_load_2d_mc(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb, MASK_A);
+                            tma_load_2d_mc(sa + j * CHUNK, &tmA, m0 + MNC * j, (int)k0, fb, MASK_A);
                         }
                     } else {                                       // K-major A: my BLOCK_M / CLN rows, to my cluster row
                         constexpr int ROWS = BLOCK_M / CLN;
-                        tma_load_2d_mc(sa + rn * (ROWS * BLOCK_K * 4), &tmA, (int)k0, m0 + (int)rn * ROWS, fb, MASK_A);
+                        tma_load_2d_mc(sa + rn * (ROWS * 128), &tmA, (int)k0, m0 + (int)rn * ROWS, fb, MASK_A);
                     }
                     if (CLM == 1) {
                         if (B_MN) {
 #pragma unroll
-                            for (int j = 0; j < BLOCK_N / 32; ++j) tma_load_2d(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb);
+                            for (int j = 0; j < BLOCK_N / MNC; ++j) tma_load_2d(sb + j * CHUNK, &tmB, n0 + MNC * j, (int)k0, fb);
                         } else {
                             tma_load_2d(sb, &tmB, (int)k0, n0, fb);
                         }
                     } else if (B_MN) {                             // my share of the 8 column chunks, to my cluster column
-                        constexpr int PER = BLOCK_N / 32 / CLM;
+                        constexpr int PER = BLOCK_N / MNC / CLM;
 #pragma unroll
                         for (int jj = 0; jj < PER; ++jj) {
                             const int j = (int)rm * PER + jj;
-                            tma_load_2d_mc(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb, MASK_B);
+                            tma_load_2d_mc(sb + j * CHUNK, &tmB, n0 + MNC * j, (int)k0, fb, MASK_B);
                         }
                     } else {                                       // K-major B: my BLOCK_N / CLM rows, to my cluster column
                         constexpr int ROWS = BLOCK_N / CLM;
-                        tma_load_2d_mc(sb + rm * (ROWS * BLOCK_K * 4), &tmB, (int)k0, n0 + (int)rm * ROWS, fb, MASK_B);
+                        tma_load_2d_mc(sb + rm * (ROWS * 128), &tmB, (int)k0, n0 + (int)rm * ROWS, fb, MASK_B);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -283,13 +300,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+        constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BF16);
         // K-major : SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1 = CUTLASS convention)
         // MN-major: SWIZZLE_128B_BASE32B, 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart (SBO)
-        const uint32_t a_lbo = A_MN ? CHUNK_BYTES : 16, b_lbo = B_MN ? CHUNK_BYTES : 16;
-        const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
-        const uint32_t a_lay = A_MN ? 1 : 2, b_lay = B_MN ? 1 : 2;
-        const uint32_t a_step = A_MN ? 1024 : UMMA_K * 4, b_step = B_MN ? 1024 : UMMA_K * 4;
+        // 16-bit MN-major: plain SWIZZLE_128B, 64-element chunks CHUNK apart (LBO), 8-k-row atoms 1024 B apart (SBO)
+        // (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
+        constexpr uint32_t MN_SBO = BF16 ? 1024 : 512, MN_LAY = BF16 ? 2 : 1, MN_STEP = UK * 128;
+        const uint32_t a_lbo = A_MN ? CHUNK : 16, b_lbo = B_MN ? CHUNK : 16;
+        const uint32_t a_sbo = A_MN ? MN_SBO : 1024, b_sbo = B_MN ? MN_SBO : 1024;
+        const uint32_t a_lay = A_MN ? MN_LAY : 2, b_lay = B_MN ? MN_LAY : 2;
+        const uint32_t a_step = A_MN ? MN_STEP : 32, b_step = B_MN ? MN_STEP : 32;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int64_t w = cw0; w < n_work; w += cw_step) {
@@ -300,22 +320,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
             uint32_t first = 1;
-            for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+            for (int64_t k0 = kb; k0 < ke; k0 += BK) {
                 mbar_wait(full_bar + 8 * stage, phase);
                 tc_fence_after();
                 __syncwarp();
                 if (elect_one()) {
                     const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    for (int k = 0; k < BK / UK; ++k) {
                         const uint64_t ad = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
                         const uint64_t bd = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
-                        umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                        if (BF16) umma_bf16(d_tmem, ad, bd, idesc, first ? 0u : 1u); else umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
                         first = 0;
                     }
                     // smem stage reusable once these MMAs retire -- in every CTA of the cluster
                     if (CL == 1) umma_commit(empty_bar + 8 * stage); else umma_commit_mc(empty_bar + 8 * stage, MASK_ALL);
-                    if (k0 + BLOCK_K >= ke) umma_commit(tfull_bar + 8 * acc);
+                    if (k0 + BK >= ke) umma_commit(tfull_bar + 8 * acc);
                 }
                 __syncwarp();
                 first = 0;
@@ -632,21 +652,22 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp32 tensor [outer rows, inner cols] with row pitch ld (elements); box = [box_outer, box_inner]
-static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                    uint32_t box_inner, uint32_t box_outer, bool mn_major) {
+// 2-D tensor [outer rows, inner cols] of fp32 (elt = 4) or bf16 (elt = 2) with row pitch ld (elements);
+// box = [box_outer, box_inner]
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer, bool mn_major, int elt = 4) {
     EncodeTiledFn enc = encode_fn();
-    if (!enc) { set_error("gmc_gemm(tf32): cuTensorMapEncodeTiled entry point not available"); return GMC_ERR_UNSUPPORTED; }
+    if (!enc) { set_error("gmc_gemm: cuTensorMapEncodeTiled entry point not available"); return GMC_ERR_UNSUPPORTED; }
     cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint64_t strides[1] = {ld * (uint64_t)elt};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("gmc_gemm(tf32): cuTensorMapEncodeTiled failed (%d)", (int)r); return GMC_ERR_INVALID_ARG; }
+    // 32-bit MN-major operands need the 32-byte-atom swizzle; everything else (K-major, 16-bit MN-major) plain 128B
+    const CUtensorMapSwizzle sw = (mn_major && elt == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = enc(map, elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gmc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return GMC_ERR_INVALID_ARG; }
     return GMC_OK;
 }
 
@@ -686,12 +707,12 @@ static bool no_tma_store() {
 }
 
 // co-resident clusters of the kernel on this device: the GPC geometry may admit fewer than SMs / CL
-template <bool A_MN, bool B_MN, int CLM, int CLN>
+template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
 static int cluster_slots() {
     constexpr int CL = CLM * CLN;
     static int cached = -1;
     if (cached < 0) {
-        cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, CLM, CLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         cached = sm_count() / CL;
         if (CL > 1) {
             cudaLaunchConfig_t probe = {};
@@ -704,7 +725,7 @@ static int cluster_slots() {
             probe.attrs = attr;
             probe.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<A_MN, B_MN, CLM, CLN>, &probe) == cudaSuccess && n > 0) {
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16>, &probe) == cudaSuccess && n > 0) {
                 if (n < cached) cached = n;
             } else {
                 cudaGetLastError();
@@ -715,17 +736,19 @@ static int cluster_slots() {
     return cached;
 }
 
-template <bool A_MN, bool B_MN, int CLM, int CLN>
-static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
+static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     constexpr int CL = CLM * CLN;
+    constexpr int ELT = BF16 ? 2 : 4;
+    constexpr int BK = 128 / ELT, MNC = 128 / ELT;                 // k elements per stage, m/n elements per MN-major chunk
     CUtensorMap tmA, tmB;
     int rc;
-    if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BLOCK_K, true);       // A[K rows, M cols]
-    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M / CLN, false);  // A[M rows, K cols]
+    if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, MNC, BK, true, ELT);       // A[K rows, M cols]
+    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BLOCK_M / CLN, false, ELT);  // A[M rows, K cols]
     if (rc) return rc;
-    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BLOCK_K, true);       // B[K rows, N cols]
-    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, BLOCK_N / CLM, false);  // B[N rows, K cols]
+    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, MNC, BK, true, ELT);       // B[K rows, N cols]
+    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BLOCK_N / CLM, false, ELT);  // B[N rows, K cols]
     if (rc) return rc;
 
     cudaLaunchConfig_t cfg = {};
@@ -737,7 +760,7 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const int slots = cluster_slots<A_MN, B_MN, CLM, CLN>();      // co-resident clusters (GPC geometry), <= SMs / CL
+    const int slots = cluster_slots<A_MN, B_MN, CLM, CLN, BF16>();  // co-resident clusters (GPC geometry), <= SMs / CL
 
     Params p = {};
     p.M = M; p.N = N; p.K = K;
@@ -751,7 +774,7 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
         if (splits < 1) splits = 1;
     }
-    int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(K, splits), BLOCK_K) * BLOCK_K;
+    int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(K, splits), BK) * BK;
     splits = (int)ceil_div<int64_t>(K, k_per);
     p.k_splits = splits;
     p.k_per_split = k_per;
@@ -774,7 +797,7 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
     const int64_t n_work = ctiles * splits;
     const int grid = (int)(n_work < slots ? n_work : slots) * CL;
     cfg.gridDim = dim3(grid);
-    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<A_MN, B_MN, CLM, CLN>, tmA, tmB, tmC, p));
+    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16>, tmA, tmB, tmC, p));
     if (splits > 1) {
         const int64_t MN = M * N;
         tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
@@ -783,17 +806,17 @@ static int launch(const float* A, const float* B, float* C, int64_t M, int64_t N
     return GMC_OK;
 }
 
-template <bool A_MN, bool B_MN>
-static int launch_cl(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+template <bool A_MN, bool B_MN, bool BF16 = false>
+static int launch_cl(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     int clm, cln;
     cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln);
 #define GMC_GEMM_CASE(CM, CN)                                                                                       \
     if (clm == CM && cln == CN)                                                                                     \
-        return launch<A_MN, B_MN, CM, CN>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
     GMC_GEMM_CASE(1, 1) GMC_GEMM_CASE(2, 1) GMC_GEMM_CASE(4, 1) GMC_GEMM_CASE(8, 1) GMC_GEMM_CASE(2, 2) GMC_GEMM_CASE(4, 2)
 #undef GMC_GEMM_CASE
-    return launch<A_MN, B_MN, 4, 1>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    return launch<A_MN, B_MN, 4, 1, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
 }
 
 static bool use_two_cta() {
@@ -998,6 +1021,30 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
     rc = tc_gemm_pass(op, A_lo, B, C, M, N, K, tc::lo_ld(ca), ldb, ldc, 1, workspace, split_bytes, s);
     if (rc) return rc;
     return tc_gemm_pass(op, A, B_lo, C, M, N, K, lda, tc::lo_ld(cb), ldc, 1, workspace, split_bytes, s);
+}
+
+// bf16 operands (A, B point at __nv_bfloat16, leading dimensions in elements), fp32 accumulation and fp32 output:
+// the same kernel with 64-element stages and tcgen05.mma kind::f16 -- half the operand bytes per flop through HBM,
+// L2 and shared memory, twice the MMA rate.
+size_t tc_bf16_workspace_bytes(int op, int64_t M, int64_t N, int64_t K) { return (tc_splitk_bytes(op, M, N, K) + 255) & ~(size_t)255; }
+
+int tc_gemm_bf16(int op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                 int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    GMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B),
+                "gmc_gemm_bf16: TMA needs 16-byte aligned bases and leading dimensions that are multiples of 8 elements");
+    GMC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gmc_gemm_bf16: dimension exceeds int32 TMA coordinates");
+    if (M == 0 || N == 0) return GMC_OK;
+    if (K == 0) {
+        if (!accumulate) GMC_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, s));
+        return GMC_OK;
+    }
+    switch (op) {
+        case 0: return tc::launch_cl<false, true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 1: return tc::launch_cl<false, false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 2: return tc::launch_cl<true, true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    }
+    set_error("gmc_gemm_bf16: bad op %d", op);
+    return GMC_ERR_INVALID_ARG;
 }
 
 }  // namespace gmc

@@ -1,5 +1,7 @@
 // graph_ops.cu -- per-batch graph preparation: degree norms, A_hat edge coefficients,
 // dense padded adjacency rows (device-side graphExtender).  HBM-bound integer/float work.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gmc {
@@ -53,6 +55,44 @@ __global__ void densify_kernel(const int32_t* __restrict__ rowptr, const int32_t
     }
 }
 
+__global__ void densify_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                    const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr, int n_graphs,
+                                    int64_t n_rows, int n_cols, __nv_bfloat16* __restrict__ X, int64_t ldx) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    int g = find_graph(graph_ptr, n_graphs, row);
+    int base = graph_ptr[g];
+    int e0 = rowptr[row], e1 = rowptr[row + 1];
+    for (int e = e0 + lane; e < e1; e += 32) {
+        int local = colidx[e] - base;
+        if (local < 0 || local >= n_cols) continue;
+        X[row * ldx + local] = __float2bfloat16_rn(vals ? vals[e] : 1.0f);
+    }
+}
+
+// 8 elements per thread: two 128-bit loads, one 128-bit store
+__global__ void __launch_bounds__(256)
+f32_to_bf16_kernel(const float* __restrict__ src, int64_t lds, __nv_bfloat16* __restrict__ dst, int64_t ldd, int64_t n_rows,
+                   int n_cols) {
+    const int c8 = (n_cols + 7) / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = i / c8;
+    const int c = (int)(i - r * c8) * 8;
+    if (r >= n_rows) return;
+    const float* s = src + r * lds + c;
+    __nv_bfloat16* d = dst + r * ldd + c;
+    if (c + 8 <= n_cols && ((lds | ldd) % 8 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) &&
+        (reinterpret_cast<uintptr_t>(dst) % 16 == 0)) {
+        const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+        __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                               __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(o);
+    } else {
+        for (int k = 0; k < 8 && c + k < n_cols; ++k) d[k] = __float2bfloat16_rn(s[k]);
+    }
+}
+
 }  // namespace gmc
 
 extern "C" {
@@ -88,11 +128,41 @@ int gmc_csr_densify_f32(const int32_t* rowptr, const int32_t* colidx, const floa
     GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0 && n_cols > 0 && ldx >= n_cols, "gmc_csr_densify_f32: bad sizes");
     if (n_rows == 0) return GMC_OK;
     cudaStream_t s = gmc::as_stream(stream);
-    GMC_CUDA(cudaMemset2DAsync(X, (size_t)ldx * sizeof(float), 0, (size_t)n_cols * sizeof(float), (size_t)n_rows, s));
+    // rows are stored back to back: one flat memset (pad columns included) runs at write bandwidth, the pitched 2-D
+    // form does not
+    GMC_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * sizeof(float) * (size_t)(n_rows - 1) + (size_t)n_cols * sizeof(float), s));
     int threads = 256;
     int64_t blocks = gmc::ceil_div<int64_t>(n_rows * 32, threads);
     gmc::densify_kernel<<<(unsigned)blocks, threads, 0, s>>>(rowptr, colidx, vals, graph_ptr, n_graphs, n_rows,
                                                              n_cols, X, ldx, nullptr);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+// bf16 twin of gmc_csr_densify_f32 (0/1 adjacency entries are exact in bf16): the features of the bf16 GEMM path
+int gmc_csr_densify_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals, const int32_t* graph_ptr,
+                         int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X, int64_t ldx, void* stream) {
+    GMC_REQUIRE(rowptr && colidx && graph_ptr && X, "gmc_csr_densify_bf16: null pointer");
+    GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0 && n_cols > 0 && ldx >= n_cols, "gmc_csr_densify_bf16: bad sizes");
+    if (n_rows == 0) return GMC_OK;
+    cudaStream_t s = gmc::as_stream(stream);
+    GMC_CUDA(cudaMemsetAsync(X, 0, (size_t)ldx * 2 * (size_t)(n_rows - 1) + (size_t)n_cols * 2, s));
+    int threads = 256;
+    int64_t blocks = gmc::ceil_div<int64_t>(n_rows * 32, threads);
+    gmc::densify_bf16_kernel<<<(unsigned)blocks, threads, 0, s>>>(rowptr, colidx, vals, graph_ptr, n_graphs, n_rows, n_cols,
+                                                                  reinterpret_cast<__nv_bfloat16*>(X), ldx);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+// dst[r, c] = bf16(src[r, c]), round to nearest even; leading dimensions in elements
+int gmc_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t n_rows, int32_t n_cols, void* stream) {
+    GMC_REQUIRE(src && dst, "gmc_f32_to_bf16: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_cols >= 0 && lds >= n_cols && ldd >= n_cols, "gmc_f32_to_bf16: bad sizes");
+    if (n_rows == 0 || n_cols == 0) return GMC_OK;
+    const int64_t total = n_rows * ((n_cols + 7) / 8);
+    gmc::f32_to_bf16_kernel<<<(unsigned)gmc::ceil_div<int64_t>(total, 256), 256, 0, gmc::as_stream(stream)>>>(
+        src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, n_rows, n_cols);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
 }

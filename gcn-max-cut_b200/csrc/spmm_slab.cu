@@ -24,6 +24,7 @@
 // degree <= 8 and uniform neighbour norms (regular graphs); otherwise gmc_spmm_batched_f32 runs the
 // warp-per-row kernel.  The two kernels differ only in rounding order (sum-then-scale vs fused coef).
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -120,7 +121,7 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
                  const uint4* __restrict__ ell_col, const float* __restrict__ plan_nd,
                  const int32_t* __restrict__ graph_ptr, const float4* __restrict__ X, float4* __restrict__ Y,
                  int n_graphs, int c4, int64_t ldx4, int64_t ldy4, const float4* __restrict__ bias, int relu,
-                 int n_slabs, int rows_cap) {
+                 int n_slabs, int rows_cap, int out_bf16) {
     extern __shared__ __align__(128) float4 sbuf_all[];   // NBUF x [rows_cap][W4]: rows, the all-zero row, one pad row; mbarriers
     constexpr int GROUPS = THREADS / LANES;
     constexpr uint32_t BOX_BYTES = kBoxRows * W4 * 16;
@@ -239,7 +240,14 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
             acc.x = fmaf(acc.x, S.d, b4.x); acc.y = fmaf(acc.y, S.d, b4.y);
             acc.z = fmaf(acc.z, S.d, b4.z); acc.w = fmaf(acc.w, S.d, b4.w);
             if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-            if (active) Y[(int64_t)(base + row) * ldy4 + col0 + lg] = acc;
+            if (active) {
+                if (out_bf16) {                           // Y is a bf16 matrix: ldy4 counts 4-element (8-byte) units
+                    __nv_bfloat162 o[2] = {__floats2bfloat162_rn(acc.x, acc.y), __floats2bfloat162_rn(acc.z, acc.w)};
+                    reinterpret_cast<uint2*>(Y)[(int64_t)(base + row) * ldy4 + col0 + lg] = *reinterpret_cast<const uint2*>(o);
+                } else {
+                    Y[(int64_t)(base + row) * ldy4 + col0 + lg] = acc;
+                }
+            }
         };
         for (int r = r0; r < n_g; r += DEPTH * GROUPS) {
 #pragma unroll
@@ -298,7 +306,7 @@ static EncodeTiledFn slab_encode_fn() {
 template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF>
 static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_graphs, int max_nodes, const float4* X4,
                            float4* Y4, int64_t n_rows, int c4, int64_t ldx4, int64_t ldy4, const float4* b4, int relu,
-                           cudaStream_t s, int* launched) {
+                           cudaStream_t s, int* launched, int out_bf16 = 0) {
     const int rows_cap = (max_nodes + 2 + 7) & ~7;         // buffers stay 128-byte aligned (TMA destination)
     const size_t smem = (size_t)NBUF * rows_cap * W4 * sizeof(float4) + 16;
     if (smem + 1024 > (228 * 1024) / MINB || smem > kSlabSmemMax) return GMC_OK;
@@ -332,19 +340,20 @@ static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_gra
     const int64_t slots = (int64_t)sm_count() * MINB;
     const int grid = (int)(items < slots ? items : slots);
     spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF><<<grid, THREADS, smem, s>>>(
-        tm, header, ecol, pnd, graph_ptr, X4, Y4, n_graphs, c4, ldx4, ldy4, b4, relu, n_slabs, rows_cap);
+        tm, header, ecol, pnd, graph_ptr, X4, Y4, n_graphs, c4, ldx4, ldy4, b4, relu, n_slabs, rows_cap, out_bf16);
     GMC_LAUNCH_CHECK();
     *launched = 1;
     return GMC_OK;
 }
 
-static int slab_launch(const void* plan, const int32_t* graph_ptr, int n_graphs, int max_nodes, const float* X, float* Y,
+static int slab_launch(const void* plan, const int32_t* graph_ptr, int n_graphs, int max_nodes, const float* X, void* Y,
                        int64_t n_rows, int n_cols, int64_t ldx, int64_t ldy, const float* bias, int relu,
-                       cudaStream_t s, int* launched) {
+                       cudaStream_t s, int* launched, int out_bf16 = 0) {
     *launched = 0;
     if (!plan || !graph_ptr || n_graphs <= 0 || max_nodes < 128 || n_cols < 16 || n_cols % 4 || ldx % 4 || ldy % 4)
         return GMC_OK;
-    if (!aligned16(X) || !aligned16(Y) || (bias && !aligned16(bias)) || !aligned16(plan)) return GMC_OK;
+    if (!aligned16(X) || (reinterpret_cast<uintptr_t>(Y) & (out_bf16 ? 7u : 15u)) || (bias && !aligned16(bias)) || !aligned16(plan))
+        return GMC_OK;
     const int c4 = n_cols / 4;
     const float4* X4 = reinterpret_cast<const float4*>(X);
     float4* Y4 = reinterpret_cast<float4*>(Y);
@@ -354,7 +363,7 @@ static int slab_launch(const void* plan, const int32_t* graph_ptr, int n_graphs,
         const int rc = slab_launch_one<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF>(plan, graph_ptr, n_graphs,      \
                                                                              max_nodes, X4, Y4, n_rows, c4,       \
                                                                              ldx / 4, ldy / 4, b4, relu, s,       \
-                                                                             launched);                            \
+                                                                             launched, out_bf16);                  \
         if (rc != GMC_OK || *launched) return rc;                                                                  \
     }
     switch (slab_variant()) {
@@ -420,6 +429,27 @@ int gmc_spmm_batched_f32(const int32_t* rowptr, const int32_t* colidx, const flo
                                as_stream(stream), &launched);
     if (rc != GMC_OK || launched) return rc;
     return gmc_spmm_symnorm_f32(rowptr, colidx, coef, nullptr, nullptr, X, Y, n_rows, n_cols, ldx, ldy, bias, relu, stream);
+}
+
+// Same product with the output rounded to bf16 on the way out (Y: bf16 matrix, ldy in elements): the B operand of
+// the bf16 weight-gradient GEMM, written once instead of fp32 + a conversion pass.  Slab kernel only: returns
+// GMC_ERR_UNSUPPORTED when the batch has no usable plan (the caller then runs the fp32 SpMM and gmc_f32_to_bf16).
+int gmc_spmm_batched_bf16out(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, const void* plan,
+                             const float* X, void* Y, int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy,
+                             void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(graph_ptr && X && Y, "gmc_spmm_batched_bf16out: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_cols > 0 && ldx >= n_cols && ldy >= n_cols, "gmc_spmm_batched_bf16out: bad sizes");
+    if (n_rows == 0) return GMC_OK;
+    int launched = 0;
+    const int rc = slab_launch(plan, graph_ptr, n_graphs, max_nodes, X, Y, n_rows, n_cols, ldx, ldy, nullptr, 0,
+                               as_stream(stream), &launched, 1);
+    if (rc != GMC_OK) return rc;
+    if (!launched) {
+        set_error("gmc_spmm_batched_bf16out: the batch cannot take the slab kernel (no plan, narrow or unaligned matrix)");
+        return GMC_ERR_UNSUPPORTED;
+    }
+    return GMC_OK;
 }
 
 }  // extern "C"

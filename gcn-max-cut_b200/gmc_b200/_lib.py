@@ -17,6 +17,9 @@ LIB_PATH = os.environ.get("GMC_LIB", os.path.join(PKG_ROOT, "lib", "libgcnmaxcut
 GMC_GEMM_FP32, GMC_GEMM_TF32, GMC_GEMM_TF32X3 = 0, 1, 2
 GMC_LOSS_STE, GMC_LOSS_SOFT = 0, 1
 PRECISIONS = {"fp32": GMC_GEMM_FP32, "tf32": GMC_GEMM_TF32, "tf32x3": GMC_GEMM_TF32X3}
+# engine-level precision (GCNEngine / TrainingConfig.gemm_precision): the three above plus "bf16" (bf16 operands
+# through gmc_gemm_bf16; not a gmc_gemm_* precision code because its operands are a different type)
+ENGINE_PRECISIONS = tuple(PRECISIONS) + ("bf16",)
 LOSS_MODES = {"ste": GMC_LOSS_STE, "soft": GMC_LOSS_SOFT}
 
 
@@ -41,6 +44,12 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_spmm_batched_f32": (c_int, [P, P, P, P, c_int32, c_int32, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P]),
     "gmc_spmm_fused_skinny_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P, c_int32,
                                           P, c_int64, P]),
+    "gmc_spmm_batched_bf16out": (c_int, [P, c_int32, c_int32, P, P, P, c_int64, c_int32, c_int64, c_int64, P]),
+    "gmc_gemm_bf16_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64]),
+    "gmc_gemm_bf16": (c_int, [c_int32, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, P,
+                              c_size_t, P]),
+    "gmc_f32_to_bf16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P]),
+    "gmc_csr_densify_bf16": (c_int, [P, P, P, P, c_int32, c_int64, c_int32, P, c_int64, P]),
     "gmc_adj_features_fwd_f32": (c_int, [P, P, c_int32, c_int32, P, c_int64, c_int32, P, c_int64, c_int64, c_int32, P]),
     "gmc_adj_features_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "gmc_adj_features_bwd_f32": (c_int, [P, P, c_int32, c_int32, P, c_int64, c_int64, c_int32, P, c_int64, c_int32, P,

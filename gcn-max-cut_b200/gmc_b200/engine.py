@@ -83,7 +83,7 @@ class GCNEngine:
         self.C, self.loss_mode, self.override, self.penalty = float(C), loss_mode, bool(override_terminals), float(penalty)
         if loss_mode not in _lib.LOSS_MODES:
             raise ValueError(f"unknown loss_mode {loss_mode!r}")
-        if precision not in _lib.PRECISIONS:
+        if precision not in _lib.ENGINE_PRECISIONS:
             raise ValueError(f"unknown precision {precision!r}")
         self.precision = precision
         # adjacency_kernels: the caller guarantees that the features ARE the zero-padded unit-weight adjacency rows of
@@ -112,6 +112,11 @@ class GCNEngine:
         self.gb2 = self.grads_flat[offs[3]: offs[3] + sizes[3]]
         self.ws = ops.Workspace()
         self.W1p = ops.padded_empty(self.F, self.H, self.device, zero=True)   # 128-byte pitched copy of W1 per step
+        # precision 'bf16': bf16 copies of W1 (per step), of the features (once per feature tensor) and of dT1
+        # (written directly by the slab SpMM) feed gmc_gemm_bf16; everything else stays fp32
+        self.W1b = ops.padded_empty_bf16(self.F, self.H, self.device, zero=True) if precision == "bf16" else None
+        self._xb_cache: Dict[tuple, torch.Tensor] = {}
+        self.bufB16 = None
         self._cap_nodes = 0
         self._cap_graphs = 0
         self.bufA = self.bufB = self.T2 = self.Z = self.P = self.dZ = self.dT2 = None
@@ -153,6 +158,8 @@ class GCNEngine:
             self.P = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.dZ = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.dT2 = torch.empty((cap, self.K), dtype=f32, device=dev)
+            if self.precision == "bf16":
+                self.bufB16 = ops.padded_empty_bf16(cap, self.H, dev)
             self._cap_nodes = cap
         if n_graphs > self._cap_graphs:
             self.loss = torch.empty(n_graphs, dtype=torch.float64, device=self.device)
@@ -168,10 +175,27 @@ class GCNEngine:
             return None
         if X.dim() != 2 or X.shape[0] != batch.num_nodes or X.shape[1] != self.F:
             raise ValueError(f"features must be [{batch.num_nodes}, {self.F}], got {tuple(X.shape)}")
+        if X.dtype == torch.bfloat16:
+            if self.precision != "bf16" or not X.is_cuda:
+                raise ValueError("bf16 feature tensors need precision='bf16' and a CUDA tensor")
+            return X
         if not X.is_cuda:
             from .model import to_device_features
             X = to_device_features(X, self.device)
         return X
+
+    def _bf16_features(self, X: torch.Tensor) -> torch.Tensor:
+        """bf16 copy of a (static) fp32 feature tensor, converted once and cached on its identity and version."""
+        if X.dtype == torch.bfloat16:
+            return X
+        key = (X.data_ptr(), tuple(X.shape), X.stride(0), X._version)
+        hit = self._xb_cache.get(key)
+        if hit is None:
+            if len(self._xb_cache) >= 64:
+                self._xb_cache.clear()
+            hit = ops.to_bf16(X)
+            self._xb_cache[key] = hit
+        return hit
 
     # ------------------------------------------------------------------ forward
     def forward_logits(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
@@ -184,6 +208,9 @@ class GCNEngine:
         ops.copy2d(self.W1p, W1.data)
         if self._sparse_layer1(batch):
             self._op("adj_fwd_xw1", 1, ops.adj_features_fwd, batch, self.W1p, out=A)
+        elif self.precision == "bf16":
+            ops.to_bf16(W1.data, out=self.W1b)
+            self._op("gemm_nn_xw1", 1, ops.gemm_bf16, "nn", self._bf16_features(X), self.W1b, out=A, workspace=self.ws)
         else:
             self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, self.W1p, out=A, precision=self.precision, workspace=self.ws)
         if 16 <= self.H <= 512 and self.H % 4 == 0 and not (_FWD_SLAB and getattr(batch, "plan", None) is not None):
@@ -227,6 +254,12 @@ class GCNEngine:
         self._op("spmm_k", 1, ops.spmm, batch, self.dZ[:N], out=self.dT2[:N])
         self._op("skinny_bwd", 2, ops.skinny_bwd, self.dT2[:N], W2.data, Bf, dH=A, dW=self.gW2, dbias=self.gb1,
                  workspace=self.ws)
+        if self.precision == "bf16" and not self._sparse_layer1(batch):
+            if dX is not None:
+                raise NotImplementedError("trainable features (dX) are not wired to the bf16 GEMM path; use tf32")
+            dT1b = self._op("spmm_h", 1, ops.spmm_bf16out, batch, A, out=self.bufB16[:N])            # dT1, bf16
+            self._op("gemm_tn_dw1", 2, ops.gemm_bf16, "tn", self._bf16_features(X), dT1b, out=self.gW1, workspace=self.ws)
+            return loss
         self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf)                                   # dT1
         if self._sparse_layer1(batch):
             self._op("adj_bwd_dw1", 2, ops.adj_features_bwd, batch, Bf, out=self.gW1, workspace=self.ws)

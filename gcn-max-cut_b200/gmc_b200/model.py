@@ -172,10 +172,13 @@ class GCNSoftmax(nn.Module):
         self.conv2 = GraphConv(hidden_size, num_classes).to(device)
 
     def set_gemm_precision(self, precision: str) -> None:
-        if precision not in _lib.PRECISIONS:
+        if precision not in _lib.ENGINE_PRECISIONS:
             raise ValueError(f"unknown precision {precision!r}")
-        self.conv1.gemm_precision = precision
-        self.conv2.gemm_precision = precision
+        # 'bf16' is an engine (training-step) mode with resident bf16 operands; this generic autograd path keeps fp32
+        # operands and runs them through the one-pass TF32 kernel instead
+        generic = "tf32" if precision == "bf16" else precision
+        self.conv1.gemm_precision = generic
+        self.conv2.gemm_precision = generic
 
     def forward(self, g: GraphLike, inputs: torch.Tensor) -> torch.Tensor:
         # ReLU is fused into the first SpMM's epilogue (F.relu, TrainingNeural.py:81)

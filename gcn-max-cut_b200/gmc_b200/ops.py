@@ -203,6 +203,83 @@ def gemm(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] 
     return out
 
 
+# ---------------------------------------------------------------- bf16 operands
+def _bf16_rowmajor(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+        raise TypeError(f"{name}: expected a row-major CUDA bfloat16 matrix")
+    return t, t.stride(0)
+
+
+def padded_empty_bf16(rows: int, cols: int, device, zero: bool = False) -> torch.Tensor:
+    """[rows, cols] bf16 view whose row pitch is a multiple of 128 bytes (64 elements)."""
+    make = torch.zeros if zero else torch.empty
+    return make((rows, (cols + 63) // 64 * 64), dtype=torch.bfloat16, device=device)[:, :cols]
+
+
+def to_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 copy (round to nearest even) of a row-major fp32 matrix, 128-byte row pitch."""
+    src, lds = _rowmajor(src, "src")
+    if out is None:
+        out = padded_empty_bf16(src.shape[0], src.shape[1], src.device)
+    out, ldd = _bf16_rowmajor(out, "out")
+    check(lib().gmc_f32_to_bf16(src.data_ptr(), lds, out.data_ptr(), ldd, src.shape[0], src.shape[1], _stream()),
+          "gmc_f32_to_bf16")
+    return out
+
+
+def densify_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 twin of densify: padded adjacency rows X[N, n_cols] (0/1 entries are exact in bf16)."""
+    if out is None:
+        out = padded_empty_bf16(batch.num_nodes, n_cols, batch.device)
+    out, ld = _bf16_rowmajor(out, "out")
+    check(lib().gmc_csr_densify_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), _ptr(batch.wts_f32),
+                                     batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
+                                     out.data_ptr(), ld, _stream()), "gmc_csr_densify_bf16")
+    return out
+
+
+def spmm_bf16out(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A_hat X rounded to bf16 (slab kernel; falls back to the fp32 SpMM + conversion when the batch has no plan)."""
+    X, ldx = _rowmajor(X, "X")
+    n, c = X.shape
+    if out is None:
+        out = padded_empty_bf16(n, c, X.device)
+    out, ldy = _bf16_rowmajor(out, "out")
+    if getattr(batch, "plan", None) is not None and batch.max_nodes >= 128 and c >= 16 and c % 4 == 0:
+        check(lib().gmc_spmm_batched_bf16out(batch.graph_ptr.data_ptr(), batch.num_graphs, batch.max_nodes,
+                                             batch.plan.data_ptr(), X.data_ptr(), out.data_ptr(), n, c, ldx, ldy,
+                                             _stream()), "gmc_spmm_batched_bf16out")
+        return out
+    return to_bf16(spmm(batch, X), out=out)
+
+
+def gemm_bf16(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+              workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """gemm with bf16 operands and fp32 output.  nn: A[M,K] B[K,N];  nt: A[M,K] B[N,K];  tn: A[K,M] B[K,N]."""
+    A, lda = _bf16_rowmajor(A, "A")
+    B, ldb = _bf16_rowmajor(B, "B")
+    if op == "nn":
+        M, K = A.shape; K2, N = B.shape
+    elif op == "nt":
+        M, K = A.shape; N, K2 = B.shape
+    elif op == "tn":
+        K, M = A.shape; K2, N = B.shape
+    else:
+        raise ValueError(f"unknown gemm op {op!r}")
+    if K != K2:
+        raise ValueError(f"gemm_bf16 {op}: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs an output tensor")
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    out, ldc = _rowmajor(out, "out")
+    ws = workspace or _default_ws
+    wptr, wbytes = ws.get(lib().gmc_gemm_bf16_workspace_bytes(_OPS[op], M, N, K), A.device)
+    check(lib().gmc_gemm_bf16(_OPS[op], A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
+                              int(accumulate), wptr, wbytes, _stream()), "gmc_gemm_bf16")
+    return out
+
+
 def adjacency_kernels_apply(batch, n_w_rows: int) -> bool:
     """Can X W / X^T dT for X = zero-padded unit-weight adjacency rows be computed as aggregations for this batch?"""
     return (getattr(batch, "plan", None) is not None and bool(getattr(batch, "unit_weights", False))

@@ -210,6 +210,28 @@ int gmc_adam_multi_devstep(int32_t n_tensors, float* const* params, const float*
                            double lr, double beta1, double beta2, double eps, int64_t* step_dev,
                            void* stream);
 
+/* gmc_spmm_batched_f32 with the output rounded to bf16 on the way out (Y: bf16 matrix, ldy in elements): feeds
+ * the B operand of the bf16 weight-gradient GEMM without an fp32 round trip.  Slab kernel only:
+ * GMC_ERR_UNSUPPORTED when the batch has no usable plan. */
+int gmc_spmm_batched_bf16out(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, const void* plan,
+                             const float* X, void* Y, int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy,
+                             void* stream);
+
+/* bf16 operands (the north-star's "TF32/bf16 with fp32 accumulation"): A and B point at bf16 data in device
+ * memory (leading dimensions in ELEMENTS, multiples of 8; 16-byte aligned bases), C is fp32.  Same tcgen05 / TMA /
+ * cluster-multicast kernel as gmc_gemm_* with 64-element stages and kind::f16 MMAs: half the operand bytes per
+ * flop, twice the MMA rate.  op: 0 nn, 1 nt, 2 tn.  gmc_f32_to_bf16 (round to nearest even) and
+ * gmc_csr_densify_bf16 (0/1 adjacency rows are exact in bf16) produce the operands. */
+size_t gmc_gemm_bf16_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K);
+int gmc_gemm_bf16(int32_t op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K,
+                  int64_t lda, int64_t ldb, int64_t ldc, int32_t accumulate, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int gmc_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t n_rows, int32_t n_cols,
+                    void* stream);
+int gmc_csr_densify_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                         const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                         int64_t ldx, void* stream);
+
 /* ---- (b') layer-1 feature transform when the features ARE the zero-padded adjacency rows ----------------
  * The reference feeds `adjacency_matrix` [n, 1000] as input features (TrainingNeural.py:373; built by
  * DataGenerator/graphExtender.py:106-111).  For unit edge weights X W1 is a row gather of W1 and X^T dT1 a

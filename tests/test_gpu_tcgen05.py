@@ -111,6 +111,32 @@ def test_tf32x3_is_fp32_grade(op, M, N, K):
     assert relerr(acc.cpu(), exact - 1.0) < tol
 
 
+@pytest.mark.parametrize("op,M,N,K", [("nn", 128, 256, 64), ("nn", 1000, 500, 1000), ("nn", 40000, 500, 1000),
+                                      ("nn", 130, 260, 72), ("nt", 128, 256, 64), ("nt", 200, 96, 500),
+                                      ("nt", 1000, 1000, 500), ("tn", 128, 256, 64), ("tn", 1000, 500, 3000),
+                                      ("tn", 1000, 500, 200000), ("tn", 100, 64, 128)])
+def test_bf16_gemm_matches_float64_of_rounded_operands(op, M, N, K):
+    """bf16 operands (round to nearest even), exact products, fp32 accumulation in TMEM: the float64 product of the
+    ROUNDED operands must agree to fp32 accumulation error -- for K-major and MN-major operands alike."""
+    torch.manual_seed(M + 3 * N + 7 * K)
+    if op == "nn":
+        A, B = torch.randn(M, K), torch.randn(K, N)
+    elif op == "nt":
+        A, B = torch.randn(M, K), torch.randn(N, K)
+    else:
+        A, B = torch.randn(K, M), torch.randn(K, N)
+    Ab, Bb = ops.to_bf16(A.to(DEV)), ops.to_bf16(B.to(DEV))
+    assert torch.equal(Ab.cpu(), A.to(torch.bfloat16)) and torch.equal(Bb.cpu(), B.to(torch.bfloat16))
+    Ad, Bd = Ab.cpu().double(), Bb.cpu().double()
+    want = Ad @ Bd if op == "nn" else Ad @ Bd.t() if op == "nt" else Ad.t() @ Bd
+    got = ops.gemm_bf16(op, Ab, Bb)
+    tol = 2e-6 * max(1.0, math.sqrt(K) / 8)
+    assert relerr(got.cpu(), want) < tol
+    acc = torch.full((M, N), 3.0, device=DEV)
+    ops.gemm_bf16(op, Ab, Bb, out=acc, accumulate=True)
+    assert relerr(acc.cpu(), want + 3.0) < tol
+
+
 def test_tf32_rejects_unaligned():
     A = torch.randn(64, 33, device=DEV)
     with pytest.raises(_lib.GmcError):
