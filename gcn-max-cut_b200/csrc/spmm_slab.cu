@@ -115,13 +115,23 @@ constexpr int kBoxRows = 128;                             // rows per TMA box
 // W4: float4 columns per slab; LANES: lanes per output row (power of two >= W4); MINB: CTAs per SM;
 // DEPTH: rows whose neighbour lists are prefetched ahead per row group; TMA: stage full 128-row boxes with
 // cp.async.bulk.tensor (one elected thread, mbarrier completion) and only the tail rows with cp.async
-template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF>
+// PROJ: also emit this slab's share of the skinny projection T = Y W (W [n_cols, n_out <= 4]) -- the second GraphConv
+// layer's th.matmul (TrainingNeural.py:83) -- as one float4 per (slab, row) into Tpart[n_slabs][n_rows]; a fixed-order
+// reduction over the slabs (proj_reduce_kernel) finishes it, so the result stays deterministic.
+struct SlabProj {
+    const float* W;          // [n_cols, n_out] row-major
+    float4* Tpart;           // [n_slabs][n_rows]
+    int64_t n_rows;
+    int n_out;
+};
+
+template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF, bool PROJ = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restrict__ header,
                  const uint4* __restrict__ ell_col, const float* __restrict__ plan_nd,
                  const int32_t* __restrict__ graph_ptr, const float4* __restrict__ X, float4* __restrict__ Y,
                  int n_graphs, int c4, int64_t ldx4, int64_t ldy4, const float4* __restrict__ bias, int relu,
-                 int n_slabs, int rows_cap, int out_bf16) {
+                 int n_slabs, int rows_cap, int out_bf16, const SlabProj proj) {
     extern __shared__ __align__(128) float4 sbuf_all[];   // NBUF x [rows_cap][W4]: rows, the all-zero row, one pad row; mbarriers
     constexpr int GROUPS = THREADS / LANES;
     constexpr uint32_t BOX_BYTES = kBoxRows * W4 * 16;
@@ -133,6 +143,8 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
     const uint32_t BUF_BYTES = (uint32_t)rows_cap * W4 * 16;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sbuf_all);
     const uint32_t bar0 = sbase + NBUF * BUF_BYTES;
+    // PROJ: W slab transposed, wsm[k][W4] float4 (k < 4), 16 bytes past the barriers
+    float4* wsm = reinterpret_cast<float4*>(reinterpret_cast<char*>(sbuf_all) + NBUF * BUF_BYTES + 16);
     uint32_t parity = 0;                                  // bit b = phase of buffer b's mbarrier
     if (TMA) {
         if (tid == 0) {
@@ -215,6 +227,14 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
             if (!pre[k] && r0 + k * GROUPS < n_g) load_slots(S[k], base, r0 + k * GROUPS);
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias && active) b4 = __ldg(bias + col0 + lg);
+        if (PROJ) {                                       // W slab, transposed: wsm[k][column] (0 beyond n_out / n_cols)
+            float* wf = reinterpret_cast<float*>(wsm);
+            for (int i = tid; i < 4 * W4 * 4; i += THREADS) {
+                const int k = i / (W4 * 4), c = i - k * (W4 * 4);
+                const int col = col0 * 4 + c;
+                wf[i] = (k < proj.n_out && col < c4 * 4) ? __ldg(proj.W + (int64_t)col * proj.n_out + k) : 0.f;
+            }
+        }
 
         if (NBUF == 2) cp_async_wait<1>(); else cp_async_wait<0>();
         if (TMA && n_g >= kBoxRows) { mbar_wait(bar0 + 8 * cur, (parity >> cur) & 1u); parity ^= 1u << cur; }
@@ -248,6 +268,21 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
                     Y[(int64_t)(base + row) * ldy4 + col0 + lg] = acc;
                 }
             }
+            if (PROJ) {
+                // this lane's 4 columns against the W slab, then a sum over the row group's LANES lanes
+                float p[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 wk = wsm[k * W4 + (active ? lg : 0)];
+                    p[k] = active ? fmaf(acc.x, wk.x, fmaf(acc.y, wk.y, fmaf(acc.z, wk.z, acc.w * wk.w))) : 0.f;
+                }
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) p[k] += __shfl_xor_sync(0xffffffffu, p[k], o);
+                }
+                if (lg == 0) proj.Tpart[(int64_t)s * proj.n_rows + base + row] = make_float4(p[0], p[1], p[2], p[3]);
+            }
         };
         for (int r = r0; r < n_g; r += DEPTH * GROUPS) {
 #pragma unroll
@@ -271,6 +306,20 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
         if (NBUF == 2) cur ^= 1;
     }
     cp_async_wait<0>();
+}
+
+// T[row, k] = sum over slabs of Tpart[slab][row][k], slabs in index order (deterministic)
+__global__ void __launch_bounds__(256)
+proj_reduce_kernel(const float4* __restrict__ Tpart, int n_slabs, int64_t n_rows, int n_out, float* __restrict__ T, int64_t ldt) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < n_slabs; ++i) {
+        const float4 v = __ldg(Tpart + (int64_t)i * n_rows + row);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float o[4] = {s.x, s.y, s.z, s.w};
+    for (int k = 0; k < n_out; ++k) T[row * ldt + k] = o[k];
 }
 
 static size_t plan_bytes(int64_t n_rows) { return kPlanHeader + (size_t)n_rows * (kEll * sizeof(uint16_t) + sizeof(float)); }
@@ -303,12 +352,12 @@ static EncodeTiledFn slab_encode_fn() {
     return fn;
 }
 
-template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF>
+template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF, bool PROJ = false>
 static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_graphs, int max_nodes, const float4* X4,
                            float4* Y4, int64_t n_rows, int c4, int64_t ldx4, int64_t ldy4, const float4* b4, int relu,
-                           cudaStream_t s, int* launched, int out_bf16 = 0) {
+                           cudaStream_t s, int* launched, int out_bf16 = 0, SlabProj proj = SlabProj{nullptr, nullptr, 0, 0}) {
     const int rows_cap = (max_nodes + 2 + 7) & ~7;         // buffers stay 128-byte aligned (TMA destination)
-    const size_t smem = (size_t)NBUF * rows_cap * W4 * sizeof(float4) + 16;
+    const size_t smem = (size_t)NBUF * rows_cap * W4 * sizeof(float4) + 16 + (PROJ ? 4 * W4 * sizeof(float4) : 0);
     if (smem + 1024 > (228 * 1024) / MINB || smem > kSlabSmemMax) return GMC_OK;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
@@ -326,9 +375,9 @@ static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_gra
     }
     static bool attr = false;
     if (!attr) {
-        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF>,
+        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabSmemMax));
-        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF>,
+        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ>,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr = true;
     }
@@ -339,8 +388,8 @@ static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_gra
     const int64_t items = (int64_t)n_graphs * n_slabs;
     const int64_t slots = (int64_t)sm_count() * MINB;
     const int grid = (int)(items < slots ? items : slots);
-    spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF><<<grid, THREADS, smem, s>>>(
-        tm, header, ecol, pnd, graph_ptr, X4, Y4, n_graphs, c4, ldx4, ldy4, b4, relu, n_slabs, rows_cap, out_bf16);
+    spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ><<<grid, THREADS, smem, s>>>(
+        tm, header, ecol, pnd, graph_ptr, X4, Y4, n_graphs, c4, ldx4, ldy4, b4, relu, n_slabs, rows_cap, out_bf16, proj);
     GMC_LAUNCH_CHECK();
     *launched = 1;
     return GMC_OK;
@@ -449,6 +498,47 @@ int gmc_spmm_batched_bf16out(const int32_t* graph_ptr, int32_t n_graphs, int32_t
         set_error("gmc_spmm_batched_bf16out: the batch cannot take the slab kernel (no plan, narrow or unaligned matrix)");
         return GMC_ERR_UNSUPPORTED;
     }
+    return GMC_OK;
+}
+
+size_t gmc_spmm_batched_fused_workspace_bytes(int64_t n_rows, int32_t n_cols) {
+    return (size_t)gmc::ceil_div(n_cols / 4, 7) * (size_t)n_rows * sizeof(float4);
+}
+
+// Y = act(A_hat X + bias) AND T = Y W (W [n_cols, n_out <= 4]) for a block-diagonal batch with an ELL plan: the slab
+// kernel with the skinny projection of the second GraphConv layer (TrainingNeural.py:83) folded into its epilogue
+// (per-slab partials in `workspace`, reduced in slab order: deterministic).  GMC_ERR_UNSUPPORTED when the batch cannot
+// take the slab kernel or n_out > 4 -- gmc_spmm_fused_skinny_f32 is the general form.
+int gmc_spmm_batched_fused_skinny_f32(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, const void* plan,
+                                      const float* X, float* Y, int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy,
+                                      const float* bias, int32_t relu, const float* W, int32_t n_out, float* T,
+                                      int64_t ldt, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(graph_ptr && X && Y && W && T, "gmc_spmm_batched_fused_skinny_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_cols > 0 && ldx >= n_cols && ldy >= n_cols && ldt >= n_out && n_out >= 1,
+                "gmc_spmm_batched_fused_skinny_f32: bad sizes");
+    if (n_rows == 0) return GMC_OK;
+    const bool ok = plan && n_out <= 4 && n_graphs > 0 && max_nodes >= 128 && n_cols >= 16 && n_cols % 4 == 0 &&
+                    ldx % 4 == 0 && ldy % 4 == 0 && aligned16(X) && aligned16(Y) && (!bias || aligned16(bias)) &&
+                    aligned16(plan) && workspace && aligned16(workspace) &&
+                    workspace_bytes >= gmc_spmm_batched_fused_workspace_bytes(n_rows, n_cols);
+    int launched = 0;
+    if (ok) {
+        SlabProj proj{W, reinterpret_cast<float4*>(workspace), n_rows, n_out};
+        const int rc = slab_launch_one<7, 8, 512, 2, 2, true, 1, true>(
+            plan, graph_ptr, n_graphs, max_nodes, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y), n_rows,
+            n_cols / 4, ldx / 4, ldy / 4, reinterpret_cast<const float4*>(bias), relu, as_stream(stream), &launched, 0, proj);
+        if (rc != GMC_OK) return rc;
+    }
+    if (!launched) {
+        set_error("gmc_spmm_batched_fused_skinny_f32: the batch cannot take the slab kernel (plan, n_out <= 4, graphs of "
+                  "128..1006 nodes, 16-byte aligned rows, workspace)");
+        return GMC_ERR_UNSUPPORTED;
+    }
+    const int n_slabs = ceil_div(n_cols / 4, 7);
+    proj_reduce_kernel<<<(unsigned)ceil_div<int64_t>(n_rows, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(workspace), n_slabs, n_rows, n_out, T, ldt);
+    GMC_LAUNCH_CHECK();
     return GMC_OK;
 }
 

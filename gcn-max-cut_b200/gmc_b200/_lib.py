@@ -44,6 +44,9 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_spmm_batched_f32": (c_int, [P, P, P, P, c_int32, c_int32, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P]),
     "gmc_spmm_fused_skinny_f32": (c_int, [P, P, P, P, P, P, P, c_int64, c_int32, c_int64, c_int64, P, c_int32, P, c_int32,
                                           P, c_int64, P]),
+    "gmc_spmm_batched_fused_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "gmc_spmm_batched_fused_skinny_f32": (c_int, [P, c_int32, c_int32, P, P, P, c_int64, c_int32, c_int64, c_int64, P,
+                                                  c_int32, P, c_int32, P, c_int64, P, c_size_t, P]),
     "gmc_spmm_batched_bf16out": (c_int, [P, c_int32, c_int32, P, P, P, c_int64, c_int32, c_int64, c_int64, P]),
     "gmc_gemm_bf16_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64]),
     "gmc_gemm_bf16": (c_int, [c_int32, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, P,

@@ -216,7 +216,7 @@ class GCNEngine:
         if 16 <= self.H <= 512 and self.H % 4 == 0 and not (_FWD_SLAB and getattr(batch, "plan", None) is not None):
             # aggregation + bias + ReLU + the skinny projection H1 W2 in one pass over the row
             self._op("spmm_h_fused", 1, ops.spmm_fused_skinny, batch, A, W2.data, out=Bf, proj=self.T2[:N],
-                     bias=b1.data, relu=True)
+                     bias=b1.data, relu=True, workspace=self.ws)
         else:
             self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf, bias=b1.data, relu=True)
             self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])

@@ -7,6 +7,7 @@ falls back to a PyTorch implementation.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -58,6 +59,10 @@ class Workspace:
 
 
 _default_ws = Workspace()
+# GMC_SLAB_FUSED=1 sends the forward aggregation + projection through the slab kernel with the projection in its
+# epilogue (gmc_spmm_batched_fused_skinny_f32).  Measured at config 3: 6.13 ms against 5.29 ms for the warp-per-row
+# fused kernel -- the 12 shuffles + 12 FMAs per row and slab cost more than the L2 traffic they save -- so it is opt-in.
+_SLAB_FUSED = os.environ.get("GMC_SLAB_FUSED", "0") == "1"
 
 
 # ---------------------------------------------------------------- graph preparation
@@ -150,8 +155,10 @@ def spmm(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optio
 
 
 def spmm_fused_skinny(batch, X: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None,
-                      proj: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, relu: bool = True):
-    """(Y, T) with Y = act(A_hat X + bias) and T = Y W in one pass (n_cols <= 512, W [n_cols, n_out<=8])."""
+                      proj: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, relu: bool = True,
+                      workspace: Optional[Workspace] = None):
+    """(Y, T) with Y = act(A_hat X + bias) and T = Y W in one pass (n_cols <= 512, W [n_cols, n_out<=8]).  Batches
+    with an ELL plan and n_out <= 4 take the TMA-staged slab kernel with the projection in its epilogue."""
     X, ldx = _rowmajor(X, "X")
     W = _f32(W, "W").contiguous()
     n, c = X.shape
@@ -162,6 +169,18 @@ def spmm_fused_skinny(batch, X: torch.Tensor, W: torch.Tensor, out: Optional[tor
     if proj is None:
         proj = torch.empty((n, n_out), dtype=torch.float32, device=X.device)
     proj, ldt = _rowmajor(proj, "proj")
+    if (getattr(batch, "plan", None) is not None and n_out <= 4 and batch.max_nodes >= 128 and c >= 16 and c % 4 == 0
+            and ldx % 4 == 0 and ldy % 4 == 0 and _SLAB_FUSED):
+        ws = workspace or _default_ws
+        wptr, wbytes = ws.get(lib().gmc_spmm_batched_fused_workspace_bytes(n, c), X.device)
+        rc = lib().gmc_spmm_batched_fused_skinny_f32(batch.graph_ptr.data_ptr(), batch.num_graphs, batch.max_nodes,
+                                                     batch.plan.data_ptr(), X.data_ptr(), out.data_ptr(), n, c, ldx, ldy,
+                                                     _ptr(bias), int(relu), W.data_ptr(), n_out, proj.data_ptr(), ldt,
+                                                     wptr, wbytes, _stream())
+        if rc == 0:
+            return out, proj
+        if rc != -2:                                   # GMC_ERR_UNSUPPORTED: fall through to the row kernel
+            check(rc, "gmc_spmm_batched_fused_skinny_f32")
     check(lib().gmc_spmm_fused_skinny_f32(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(), None,
                                           None, X.data_ptr(), out.data_ptr(), n, c, ldx, ldy, _ptr(bias), int(relu),
                                           W.data_ptr(), n_out, proj.data_ptr(), ldt, _stream()),

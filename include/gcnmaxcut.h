@@ -210,6 +210,17 @@ int gmc_adam_multi_devstep(int32_t n_tensors, float* const* params, const float*
                            double lr, double beta1, double beta2, double eps, int64_t* step_dev,
                            void* stream);
 
+/* gmc_spmm_fused_skinny_f32 for a block-diagonal batch with an ELL plan: the TMA-staged slab kernel with the
+ * skinny projection T = Y W (n_out <= 4) folded into its epilogue; per-slab partial sums go to `workspace`
+ * (gmc_spmm_batched_fused_workspace_bytes) and are reduced in slab order, so T is deterministic.
+ * GMC_ERR_UNSUPPORTED when the batch cannot take the slab kernel: use gmc_spmm_fused_skinny_f32. */
+size_t gmc_spmm_batched_fused_workspace_bytes(int64_t n_rows, int32_t n_cols);
+int gmc_spmm_batched_fused_skinny_f32(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes,
+                                      const void* plan, const float* X, float* Y, int64_t n_rows, int32_t n_cols,
+                                      int64_t ldx, int64_t ldy, const float* bias, int32_t relu, const float* W,
+                                      int32_t n_out, float* T, int64_t ldt, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+
 /* gmc_spmm_batched_f32 with the output rounded to bf16 on the way out (Y: bf16 matrix, ldy in elements): feeds
  * the B operand of the bf16 weight-gradient GEMM without an fp32 round trip.  Slab kernel only:
  * GMC_ERR_UNSUPPORTED when the batch has no usable plan. */
