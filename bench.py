@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "bf16"),
                     choices=["fp32", "tf32", "tf32x3", "bf16"])
+    ap.add_argument("--activations", default=os.environ.get("GMC_BENCH_ACTIVATIONS", "fp32"), choices=["fp32", "bf16"],
+                    help="storage type of the four [nodes, hidden] layer-1 tensors (T1, H1, dH1pre, dT1); bf16 needs "
+                         "--precision bf16.  Arithmetic is fp32 either way")
     ap.add_argument("--workload", default="config3", choices=["config3", "config5", "config2", "config1"],
                     help="config3 (default, the headline): 4096 graphs n=1000 per GPU; config5: one 7-regular graph "
                          "n=1M, F=256, H=128, learned embeddings (SpMM/GEMM roofline stress); config2: inference + "
@@ -76,6 +79,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(--steps, 10)")
     args = ap.parse_args()
+    if args.precision != "bf16" or args.feature_source != "adjacency":
+        args.activations = "fp32"
     if args.workload == "config5":
         args.graphs_per_gpu, args.nodes, args.degree, args.features, args.hidden = 1, 1000000, 7, 256, 128
         args.feature_source = "embedding"
@@ -262,7 +267,8 @@ def run_b200_arm(args):
         X = ops.densify_bf16(batch, F)                   # dense padded adjacency rows in bf16 (0/1: exact), 128-byte pitch
     else:
         X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
-    eng = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=sparse_adj)
+    eng = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=sparse_adj, activations=args.activations)
+    act16 = args.activations == "bf16" and eng._b16_activations(batch)
 
     def train_step(b):
         return eng.train_step(b, X, feature_param=x_param, feature_grad=x_grad)
@@ -394,6 +400,13 @@ def run_b200_arm(args):
                      "zero-padded adjacency rows; bench.py --feature-source adjacency-sparse gives the full line")
             del eng_s
             torch.cuda.empty_cache()
+        if act16:
+            eng_f = GCNEngine(net, opt, precision="bf16", activations="fp32")
+            alt["bf16_fp32_activations"] = dict(timed_alt(eng_f, X, k_alt), dtype="bf16",
+                what="the same step with the layer-1 activations stored in fp32 (bench.py --activations fp32): bf16 GEMM "
+                     "operands only")
+            del eng_f
+            torch.cuda.empty_cache()
         if args.precision == "bf16":
             X32 = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))
             eng_t = GCNEngine(net, opt, precision="tf32")
@@ -416,13 +429,19 @@ def run_b200_arm(args):
     spmm_bytes_h_bwd = spmm_bytes_h
     if args.precision == "bf16" and not sparse_adj and not embedding:
         spmm_bytes_h_bwd -= 2.0 * N * H                  # dT1 leaves the backward slab SpMM as bf16
+    spmm_bytes_fused = spmm_bytes_h + 4.0 * N * K
+    skinny_bwd_bytes = 8.0 * N * H + 4.0 * N * K
+    if act16:                                            # T1, H1, dH1pre, dT1 are 2-byte matrices
+        spmm_bytes_fused -= 4.0 * N * H
+        spmm_bytes_h_bwd = spmm_bytes_h - 4.0 * N * H
+        skinny_bwd_bytes -= 4.0 * N * H
     ldx = ops.pad_cols(F)
     gemm_flops = 2.0 * N * F * H
     algo = {
         "gemm_nn_xw1": ("tensor", gemm_flops), "gemm_tn_dw1": ("tensor", gemm_flops),
         "spmm_h": ("hbm", spmm_bytes_h_bwd), "spmm_k": ("hbm", spmm_bytes_k),
-        "spmm_h_fused": ("hbm", spmm_bytes_h + 4.0 * N * K),
-        "skinny_fwd": ("hbm", 4.0 * N * H + 4.0 * N * K), "skinny_bwd": ("hbm", 8.0 * N * H + 4.0 * N * K),
+        "spmm_h_fused": ("hbm", spmm_bytes_fused), "spmm_h_fwd": ("hbm", spmm_bytes_h_bwd),
+        "skinny_fwd": ("hbm", (2.0 if act16 else 4.0) * N * H + 4.0 * N * K), "skinny_bwd": ("hbm", skinny_bwd_bytes),
         "cut_loss": ("hbm", 12.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)), "colsum_db2": ("hbm", 4.0 * N * K),
         "adam": ("hbm", 28.0 * (F * H + H + H * K + K)),
         "gemm_nt_dx": ("tensor", gemm_flops), "adam_features": ("hbm", 28.0 * N * ldx),
@@ -457,7 +476,8 @@ def run_b200_arm(args):
                             "frac": achieved / peak if peak else None, "avg_ms": avg_ms, "calls": calls,
                             "share_of_step": tot / ms,
                             # DRAM bytes per launch from the committed ncu --set full capture (per graph x graphs/GPU)
-                            "traffic": (traffic_db.get("per_graph_bytes", {}).get(name) or 0.0) * B or None}
+                            "traffic": (traffic_db.get("per_graph_bytes_bf16_activations" if act16 else "per_graph_bytes",
+                                                       {}).get(name) or 0.0) * B or None}
     dominant = max(timer.total_ms, key=lambda k: timer.total_ms[k]) if timer.total_ms else None
     roofline = None
     if dominant:
@@ -500,8 +520,11 @@ def run_b200_arm(args):
                 "model": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
                 "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",
                 "gemm_precision": args.precision, "parallelism": f"dp{world}",
+                "activations": ("bf16 storage of T1 / H1 / dH1pre / dT1 (fp32 arithmetic, logits, loss, gradients, Adam)"
+                                if act16 else "fp32"),
                 "l2": (f"inputs larger than L2 (activations {2 * N * H * 4 / 1e9:.1f} GB)" if sparse_adj else
-                       f"inputs larger than L2 (X {N * F * 4 / 1e9:.1f} GB, activations {2 * N * H * 4 / 1e9:.1f} GB)"),
+                       f"inputs larger than L2 (X {N * F * (2 if args.precision == 'bf16' else 4) / 1e9:.1f} GB, "
+                       f"activations {2 * N * H * (2 if act16 else 4) / 1e9:.1f} GB)"),
                 "graph_generation_s": t_gen,
             },
             "roofline": roofline,

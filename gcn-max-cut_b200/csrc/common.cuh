@@ -75,6 +75,27 @@ __device__ __forceinline__ long long warp_max(long long v) {
     return v;
 }
 
+// Sums P (power of two <= 32) per-lane values over the warp in P - 1 + log2(32 / P) shuffles instead of 5 P: every
+// halving step exchanges the half a lane does not keep.  Returns the total of value index (lane >> log2(32 / P)),
+// valid in every lane (lanes that share an index hold the same total).
+template <int P>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[P], int lane) {
+    int m = 16;
+#pragma unroll
+    for (int n = P; n > 1; n >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+#pragma unroll
+    for (; m > 0; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+    return v[0];
+}
+
 // graph id of node v: largest g with graph_ptr[g] <= v   (graph_ptr has n_graphs+1 entries)
 __device__ __forceinline__ int find_graph(const int32_t* __restrict__ graph_ptr, int n_graphs, int64_t v) {
     int lo = 0, hi = n_graphs;          // invariant: graph_ptr[lo] <= v < graph_ptr[hi]

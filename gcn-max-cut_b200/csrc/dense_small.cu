@@ -59,6 +59,65 @@ skinny_fwd_kernel(const float* __restrict__ H, int64_t ldh, const float* __restr
     }
 }
 
+// bf16 H (8 columns per 16-byte unit): a warp takes four rows per step -- eight 16-byte loads in flight per lane --
+// keeps its 16 columns of W in registers, and folds the 4 x NOUT partial sums with warp_multi_sum (one shuffle per
+// value instead of five).  T = H W of TrainingNeural.py:83 when H1 is stored in bf16 (forward via the slab SpMM).
+template <int NU, int NOUT>
+__global__ void __launch_bounds__(256)
+skinny_fwd_b16_kernel(const uint4* __restrict__ H, int64_t ldh8, const float* __restrict__ W, float* __restrict__ T,
+                      int64_t ldt, int64_t n_rows, int n_in, int c8) {
+    constexpr int R = 4, V = R * NOUT;
+    constexpr int P = V <= 4 ? 4 : (V <= 8 ? 8 : (V <= 16 ? 16 : 32));
+    constexpr int SH = P == 4 ? 3 : (P == 8 ? 2 : (P == 16 ? 1 : 0));
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t total_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float w[NU][8][NOUT];
+#pragma unroll
+    for (int q = 0; q < NU; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int col = (lane + 32 * q) * 8 + i;
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) w[q][i][k] = col < n_in ? __ldg(W + (int64_t)col * NOUT + k) : 0.f;
+        }
+    for (int64_t r0 = gwarp * R; r0 < n_rows; r0 += total_warps * R) {
+        uint4 h[R][NU];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < NU; ++q) {
+                const int u = lane + 32 * q;
+                h[r][q] = (r0 + r < n_rows && u < c8) ? __ldg(H + (r0 + r) * ldh8 + u) : make_uint4(0u, 0u, 0u, 0u);
+                if (u * 8 + 4 >= n_in) { h[r][q].z = 0u; h[r][q].w = 0u; }     // pad columns never reach the sums
+            }
+        float v[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < NU; ++q) {
+                const uint32_t ww[4] = {h[r][q].x, h[r][q].y, h[r][q].z, h[r][q].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float lo = __uint_as_float(ww[i] << 16), hi = __uint_as_float(ww[i] & 0xffff0000u);
+#pragma unroll
+                    for (int k = 0; k < NOUT; ++k) {
+                        v[r * NOUT + k] = fmaf(lo, w[q][2 * i][k], v[r * NOUT + k]);
+                        v[r * NOUT + k] = fmaf(hi, w[q][2 * i + 1][k], v[r * NOUT + k]);
+                    }
+                }
+            }
+        const float tot = warp_multi_sum<P>(v, lane);
+        const int idx = lane >> SH;
+        if ((lane & ((1 << SH) - 1)) == 0 && idx < V) {
+            const int r = idx / NOUT, k = idx - r * NOUT;
+            if (r0 + r < n_rows) T[(r0 + r) * ldt + k] = tot;
+        }
+    }
+}
+
 // ws layout: [n_ctas][n_in][NOUT + 1]   (last slot = dbias partial)
 template <int NOUT>
 __global__ void __launch_bounds__(128)
@@ -108,6 +167,77 @@ skinny_bwd_kernel(const float* __restrict__ dT, int64_t lddt, const float* __res
 #pragma unroll
             for (int k = 0; k < NOUT; ++k) t[k] = __ldg(dT + v * lddt + k);
             row(t, __ldg(reinterpret_cast<const float4*>(H + v * ldh + j0)), v);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (j0 + i < n_in) {
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) my_ws[(int64_t)(j0 + i) * (NOUT + 1) + k] = dw[i][k];
+                my_ws[(int64_t)(j0 + i) * (NOUT + 1) + NOUT] = db[i];
+            }
+        }
+    }
+}
+
+// bf16 activations: H (the forward's rounded ReLU output) and dHpre are bf16 matrices, so the pass moves 4 bytes per
+// (node, hidden unit) instead of 16.  A thread still owns 4 columns (one 8-byte load and store per row); four rows are
+// in flight per thread to keep the bytes in flight of the fp32 kernel.  dW, dbias and the products are fp32; dbias sums
+// the unrounded values.
+template <int NOUT>
+__global__ void __launch_bounds__(128)
+skinny_bwd_b16_kernel(const float* __restrict__ dT, int64_t lddt, const float* __restrict__ W, const uint2* __restrict__ H,
+                      int64_t ldh4, uint2* __restrict__ dH, int64_t lddh4, int64_t n_rows, int n_in, float* __restrict__ ws) {
+    const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per;
+    const int64_t r1 = min(n_rows, r0 + rows_per);
+    float* my_ws = ws + (int64_t)blockIdx.x * n_in * (NOUT + 1);
+    for (int j0 = threadIdx.x * 4; j0 < n_in; j0 += blockDim.x * 4) {
+        const int j4 = j0 >> 2;
+        float w[4][NOUT], dw[4][NOUT], db[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            db[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) {
+                w[i][k] = (j0 + i < n_in) ? __ldg(W + (int64_t)(j0 + i) * NOUT + k) : 0.f;
+                dw[i][k] = 0.f;
+            }
+        }
+        auto row = [&](const float (&t)[NOUT], const uint2 h2, int64_t v) {
+            const float h[4] = {__uint_as_float(h2.x << 16), __uint_as_float(h2.x & 0xffff0000u),
+                                __uint_as_float(h2.y << 16), __uint_as_float(h2.y & 0xffff0000u)};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) { s = fmaf(t[k], w[i][k], s); dw[i][k] = fmaf(h[i], t[k], dw[i][k]); }
+                o[i] = h[i] > 0.f ? s : 0.f;
+                db[i] += o[i];
+            }
+            uint2 pk;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
+            dH[v * lddh4 + j4] = pk;
+        };
+        int64_t v = r0;
+        for (; v + 4 <= r1; v += 4) {
+            float t[4][NOUT];
+            uint2 h[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) h[r] = __ldg(H + (v + r) * ldh4 + j4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) t[r][k] = __ldg(dT + (v + r) * lddt + k);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) row(t[r], h[r], v + r);
+        }
+        for (; v < r1; ++v) {
+            float t[NOUT];
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) t[k] = __ldg(dT + v * lddt + k);
+            row(t, __ldg(H + v * ldh4 + j4), v);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -212,6 +342,36 @@ int gmc_skinny_fwd_f32(const float* H, int64_t ldh, const float* W, float* T, in
     return GMC_OK;
 }
 
+// T = H W with H stored in bf16 (ldh in elements, multiple of 8 covering n_in rounded up to 8; 16-byte aligned base),
+// W and T fp32.  n_in <= 512, n_out <= 4 (W lives in registers); GMC_ERR_UNSUPPORTED otherwise.
+int gmc_skinny_fwd_bf16(const void* H, int64_t ldh, const float* W, float* T, int64_t ldt, int64_t n_rows,
+                        int32_t n_in, int32_t n_out, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(H && W && T, "gmc_skinny_fwd_bf16: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_in > 0 && n_out >= 1 && ldh >= n_in && ldt >= n_out, "gmc_skinny_fwd_bf16: bad sizes");
+    const int c8 = (n_in + 7) / 8;
+    if (n_out > 4 || n_in > 512 || n_in % 4 != 0 || ldh % 8 != 0 || ldh < (int64_t)c8 * 8 || !aligned16(H)) {
+        set_error("gmc_skinny_fwd_bf16: needs n_out <= 4, n_in <= 512, n_in %% 4 == 0, ldh %% 8 == 0 covering n_in rounded "
+                  "up to 8 and a 16-byte aligned H");
+        return GMC_ERR_UNSUPPORTED;
+    }
+    if (n_rows == 0) return GMC_OK;
+    cudaStream_t s = as_stream(stream);
+    const uint4* H8 = reinterpret_cast<const uint4*>(H);
+    int64_t blocks = ceil_div<int64_t>(n_rows, 8 * 4);
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+#define GMC_CASE(K)                                                                                                   \
+    case K:                                                                                                           \
+        if (c8 <= 32) skinny_fwd_b16_kernel<1, K><<<(unsigned)blocks, 256, 0, s>>>(H8, ldh / 8, W, T, ldt, n_rows, n_in, c8); \
+        else skinny_fwd_b16_kernel<2, K><<<(unsigned)blocks, 256, 0, s>>>(H8, ldh / 8, W, T, ldt, n_rows, n_in, c8);          \
+        break;
+    switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) }
+#undef GMC_CASE
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
 size_t gmc_skinny_bwd_workspace_bytes(int32_t n_in, int32_t n_out) {
     return (size_t)gmc::reduce_ctas() * 2 * (size_t)n_in * (size_t)(n_out + 1) * sizeof(float);
 }
@@ -240,6 +400,44 @@ int gmc_skinny_bwd_f32(const float* dT, int64_t lddt, const float* W, const floa
         return GMC_OK;
     }
 #define GMC_CASE(K) case K: skinny_bwd_kernel<K><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, dHpre, lddh, n_rows, n_in, ws); break;
+    switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
+#undef GMC_CASE
+    GMC_LAUNCH_CHECK();
+    const int total = n_in * (n_out + 1);
+    skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+// gmc_skinny_bwd_f32 with H and dHpre stored in bf16 (leading dimensions in elements, multiples of 4; 8-byte aligned
+// bases): autograd of TrainingNeural.py:81-83 when the layer-1 activations are kept in bf16.  Same workspace.
+int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const void* H, int64_t ldh, void* dHpre,
+                        int64_t lddh, float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(dT && W && H && dHpre && dW, "gmc_skinny_bwd_bf16: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_in > 0 && n_out >= 1 && n_out <= kMaxClasses && ldh >= n_in && lddh >= n_in && lddt >= n_out,
+                "gmc_skinny_bwd_bf16: bad sizes (n_out must be 1..8)");
+    GMC_REQUIRE(n_in % 4 == 0 && ldh % 4 == 0 && lddh % 4 == 0 && (reinterpret_cast<uintptr_t>(H) & 7u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dHpre) & 7u) == 0,
+                "gmc_skinny_bwd_bf16: n_in and leading dimensions must be multiples of 4 with 8-byte aligned bases");
+    int n_ctas = reduce_ctas() * 2;
+    if ((int64_t)n_ctas > n_rows) n_ctas = (int)(n_rows > 0 ? n_rows : 1);
+    const size_t need = (size_t)n_ctas * n_in * (n_out + 1) * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+        set_error("gmc_skinny_bwd_bf16: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GMC_ERR_WORKSPACE;
+    }
+    cudaStream_t s = as_stream(stream);
+    float* ws = reinterpret_cast<float*>(workspace);
+    if (n_rows == 0) {
+        GMC_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * n_in * n_out, s));
+        if (dbias) GMC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * n_in, s));
+        return GMC_OK;
+    }
+    const uint2* H2 = reinterpret_cast<const uint2*>(H);
+    uint2* dH2 = reinterpret_cast<uint2*>(dHpre);
+#define GMC_CASE(K) case K: skinny_bwd_b16_kernel<K><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H2, ldh / 4, dH2, lddh / 4, n_rows, n_in, ws); break;
     switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();

@@ -94,6 +94,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// two fp32 -> one word of two bf16 (round to nearest even); lo lands at the lower address
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t w;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+    return w;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -178,6 +184,7 @@ struct Params {
     int accumulate;
     int vec_ok;              // 16-byte aligned C rows
     int tma_store;           // epilogue through shared memory + cp.async.bulk.tensor stores (tmC valid)
+    int c_bf16;              // C is a bf16 matrix (tmC describes it): accumulators rounded to nearest even on the way out
 };
 
 // Thread-block cluster of CLM x CLN CTAs (rank = rm + CLM * rn) that owns CLM consecutive m-tiles x CLN consecutive
@@ -358,6 +365,39 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const int64_t m = m0 + 32 * q + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BLOCK_N;
+            if (p.c_bf16) {
+                // bf16 output: 64 accumulator columns -> 32 packed words = one 128-byte staging row per lane, same swizzle
+                // and the same 32-row TMA store as the fp32 path (box 64 x 32 bf16); half the store traffic of the tile
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 64; ++c) {
+                    const int n = n0 + 64 * c;
+                    if (n >= p.N || m0 >= p.M) break;              // warp-uniform
+                    uint32_t ra[32], rb[32], wv[32];
+                    tmem_ld32(t_row + 64 * c, ra);
+                    tmem_ld32(t_row + 64 * c + 32, rb);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        wv[i] = pack_bf16x2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
+                        wv[16 + i] = pack_bf16x2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+                    }
+                    const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+                    const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((i ^ (lane & 7)) << 4)),
+                                     "r"(wv[4 * i]), "r"(wv[4 * i + 1]), "r"(wv[4 * i + 2]), "r"(wv[4 * i + 3]) : "memory");
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, buf, n, (int)(m0 + 32 * q));
+                        bulk_commit();
+                    }
+                    ebuf ^= 1;
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 const int n = n0 + 32 * c;
@@ -400,6 +440,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (n + i < p.N) dst[i] = p.accumulate ? dst[i] + __uint_as_float(r[i]) : __uint_as_float(r[i]);
                     }
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();
@@ -738,7 +779,7 @@ static int cluster_slots() {
 
 template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
 static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                  int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                  int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0) {
     constexpr int CL = CLM * CLN;
     constexpr int ELT = BF16 ? 2 : 4;
     constexpr int BK = 128 / ELT, MNC = 128 / ELT;                 // k elements per stage, m/n elements per MN-major chunk
@@ -769,7 +810,7 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     p.mg_tiles = ceil_div(p.m_tiles, CLM);
     p.ng_tiles = ceil_div(p.n_tiles, CLN);
     const int64_t ctiles = (int64_t)p.mg_tiles * p.ng_tiles;
-    int splits = pick_splits_cl(ctiles, K, slots);
+    int splits = c_bf16 ? 1 : pick_splits_cl(ctiles, K, slots);   // a bf16 C leaves straight from the accumulators
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
         if (splits < 1) splits = 1;
@@ -780,7 +821,7 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     p.k_per_split = k_per;
     if (splits == 1) {
         p.C = C; p.ldc = ldc; p.split_stride = 0; p.accumulate = accumulate;
-        p.vec_ok = (ldc % 4 == 0) && aligned16(C);
+        p.vec_ok = (ldc % (c_bf16 ? 8 : 4) == 0) && aligned16(C);
     } else {
         p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
         p.vec_ok = (N % 4 == 0) && aligned16(workspace);
@@ -789,7 +830,16 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     CUtensorMap tmC;
     memset(&tmC, 0, sizeof(tmC));
     p.tma_store = 0;
-    if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
+    if (c_bf16) {
+        if (accumulate || !p.vec_ok) {
+            set_error("gmc_gemm_bf16_bf16out: needs accumulate = 0, a 16-byte aligned C and ldc %% 8 == 0");
+            return GMC_ERR_INVALID_ARG;
+        }
+        rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 64, 32, false, 2);
+        if (rc) return rc;
+        p.tma_store = 1;
+        p.c_bf16 = 1;
+    } else if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
         rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
         if (rc) return rc;
         p.tma_store = 1;
@@ -808,15 +858,15 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
 
 template <bool A_MN, bool B_MN, bool BF16 = false>
 static int launch_cl(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                     int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                     int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0) {
     int clm, cln;
     cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln);
 #define GMC_GEMM_CASE(CM, CN)                                                                                       \
     if (clm == CM && cln == CN)                                                                                     \
-        return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
     GMC_GEMM_CASE(1, 1) GMC_GEMM_CASE(2, 1) GMC_GEMM_CASE(4, 1) GMC_GEMM_CASE(8, 1) GMC_GEMM_CASE(2, 2) GMC_GEMM_CASE(4, 2)
 #undef GMC_GEMM_CASE
-    return launch<A_MN, B_MN, 4, 1, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+    return launch<A_MN, B_MN, 4, 1, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
 }
 
 static bool use_two_cta() {
@@ -857,7 +907,7 @@ static int launch2(const float* A, const float* B, float* C, int64_t M, int64_t 
     else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, HALF, false);
     if (rc) return rc;
 
-    Params p;
+    Params p = {};
     p.M = M; p.N = N; p.K = K;
     p.m_tiles = (int)ceil_div<int64_t>(M, 256);
     p.n_tiles = (int)ceil_div<int64_t>(N, 256);
@@ -1028,20 +1078,22 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
 // L2 and shared memory, twice the MMA rate.
 size_t tc_bf16_workspace_bytes(int op, int64_t M, int64_t N, int64_t K) { return (tc_splitk_bytes(op, M, N, K) + 255) & ~(size_t)255; }
 
-int tc_gemm_bf16(int op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                 int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                 int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16) {
     GMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B),
                 "gmc_gemm_bf16: TMA needs 16-byte aligned bases and leading dimensions that are multiples of 8 elements");
     GMC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gmc_gemm_bf16: dimension exceeds int32 TMA coordinates");
     if (M == 0 || N == 0) return GMC_OK;
+    const size_t celt = c_bf16 ? 2 : 4;
     if (K == 0) {
-        if (!accumulate) GMC_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, s));
+        if (!accumulate) GMC_CUDA(cudaMemset2DAsync(C, (size_t)ldc * celt, 0, (size_t)N * celt, (size_t)M, s));
         return GMC_OK;
     }
+    float* Cf = reinterpret_cast<float*>(C);                       // reinterpreted by the kernel when c_bf16 is set
     switch (op) {
-        case 0: return tc::launch_cl<false, true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-        case 1: return tc::launch_cl<false, false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-        case 2: return tc::launch_cl<true, true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+        case 0: return tc::launch_cl<false, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
+        case 1: return tc::launch_cl<false, false, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
+        case 2: return tc::launch_cl<true, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
     }
     set_error("gmc_gemm_bf16: bad op %d", op);
     return GMC_ERR_INVALID_ARG;

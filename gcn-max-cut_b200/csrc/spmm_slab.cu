@@ -125,13 +125,16 @@ struct SlabProj {
     int n_out;
 };
 
-template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF, bool PROJ = false>
+// XB: X and Y are bf16 matrices.  A 16-byte unit then holds 8 columns, so a 112-byte slab row covers 56 columns and
+// the per-row work (id load, d shared-memory wavefronts) is amortised over twice the columns; c4 / ldx4 / ldy4 count
+// 16-byte units, accumulation is fp32, the result is rounded to nearest even.  No bias / ReLU / projection.
+template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF, bool PROJ = false, bool XB = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restrict__ header,
                  const uint4* __restrict__ ell_col, const float* __restrict__ plan_nd,
                  const int32_t* __restrict__ graph_ptr, const float4* __restrict__ X, float4* __restrict__ Y,
                  int n_graphs, int c4, int64_t ldx4, int64_t ldy4, const float4* __restrict__ bias, int relu,
-                 int n_slabs, int rows_cap, int out_bf16, const SlabProj proj) {
+                 int n_slabs, int rows_cap, int out_bf16, const SlabProj proj, int n_cols_b16) {
     extern __shared__ __align__(128) float4 sbuf_all[];   // NBUF x [rows_cap][W4]: rows, the all-zero row, one pad row; mbarriers
     constexpr int GROUPS = THREADS / LANES;
     constexpr uint32_t BOX_BYTES = kBoxRows * W4 * 16;
@@ -163,7 +166,7 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
         if (TMA && tid == 0 && n_box > 0) {
             mbar_expect_tx(bar0 + 8 * b, (uint32_t)n_box * BOX_BYTES);
             for (int k = 0; k < n_box; ++k)
-                tma_load_2d(sbase + b * BUF_BYTES + (uint32_t)k * BOX_BYTES, &tmX, col * 4, b0 + k * kBoxRows, bar0 + 8 * b);
+                tma_load_2d(sbase + b * BUF_BYTES + (uint32_t)k * BOX_BYTES, &tmX, col * (XB ? 8 : 4), b0 + k * kBoxRows, bar0 + 8 * b);
         }
         const int rt = n_box * kBoxRows;
         const float4* src = X + (int64_t)(b0 + rt) * ldx4 + col;
@@ -225,8 +228,14 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
 #pragma unroll
         for (int k = 0; k < DEPTH; ++k)
             if (!pre[k] && r0 + k * GROUPS < n_g) load_slots(S[k], base, r0 + k * GROUPS);
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && active) b4 = __ldg(bias + col0 + lg);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), b4h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (XB) {                                         // a 16-byte unit = 8 columns = two float4 of the fp32 bias
+            if (bias && active) {
+                const int c = (col0 + lg) * 8;
+                if (c < n_cols_b16) b4 = __ldg(bias + (col0 + lg) * 2);
+                if (c + 4 < n_cols_b16) b4h = __ldg(bias + (col0 + lg) * 2 + 1);
+            }
+        } else if (bias && active) b4 = __ldg(bias + col0 + lg);
         if (PROJ) {                                       // W slab, transposed: wsm[k][column] (0 beyond n_out / n_cols)
             float* wf = reinterpret_cast<float*>(wsm);
             for (int i = tid; i < 4 * W4 * 4; i += THREADS) {
@@ -247,6 +256,42 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
         auto gather = [&](uint32_t u) { return sl[u * W4]; };
         auto add4 = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
         auto row_out = [&](const Slots& S, int row) {
+            if constexpr (XB) {
+                float a[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = 0.f;
+                auto add8 = [&](const float4& v) {
+                    const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        a[2 * i] += __uint_as_float(w[i] << 16);
+                        a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+                    }
+                };
+                {
+                    const float4 v0 = gather(S.c.x & 0xffffu), v1 = gather(S.c.x >> 16), v2 = gather(S.c.y & 0xffffu),
+                                 v3 = gather(S.c.y >> 16);
+                    add8(v0); add8(v1); add8(v2); add8(v3);
+                }
+                {
+                    const float4 v4 = gather(S.c.z & 0xffffu), v5 = gather(S.c.z >> 16), v6 = gather(S.c.w & 0xffffu);
+                    add8(v4); add8(v5); add8(v6);
+                }
+                if (slot7) add8(gather(S.c.w >> 16));
+                if (active) {
+                    const float bb[8] = {b4.x, b4.y, b4.z, b4.w, b4h.x, b4h.y, b4h.z, b4h.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        a[i] = fmaf(a[i], S.d, bb[i]);
+                        if (relu) a[i] = fmaxf(a[i], 0.f);
+                    }
+                    __nv_bfloat162 o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+                    reinterpret_cast<uint4*>(Y)[(int64_t)(base + row) * ldy4 + col0 + lg] = *reinterpret_cast<const uint4*>(o);
+                }
+                return;
+            }
             float4 acc = gather(S.c.x & 0xffffu);
             {
                 const float4 v1 = gather(S.c.x >> 16), v2 = gather(S.c.y & 0xffffu), v3 = gather(S.c.y >> 16);
@@ -352,10 +397,11 @@ static EncodeTiledFn slab_encode_fn() {
     return fn;
 }
 
-template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF, bool PROJ = false>
+template <int W4, int LANES, int THREADS, int MINB, int DEPTH, bool TMA, int NBUF, bool PROJ = false, bool XB = false>
 static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_graphs, int max_nodes, const float4* X4,
                            float4* Y4, int64_t n_rows, int c4, int64_t ldx4, int64_t ldy4, const float4* b4, int relu,
-                           cudaStream_t s, int* launched, int out_bf16 = 0, SlabProj proj = SlabProj{nullptr, nullptr, 0, 0}) {
+                           cudaStream_t s, int* launched, int out_bf16 = 0, SlabProj proj = SlabProj{nullptr, nullptr, 0, 0},
+                           int n_cols_b16 = 0) {
     const int rows_cap = (max_nodes + 2 + 7) & ~7;         // buffers stay 128-byte aligned (TMA destination)
     const size_t smem = (size_t)NBUF * rows_cap * W4 * sizeof(float4) + 16 + (PROJ ? 4 * W4 * sizeof(float4) : 0);
     if (smem + 1024 > (228 * 1024) / MINB || smem > kSlabSmemMax) return GMC_OK;
@@ -364,20 +410,21 @@ static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_gra
     if (TMA) {
         EncodeTiledFn enc = slab_encode_fn();
         if (!enc) return GMC_OK;                          // no driver entry point: let the caller take another kernel
-        cuuint64_t dims[2] = {(cuuint64_t)c4 * 4, (cuuint64_t)n_rows};
+        // XB: the real column count bounds the map, so the last unit's pad columns arrive as zeros
+        cuuint64_t dims[2] = {XB ? (cuuint64_t)n_cols_b16 : (cuuint64_t)c4 * 4, (cuuint64_t)n_rows};
         cuuint64_t strides[1] = {(cuuint64_t)ldx4 * 16};
-        cuuint32_t box[2] = {W4 * 4, kBoxRows};
+        cuuint32_t box[2] = {W4 * (XB ? 8 : 4), kBoxRows};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float4*>(X4), dims, strides, box, estr,
+        CUresult r = enc(&tm, XB ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float4*>(X4), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("gmc_spmm_batched_f32: cuTensorMapEncodeTiled failed (%d)", (int)r); return GMC_ERR_INVALID_ARG; }
     }
     static bool attr = false;
     if (!attr) {
-        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ>,
+        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ, XB>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabSmemMax));
-        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ>,
+        GMC_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ, XB>,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr = true;
     }
@@ -388,8 +435,9 @@ static int slab_launch_one(const void* plan, const int32_t* graph_ptr, int n_gra
     const int64_t items = (int64_t)n_graphs * n_slabs;
     const int64_t slots = (int64_t)sm_count() * MINB;
     const int grid = (int)(items < slots ? items : slots);
-    spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ><<<grid, THREADS, smem, s>>>(
-        tm, header, ecol, pnd, graph_ptr, X4, Y4, n_graphs, c4, ldx4, ldy4, b4, relu, n_slabs, rows_cap, out_bf16, proj);
+    spmm_slab_kernel<W4, LANES, THREADS, MINB, DEPTH, TMA, NBUF, PROJ, XB><<<grid, THREADS, smem, s>>>(
+        tm, header, ecol, pnd, graph_ptr, X4, Y4, n_graphs, c4, ldx4, ldy4, b4, relu, n_slabs, rows_cap, out_bf16, proj,
+        n_cols_b16);
     GMC_LAUNCH_CHECK();
     *launched = 1;
     return GMC_OK;
@@ -496,6 +544,47 @@ int gmc_spmm_batched_bf16out(const int32_t* graph_ptr, int32_t n_graphs, int32_t
     if (rc != GMC_OK) return rc;
     if (!launched) {
         set_error("gmc_spmm_batched_bf16out: the batch cannot take the slab kernel (no plan, narrow or unaligned matrix)");
+        return GMC_ERR_UNSUPPORTED;
+    }
+    return GMC_OK;
+}
+
+// Y = A_hat X with both matrices stored in bf16 (leading dimensions in elements, multiples of 8, covering n_cols
+// rounded up to 8; pad columns of X must be finite -- the engine keeps them zero): Y = act(A_hat X + bias), the
+// backward aggregation dT1 = A_hat dH1pre (no bias, no ReLU) and, with bias + ReLU, the forward H1 when the layer-1
+// activations are kept in bf16.  fp32 accumulation and bias, result rounded to nearest even.
+// Slab kernel only: GMC_ERR_UNSUPPORTED when the batch has no usable plan.
+int gmc_spmm_batched_bf16(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, const void* plan, const void* X,
+                          void* Y, int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy, const float* bias,
+                          int32_t relu, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(graph_ptr && X && Y, "gmc_spmm_batched_bf16: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_cols > 0 && ldx >= n_cols && ldy >= n_cols, "gmc_spmm_batched_bf16: bad sizes");
+    GMC_REQUIRE(X != Y, "gmc_spmm_batched_bf16: in-place SpMM is not supported");
+    if (n_rows == 0) return GMC_OK;
+    const int c8 = (n_cols + 7) / 8;
+    const bool ok = plan && n_graphs > 0 && max_nodes >= 128 && n_cols >= 16 && ldx % 8 == 0 && ldy % 8 == 0 &&
+                    ldx >= (int64_t)c8 * 8 && ldy >= (int64_t)c8 * 8 && aligned16(X) && aligned16(Y) && aligned16(plan) &&
+                    n_cols % 4 == 0 && (!bias || aligned16(bias));
+    int launched = 0;
+    if (ok) {
+        const float4* X4 = reinterpret_cast<const float4*>(X);
+        float4* Y4 = reinterpret_cast<float4*>(Y);
+        const SlabProj none{nullptr, nullptr, 0, 0};
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
+        int rc = slab_launch_one<7, 8, 512, 2, 2, true, 1, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows, c8,
+                                                                        ldx / 8, ldy / 8, b4, relu, as_stream(stream),
+                                                                        &launched, 1, none, n_cols);
+        if (rc != GMC_OK) return rc;
+        if (!launched) {
+            rc = slab_launch_one<4, 4, 1024, 1, 2, true, 1, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows,
+                                                                         c8, ldx / 8, ldy / 8, b4, relu, as_stream(stream),
+                                                                         &launched, 1, none, n_cols);
+            if (rc != GMC_OK) return rc;
+        }
+    }
+    if (!launched) {
+        set_error("gmc_spmm_batched_bf16: the batch cannot take the slab kernel (no plan, graphs too large, narrow or unaligned matrix)");
         return GMC_ERR_UNSUPPORTED;
     }
     return GMC_OK;

@@ -37,6 +37,9 @@ from .optim import FusedAdam
 # forward aggregation: the fused row kernel (aggregate + bias + ReLU + H1 W2 in one pass) unless GMC_FWD_SLAB=1 asks
 # for the slab SpMM followed by the separate skinny projection
 _FWD_SLAB = os.environ.get("GMC_FWD_SLAB", "0") == "1"
+# bf16 activations: GMC_FWD16 = 'slab' (default: bf16 slab SpMM + bf16 skinny projection, 2.4 + 1.3 ms at config 3) |
+# 'row' (fused row kernel with bf16 gathers, 4.95 ms: ~775 warp instructions per row, issue-bound)
+_FWD16_SLAB = os.environ.get("GMC_FWD16", "slab") == "slab"
 
 
 def _pad4(n: int) -> int:
@@ -76,7 +79,7 @@ class OpTimer:
 class GCNEngine:
     def __init__(self, net, optimizer: Optional[FusedAdam] = None, *, C: float = 1.0, loss_mode: str = "ste",
                  override_terminals: bool = True, penalty: float = 0.0, precision: str = "fp32",
-                 process_group=None, adjacency_kernels: bool = False):
+                 process_group=None, adjacency_kernels: bool = False, activations: str = "fp32"):
         self.device = _lib.require_cuda()
         self.net = net
         self.optimizer = optimizer
@@ -86,6 +89,16 @@ class GCNEngine:
         if precision not in _lib.ENGINE_PRECISIONS:
             raise ValueError(f"unknown precision {precision!r}")
         self.precision = precision
+        # activations='bf16' (needs precision='bf16'): the four [n_nodes, hidden] layer-1 tensors -- T1 = X W1,
+        # H1 = relu(A_hat T1 + b1), dH1pre, dT1 -- are STORED in bf16 (standard mixed-precision practice: bf16 storage,
+        # fp32 arithmetic).  Each is written once and read once (T1: d times by the gather), so every layer-1 pass
+        # moves half the bytes; logits, loss, all reductions, gradients and Adam stay fp32.  Batches without an ELL
+        # plan (irregular graphs) keep fp32 activations.
+        if activations not in ("fp32", "bf16"):
+            raise ValueError(f"unknown activations {activations!r}")
+        if activations == "bf16" and precision != "bf16":
+            raise ValueError("activations='bf16' needs precision='bf16'")
+        self.activations = activations
         # adjacency_kernels: the caller guarantees that the features ARE the zero-padded unit-weight adjacency rows of
         # the batch (the reference's live input, TrainingNeural.py:373).  X W1 and X^T dT1 then run as aggregations
         # over the batch's ELL plan (csrc/spmm_adj.cu) whenever the batch qualifies, and X itself is never read.
@@ -117,6 +130,7 @@ class GCNEngine:
         self.W1b = ops.padded_empty_bf16(self.F, self.H, self.device, zero=True) if precision == "bf16" else None
         self._xb_cache: Dict[tuple, torch.Tensor] = {}
         self.bufB16 = None
+        self.bufA16 = None
         self._cap_nodes = 0
         self._cap_graphs = 0
         self.bufA = self.bufB = self.T2 = self.Z = self.P = self.dZ = self.dT2 = None
@@ -146,27 +160,36 @@ class GCNEngine:
     def grads(self) -> List[torch.Tensor]:
         return [self.gW1, self.gb1, self.gW2, self.gb2]
 
-    def _ensure(self, n_nodes: int, n_graphs: int) -> None:
+    def _ensure(self, n_nodes: int, n_graphs: int, b16: bool = False) -> None:
+        dev, f32 = self.device, torch.float32
         if n_nodes > self._cap_nodes:
             cap = n_nodes
-            dev, f32 = self.device, torch.float32
-            # row pitch padded to 128 B: TMA boxes / 128-bit gathers never straddle cache lines
-            self.bufA = ops.padded_empty(cap, self.H, dev)
-            self.bufB = ops.padded_empty(cap, self.H, dev)
             self.T2 = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.Z = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.P = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.dZ = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.dT2 = torch.empty((cap, self.K), dtype=f32, device=dev)
-            if self.precision == "bf16":
-                self.bufB16 = ops.padded_empty_bf16(cap, self.H, dev)
             self._cap_nodes = cap
+        if not b16 and (self.bufA is None or self.bufA.shape[0] < n_nodes):
+            # row pitch padded to 128 B: TMA boxes / 128-bit gathers never straddle cache lines
+            self.bufA = ops.padded_empty(n_nodes, self.H, dev)
+            self.bufB = ops.padded_empty(n_nodes, self.H, dev)
+        if self.precision == "bf16" and (self.bufB16 is None or self.bufB16.shape[0] < n_nodes):
+            # zero-initialised: the pad columns (hidden .. pitch) stay zero, every kernel that writes it preserves that
+            self.bufB16 = ops.padded_empty_bf16(n_nodes, self.H, dev, zero=True)
+        if b16 and (self.bufA16 is None or self.bufA16.shape[0] < n_nodes):
+            # bf16 activations: two bf16 buffers carry the whole layer-1 chain (A16 = T1 then dH1pre, B16 = H1 then dT1)
+            self.bufA16 = ops.padded_empty_bf16(n_nodes, self.H, dev, zero=True)
         if n_graphs > self._cap_graphs:
             self.loss = torch.empty(n_graphs, dtype=torch.float64, device=self.device)
             self._cap_graphs = n_graphs
 
     def _sparse_layer1(self, batch: GraphBatch) -> bool:
         return self.adjacency_kernels and ops.adjacency_kernels_apply(batch, self.F)
+
+    def _b16_activations(self, batch: GraphBatch) -> bool:
+        return (self.activations == "bf16" and not self._sparse_layer1(batch)
+                and ops.bf16_activations_apply(batch, self.H))
 
     def _features(self, batch: GraphBatch, X: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if X is None:
@@ -202,8 +225,22 @@ class GCNEngine:
         """Z (pre-softmax) for the batch; leaves H1 in bufB."""
         X = self._features(batch, X)
         N = batch.num_nodes
-        self._ensure(N, batch.num_graphs)
         W1, b1, W2, b2 = self.params()
+        if self._b16_activations(batch):
+            self._ensure(N, batch.num_graphs, b16=True)
+            A16, B16 = self.bufA16[:N], self.bufB16[:N]
+            ops.to_bf16(W1.data, out=self.W1b)
+            self._op("gemm_nn_xw1", 1, ops.gemm_bf16_bf16out, "nn", self._bf16_features(X), self.W1b, out=A16)   # T1, bf16
+            if _FWD16_SLAB and self.K <= 4:
+                # aggregation through the shared-memory slab kernel, then the skinny projection as its own pass over H1
+                self._op("spmm_h_fwd", 1, ops.spmm_bf16, batch, A16, out=B16, bias=b1.data, relu=True)           # H1 bf16
+                self._op("skinny_fwd", 1, ops.skinny_fwd_bf16, B16, W2.data, out=self.T2[:N])                  # T2
+            else:
+                self._op("spmm_h_fused", 1, ops.spmm_fused_skinny_bf16, batch, A16, W2.data, out=B16, proj=self.T2[:N],
+                         bias=b1.data, relu=True)                                                               # H1 bf16, T2
+            self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
+            return self.Z[:N]
+        self._ensure(N, batch.num_graphs)
         A, Bf = self.bufA[:N], self.bufB[:N]
         ops.copy2d(self.W1p, W1.data)
         if self._sparse_layer1(batch):
@@ -246,12 +283,21 @@ class GCNEngine:
         N, B = batch.num_nodes, batch.num_graphs
         Z = self.forward_logits(batch, X)
         W1, b1, W2, b2 = self.params()
-        A, Bf = self.bufA[:N], self.bufB[:N]
         loss = self.loss[:B]
         self._op("cut_loss", 1, ops.cut_loss, batch, Z, self.loss_mode, self.override, self.penalty, self.C,
                  need_P=True, need_dZ=True, P=self.P[:N], dZ=self.dZ[:N], loss=loss)
         self._op("colsum_db2", 2, ops.colsum, self.dZ[:N], out=self.gb2, workspace=self.ws)
         self._op("spmm_k", 1, ops.spmm, batch, self.dZ[:N], out=self.dT2[:N])
+        if self._b16_activations(batch):
+            if dX is not None:
+                raise NotImplementedError("trainable features (dX) are not wired to the bf16 GEMM path; use tf32")
+            A16, B16 = self.bufA16[:N], self.bufB16[:N]
+            self._op("skinny_bwd", 2, ops.skinny_bwd_bf16, self.dT2[:N], W2.data, B16, dH=A16, dW=self.gW2,
+                     dbias=self.gb1, workspace=self.ws)                                              # dH1pre, bf16
+            self._op("spmm_h", 1, ops.spmm_bf16, batch, A16, out=B16)                                # dT1, bf16
+            self._op("gemm_tn_dw1", 2, ops.gemm_bf16, "tn", self._bf16_features(X), B16, out=self.gW1, workspace=self.ws)
+            return loss
+        A, Bf = self.bufA[:N], self.bufB[:N]
         self._op("skinny_bwd", 2, ops.skinny_bwd, self.dT2[:N], W2.data, Bf, dH=A, dW=self.gW2, dbias=self.gb1,
                  workspace=self.ws)
         if self.precision == "bf16" and not self._sparse_layer1(batch):

@@ -299,6 +299,118 @@ def gemm_bf16(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Ten
     return out
 
 
+# ---------------------------------------------------------------- bf16 layer-1 activations
+def gemm_bf16_bf16out(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gemm_bf16 whose result is rounded to bf16 in the epilogue (no split-K, no accumulate)."""
+    A, lda = _bf16_rowmajor(A, "A")
+    B, ldb = _bf16_rowmajor(B, "B")
+    if op == "nn":
+        M, K = A.shape; K2, N = B.shape
+    elif op == "nt":
+        M, K = A.shape; N, K2 = B.shape
+    elif op == "tn":
+        K, M = A.shape; K2, N = B.shape
+    else:
+        raise ValueError(f"unknown gemm op {op!r}")
+    if K != K2:
+        raise ValueError(f"gemm_bf16_bf16out {op}: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        out = padded_empty_bf16(M, N, A.device, zero=True)
+    out, ldc = _bf16_rowmajor(out, "out")
+    check(lib().gmc_gemm_bf16_bf16out(_OPS[op], A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
+                                      _stream()), "gmc_gemm_bf16_bf16out")
+    return out
+
+
+def spmm_fused_skinny_bf16(batch, X: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None,
+                           proj: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                           relu: bool = True, out_bf16: bool = True):
+    """spmm_fused_skinny with a bf16 X; Y is bf16 (default) or fp32.  Returns (Y, T)."""
+    X, ldx = _bf16_rowmajor(X, "X")
+    W = _f32(W, "W").contiguous()
+    n, c = X.shape
+    n_out = W.shape[1]
+    if out is None:
+        out = padded_empty_bf16(n, c, X.device, zero=True) if out_bf16 else padded_empty(n, c, X.device)
+    if out.dtype == torch.bfloat16:
+        out, ldy = _bf16_rowmajor(out, "out")
+        y_bf16 = 1
+    else:
+        out, ldy = _rowmajor(out, "out")
+        y_bf16 = 0
+    if proj is None:
+        proj = torch.empty((n, n_out), dtype=torch.float32, device=X.device)
+    proj, ldt = _rowmajor(proj, "proj")
+    if bias is not None:
+        _f32(bias, "bias")
+    check(lib().gmc_spmm_fused_skinny_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(),
+                                           None, None, X.data_ptr(), out.data_ptr(), y_bf16, n, c, ldx, ldy,
+                                           _ptr(bias), int(relu), W.data_ptr(), n_out, proj.data_ptr(), ldt,
+                                           _stream()), "gmc_spmm_fused_skinny_bf16")
+    return out, proj
+
+
+def skinny_bwd_bf16(dT: torch.Tensor, W: torch.Tensor, H: torch.Tensor, dH: Optional[torch.Tensor] = None,
+                    dW: Optional[torch.Tensor] = None, dbias: Optional[torch.Tensor] = None,
+                    workspace: Optional[Workspace] = None):
+    """skinny_bwd with bf16 H and dH."""
+    dT, lddt = _rowmajor(dT, "dT")
+    H, ldh = _bf16_rowmajor(H, "H")
+    W = _f32(W, "W").contiguous()
+    n, n_in = H.shape
+    n_out = W.shape[1]
+    if dH is None:
+        dH = padded_empty_bf16(n, n_in, H.device, zero=True)
+    dH, lddh = _bf16_rowmajor(dH, "dH")
+    if dW is None:
+        dW = torch.empty((n_in, n_out), dtype=torch.float32, device=H.device)
+    if dbias is None:
+        dbias = torch.empty(n_in, dtype=torch.float32, device=H.device)
+    ws = workspace or _default_ws
+    wptr, wbytes = ws.get(lib().gmc_skinny_bwd_workspace_bytes(n_in, n_out), H.device)
+    check(lib().gmc_skinny_bwd_bf16(dT.data_ptr(), lddt, W.data_ptr(), H.data_ptr(), ldh, dH.data_ptr(), lddh,
+                                    dW.data_ptr(), dbias.data_ptr(), n, n_in, n_out, wptr, wbytes, _stream()),
+          "gmc_skinny_bwd_bf16")
+    return dH, dW, dbias
+
+
+def spmm_bf16(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+              relu: bool = False) -> torch.Tensor:
+    """act(A_hat X + bias) with bf16 X and bf16 result (slab kernel; the batch needs an ELL plan)."""
+    X, ldx = _bf16_rowmajor(X, "X")
+    n, c = X.shape
+    if n != batch.num_nodes:
+        raise ValueError(f"X has {n} rows, batch has {batch.num_nodes} nodes")
+    if out is None:
+        out = padded_empty_bf16(n, c, X.device, zero=True)
+    out, ldy = _bf16_rowmajor(out, "out")
+    check(lib().gmc_spmm_batched_bf16(batch.graph_ptr.data_ptr(), batch.num_graphs, batch.max_nodes,
+                                      _ptr(getattr(batch, "plan", None)), X.data_ptr(), out.data_ptr(), n, c, ldx, ldy,
+                                      _ptr(_f32(bias, "bias")) if bias is not None else None, int(relu), _stream()),
+          "gmc_spmm_batched_bf16")
+    return out
+
+
+def skinny_fwd_bf16(H: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """T = H W with a bf16 H [n, n_in <= 512] and fp32 W [n_in, n_out <= 4]."""
+    H, ldh = _bf16_rowmajor(H, "H")
+    W = _f32(W, "W").contiguous()
+    n, n_in = H.shape
+    n_out = W.shape[1]
+    if out is None:
+        out = torch.empty((n, n_out), dtype=torch.float32, device=H.device)
+    out, ldt = _rowmajor(out, "out")
+    check(lib().gmc_skinny_fwd_bf16(H.data_ptr(), ldh, W.data_ptr(), out.data_ptr(), ldt, n, n_in, n_out, _stream()),
+          "gmc_skinny_fwd_bf16")
+    return out
+
+
+def bf16_activations_apply(batch, hidden: int) -> bool:
+    """True when a batch can run the bf16-activation step: ELL plan (regular graphs, degree <= 8, 128..3600 nodes per graph)."""
+    return (getattr(batch, "plan", None) is not None and 128 <= batch.max_nodes <= 3600 and 16 <= hidden <= 512
+            and hidden % 4 == 0)
+
+
 def adjacency_kernels_apply(batch, n_w_rows: int) -> bool:
     """Can X W / X^T dT for X = zero-padded unit-weight adjacency rows be computed as aggregations for this batch?"""
     return (getattr(batch, "plan", None) is not None and bool(getattr(batch, "unit_weights", False))

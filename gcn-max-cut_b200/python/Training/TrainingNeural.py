@@ -85,6 +85,7 @@ class TrainingConfig:
     use_terminal_penalty: bool = False
     feature_source: str = "adjacency"
     adjacency_kernels: bool = False          # batched steps only: X W1 / X^T dT1 as aggregations (csrc/spmm_adj.cu)
+    activations: str = "fp32"                # 'bf16' (with gemm_precision='bf16'): layer-1 activations stored in bf16
 
     def __post_init__(self):
         if self.feature_source not in ("adjacency", "embedding"):
@@ -226,14 +227,16 @@ def _engine_for(net, optimizer, config: TrainingConfig) -> GCNEngine:
            bool(getattr(config, "use_terminal_penalty", False)), float(config.penalty),
            getattr(config, "gemm_precision", "fp32"),
            bool(getattr(config, "adjacency_kernels", False))
-           and getattr(config, "feature_source", "adjacency") == "adjacency")
+           and getattr(config, "feature_source", "adjacency") == "adjacency",
+           getattr(config, "activations", "fp32"))
     cached = _ENGINES.get(net)
     if cached is not None and cached[0] == key:
         return cached[1]
     if optimizer is not None and not isinstance(optimizer, FusedAdam):
         raise TypeError("the B200 training loop needs the FusedAdam returned by setup_model_and_optimizer")
     engine = GCNEngine(net, optimizer, C=config.C, loss_mode=key[2], override_terminals=True,
-                       penalty=config.penalty if key[3] else 0.0, precision=key[5], adjacency_kernels=key[6])
+                       penalty=config.penalty if key[3] else 0.0, precision=key[5], adjacency_kernels=key[6],
+                       activations=key[7])
     _ENGINES[net] = (key, engine)
     return engine
 

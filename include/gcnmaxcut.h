@@ -243,6 +243,37 @@ int gmc_csr_densify_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
                          const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
                          int64_t ldx, void* stream);
 
+/* ---- bf16 layer-1 activations (engine option activations='bf16', on top of the bf16 GEMM operands) ----------------
+ * T1 = X W1, H1 = relu(A_hat T1 + b1), dH1pre and dT1 are [n_nodes, hidden] matrices that are each written once and
+ * read once (or d times by a gather) per step; stored in bf16 they move half the bytes through HBM, L2 and shared
+ * memory.  All arithmetic stays fp32 (TMEM accumulators, fp32 aggregation / bias / ReLU / projection / reductions);
+ * values are rounded to nearest even when stored.  Leading dimensions are in ELEMENTS and multiples of 8 that cover
+ * n_cols rounded up to 8; pad columns are written as zeros / must be finite on input.
+ *
+ * gmc_gemm_bf16_bf16out       : gmc_gemm_bf16 with a bf16 C (epilogue rounds the accumulators, TMA stores); no split-K,
+ *                               no accumulate -- th.matmul of GraphConv layer 1 (TrainingNeural.py:80).
+ * gmc_spmm_fused_skinny_bf16  : gmc_spmm_fused_skinny_f32 with a bf16 X and an fp32 (y_bf16 = 0) or bf16 (y_bf16 = 1) Y;
+ *                               with a bf16 Y the projection T = Y W uses the rounded Y (what the backward pass reads).
+ * gmc_skinny_bwd_bf16         : gmc_skinny_bwd_f32 with bf16 H and dHpre (ldh, lddh multiples of 4).
+ * gmc_spmm_batched_bf16       : gmc_spmm_batched_f32 (slab kernel only, plan required) with bf16 X and Y; fp32 bias.
+ * gmc_skinny_fwd_bf16         : gmc_skinny_fwd_f32 with a bf16 H (n_out <= 4, n_in <= 512): the projection T = H1 W2
+ *                               when the forward aggregation runs through the slab kernel. */
+int gmc_gemm_bf16_bf16out(int32_t op, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
+                          int64_t lda, int64_t ldb, int64_t ldc, void* stream);
+int gmc_spmm_fused_skinny_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                               const float* norm_src, const float* norm_dst, const void* X, void* Y, int32_t y_bf16,
+                               int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy, const float* bias,
+                               int32_t relu, const float* W, int32_t n_out, float* T, int64_t ldt, void* stream);
+int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const void* H, int64_t ldh, void* dHpre,
+                        int64_t lddh, float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int gmc_spmm_batched_bf16(const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, const void* plan,
+                          const void* X, void* Y, int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy,
+                          const float* bias, int32_t relu, void* stream);
+int gmc_skinny_fwd_bf16(const void* H, int64_t ldh, const float* W, float* T, int64_t ldt, int64_t n_rows,
+                        int32_t n_in, int32_t n_out, void* stream);
+
+
 /* ---- (b') layer-1 feature transform when the features ARE the zero-padded adjacency rows ----------------
  * The reference feeds `adjacency_matrix` [n, 1000] as input features (TrainingNeural.py:373; built by
  * DataGenerator/graphExtender.py:106-111).  For unit edge weights X W1 is a row gather of W1 and X^T dT1 a

@@ -1,0 +1,264 @@
+"""GPU tests (`-m gpu`) of the bf16 layer-1 activation chain (engine option activations='bf16'):
+gmc_gemm_bf16_bf16out -> gmc_spmm_fused_skinny_bf16 -> gmc_skinny_bwd_bf16 -> gmc_spmm_batched_bf16, each called
+through the C ABI and checked against a float64 evaluation of the SAME bf16-rounded inputs (so the only differences
+are fp32 accumulation order and the final round-to-nearest-even, 2^-8 relative), then the whole engine step against the
+fp32-activation engine.  Replaces autograd of TrainingNeural.py:80-83 for the throughput configuration only; the
+fp32 / tf32x3 parity paths are untouched (tests/test_gpu_api.py)."""
+import numpy as np
+import pytest
+import torch
+
+from gmc_b200 import ops, synth
+from gmc_b200.engine import GCNEngine
+from gmc_b200.graph import GraphBatch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16_ULP = 2.0 ** -8          # round-to-nearest-even: half an ulp of an 8-bit significand = 2^-9; one ulp allowed
+
+
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+def assert_bf16_close(got: torch.Tensor, want: torch.Tensor, extra: float = 0.0):
+    """got (bf16 tensor) equals want (float64) up to one bf16 ulp plus `extra` (absolute accumulation noise)."""
+    g, w = got.double().cpu(), want.double().cpu()
+    tol = BF16_ULP * w.abs() + extra + 1e-30
+    bad = (g - w).abs() > tol
+    assert not bool(bad.any()), f"{int(bad.sum())} entries off, worst {float(((g - w).abs() / tol).max()):.2f} x tol"
+
+
+def regular_batch(n_graphs, n, d, seed):
+    rowptr, colidx, gp = synth.regular_batch_arrays(n_graphs, n, d, seed=seed)
+    batch = GraphBatch.from_arrays(rowptr, colidx, gp, device=DEV)
+    if batch.plan is None:                                  # built automatically only for >= 32 graphs
+        batch.build_plan()
+    return batch
+
+
+def ahat_times(batch: GraphBatch, X64: torch.Tensor) -> torch.Tensor:
+    """A_hat X in float64 on the host, from the batch's own CSR and per-edge coefficients."""
+    rowptr = batch.rowptr.cpu().numpy().astype(np.int64)
+    colidx = batch.colidx.cpu().numpy().astype(np.int64)
+    coef = batch.coef.cpu().double()
+    rows = torch.from_numpy(np.repeat(np.arange(batch.num_nodes), np.diff(rowptr)))
+    out = torch.zeros_like(X64)
+    out.index_add_(0, rows, X64[torch.from_numpy(colidx)] * coef[:, None])
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 500, 1000), (1000, 500, 256), (4000, 136, 72), (257, 24, 520)])
+def test_gemm_bf16_bf16out(M, N, K):
+    torch.manual_seed(M + N + K)
+    A, B = torch.randn(M, K), torch.randn(K, N)
+    Ab, Bb = ops.to_bf16(A.to(DEV)), ops.to_bf16(B.to(DEV))
+    want = bf16_round(A) @ bf16_round(B)
+    out = ops.padded_empty_bf16(M, N, DEV, zero=True)
+    got = ops.gemm_bf16_bf16out("nn", Ab, Bb, out=out)
+    assert got.dtype == torch.bfloat16
+    # fp32 accumulation of K products of O(1) values: absolute noise ~ K * 2^-24 * |a||b|
+    assert_bf16_close(got, want, extra=K * 2.0 ** -22)
+    # the pad columns of the pitched buffer are never written
+    full = out._base if out._base is not None else out
+    assert float(full[:, N:].abs().max() if full.shape[1] > N else 0.0) == 0.0
+    # the fp32-output GEMM rounded afterwards: identical when it runs without split-K (same accumulators, same rounding),
+    # within one bf16 ulp when its summation order differs
+    ref32 = ops.gemm_bf16("nn", Ab, Bb)
+    assert_bf16_close(got, ref32.double(), extra=K * 2.0 ** -22)
+    if K <= 64:
+        assert torch.equal(got.cpu(), ref32.to(torch.bfloat16).cpu())
+
+
+def test_gemm_bf16_bf16out_nt_tn_and_errors():
+    torch.manual_seed(3)
+    A, B = torch.randn(200, 96), torch.randn(72, 96)
+    got = ops.gemm_bf16_bf16out("nt", ops.to_bf16(A.to(DEV)), ops.to_bf16(B.to(DEV)))
+    assert_bf16_close(got, bf16_round(A) @ bf16_round(B).T, extra=1e-4)
+    At, Bt = torch.randn(512, 136), torch.randn(512, 64)
+    got = ops.gemm_bf16_bf16out("tn", ops.to_bf16(At.to(DEV)), ops.to_bf16(Bt.to(DEV)))
+    assert_bf16_close(got, bf16_round(At).T @ bf16_round(Bt), extra=1e-3)
+    with pytest.raises(Exception):                       # ldc must be a multiple of 8 elements
+        bad = torch.zeros((200, 70), dtype=torch.bfloat16, device=DEV)[:, :67]
+        ops.gemm_bf16_bf16out("nt", ops.to_bf16(A.to(DEV)), ops.to_bf16(B[:67].contiguous().to(DEV)), out=bad)
+
+
+@pytest.mark.parametrize("C,K", [(500, 3), (128, 3), (64, 2), (20, 8), (512, 4), (36, 1)])
+@pytest.mark.parametrize("out_bf16", [True, False])
+def test_spmm_fused_skinny_bf16(C, K, out_bf16):
+    batch = regular_batch(6, 130, 7, seed=C + K)
+    N = batch.num_nodes
+    torch.manual_seed(C * 7 + K)
+    X = torch.randn(N, C)
+    W, bias = torch.randn(C, K) / C ** 0.5, torch.randn(C) * 0.3
+    Xb = ops.to_bf16(X.to(DEV))
+    want_Y = torch.relu(ahat_times(batch, bf16_round(X)) + bias.double())
+    Y, T = ops.spmm_fused_skinny_bf16(batch, Xb, W.to(DEV), bias=bias.to(DEV), relu=True, out_bf16=out_bf16)
+    if out_bf16:
+        assert Y.dtype == torch.bfloat16
+        assert_bf16_close(Y, want_Y, extra=2e-6)
+        want_T = Y.double().cpu() @ W.double()              # the projection consumes the rounded activations
+        full = Y._base if Y._base is not None else Y
+        if full.shape[1] > C:
+            assert float(full[:, C:].abs().max()) == 0.0    # pad columns are exact zeros
+    else:
+        assert Y.dtype == torch.float32
+        assert float((Y.double().cpu() - want_Y).abs().max()) < 2e-5
+        want_T = want_Y @ W.double()
+    assert float((T.double().cpu() - want_T).abs().max()) < 2e-5 * max(1.0, float(want_T.abs().max()))
+    # no bias / no relu variant
+    Y2, _ = ops.spmm_fused_skinny_bf16(batch, Xb, W.to(DEV), bias=None, relu=False, out_bf16=out_bf16)
+    assert_bf16_close(Y2.to(torch.bfloat16), ahat_times(batch, bf16_round(X)), extra=2e-5)
+
+
+@pytest.mark.parametrize("n_in,K", [(500, 3), (128, 3), (36, 8), (512, 1)])
+def test_skinny_bwd_bf16(n_in, K):
+    torch.manual_seed(n_in + K)
+    n = 5000
+    H = torch.relu(torch.randn(n, n_in))
+    dT, W = torch.randn(n, K), torch.randn(n_in, K)
+    Hb = ops.to_bf16(H.to(DEV))
+    H64 = bf16_round(H)
+    want_dH = (dT.double() @ W.double().T) * (H64 > 0)
+    want_dW = H64.T @ dT.double()
+    dH, dW, db = ops.skinny_bwd_bf16(dT.to(DEV), W.to(DEV), Hb)
+    assert dH.dtype == torch.bfloat16
+    assert_bf16_close(dH, want_dH, extra=1e-5)
+    assert float((dW.double().cpu() - want_dW).abs().max()) < 1e-4 * float(want_dW.abs().max())
+    assert float((db.double().cpu() - want_dH.sum(0)).abs().max()) < 1e-4 * float(want_dH.sum(0).abs().max() + 1)
+    # bitwise reproducible (fixed-order two-stage reduction)
+    dH2, dW2, db2 = ops.skinny_bwd_bf16(dT.to(DEV), W.to(DEV), Hb)
+    assert torch.equal(dW, dW2) and torch.equal(db, db2) and torch.equal(dH, dH2)
+
+
+@pytest.mark.parametrize("n,d,C", [(1000, 7, 500), (128, 6, 56), (130, 8, 64), (300, 7, 128), (1030, 3, 24), (2000, 7, 40)])
+def test_spmm_batched_bf16(n, d, C):
+    batch = regular_batch(5, n, d, seed=n + d + C)
+    assert batch.plan is not None
+    torch.manual_seed(n + C)
+    X = torch.randn(batch.num_nodes, C)
+    Xb = ops.padded_empty_bf16(batch.num_nodes, C, DEV, zero=True)
+    ops.to_bf16(X.to(DEV), out=Xb)
+    got = ops.spmm_bf16(batch, Xb)
+    assert got.dtype == torch.bfloat16
+    assert_bf16_close(got, ahat_times(batch, bf16_round(X)), extra=2e-6)
+    # agrees with the fp32 slab kernel fed the same (rounded) values
+    ref = ops.spmm(batch, Xb.float().contiguous())
+    assert float((got.float() - ref).abs().max()) <= BF16_ULP * float(ref.abs().max())
+    # forward form: fp32 bias + ReLU in the epilogue, pad columns stay zero
+    if C % 4 == 0:
+        bias = torch.randn(C) * 0.3
+        got2 = ops.spmm_bf16(batch, Xb, bias=bias.to(DEV), relu=True)
+        assert_bf16_close(got2, torch.relu(ahat_times(batch, bf16_round(X)) + bias.double()), extra=2e-6)
+        full = got2._base if got2._base is not None else got2
+        if full.shape[1] > C:
+            assert float(full[:, C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n_in,K", [(500, 3), (128, 3), (36, 4), (512, 1), (64, 2)])
+def test_skinny_fwd_bf16(n_in, K):
+    torch.manual_seed(n_in * 3 + K)
+    n = 4099                                                # not a multiple of the 4-row step
+    H = torch.randn(n, n_in)
+    W = torch.randn(n_in, K) / n_in ** 0.5
+    Hb = ops.to_bf16(H.to(DEV))
+    got = ops.skinny_fwd_bf16(Hb, W.to(DEV))
+    want = bf16_round(H) @ W.double()
+    assert float((got.double().cpu() - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+    with pytest.raises(Exception):
+        ops.skinny_fwd_bf16(Hb, torch.randn(n_in, 5, device=DEV))       # n_out > 4: not supported by this kernel
+
+
+def test_spmm_batched_bf16_needs_a_plan():
+    from gmc_b200 import _lib
+    import networkx as nx
+    from gmc_b200.graph import CSRGraph
+    g = nx.barabasi_albert_graph(200, 3, seed=1)           # irregular: no ELL plan
+    for u, v in g.edges():
+        g[u][v]["weight"] = 1
+    batch = GraphBatch([CSRGraph.from_networkx(g)])
+    assert getattr(batch, "plan", None) is None
+    Xb = torch.zeros((200, 64), dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(_lib.GmcError):
+        ops.spmm_bf16(batch, Xb)
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_bf16_activation_engine_step_tracks_the_fp32_activation_step():
+    """activations='bf16' vs activations='fp32' (both gemm_precision='bf16') and vs the fp32 engine: same weights,
+    same batch.  Storing T1 / H1 / dH1pre / dT1 in bf16 adds 2^-9 relative rounding per stored value; probabilities,
+    loss and gradients stay within 2e-2 of the fp32 engine, and a few training steps follow the same trajectory."""
+    from Training import TrainingNeural as T
+    batch = regular_batch(48, 256, 7, seed=9)
+    X = ops.densify(batch, 256)
+    out = {}
+    for name, precision, act in (("fp32", "fp32", "fp32"), ("bf16", "bf16", "fp32"), ("bf16act", "bf16", "bf16")):
+        cfg = T.TrainingConfig(n_nodes=256, dim_embedding=256, hidden_dim=128, gemm_precision=precision, loss_mode="soft")
+        torch.manual_seed(11)
+        net, embed, opt = T.setup_model_and_optimizer(cfg)
+        eng = GCNEngine(net, opt, loss_mode="soft", precision=precision, activations=act)
+        loss = eng.loss_and_grads(batch, X).clone()
+        grads = [g.cpu().clone() for g in eng.grads()]
+        P = eng.P[: batch.num_nodes].cpu().clone()
+        if act == "bf16":
+            assert eng.bufA is None and eng.bufA16 is not None       # no fp32 [N, hidden] buffers were allocated
+            assert torch.equal(eng.loss_and_grads(batch, X).cpu(), loss.cpu())     # deterministic
+        losses = [float(eng.train_step(batch, X).sum()) for _ in range(5)]
+        out[name] = (loss.cpu(), P, grads, losses, net.conv1.weight.detach().cpu().clone())
+    for name in ("bf16", "bf16act"):
+        assert relerr(out[name][0], out["fp32"][0]) < 1e-2
+        assert float((out[name][1] - out["fp32"][1]).abs().max()) < 1e-2
+        for a, b in zip(out[name][2], out["fp32"][2]):
+            assert relerr(a, b) < 3e-2
+        np.testing.assert_allclose(out[name][3], out["fp32"][3], rtol=1e-2)
+        # five Adam steps of lr 1e-3: the first updates are ~ lr * sign(g), so a near-zero gradient entry whose sign
+        # differs moves a weight by up to 2 lr per step -- 5 * 2e-3 against max |W1| ~ 0.15
+        assert relerr(out[name][4], out["fp32"][4]) < 7e-2
+    # the two bf16 variants differ only by the storage rounding of the activations
+    for a, b in zip(out["bf16act"][2], out["bf16"][2]):
+        assert relerr(a, b) < 2e-2
+
+
+def test_bf16_activation_forward_variants_agree(monkeypatch):
+    """GMC_FWD16=slab (bf16 slab SpMM + bf16 skinny projection) and the fused row kernel compute the same forward."""
+    from Training import TrainingNeural as T
+    from gmc_b200 import engine as E
+    batch = regular_batch(40, 256, 7, seed=4)
+    X = ops.densify(batch, 256)
+    cfg = T.TrainingConfig(n_nodes=256, dim_embedding=256, hidden_dim=128, gemm_precision="bf16", loss_mode="soft")
+    torch.manual_seed(5)
+    net, embed, opt = T.setup_model_and_optimizer(cfg)
+    res = {}
+    for slab in (False, True):
+        monkeypatch.setattr(E, "_FWD16_SLAB", slab)
+        eng = GCNEngine(net, None, loss_mode="soft", precision="bf16", activations="bf16")
+        loss = eng.loss_and_grads(batch, X).cpu().clone()
+        res[slab] = (loss, eng.Z[: batch.num_nodes].cpu().clone(), [g.cpu().clone() for g in eng.grads()])
+    assert relerr(res[True][1], res[False][1]) < 2e-3        # H1 may round differently by one bf16 ulp (fma order)
+    assert relerr(res[True][0], res[False][0]) < 2e-3
+    for a, b in zip(res[True][2], res[False][2]):
+        assert relerr(a, b) < 1e-2
+
+
+def test_bf16_activations_need_bf16_gemms_and_fall_back_without_a_plan():
+    from Training import TrainingNeural as T
+    import networkx as nx
+    from gmc_b200.graph import CSRGraph
+    cfg = T.TrainingConfig(n_nodes=200, dim_embedding=200, hidden_dim=64, gemm_precision="bf16", loss_mode="soft")
+    net, embed, opt = T.setup_model_and_optimizer(cfg)
+    with pytest.raises(ValueError):
+        GCNEngine(net, opt, precision="tf32", activations="bf16")
+    with pytest.raises(ValueError):
+        GCNEngine(net, opt, precision="bf16", activations="fp8")
+    g = nx.barabasi_albert_graph(200, 3, seed=2)            # irregular graph: the engine keeps fp32 activations
+    for u, v in g.edges():
+        g[u][v]["weight"] = 1
+    batch = GraphBatch([CSRGraph.from_networkx(g)])
+    X = ops.densify(batch, 200)
+    a = GCNEngine(net, None, loss_mode="soft", precision="bf16", activations="bf16").loss_and_grads(batch, X).cpu()
+    b = GCNEngine(net, None, loss_mode="soft", precision="bf16", activations="fp32").loss_and_grads(batch, X).cpu()
+    assert torch.equal(a, b)
