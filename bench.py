@@ -12,9 +12,11 @@ weak scaling).  Features are the zero-padded adjacency rows held DENSE in HBM ([
 what the reference feeds its GraphConv (TrainingNeural.py:373), so the feature transforms are true
 dense GEMMs on the tensor cores.  --precision picks their operand type: bf16 (default; the north-star's
 "TF32/bf16 with fp32 accumulation": 0/1 features are exact in bf16, W1 and dT1 are rounded to bf16,
-master weights / activations / loss / Adam stay fp32), tf32 (fp32 operands, one TF32 pass), tf32x3 and
-fp32 (fp32-grade parity paths).  The default line also carries `alt_paths`: the same step with TF32
-GEMMs and with layer 1 in aggregation form (--feature-source adjacency-sparse).
+master weights / logits / loss / reductions / Adam stay fp32), tf32 (fp32 operands, one TF32 pass), tf32x3 and
+fp32 (fp32-grade parity paths).  With bf16 operands, --activations bf16 (default; ordinary mixed precision:
+bf16 storage, fp32 arithmetic) also STORES the four [nodes, hidden] layer-1 tensors T1, H1, dH1pre, dT1 in
+bf16; --activations fp32 keeps them fp32.  The default line also carries `alt_paths`: the same step with fp32
+activations, with TF32 GEMMs, and with layer 1 in aggregation form (--feature-source adjacency-sparse).
 Other workloads: --workload config1 | config2 | config5, --feature-source embedding.
 
 Output: ONE JSON line on rank 0 (contract in the task statement) with `roofline`, `cpu_baseline`,
@@ -59,7 +61,7 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "bf16"),
                     choices=["fp32", "tf32", "tf32x3", "bf16"])
-    ap.add_argument("--activations", default=os.environ.get("GMC_BENCH_ACTIVATIONS", "fp32"), choices=["fp32", "bf16"],
+    ap.add_argument("--activations", default=os.environ.get("GMC_BENCH_ACTIVATIONS", "bf16"), choices=["fp32", "bf16"],
                     help="storage type of the four [nodes, hidden] layer-1 tensors (T1, H1, dH1pre, dT1); bf16 needs "
                          "--precision bf16.  Arithmetic is fp32 either way")
     ap.add_argument("--workload", default="config3", choices=["config3", "config5", "config2", "config1"],

@@ -8,7 +8,10 @@
 //                        in ONE pass over H (autograd of TrainingNeural.py:81-83)
 //   gmc_colsum_f32     : bias gradients
 // All reductions over nodes are two-stage with a fixed order -> bitwise reproducible.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tma_util.cuh"
 
 namespace gmc {
 
@@ -250,6 +253,206 @@ skinny_bwd_b16_kernel(const float* __restrict__ dT, int64_t lddt, const float* _
     }
 }
 
+// ---- TMA-streamed forms of the two bf16 skinny kernels -----------------------------------------------------------
+// The register-staged kernels above are latency-bound (ncu, profiles/r01c_*: 8-10 warps stalled on the long scoreboard
+// per issue, 0.50-0.60 of the HBM roofline): the bytes in flight are capped by the registers that hold them.  Here the
+// H rows arrive through cp.async.bulk.tensor boxes (256 columns x TR rows, out-of-range rows / pad columns zero-filled)
+// in a 4-stage shared-memory ring filled by one thread, so ~3 stages per CTA are always in flight and the compute reads
+// shared memory.  A tile is released with one __syncthreads, after which thread 0 refills its stage.
+constexpr int kStreamStages = 4;
+constexpr int kFwdTileRows = 32;
+constexpr int kBwdTileRows = 8;
+
+template <int NB, int NOUT>
+__global__ void __launch_bounds__(512, 1)
+skinny_fwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* __restrict__ W, float* __restrict__ T,
+                          int64_t ldt, int64_t n_rows, int n_in, int64_t n_tiles) {
+    constexpr int TR = kFwdTileRows, NST = kStreamStages, R = 2, V = R * NOUT;
+    constexpr int P = V <= 2 ? 2 : (V <= 4 ? 4 : 8);
+    constexpr int SH = P == 2 ? 4 : (P == 4 ? 3 : 2);
+    constexpr uint32_t BOX_BYTES = TR * 512, STAGE_BYTES = NB * BOX_BYTES;
+    extern __shared__ __align__(128) uint8_t stream_smem[];
+    const uint32_t sbase = tma::smem_u32(stream_smem);
+    const uint32_t bar0 = sbase + NST * STAGE_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        tma::prefetch_map(&tmH);
+        for (int s = 0; s < NST; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+        tma::mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int64_t t, int st) {
+        const uint32_t bar = bar0 + 8 * st;
+        tma::mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+            tma::load_2d(sbase + st * STAGE_BYTES + q * BOX_BYTES, &tmH, q * 256, (int)(t * TR), bar);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+            if (t < n_tiles) issue(t, s);
+        }
+    }
+    float w[NB][8][NOUT];
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int col = q * 256 + lane * 8 + i;
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) w[q][i][k] = col < n_in ? __ldg(W + (int64_t)col * NOUT + k) : 0.f;
+        }
+    int st = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        tma::mbar_wait(bar0 + 8 * st, phase);
+        const uint8_t* stage = stream_smem + st * STAGE_BYTES;
+        float v[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const uint4 h = *reinterpret_cast<const uint4*>(stage + q * BOX_BYTES + (R * warp + r) * 512 + lane * 16);
+                const uint32_t ww[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float lo = __uint_as_float(ww[i] << 16), hi = __uint_as_float(ww[i] & 0xffff0000u);
+#pragma unroll
+                    for (int k = 0; k < NOUT; ++k) {
+                        v[r * NOUT + k] = fmaf(lo, w[q][2 * i][k], v[r * NOUT + k]);
+                        v[r * NOUT + k] = fmaf(hi, w[q][2 * i + 1][k], v[r * NOUT + k]);
+                    }
+                }
+            }
+        const float tot = warp_multi_sum<P>(v, lane);
+        const int idx = lane >> SH;
+        if ((lane & ((1 << SH) - 1)) == 0 && idx < V) {
+            const int r = idx / NOUT, k = idx - r * NOUT;
+            const int64_t row = t * TR + R * warp + r;
+            if (row < n_rows) T[row * ldt + k] = tot;
+        }
+        __syncthreads();                                   // every warp is done with the stage
+        const int64_t tn = t + (int64_t)NST * gridDim.x;
+        if (tid == 0 && tn < n_tiles) issue(tn, st);
+        if (++st == NST) { st = 0; phase ^= 1; }
+    }
+}
+
+// CTA b owns rows [b * rows_per, ...) with rows_per a multiple of the tile height, walks them in tiles of 8 rows;
+// thread j owns columns 4j .. 4j+3.  The tile's dT rows (8 x NOUT floats) are fetched one tile ahead by the first
+// 8 * NOUT threads and handed over through shared memory.  ws layout as skinny_bwd_kernel.
+template <int NB, int NOUT>
+__global__ void __launch_bounds__(128)
+skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* __restrict__ dT, int64_t lddt,
+                          const float* __restrict__ W, uint2* __restrict__ dH, int64_t lddh4, int64_t n_rows, int n_in,
+                          int64_t rows_per, float* __restrict__ ws) {
+    constexpr int TR = kBwdTileRows, NST = kStreamStages;
+    constexpr uint32_t BOX_BYTES = TR * 512, STAGE_BYTES = NB * BOX_BYTES;
+    extern __shared__ __align__(128) uint8_t stream_smem[];
+    __shared__ float tsm[2][TR * NOUT];
+    const uint32_t sbase = tma::smem_u32(stream_smem);
+    const uint32_t bar0 = sbase + NST * STAGE_BYTES;
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per;
+    const int64_t r1 = min(n_rows, r0 + rows_per);
+    const int n_tiles = r1 > r0 ? (int)ceil_div<int64_t>(r1 - r0, TR) : 0;
+    if (tid == 0) {
+        tma::prefetch_map(&tmH);
+        for (int s = 0; s < NST; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+        tma::mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t, int st) {
+        const uint32_t bar = bar0 + 8 * st;
+        tma::mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+            tma::load_2d(sbase + st * STAGE_BYTES + q * BOX_BYTES, &tmH, q * 256, (int)(r0 + (int64_t)t * TR), bar);
+    };
+    if (tid == 0)
+        for (int s = 0; s < NST && s < n_tiles; ++s) issue(s, s);
+    auto fetch_t = [&](int t) -> float {                   // thread tid < TR * NOUT: element (row tid / NOUT, k) of tile t
+        const int64_t v = r0 + (int64_t)t * TR + tid / NOUT;
+        return (tid < TR * NOUT && t < n_tiles && v < r1) ? __ldg(dT + v * lddt + (tid % NOUT)) : 0.f;
+    };
+    if (tid < TR * NOUT) tsm[0][tid] = fetch_t(0);
+
+    const int j0 = tid * 4;
+    const bool owner = j0 < n_in;
+    float w[4][NOUT], dw[4][NOUT], db[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        db[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+            w[i][k] = (j0 + i < n_in) ? __ldg(W + (int64_t)(j0 + i) * NOUT + k) : 0.f;
+            dw[i][k] = 0.f;
+        }
+    }
+    const uint32_t my_off = (uint32_t)(tid >> 6) * BOX_BYTES + (uint32_t)(tid & 63) * 8;   // box, then 8 bytes per thread
+    __syncthreads();
+    int st = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        const float t_next = fetch_t(t + 1);               // in flight during this tile
+        tma::mbar_wait(bar0 + 8 * st, phase);
+        const uint8_t* stage = stream_smem + st * STAGE_BYTES + my_off;
+        const float* ts = tsm[t & 1];
+        const int64_t vb = r0 + (int64_t)t * TR;
+        if (owner) {
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+                const int64_t v = vb + r;
+                if (v < r1) {                              // CTA-uniform
+                    const uint2 h2 = *reinterpret_cast<const uint2*>(stage + r * 512);
+                    const float h[4] = {__uint_as_float(h2.x << 16), __uint_as_float(h2.x & 0xffff0000u),
+                                        __uint_as_float(h2.y << 16), __uint_as_float(h2.y & 0xffff0000u)};
+                    float tk[NOUT];
+#pragma unroll
+                    for (int k = 0; k < NOUT; ++k) tk[k] = ts[r * NOUT + k];
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int k = 0; k < NOUT; ++k) { s = fmaf(tk[k], w[i][k], s); dw[i][k] = fmaf(h[i], tk[k], dw[i][k]); }
+                        o[i] = h[i] > 0.f ? s : 0.f;
+                        db[i] += o[i];
+                    }
+                    uint2 pk;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
+                    dH[v * lddh4 + tid] = pk;
+                }
+            }
+        }
+        if (tid < TR * NOUT) tsm[(t + 1) & 1][tid] = t_next;
+        __syncthreads();                                   // stage and tsm[t & 1] are free, tsm[(t + 1) & 1] is published
+        if (tid == 0 && t + NST < n_tiles) issue(t + NST, st);
+        if (++st == NST) { st = 0; phase ^= 1; }
+    }
+    if (owner) {
+        float* my_ws = ws + (int64_t)blockIdx.x * n_in * (NOUT + 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (j0 + i < n_in) {
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) my_ws[(int64_t)(j0 + i) * (NOUT + 1) + k] = dw[i][k];
+                my_ws[(int64_t)(j0 + i) * (NOUT + 1) + NOUT] = db[i];
+            }
+        }
+    }
+}
+
+static bool stream_kernels_enabled() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("GMC_SKINNY_TMA"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached == 1;
+}
+
 __global__ void skinny_bwd_reduce_kernel(const float* __restrict__ ws, int n_ctas, int n_in, int nout,
                                          float* __restrict__ dW, float* __restrict__ dbias) {
     // block = 32 outputs (x) x 32 partial-groups (y): coalesced 128-byte reads, fixed summation order
@@ -357,6 +560,37 @@ int gmc_skinny_fwd_bf16(const void* H, int64_t ldh, const float* W, float* T, in
     }
     if (n_rows == 0) return GMC_OK;
     cudaStream_t s = as_stream(stream);
+    if (stream_kernels_enabled() && n_rows >= 4096 && n_rows < (1ll << 31) - 64) {
+        // TMA-streamed kernel: one persistent CTA per SM, 4 stages of 32 rows
+        CUtensorMap tm;
+        int rc = tma::make_bf16_map(&tm, H, (uint64_t)n_in, (uint64_t)n_rows, (uint64_t)ldh, 256, kFwdTileRows, "gmc_skinny_fwd_bf16");
+        if (rc != GMC_OK) return rc;
+        const int nb = n_in > 256 ? 2 : 1;
+        const size_t smem = (size_t)kStreamStages * nb * kFwdTileRows * 512 + 64;
+        const int64_t n_tiles = ceil_div<int64_t>(n_rows, kFwdTileRows);
+        const unsigned grid = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());
+#define GMC_CASE(NB, K)                                                                                                \
+        {                                                                                                              \
+            static bool attr = false;                                                                                  \
+            if (!attr) {                                                                                               \
+                GMC_CUDA(cudaFuncSetAttribute(skinny_fwd_b16_tma_kernel<NB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              kStreamStages * NB * kFwdTileRows * 512 + 64));                          \
+                attr = true;                                                                                           \
+            }                                                                                                          \
+            skinny_fwd_b16_tma_kernel<NB, K><<<grid, 512, smem, s>>>(tm, W, T, ldt, n_rows, n_in, n_tiles);          \
+        }
+#define GMC_NB(K) if (nb == 2) GMC_CASE(2, K) else GMC_CASE(1, K)
+        switch (n_out) {
+            case 1: GMC_NB(1); break;
+            case 2: GMC_NB(2); break;
+            case 3: GMC_NB(3); break;
+            default: GMC_NB(4); break;
+        }
+#undef GMC_NB
+#undef GMC_CASE
+        GMC_LAUNCH_CHECK();
+        return GMC_OK;
+    }
     const uint4* H8 = reinterpret_cast<const uint4*>(H);
     int64_t blocks = ceil_div<int64_t>(n_rows, 8 * 4);
     const int64_t cap = (int64_t)sm_count() * 4;
@@ -437,6 +671,48 @@ int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const voi
     }
     const uint2* H2 = reinterpret_cast<const uint2*>(H);
     uint2* dH2 = reinterpret_cast<uint2*>(dHpre);
+    if (stream_kernels_enabled() && n_rows >= 65536 && n_rows < (1ll << 31) - 64 && n_in <= 512 && ldh % 8 == 0 && aligned16(H)) {
+        // TMA-streamed kernel: 6 CTAs per SM (32 KB ring each + 1 KB reserved: 7 do not fit in 227 KB), one wave;
+        // row ranges in multiples of the 8-row tile
+        CUtensorMap tm;
+        int rc = tma::make_bf16_map(&tm, H, (uint64_t)n_in, (uint64_t)n_rows, (uint64_t)ldh, 256, kBwdTileRows, "gmc_skinny_bwd_bf16");
+        if (rc != GMC_OK) return rc;
+        int nc = sm_count() * 6;
+        if (nc > n_ctas) nc = n_ctas;
+        const int64_t rows_per = ceil_div<int64_t>(ceil_div<int64_t>(n_rows, nc), kBwdTileRows) * kBwdTileRows;
+        nc = (int)ceil_div<int64_t>(n_rows, rows_per);
+        const int nb = n_in > 256 ? 2 : 1;
+        const size_t smem = (size_t)kStreamStages * nb * kBwdTileRows * 512 + 64;
+#define GMC_CASE(NB, K)                                                                                                \
+        {                                                                                                              \
+            static bool attr = false;                                                                                  \
+            if (!attr) {                                                                                               \
+                GMC_CUDA(cudaFuncSetAttribute(skinny_bwd_b16_tma_kernel<NB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              kStreamStages * NB * kBwdTileRows * 512 + 64));                          \
+                GMC_CUDA(cudaFuncSetAttribute(skinny_bwd_b16_tma_kernel<NB, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+                attr = true;                                                                                           \
+            }                                                                                                          \
+            skinny_bwd_b16_tma_kernel<NB, K><<<nc, 128, smem, s>>>(tm, dT, lddt, W, dH2, lddh / 4, n_rows, n_in, rows_per, ws); \
+        }
+#define GMC_NB(K) if (nb == 2) GMC_CASE(2, K) else GMC_CASE(1, K)
+        switch (n_out) {
+            case 1: GMC_NB(1); break;
+            case 2: GMC_NB(2); break;
+            case 3: GMC_NB(3); break;
+            case 4: GMC_NB(4); break;
+            case 5: GMC_NB(5); break;
+            case 6: GMC_NB(6); break;
+            case 7: GMC_NB(7); break;
+            default: GMC_NB(8); break;
+        }
+#undef GMC_NB
+#undef GMC_CASE
+        GMC_LAUNCH_CHECK();
+        const int total = n_in * (n_out + 1);
+        skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, nc, n_in, n_out, dW, dbias);
+        GMC_LAUNCH_CHECK();
+        return GMC_OK;
+    }
 #define GMC_CASE(K) case K: skinny_bwd_b16_kernel<K><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H2, ldh / 4, dH2, lddh / 4, n_rows, n_in, ws); break;
     switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
 #undef GMC_CASE

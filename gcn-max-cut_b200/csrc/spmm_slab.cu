@@ -260,12 +260,15 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
                 float a[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) a[i] = 0.f;
+                // add.rn.f32.bf16 (PTX 8.6, sm_100): fp32 accumulator += bf16 operand taken straight from a register half
+                // (SASS FHADD.BF16 with .H0 / .H1 selectors) -- no unpack instructions, one issue slot per element
                 auto add8 = [&](const float4& v) {
                     const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        a[2 * i] += __uint_as_float(w[i] << 16);
-                        a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+                        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\t"
+                            "add.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+                            : "+f"(a[2 * i]), "+f"(a[2 * i + 1]) : "r"(w[i]));
                     }
                 };
                 {
@@ -572,7 +575,17 @@ int gmc_spmm_batched_bf16(const int32_t* graph_ptr, int32_t n_graphs, int32_t ma
         float4* Y4 = reinterpret_cast<float4*>(Y);
         const SlabProj none{nullptr, nullptr, 0, 0};
         const float4* b4 = reinterpret_cast<const float4*>(bias);
-        int rc = slab_launch_one<7, 8, 512, 2, 2, true, 1, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows, c8,
+        int rc = GMC_OK;
+        static int variant = -1;                          // GMC_SLAB16_VARIANT=C: one CTA of 1024 threads, two slab buffers
+        if (variant < 0) { const char* e = getenv("GMC_SLAB16_VARIANT"); variant = (e && e[0] == 'C') ? 1 : 0; }
+        if (variant == 1) {
+            rc = slab_launch_one<7, 8, 1024, 1, 2, true, 2, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows, c8,
+                                                                         ldx / 8, ldy / 8, b4, relu, as_stream(stream),
+                                                                         &launched, 1, none, n_cols);
+            if (rc != GMC_OK) return rc;
+        }
+        if (!launched)
+        rc = slab_launch_one<7, 8, 512, 2, 2, true, 1, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows, c8,
                                                                         ldx / 8, ldy / 8, b4, relu, as_stream(stream),
                                                                         &launched, 1, none, n_cols);
         if (rc != GMC_OK) return rc;

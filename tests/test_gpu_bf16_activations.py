@@ -111,10 +111,10 @@ def test_spmm_fused_skinny_bf16(C, K, out_bf16):
     assert_bf16_close(Y2.to(torch.bfloat16), ahat_times(batch, bf16_round(X)), extra=2e-5)
 
 
-@pytest.mark.parametrize("n_in,K", [(500, 3), (128, 3), (36, 8), (512, 1)])
-def test_skinny_bwd_bf16(n_in, K):
+@pytest.mark.parametrize("n_in,K,n", [(500, 3, 5000), (128, 3, 5000), (36, 8, 5000), (512, 1, 5000),
+                                      (500, 3, 70001), (256, 8, 66000), (20, 2, 65536)])     # >= 65536 rows: TMA-streamed kernel
+def test_skinny_bwd_bf16(n_in, K, n):
     torch.manual_seed(n_in + K)
-    n = 5000
     H = torch.relu(torch.randn(n, n_in))
     dT, W = torch.randn(n, K), torch.randn(n_in, K)
     Hb = ops.to_bf16(H.to(DEV))
@@ -155,10 +155,10 @@ def test_spmm_batched_bf16(n, d, C):
             assert float(full[:, C:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("n_in,K", [(500, 3), (128, 3), (36, 4), (512, 1), (64, 2)])
-def test_skinny_fwd_bf16(n_in, K):
+@pytest.mark.parametrize("n_in,K,n", [(500, 3, 4099), (128, 3, 4099), (36, 4, 4099), (512, 1, 4099), (64, 2, 4099),
+                                      (500, 3, 1001), (256, 2, 777), (500, 3, 40000)])    # < 4096 rows: register-staged kernel
+def test_skinny_fwd_bf16(n_in, K, n):
     torch.manual_seed(n_in * 3 + K)
-    n = 4099                                                # not a multiple of the 4-row step
     H = torch.randn(n, n_in)
     W = torch.randn(n_in, K) / n_in ** 0.5
     Hb = ops.to_bf16(H.to(DEV))
