@@ -113,7 +113,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 constexpr int kBoxRows = 128;                             // rows per TMA box
 
 // W4: float4 columns per slab; LANES: lanes per output row (power of two >= W4); MINB: CTAs per SM;
-// DEPTH: rows whose neighbour lists are prefetched ahead per row group; TMA: stage full 128-row boxes with
+// DEPTH: unused since the batched list prefetch (kept in the instantiation list); TMA: stage full 128-row boxes with
 // cp.async.bulk.tensor (one elected thread, mbarrier completion) and only the tail rows with cp.async
 // PROJ: also emit this slab's share of the skinny projection T = Y W (W [n_cols, n_out <= 4]) -- the second GraphConv
 // layer's th.matmul (TrainingNeural.py:83) -- as one float4 per (slab, row) into Tpart[n_slabs][n_rows]; a fixed-order
@@ -184,11 +184,17 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
         cp_async_commit();
     };
 
+    // Neighbour lists ("plan" rows: 8 uint16 ids + one coefficient).  A row group owns a CONTIGUOUS block of rows of the
+    // item and fetches the lists of LANES rows with one load per lane (lane i holds row i of the batch: LANES x 16
+    // contiguous bytes), then hands them to the group one row at a time by shuffle.  The batch after the current one
+    // -- of the next item at the end of an item -- is always in flight, so a list is requested LANES..2 LANES rows
+    // before its first use at the register cost of two rows.  (The earlier scheme loaded each row's list two rows
+    // ahead: ncu showed 7.5-8.3 warps per issue stalled on exactly those loads once the bf16 gather got cheap.)
     struct Slots { uint4 c; float d; };
-    Slots S[DEPTH];
-    bool pre[DEPTH];
-#pragma unroll
-    for (int k = 0; k < DEPTH; ++k) pre[k] = false;
+    Slots cur_s, nxt_s;
+    cur_s.c = make_uint4(0u, 0u, 0u, 0u); cur_s.d = 0.f;
+    nxt_s = cur_s;
+    bool have_cur = false;
 
     int64_t w = blockIdx.x;
     int base = 0, n_g = 0, cur = 0;
@@ -217,17 +223,25 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
             else cp_async_commit();
         }
         const bool active = lg < nv;
-        auto load_slots = [&](Slots& S, int b0, int row) {
-            const int64_t v = (int64_t)b0 + row;
-            S.c = __ldg(ell_col + v);
-            S.d = __ldg(plan_nd + v);
+        // batch j of an item with ng rows dealt in blocks of rpg rows: lane lg fetches row gidx * rpg + j * LANES + lg;
+        // rows past the block or the graph get a list that points at the all-zero row with coefficient 0
+        auto load_batch = [&](Slots& S, int b0, int ng, int rpg, int j) {
+            const int i = j * LANES + lg;
+            const int row = gidx * rpg + i;
+            if (i < rpg && row < ng) {
+                const int64_t v = (int64_t)b0 + row;
+                S.c = __ldg(ell_col + v);
+                S.d = __ldg(plan_nd + v);
+            } else {
+                const uint32_t pad = (uint32_t)ng | ((uint32_t)ng << 16);
+                S.c = make_uint4(pad, pad, pad, pad);
+                S.d = 0.f;
+            }
         };
-        // neighbour lists of this row group's first DEPTH rows: normally already in flight (issued after the last
-        // use of each slot in the previous item), so that no item starts on a cold L2 round trip
-        const int r0 = gidx;
-#pragma unroll
-        for (int k = 0; k < DEPTH; ++k)
-            if (!pre[k] && r0 + k * GROUPS < n_g) load_slots(S[k], base, r0 + k * GROUPS);
+        const int rpg = ceil_div(n_g, GROUPS);
+        const int rpg_n = ceil_div(n_g_n, GROUPS);
+        const int n_batches = ceil_div(rpg, LANES);
+        if (!have_cur) { load_batch(cur_s, base, n_g, rpg, 0); have_cur = true; }   // first item only: cold round trip
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), b4h = make_float4(0.f, 0.f, 0.f, 0.f);
         if (XB) {                                         // a 16-byte unit = 8 columns = two float4 of the fp32 bias
             if (bias && active) {
@@ -255,7 +269,7 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
         const float4* sl = sbuf + lg;
         auto gather = [&](uint32_t u) { return sl[u * W4]; };
         auto add4 = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
-        auto row_out = [&](const Slots& S, int row) {
+        auto row_out = [&](const Slots& S, int row, bool valid) {
             if constexpr (XB) {
                 float a[8];
 #pragma unroll
@@ -281,7 +295,7 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
                     add8(v4); add8(v5); add8(v6);
                 }
                 if (slot7) add8(gather(S.c.w >> 16));
-                if (active) {
+                if (active && valid) {
                     const float bb[8] = {b4.x, b4.y, b4.z, b4.w, b4h.x, b4h.y, b4h.z, b4h.w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -308,7 +322,7 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
             acc.x = fmaf(acc.x, S.d, b4.x); acc.y = fmaf(acc.y, S.d, b4.y);
             acc.z = fmaf(acc.z, S.d, b4.z); acc.w = fmaf(acc.w, S.d, b4.w);
             if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-            if (active) {
+            if (active && valid) {
                 if (out_bf16) {                           // Y is a bf16 matrix: ldy4 counts 4-element (8-byte) units
                     __nv_bfloat162 o[2] = {__floats2bfloat162_rn(acc.x, acc.y), __floats2bfloat162_rn(acc.z, acc.w)};
                     reinterpret_cast<uint2*>(Y)[(int64_t)(base + row) * ldy4 + col0 + lg] = *reinterpret_cast<const uint2*>(o);
@@ -329,25 +343,27 @@ spmm_slab_kernel(const __grid_constant__ CUtensorMap tmX, const int32_t* __restr
 #pragma unroll
                     for (int k = 0; k < 4; ++k) p[k] += __shfl_xor_sync(0xffffffffu, p[k], o);
                 }
-                if (lg == 0) proj.Tpart[(int64_t)s * proj.n_rows + base + row] = make_float4(p[0], p[1], p[2], p[3]);
+                if (lg == 0 && valid) proj.Tpart[(int64_t)s * proj.n_rows + base + row] = make_float4(p[0], p[1], p[2], p[3]);
             }
         };
-        for (int r = r0; r < n_g; r += DEPTH * GROUPS) {
-#pragma unroll
-            for (int k = 0; k < DEPTH; ++k) {
-                const int rk = r + k * GROUPS;
-                if (rk < n_g) {
-                    row_out(S[k], rk);
-                    if (rk + DEPTH * GROUPS < n_g) {
-                        load_slots(S[k], base, rk + DEPTH * GROUPS);
-                    } else {                              // last use in this item: fetch the next item's row for this slot
-                        pre[k] = r0 + k * GROUPS < n_g_n;
-                        if (pre[k]) load_slots(S[k], base_n, r0 + k * GROUPS);
-                    }
-                } else if (r == r0) {
-                    pre[k] = false;                       // slot unused in this item
-                }
+        const int row_begin = gidx * rpg;
+        for (int j = 0; j < n_batches; ++j) {
+            if (j + 1 < n_batches) load_batch(nxt_s, base, n_g, rpg, j + 1);
+            else if (wn < n_items) load_batch(nxt_s, base_n, n_g_n, rpg_n, 0);
+#pragma unroll 2
+            for (int k = 0; k < LANES; ++k) {
+                const int i = j * LANES + k;
+                if (i >= rpg) break;                      // CTA-uniform
+                Slots sk;                                 // row k of the batch, from lane k of the group (all 32 lanes shuffle)
+                sk.c.x = __shfl_sync(0xffffffffu, cur_s.c.x, k, LANES);
+                sk.c.y = __shfl_sync(0xffffffffu, cur_s.c.y, k, LANES);
+                sk.c.z = __shfl_sync(0xffffffffu, cur_s.c.z, k, LANES);
+                sk.c.w = __shfl_sync(0xffffffffu, cur_s.c.w, k, LANES);
+                sk.d = __shfl_sync(0xffffffffu, cur_s.d, k, LANES);
+                const int row = row_begin + i;
+                row_out(sk, row, row < n_g);
             }
+            cur_s = nxt_s;
         }
         __syncthreads();                                  // the buffer may be overwritten by the next item
         base = base_n; n_g = n_g_n;

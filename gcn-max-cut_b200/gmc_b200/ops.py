@@ -257,6 +257,18 @@ def densify_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def scatter_features_bf16(batch, n_cols: int, X: torch.Tensor, clear: bool = False) -> torch.Tensor:
+    """Incremental densify_bf16 on a reused buffer: write the batch's adjacency entries into an all-zero X
+    (clear=False) or zero exactly those entries again (clear=True).  No memset of the [N, n_cols] matrix."""
+    X, ld = _bf16_rowmajor(X, "X")
+    if X.shape[0] != batch.num_nodes or X.shape[1] != n_cols:
+        raise ValueError(f"X must be [{batch.num_nodes}, {n_cols}]")
+    check(lib().gmc_csr_scatter_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), _ptr(batch.wts_f32),
+                                     batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
+                                     X.data_ptr(), ld, int(clear), _stream()), "gmc_csr_scatter_bf16")
+    return X
+
+
 def spmm_bf16out(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """A_hat X rounded to bf16 (slab kernel; falls back to the fp32 SpMM + conversion when the batch has no plan)."""
     X, ldx = _rowmajor(X, "X")

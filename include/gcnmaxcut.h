@@ -242,6 +242,12 @@ int gmc_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64
 int gmc_csr_densify_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
                          const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
                          int64_t ldx, void* stream);
+/* Incremental gmc_csr_densify_bf16 for a reused feature buffer: clear = 0 writes the batch's adjacency entries into an
+ * X that is zero everywhere else (no memset); clear = 1 writes zeros at the same positions (back to all-zero).
+ * graphExtender.py:106-111 for a stream of graphs: nnz sectors per step instead of the whole matrix. */
+int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                         const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                         int64_t ldx, int32_t clear, void* stream);
 
 /* ---- bf16 layer-1 activations (engine option activations='bf16', on top of the bf16 GEMM operands) ----------------
  * T1 = X W1, H1 = relu(A_hat T1 + b1), dH1pre and dT1 are [n_nodes, hidden] matrices that are each written once and

@@ -183,6 +183,17 @@ def test_spmm_batched_bf16_needs_a_plan():
         ops.spmm_bf16(batch, Xb)
 
 
+def test_incremental_feature_scatter_equals_densify():
+    batch = regular_batch(7, 130, 6, seed=2)
+    want = ops.densify_bf16(batch, 136)
+    X = ops.padded_empty_bf16(batch.num_nodes, 136, DEV, zero=True)
+    ops.scatter_features_bf16(batch, 136, X)
+    assert torch.equal(X, want)
+    ops.scatter_features_bf16(batch, 136, X, clear=True)
+    full = X._base if X._base is not None else X
+    assert int(torch.count_nonzero(full)) == 0
+
+
 def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
