@@ -485,6 +485,16 @@ def run_b200_arm(args):
             comp = 8.0 * N * Cw + 4.0 * nnz + 4.0 * (N + 1) + (4.0 * N * K if name == "spmm_h_fused" else 0.0)
             extra = {"achieved_compulsory": comp / (avg_ms * 1e-3) / 1e9,
                      "frac_compulsory": comp / (avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        if bound == "hbm":
+            extra["frac_nominal_8TBs"] = achieved / 8000.0          # also against the nominal ~8 TB/s
+        if act16 and name in ("spmm_h", "spmm_h_fwd", "spmm_h_fused"):
+            # SURVEY 8(d) states the SpMM bytes for fp32 columns (8 N C + indices); with 2-byte activations the kernel
+            # moves half of that, which is what `achieved` counts.  The fp32-form figure is the rate an fp32 kernel
+            # would need to finish in the same time.
+            fp32_form = spmm_bytes_h + (4.0 * N * K if name == "spmm_h_fused" else 0.0)
+            extra["algorithmic_bytes"] = work
+            extra["achieved_fp32_form"] = fp32_form / (avg_ms * 1e-3) / 1e9
+            extra["frac_fp32_form"] = extra["achieved_fp32_form"] / peaks["hbm_gbs"]
         ops_report[name] = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, **extra,
                             "frac": achieved / peak if peak else None, "avg_ms": avg_ms, "calls": calls,
                             "share_of_step": tot / ms,
