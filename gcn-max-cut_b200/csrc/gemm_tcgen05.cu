@@ -715,7 +715,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 // cluster shape of the multicast kernel: GMC_GEMM_CLUSTER = "1" | "2" | "4" | "8" (CLM x 1) | "2x2" | "4x2" (CLM x CLN).
 // Default: 2x2 for tn (both operands streamed from HBM) when the problem has at least two n-tiles, else 4x1 --
 // the best shapes measured at config 3 (profiles/r01_gemm_notes.md: nn 7.5 ms with 4x1, tn 7.0 ms with 2x2).
-static void cluster_shape(bool a_mn, int64_t n_tiles, int* clm, int* cln) {
+static void cluster_shape(bool a_mn, int64_t n_tiles, int* clm, int* cln, bool bf16 = false) {
     static int cm = -1, cn = -1;
     if (cm < 0) {
         const char* e = getenv("GMC_GEMM_CLUSTER");
@@ -728,6 +728,10 @@ static void cluster_shape(bool a_mn, int64_t n_tiles, int* clm, int* cln) {
         }
     }
     if (cm > 0) { *clm = cm; *cln = cn; return; }
+    // bf16 operands halve the L2 traffic per flop, so the sharing of the larger clusters buys nothing and their
+    // co-residency loss costs: 2x1 clusters keep all 148 SMs busy (4x1: 132, 2x2: 128).  Config 3, scratch/gemm_bf16_cfg3.py:
+    // tn 3.30 ms (2x2) -> 2.99 ms (2x1); nn 3.36 (4x1) -> 3.32 (2x1), 3.33 without clusters.
+    if (bf16) { *clm = 2; *cln = 1; return; }
     if (a_mn && n_tiles >= 2) { *clm = 2; *cln = 2; return; }
     *clm = 4;
     *cln = 1;
@@ -860,7 +864,7 @@ template <bool A_MN, bool B_MN, bool BF16 = false>
 static int launch_cl(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0) {
     int clm, cln;
-    cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln);
+    cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln, BF16);
 #define GMC_GEMM_CASE(CM, CN)                                                                                       \
     if (clm == CM && cln == CN)                                                                                     \
         return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
@@ -975,14 +979,14 @@ static int make_lo(const float* X, int64_t ldx, float* L, int64_t rows, int64_t 
 
 }  // namespace tc
 
-static size_t tc_splitk_bytes(int op, int64_t M, int64_t N, int64_t K) {
+static size_t tc_splitk_bytes(int op, int64_t M, int64_t N, int64_t K, bool bf16 = false) {
     int splits;
-    if (tc::use_two_cta()) {
+    if (tc::use_two_cta() && !bf16) {
         const int64_t tiles = ceil_div<int64_t>(M, 256) * ceil_div<int64_t>(N, 256);
         splits = tc::pick_splits2(tiles, K);
     } else {
         int clm, cln;
-        tc::cluster_shape(op == 2, ceil_div<int64_t>(N, tc::BLOCK_N), &clm, &cln);
+        tc::cluster_shape(op == 2, ceil_div<int64_t>(N, tc::BLOCK_N), &clm, &cln, bf16);
         const int64_t ctiles = ceil_div<int64_t>(ceil_div<int64_t>(M, tc::BLOCK_M), clm) *
                                ceil_div<int64_t>(ceil_div<int64_t>(N, tc::BLOCK_N), cln);
         splits = tc::pick_splits_cl(ctiles, K, sm_count() / (clm * cln));   // upper bound of what launch() picks
@@ -1076,7 +1080,7 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
 // bf16 operands (A, B point at __nv_bfloat16, leading dimensions in elements), fp32 accumulation and fp32 output:
 // the same kernel with 64-element stages and tcgen05.mma kind::f16 -- half the operand bytes per flop through HBM,
 // L2 and shared memory, twice the MMA rate.
-size_t tc_bf16_workspace_bytes(int op, int64_t M, int64_t N, int64_t K) { return (tc_splitk_bytes(op, M, N, K) + 255) & ~(size_t)255; }
+size_t tc_bf16_workspace_bytes(int op, int64_t M, int64_t N, int64_t K) { return (tc_splitk_bytes(op, M, N, K, true) + 255) & ~(size_t)255; }
 
 int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                  int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16) {
