@@ -64,6 +64,12 @@ def parse_args():
     ap.add_argument("--activations", default=os.environ.get("GMC_BENCH_ACTIVATIONS", "bf16"), choices=["fp32", "bf16"],
                     help="storage type of the four [nodes, hidden] layer-1 tensors (T1, H1, dH1pre, dT1); bf16 needs "
                          "--precision bf16.  Arithmetic is fp32 either way")
+    ap.add_argument("--layer1", default=os.environ.get("GMC_BENCH_LAYER1", "preaggregated"),
+                    choices=["preaggregated", "standard"],
+                    help="preaggregated (default with bf16 / bf16): layer 1 as relu((A_hat X) W1 + b1) -- the aggregation is "
+                         "applied to the features (a function of the graph alone: built once for resident graphs, every "
+                         "step in the end-to-end loop), so the step has one GEMM per direction and no [N, hidden] SpMM; "
+                         "standard: relu(A_hat (X W1) + b1) with the slab SpMM forward and backward in every step")
     ap.add_argument("--workload", default="config3", choices=["config3", "config5", "config2", "config1"],
                     help="config3 (default, the headline): 4096 graphs n=1000 per GPU; config5: one 7-regular graph "
                          "n=1M, F=256, H=128, learned embeddings (SpMM/GEMM roofline stress); config2: inference + "
@@ -83,6 +89,8 @@ def parse_args():
     args = ap.parse_args()
     if args.precision != "bf16" or args.feature_source != "adjacency":
         args.activations = "fp32"
+    if args.activations != "bf16":
+        args.layer1 = "standard"
     if args.workload == "config5":
         args.graphs_per_gpu, args.nodes, args.degree, args.features, args.hidden = 1, 1000000, 7, 256, 128
         args.feature_source = "embedding"
@@ -269,11 +277,20 @@ def run_b200_arm(args):
         X = ops.densify_bf16(batch, F)                   # dense padded adjacency rows in bf16 (0/1: exact), 128-byte pitch
     else:
         X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
-    eng = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=sparse_adj, activations=args.activations)
-    act16 = args.activations == "bf16" and eng._b16_activations(batch)
+    preagg = args.layer1 == "preaggregated" and args.workload == "config3"
+    eng = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=sparse_adj, activations=args.activations,
+                    preaggregate=preagg)
+    act16 = args.activations == "bf16" and (preagg or eng._b16_activations(batch))
+    XA = None
+    if preagg:
+        # A_hat X straight from the graph (49 entries per row at d = 7), bf16, 128-byte pitch: the resident input of the step
+        XA = ops.preaggregate_features_bf16(batch, F)
+        feats = ops.PreaggregatedFeatures(XA)
+    else:
+        feats = X
 
-    def train_step(b):
-        return eng.train_step(b, X, feature_param=x_param, feature_grad=x_grad)
+    def train_step(b, f=None):
+        return eng.train_step(b, feats if f is None else f, feature_param=x_param, feature_grad=x_grad)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -341,6 +358,13 @@ def run_b200_arm(args):
             b2.unit_weights, b2.wts_f32, b2.wts_i32, b2.integer_weights = True, None, None, True
             b2.norm, _zero = ops.degree_norm(d_rowptr, N)            # includes the zero-degree check read-back
             b2.coef = ops.edge_coef(d_rowptr, d_colidx, None, b2.norm, b2.norm, N)
+            if preagg:
+                # device-side graphExtender + layer-1 aggregation of the features, rebuilt from this step's graph
+                b2.plan = None
+                ops.preaggregate_features_bf16(b2, F, out=XA)
+                per_graph = train_step(b2, feats)
+                consumed[slot].record()
+                return per_graph.cpu()
             b2.plan = (ops.spmm_plan(d_rowptr, d_colidx, b2.norm, b2.norm, d_gptr, B, N)
                        if batch.plan is not None else None)   # slab-SpMM plan: a function of the graph, rebuilt per step
             incremental = not embedding and not sparse_adj and X.dtype == torch.bfloat16
@@ -362,7 +386,7 @@ def run_b200_arm(args):
             torch.cuda.synchronize()
             return out
 
-        x_incremental = not embedding and not sparse_adj and X.dtype == torch.bfloat16
+        x_incremental = not embedding and not sparse_adj and not preagg and X.dtype == torch.bfloat16
         if x_incremental:
             ops.scatter_features_bf16(batch, F, X, clear=True)       # the e2e steps start from (and leave) an all-zero X
         e2e_run(3)
@@ -380,7 +404,9 @@ def run_b200_arm(args):
                "d2h_bytes_per_step": int(B * 8 + 4), "steps": k_e2e,
                "path": "pinned host CSR (rowptr, colidx, graph_ptr) -> H2D (copy stream, prefetched one step ahead) "
                        "-> gmc_degree_norm/edge_coef/"
-                       + ("spmm_plan (embeddings are resident parameters)" if embedding else
+                       + ("csr_preaggregate (device-side graphExtender with GraphConv layer 1's aggregation applied to "
+                          "the features: A_hat X rebuilt from every step's graph)" if preagg else
+                          "spmm_plan (embeddings are resident parameters)" if embedding else
                           "csr_scatter (device-side graphExtender on a reused zero buffer: write nnz entries, clear them after the step)")
                        + " -> GCNEngine.train_step -> per-graph loss D2H"}
         del host_loss
@@ -402,6 +428,7 @@ def run_b200_arm(args):
                 "steps": k}
 
     alt = None
+    spmm_from_alt = None
     if args.workload == "config3" and not embedding and not sparse_adj:
         alt = {}
         k_alt = min(args.steps, 10)
@@ -412,6 +439,20 @@ def run_b200_arm(args):
                      "(csrc/spmm_adj.cu) instead of dense tensor-core GEMMs -- valid because the features are the "
                      "zero-padded adjacency rows; bench.py --feature-source adjacency-sparse gives the full line")
             del eng_s
+            torch.cuda.empty_cache()
+        if preagg:
+            eng_std = GCNEngine(net, opt, precision="bf16", activations="bf16")
+            eng_std.timer = OpTimer()
+            r_std = timed_alt(eng_std, X, k_alt)
+            eng_std.timer.collect()
+            t_s = eng_std.timer
+            alt["standard_layer1"] = dict(r_std, dtype="bf16",
+                what="the same step with GraphConv layer 1 in its per-step form relu(A_hat (X W1) + b1): bf16 slab SpMM "
+                     "forward and backward inside every step (bench.py --layer1 standard)",
+                ops_ms={k: t_s.total_ms[k] / t_s.calls[k] for k in t_s.total_ms})
+            if "spmm_h" in t_s.total_ms:
+                spmm_from_alt = t_s.total_ms["spmm_h"] / t_s.calls["spmm_h"]
+            del eng_std
             torch.cuda.empty_cache()
         if act16:
             eng_f = GCNEngine(net, opt, precision="bf16", activations="fp32")
@@ -452,6 +493,7 @@ def run_b200_arm(args):
     gemm_flops = 2.0 * N * F * H
     algo = {
         "gemm_nn_xw1": ("tensor", gemm_flops), "gemm_tn_dw1": ("tensor", gemm_flops),
+        "gemm_nn_layer1": ("tensor", gemm_flops),
         "spmm_h": ("hbm", spmm_bytes_h_bwd), "spmm_k": ("hbm", spmm_bytes_k),
         "spmm_h_fused": ("hbm", spmm_bytes_fused), "spmm_h_fwd": ("hbm", spmm_bytes_h_bwd),
         "skinny_fwd": ("hbm", (2.0 if act16 else 4.0) * N * H + 4.0 * N * K), "skinny_bwd": ("hbm", skinny_bwd_bytes),
@@ -501,6 +543,19 @@ def run_b200_arm(args):
                             # DRAM bytes per launch from the committed ncu --set full capture (per graph x graphs/GPU)
                             "traffic": (traffic_db.get("per_graph_bytes_bf16_activations" if act16 else "per_graph_bytes",
                                                        {}).get(name) or 0.0) * B or None}
+    spmm_standalone = None
+    if spmm_from_alt is not None:
+        # the pre-aggregated step has no [N, hidden] SpMM: the metric's "SpMM HBM GB/s" comes from the same bf16 slab
+        # kernel timed inside the standard-layer-1 step that ran beside it (alt_paths.standard_layer1)
+        a = spmm_bytes_h_bwd / (spmm_from_alt * 1e-3) / 1e9
+        a32 = spmm_bytes_h / (spmm_from_alt * 1e-3) / 1e9
+        spmm_standalone = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": a / peaks["hbm_gbs"], "frac_nominal_8TBs": a / 8000.0, "avg_ms": spmm_from_alt,
+                           "algorithmic_bytes": spmm_bytes_h_bwd, "achieved_fp32_form": a32,
+                           "frac_fp32_form": a32 / peaks["hbm_gbs"],
+                           "where": "dT1 = A_hat dH1pre (bf16 slab SpMM) inside alt_paths.standard_layer1; the headline "
+                                    "step applies this aggregation to the features instead",
+                           "traffic": (traffic_db.get("per_graph_bytes_bf16_activations", {}).get("spmm_h") or 0.0) * B or None}
     dominant = max(timer.total_ms, key=lambda k: timer.total_ms[k]) if timer.total_ms else None
     roofline = None
     if dominant:
@@ -537,8 +592,15 @@ def run_b200_arm(args):
                              f"zero-padded adjacency rows [{N},{F}] (implied by the graph, never formed): X W1 and "
                              "X^T dT1 run as aggregations over the ELL plan (spmm_adj.cu), no tensor-core work"
                              if sparse_adj else
+                             f"pre-aggregated dense features A_hat X [{N},{F}] bf16 resident in HBM ({N * F * 2 / 1e9:.1f} "
+                             "GB/GPU), X = the zero-padded adjacency rows: GraphConv layer 1 as relu((A_hat X) W1 + b1)"
+                             if preagg else
                              f"dense zero-padded adjacency rows [{N},{F}] {'bf16' if args.precision == 'bf16' else 'fp32'} "
                              f"resident in HBM ({N * F * (2 if args.precision == 'bf16' else 4) / 1e9:.1f} GB/GPU)"),
+                "layer1": ("preaggregated: H1 = relu((A_hat X) W1 + b1) -- one tcgen05 GEMM with bias / ReLU epilogue; "
+                           "dW1 = (A_hat X)^T dH1pre -- one GEMM; identical to the reference's relu(A_hat (X W1) + b1), with the "
+                           "aggregation moved from the activations (every step) to the features (once per graph; every step "
+                           "in e2e)" if preagg else "standard: relu(A_hat (X W1) + b1), SpMM forward and backward every step"),
                 "spmm_bytes_form": "compulsory" if n * H * 4 <= 32 * 2 ** 20 else "gather",
                 "model": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
                 "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",
@@ -551,7 +613,7 @@ def run_b200_arm(args):
                 "graph_generation_s": t_gen,
             },
             "roofline": roofline,
-            "spmm": ops_report.get("spmm_h"),
+            "spmm": ops_report.get("spmm_h") or spmm_standalone,
             "ops": ops_report,
             "cpu_baseline": cpu,
             "e2e": e2e,

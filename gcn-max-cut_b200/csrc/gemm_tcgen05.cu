@@ -185,6 +185,8 @@ struct Params {
     int vec_ok;              // 16-byte aligned C rows
     int tma_store;           // epilogue through shared memory + cp.async.bulk.tensor stores (tmC valid)
     int c_bf16;              // C is a bf16 matrix (tmC describes it): accumulators rounded to nearest even on the way out
+    const float* bias;       // c_bf16 only: fp32 bias[N] added to every row before the rounding (nullable)
+    int relu;                // c_bf16 only: max(., 0) after the bias
 };
 
 // Thread-block cluster of CLM x CLN CTAs (rank = rm + CLM * rn) that owns CLM consecutive m-tiles x CLN consecutive
@@ -375,6 +377,33 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint32_t ra[32], rb[32], wv[32];
                     tmem_ld32(t_row + 64 * c, ra);
                     tmem_ld32(t_row + 64 * c + 32, rb);
+                    if (p.bias) {                                  // same address in every lane: broadcast loads, L1-resident
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (n + 4 * i < p.N) {                 // N % 4 == 0 (checked by the launcher)
+                                const float4 b = __ldg(b4 + i);
+                                ra[4 * i] = __float_as_uint(__uint_as_float(ra[4 * i]) + b.x);
+                                ra[4 * i + 1] = __float_as_uint(__uint_as_float(ra[4 * i + 1]) + b.y);
+                                ra[4 * i + 2] = __float_as_uint(__uint_as_float(ra[4 * i + 2]) + b.z);
+                                ra[4 * i + 3] = __float_as_uint(__uint_as_float(ra[4 * i + 3]) + b.w);
+                            }
+                            if (n + 32 + 4 * i < p.N) {
+                                const float4 b = __ldg(b4 + 8 + i);
+                                rb[4 * i] = __float_as_uint(__uint_as_float(rb[4 * i]) + b.x);
+                                rb[4 * i + 1] = __float_as_uint(__uint_as_float(rb[4 * i + 1]) + b.y);
+                                rb[4 * i + 2] = __float_as_uint(__uint_as_float(rb[4 * i + 2]) + b.z);
+                                rb[4 * i + 3] = __float_as_uint(__uint_as_float(rb[4 * i + 3]) + b.w);
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            ra[i] = __float_as_uint(fmaxf(__uint_as_float(ra[i]), 0.f));
+                            rb[i] = __float_as_uint(fmaxf(__uint_as_float(rb[i]), 0.f));
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         wv[i] = pack_bf16x2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
@@ -783,7 +812,8 @@ static int cluster_slots() {
 
 template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
 static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                  int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0) {
+                  int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
+                  const float* bias = nullptr, int relu = 0) {
     constexpr int CL = CLM * CLN;
     constexpr int ELT = BF16 ? 2 : 4;
     constexpr int BK = 128 / ELT, MNC = 128 / ELT;                 // k elements per stage, m/n elements per MN-major chunk
@@ -843,6 +873,12 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
         if (rc) return rc;
         p.tma_store = 1;
         p.c_bf16 = 1;
+        if (bias && (N % 4 != 0 || !aligned16(bias))) {
+            set_error("gmc_gemm_bf16_bf16out: a bias needs N %% 4 == 0 and a 16-byte aligned pointer");
+            return GMC_ERR_INVALID_ARG;
+        }
+        p.bias = bias;
+        p.relu = relu;
     } else if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
         rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
         if (rc) return rc;
@@ -862,15 +898,16 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
 
 template <bool A_MN, bool B_MN, bool BF16 = false>
 static int launch_cl(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                     int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0) {
+                     int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
+                     const float* bias = nullptr, int relu = 0) {
     int clm, cln;
     cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln, BF16);
 #define GMC_GEMM_CASE(CM, CN)                                                                                       \
     if (clm == CM && cln == CN)                                                                                     \
-        return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
+        return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
     GMC_GEMM_CASE(1, 1) GMC_GEMM_CASE(2, 1) GMC_GEMM_CASE(4, 1) GMC_GEMM_CASE(8, 1) GMC_GEMM_CASE(2, 2) GMC_GEMM_CASE(4, 2)
 #undef GMC_GEMM_CASE
-    return launch<A_MN, B_MN, 4, 1, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
+    return launch<A_MN, B_MN, 4, 1, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
 }
 
 static bool use_two_cta() {
@@ -1083,7 +1120,8 @@ int tc_gemm(int op, const float* A, const float* B, float* C, int64_t M, int64_t
 size_t tc_bf16_workspace_bytes(int op, int64_t M, int64_t N, int64_t K) { return (tc_splitk_bytes(op, M, N, K, true) + 255) & ~(size_t)255; }
 
 int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                 int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16) {
+                 int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16,
+                 const float* bias, int relu) {
     GMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B),
                 "gmc_gemm_bf16: TMA needs 16-byte aligned bases and leading dimensions that are multiples of 8 elements");
     GMC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gmc_gemm_bf16: dimension exceeds int32 TMA coordinates");
@@ -1095,9 +1133,9 @@ int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64
     }
     float* Cf = reinterpret_cast<float*>(C);                       // reinterpreted by the kernel when c_bf16 is set
     switch (op) {
-        case 0: return tc::launch_cl<false, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
-        case 1: return tc::launch_cl<false, false, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
-        case 2: return tc::launch_cl<true, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16);
+        case 0: return tc::launch_cl<false, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
+        case 1: return tc::launch_cl<false, false, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
+        case 2: return tc::launch_cl<true, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
     }
     set_error("gmc_gemm_bf16: bad op %d", op);
     return GMC_ERR_INVALID_ARG;

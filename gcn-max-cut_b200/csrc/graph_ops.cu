@@ -32,7 +32,8 @@ constexpr int kRowLanes = 8;
 __device__ __forceinline__ int find_graph_guess(const int32_t* __restrict__ graph_ptr, int n_graphs, int64_t row) {
     const int n0 = __ldg(graph_ptr + 1) - __ldg(graph_ptr);
     if (n0 > 0) {
-        const int64_t g = row / n0;
+        // 32-bit division whenever the row index allows it: the 64-bit one is a ~100-instruction subroutine per call
+        const int64_t g = row < (1ll << 31) ? (int64_t)((uint32_t)row / (uint32_t)n0) : row / n0;
         if (g < n_graphs && (int64_t)__ldg(graph_ptr + g) <= row && row < (int64_t)__ldg(graph_ptr + g + 1)) return (int)g;
     }
     return find_graph(graph_ptr, n_graphs, row);
@@ -100,6 +101,111 @@ __global__ void scatter_bf16_kernel(const int32_t* __restrict__ rowptr, const in
         int local = colidx[e] - base;
         if (local < 0 || local >= n_cols) continue;
         X[row * ldx + local] = __float2bfloat16_rn(clear ? 0.0f : (vals ? vals[e] : 1.0f));
+    }
+}
+
+// Pre-aggregated first-layer features: XA = A_hat X with X the zero-padded (weighted) adjacency rows, written as bf16.
+//   XA[v, local(j)] = sum_{u in N(v)} coef(v,u) * w(u,j)
+// A_hat (X W1) = (A_hat X) W1, and X is a function of the graph alone, so GraphConv layer 1's aggregation
+// (TrainingNeural.py:80, dgl update_all) can be applied to the features once instead of to the activations every step.
+// One warp per row: the row is accumulated in a shared-memory fp32 buffer (neighbours u in CSR order, the lanes over
+// N(u): distinct columns within one u, so plain adds in a fixed order -- deterministic), then written out whole as
+// bf16 (zeros included: no memset of the [N, n_cols] matrix).
+constexpr int kPreaggWarps = 8;
+
+__global__ void __launch_bounds__(kPreaggWarps * 32)
+preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                         const float* __restrict__ coef, const float* __restrict__ vals,
+                         const int32_t* __restrict__ graph_ptr, int n_graphs, int64_t n_rows, int n_cols, int ncp,
+                         __nv_bfloat16* __restrict__ X, int64_t ldx) {
+    extern __shared__ __align__(16) float preagg_rows[];              // kPreaggWarps x ncp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* buf = preagg_rows + warp * ncp;
+    const int64_t stride = (int64_t)gridDim.x * kPreaggWarps;
+    // graph of a row without a division per row: equal-sized graphs (what the reference builds) give g = row / n0,
+    // evaluated in float and verified against graph_ptr; anything else takes the binary search
+    const int n0 = __ldg(graph_ptr + 1) - __ldg(graph_ptr);
+    const float inv_n0 = n0 > 0 ? 1.0f / (float)n0 : 0.f;
+
+    // ncu on the first version (gpurun_out/prof_preagg): ~690 warp instructions per row (a scan, an owner search and
+    // ordered accumulation rounds for every row, a 64-bit division for the graph id), 57 % issue slots -- instruction
+    // bound.  Software-pipelining the four dependent loads of a row (extent -> neighbours -> their extents -> 2-hop
+    // columns) made it slower both before (4.2 -> 4.6 ms) and after (3.0 -> 3.7 ms) the diet below, so the loop is the
+    // plain one and the common case is kept lean:
+    //   fast row  = unit weights, <= 32 neighbours which all have one degree D and one coefficient c, <= 64 two-hop
+    //               pairs: pair p belongs to neighbour p / D and every addend is the same c, so the adds can be
+    //               unordered shared-memory atomics and still reproduce bit for bit (equal addends commute exactly);
+    //   other rows = neighbours one after the other in CSR order, lanes over N(u) (distinct columns): fixed order.
+    // Config 3 (4.1 M rows, 8.4 GB written): 3.0 ms.
+    for (int64_t row = (int64_t)blockIdx.x * kPreaggWarps + warp; row < n_rows; row += stride) {
+        for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+        int g = (int)(((float)row + 0.5f) * inv_n0);
+        if (g >= n_graphs) g = n_graphs - 1;
+        int base = __ldg(graph_ptr + g);
+        if (n0 <= 0 || (int64_t)base > row || row >= (int64_t)__ldg(graph_ptr + g + 1)) {
+            g = find_graph(graph_ptr, n_graphs, row);
+            base = __ldg(graph_ptr + g);
+        }
+        const int cnt = e1 - e0;
+        int my_f0 = 0, my_deg = 0;
+        float my_c = 0.f;
+        if (lane < min(cnt, 32)) {
+            const int u = __ldg(colidx + e0 + lane);
+            my_c = __ldg(coef + e0 + lane);
+            my_f0 = __ldg(rowptr + u);
+            my_deg = __ldg(rowptr + u + 1) - my_f0;
+        }
+        const int D0 = __shfl_sync(0xffffffffu, my_deg, 0);
+        const float c0 = __shfl_sync(0xffffffffu, my_c, 0);
+        const bool same = __all_sync(0xffffffffu, lane >= cnt || (my_deg == D0 && my_c == c0));
+        const bool fast = same && !vals && cnt > 0 && cnt <= 32 && D0 > 0 && cnt * D0 <= 64;
+        __syncwarp();                                                  // the row buffer is zero
+        if (fast) {
+            const int total = cnt * D0;
+            const float inv_d = 1.0f / (float)D0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int p = 32 * j + lane;
+                const int owner = p < total ? (int)(((float)p + 0.5f) * inv_d) : 0;      // p / D0, exact for p < 64
+                const int o_f0 = __shfl_sync(0xffffffffu, my_f0, owner);
+                if (p < total) {
+                    const int local = __ldg(colidx + o_f0 + (p - owner * D0)) - base;
+                    if (local >= 0 && local < n_cols) atomicAdd(buf + local, c0);
+                }
+            }
+        } else {
+            for (int eb = e0; eb < e1; eb += 32) {
+                const int n_here = min(32, e1 - eb);
+                if (eb > e0) {
+                    my_f0 = 0; my_deg = 0; my_c = 0.f;
+                    if (lane < n_here) {
+                        const int u = __ldg(colidx + eb + lane);
+                        my_c = __ldg(coef + eb + lane);
+                        my_f0 = __ldg(rowptr + u);
+                        my_deg = __ldg(rowptr + u + 1) - my_f0;
+                    }
+                }
+                for (int q = 0; q < n_here; ++q) {
+                    const int f0 = __shfl_sync(0xffffffffu, my_f0, q), dg = __shfl_sync(0xffffffffu, my_deg, q);
+                    const float c = __shfl_sync(0xffffffffu, my_c, q);
+                    for (int f = f0 + lane; f < f0 + dg; f += 32) {
+                        const int local = __ldg(colidx + f) - base;
+                        if (local >= 0 && local < n_cols) buf[local] += c * (vals ? __ldg(vals + f) : 1.0f);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+        __nv_bfloat16* xr = X + row * ldx;
+        for (int c8 = lane; c8 * 8 < ncp; c8 += 32) {
+            const float4 a = *reinterpret_cast<const float4*>(buf + c8 * 8), b = *reinterpret_cast<const float4*>(buf + c8 * 8 + 4);
+            __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                                   __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+            *reinterpret_cast<uint4*>(xr + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+        }
+        __syncwarp();
     }
 }
 
@@ -201,6 +307,38 @@ int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
     int64_t blocks = gmc::ceil_div<int64_t>(n_rows * gmc::kRowLanes, threads);
     gmc::scatter_bf16_kernel<<<(unsigned)blocks, threads, 0, gmc::as_stream(stream)>>>(
         rowptr, colidx, vals, graph_ptr, n_graphs, n_rows, n_cols, reinterpret_cast<__nv_bfloat16*>(X), ldx, clear);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+// XA = A_hat X in bf16 for X = the zero-padded (weighted) adjacency rows of the batch (graphExtender.py:106-111) and
+// A_hat given by its per-edge values `coef` (gmc_edge_coef_f32): the features of the pre-aggregated first layer,
+// H1 = relu(XA W1 + b1) == relu(A_hat (X W1) + b1) (TrainingNeural.py:80-81).  Every row is written whole (ldx % 8 == 0,
+// 16-byte aligned base); rows are built in a fixed order, so the result is bitwise reproducible.
+int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                              const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                              int64_t ldx, void* stream) {
+    GMC_REQUIRE(rowptr && colidx && coef && graph_ptr && X, "gmc_csr_preaggregate_bf16: null pointer");
+    GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0 && n_cols > 0 && ldx >= n_cols, "gmc_csr_preaggregate_bf16: bad sizes");
+    const int ncp = (n_cols + 7) & ~7;
+    GMC_REQUIRE(ldx % 8 == 0 && ldx >= ncp && gmc::aligned16(X) && ncp <= 6144,
+                "gmc_csr_preaggregate_bf16: needs ldx %% 8 == 0 covering n_cols rounded up to 8, a 16-byte aligned X and "
+                "n_cols <= 6144");
+    if (n_rows == 0) return GMC_OK;
+    const size_t smem = (size_t)gmc::kPreaggWarps * ncp * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 6144 * 4));
+        attr = true;
+    }
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t blocks = gmc::ceil_div<int64_t>(n_rows, gmc::kPreaggWarps);
+    const int64_t cap = (int64_t)gmc::sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    gmc::preaggregate_bf16_kernel<<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, gmc::as_stream(stream)>>>(
+        rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, reinterpret_cast<__nv_bfloat16*>(X), ldx);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
 }

@@ -79,7 +79,8 @@ class OpTimer:
 class GCNEngine:
     def __init__(self, net, optimizer: Optional[FusedAdam] = None, *, C: float = 1.0, loss_mode: str = "ste",
                  override_terminals: bool = True, penalty: float = 0.0, precision: str = "fp32",
-                 process_group=None, adjacency_kernels: bool = False, activations: str = "fp32"):
+                 process_group=None, adjacency_kernels: bool = False, activations: str = "fp32",
+                 preaggregate: bool = False):
         self.device = _lib.require_cuda()
         self.net = net
         self.optimizer = optimizer
@@ -99,6 +100,16 @@ class GCNEngine:
         if activations == "bf16" and precision != "bf16":
             raise ValueError("activations='bf16' needs precision='bf16'")
         self.activations = activations
+        # preaggregate=True (needs precision='bf16', activations='bf16'): GraphConv layer 1 is evaluated as
+        # H1 = relu((A_hat X) W1 + b1) instead of relu(A_hat (X W1) + b1).  The two are the same matrix product; the
+        # difference is WHERE the aggregation runs: on the [N, F] features, which do not depend on the weights (once per
+        # (graph, features) pair -- for the reference's adjacency features, once per graph), instead of on the [N, H]
+        # activations in every forward and every backward pass.  Layer 1 is then ONE GEMM with a bias / ReLU epilogue,
+        # dW1 = (A_hat X)^T dH1pre ONE GEMM, and no [N, H] SpMM is left in the step.  Works for any batch (no ELL plan
+        # needed).  Not available with trainable features (dX): their aggregate changes every step.
+        self.preaggregate = bool(preaggregate)
+        if self.preaggregate and (precision != "bf16" or activations != "bf16"):
+            raise ValueError("preaggregate=True needs precision='bf16' and activations='bf16'")
         # adjacency_kernels: the caller guarantees that the features ARE the zero-padded unit-weight adjacency rows of
         # the batch (the reference's live input, TrainingNeural.py:373).  X W1 and X^T dT1 then run as aggregations
         # over the batch's ELL plan (csrc/spmm_adj.cu) whenever the batch qualifies, and X itself is never read.
@@ -129,6 +140,7 @@ class GCNEngine:
         # (written directly by the slab SpMM) feed gmc_gemm_bf16; everything else stays fp32
         self.W1b = ops.padded_empty_bf16(self.F, self.H, self.device, zero=True) if precision == "bf16" else None
         self._xb_cache: Dict[tuple, torch.Tensor] = {}
+        self._xa_cache: Dict[tuple, torch.Tensor] = {}
         self.bufB16 = None
         self.bufA16 = None
         self._cap_nodes = 0
@@ -191,6 +203,26 @@ class GCNEngine:
         return (self.activations == "bf16" and not self._sparse_layer1(batch)
                 and ops.bf16_activations_apply(batch, self.H))
 
+    def _preaggregated(self, batch: GraphBatch, X) -> torch.Tensor:
+        """XA = A_hat X in bf16: taken as is from an ops.PreaggregatedFeatures, else computed once per (batch, X) and
+        cached on their identity and version (fp32 SpMM over the F feature columns, rounded once)."""
+        if isinstance(X, ops.PreaggregatedFeatures):
+            XA = X.tensor
+            if XA.shape[0] != batch.num_nodes or XA.shape[1] != self.F:
+                raise ValueError(f"pre-aggregated features must be [{batch.num_nodes}, {self.F}], got {tuple(XA.shape)}")
+            return XA
+        X = self._features(batch, X)
+        key = (id(batch), X.data_ptr(), tuple(X.shape), X.stride(0), X._version, X.dtype)
+        hit = self._xa_cache.get(key)
+        if hit is None:
+            if len(self._xa_cache) >= 64:
+                self._xa_cache.clear()
+            X32 = X.float() if X.dtype == torch.bfloat16 else X
+            hit = (batch, ops.to_bf16(ops.spmm(batch, X32)))      # the batch is kept alive with its entry (id reuse)
+            del X32
+            self._xa_cache[key] = hit
+        return hit[1]
+
     def _features(self, batch: GraphBatch, X: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if X is None:
             if not self._sparse_layer1(batch):
@@ -223,9 +255,21 @@ class GCNEngine:
     # ------------------------------------------------------------------ forward
     def forward_logits(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
         """Z (pre-softmax) for the batch; leaves H1 in bufB."""
-        X = self._features(batch, X)
         N = batch.num_nodes
         W1, b1, W2, b2 = self.params()
+        if self.preaggregate:
+            if self.K > 4 or self.H > 512 or self.H % 4:
+                raise NotImplementedError("preaggregate=True needs number_classes <= 4 and hidden_dim <= 512 (multiple of 4)")
+            XA = self._preaggregated(batch, X)
+            self._ensure(N, batch.num_graphs, b16=True)
+            B16 = self.bufB16[:N]
+            ops.to_bf16(W1.data, out=self.W1b)
+            # the whole first layer: H1 = relu(XA W1 + b1), bias and ReLU in the GEMM epilogue, bf16 out
+            self._op("gemm_nn_layer1", 1, ops.gemm_bf16_bf16out, "nn", XA, self.W1b, out=B16, bias=b1.data, relu=True)
+            self._op("skinny_fwd", 1, ops.skinny_fwd_bf16, B16, W2.data, out=self.T2[:N])
+            self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
+            return self.Z[:N]
+        X = self._features(batch, X)
         if self._b16_activations(batch):
             self._ensure(N, batch.num_graphs, b16=True)
             A16, B16 = self.bufA16[:N], self.bufB16[:N]
@@ -277,7 +321,12 @@ class GCNEngine:
     def loss_and_grads(self, batch: GraphBatch, X: torch.Tensor, dX: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward + loss + full backward at the current weights.  Gradients land in
         self.grads_flat (overwritten); returns per-graph loss (float64 [B], device view)."""
-        X = self._features(batch, X)
+        if self.preaggregate:
+            if dX is not None:
+                raise ValueError("preaggregate=True folds the aggregation into fixed features; trainable features (dX) "
+                                 "need the standard path")
+        else:
+            X = self._features(batch, X)
         if dX is not None and self._sparse_layer1(batch):
             raise ValueError("adjacency_kernels promises fixed adjacency features; trainable features need the dense path")
         N, B = batch.num_nodes, batch.num_graphs
@@ -288,6 +337,13 @@ class GCNEngine:
                  need_P=True, need_dZ=True, P=self.P[:N], dZ=self.dZ[:N], loss=loss)
         self._op("colsum_db2", 2, ops.colsum, self.dZ[:N], out=self.gb2, workspace=self.ws)
         self._op("spmm_k", 1, ops.spmm, batch, self.dZ[:N], out=self.dT2[:N])
+        if self.preaggregate:
+            XA = self._preaggregated(batch, X)
+            A16, B16 = self.bufA16[:N], self.bufB16[:N]
+            self._op("skinny_bwd", 2, ops.skinny_bwd_bf16, self.dT2[:N], W2.data, B16, dH=A16, dW=self.gW2,
+                     dbias=self.gb1, workspace=self.ws)                                              # dH1pre, bf16
+            self._op("gemm_tn_dw1", 2, ops.gemm_bf16, "tn", XA, A16, out=self.gW1, workspace=self.ws)  # (A_hat X)^T dH1pre
+            return loss
         if self._b16_activations(batch):
             if dX is not None:
                 raise NotImplementedError("trainable features (dX) are not wired to the bf16 GEMM path; use tf32")

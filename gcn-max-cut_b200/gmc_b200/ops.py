@@ -269,6 +269,30 @@ def scatter_features_bf16(batch, n_cols: int, X: torch.Tensor, clear: bool = Fal
     return X
 
 
+class PreaggregatedFeatures:
+    """Marks a bf16 matrix as XA = A_hat X (already aggregated over the graph) for GCNEngine(preaggregate=True)."""
+    __slots__ = ("tensor",)
+
+    def __init__(self, tensor: torch.Tensor):
+        _bf16_rowmajor(tensor, "XA")
+        self.tensor = tensor
+
+
+def preaggregate_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """XA = A_hat X in bf16 for X = the zero-padded adjacency rows of the batch, straight from the graph (the dense X
+    is never formed)."""
+    if out is None:
+        out = padded_empty_bf16(batch.num_nodes, n_cols, batch.device, zero=True)
+    out, ld = _bf16_rowmajor(out, "out")
+    if out.shape[0] != batch.num_nodes or out.shape[1] != n_cols:
+        raise ValueError(f"out must be [{batch.num_nodes}, {n_cols}]")
+    check(lib().gmc_csr_preaggregate_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(),
+                                          _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(), batch.num_graphs,
+                                          batch.num_nodes, n_cols, out.data_ptr(), ld, _stream()),
+          "gmc_csr_preaggregate_bf16")
+    return out
+
+
 def spmm_bf16out(batch, X: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """A_hat X rounded to bf16 (slab kernel; falls back to the fp32 SpMM + conversion when the batch has no plan)."""
     X, ldx = _rowmajor(X, "X")
@@ -312,8 +336,10 @@ def gemm_bf16(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Ten
 
 
 # ---------------------------------------------------------------- bf16 layer-1 activations
-def gemm_bf16_bf16out(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """gemm_bf16 whose result is rounded to bf16 in the epilogue (no split-K, no accumulate)."""
+def gemm_bf16_bf16out(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """gemm_bf16 whose result is rounded to bf16 in the epilogue (no split-K, no accumulate); optional fp32 bias
+    over the columns and ReLU before the rounding."""
     A, lda = _bf16_rowmajor(A, "A")
     B, ldb = _bf16_rowmajor(B, "B")
     if op == "nn":
@@ -329,8 +355,10 @@ def gemm_bf16_bf16out(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[t
     if out is None:
         out = padded_empty_bf16(M, N, A.device, zero=True)
     out, ldc = _bf16_rowmajor(out, "out")
+    if bias is not None and (_f32(bias, "bias").numel() != N or not bias.is_contiguous()):
+        raise ValueError(f"bias must be a contiguous fp32 vector of {N} elements")
     check(lib().gmc_gemm_bf16_bf16out(_OPS[op], A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
-                                      _stream()), "gmc_gemm_bf16_bf16out")
+                                      _ptr(bias), int(relu), _stream()), "gmc_gemm_bf16_bf16out")
     return out
 
 

@@ -86,6 +86,7 @@ class TrainingConfig:
     feature_source: str = "adjacency"
     adjacency_kernels: bool = False          # batched steps only: X W1 / X^T dT1 as aggregations (csrc/spmm_adj.cu)
     activations: str = "fp32"                # 'bf16' (with gemm_precision='bf16'): layer-1 activations stored in bf16
+    preaggregate_features: bool = False      # with bf16 / bf16: layer 1 as relu((A_hat X) W1 + b1), A_hat X built once
 
     def __post_init__(self):
         if self.feature_source not in ("adjacency", "embedding"):
@@ -228,7 +229,9 @@ def _engine_for(net, optimizer, config: TrainingConfig) -> GCNEngine:
            getattr(config, "gemm_precision", "fp32"),
            bool(getattr(config, "adjacency_kernels", False))
            and getattr(config, "feature_source", "adjacency") == "adjacency",
-           getattr(config, "activations", "fp32"))
+           getattr(config, "activations", "fp32"),
+           bool(getattr(config, "preaggregate_features", False))
+           and getattr(config, "feature_source", "adjacency") == "adjacency")
     cached = _ENGINES.get(net)
     if cached is not None and cached[0] == key:
         return cached[1]
@@ -236,7 +239,7 @@ def _engine_for(net, optimizer, config: TrainingConfig) -> GCNEngine:
         raise TypeError("the B200 training loop needs the FusedAdam returned by setup_model_and_optimizer")
     engine = GCNEngine(net, optimizer, C=config.C, loss_mode=key[2], override_terminals=True,
                        penalty=config.penalty if key[3] else 0.0, precision=key[5], adjacency_kernels=key[6],
-                       activations=key[7])
+                       activations=key[7], preaggregate=key[8])
     _ENGINES[net] = (key, engine)
     return engine
 

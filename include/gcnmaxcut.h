@@ -248,6 +248,14 @@ int gmc_csr_densify_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
 int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
                          const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
                          int64_t ldx, int32_t clear, void* stream);
+/* Pre-aggregated first-layer features XA = A_hat X (bf16) for X = the zero-padded adjacency rows of the batch and A_hat
+ * given by `coef` (gmc_edge_coef_f32).  A_hat (X W1) = (A_hat X) W1 and X depends on the graph alone, so GraphConv
+ * layer 1's aggregation (TrainingNeural.py:80) moves from the activations (every step, forward and backward) to the
+ * features (once per graph): H1 = relu(XA W1 + b1) is then one GEMM with a bias/ReLU epilogue and
+ * dW1 = XA^T dH1pre one GEMM.  ldx % 8 == 0, n_cols <= 6144; rows are written whole; bitwise reproducible. */
+int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                              const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                              int64_t ldx, void* stream);
 
 /* ---- bf16 layer-1 activations (engine option activations='bf16', on top of the bf16 GEMM operands) ----------------
  * T1 = X W1, H1 = relu(A_hat T1 + b1), dH1pre and dT1 are [n_nodes, hidden] matrices that are each written once and
@@ -257,7 +265,9 @@ int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
  * n_cols rounded up to 8; pad columns are written as zeros / must be finite on input.
  *
  * gmc_gemm_bf16_bf16out       : gmc_gemm_bf16 with a bf16 C (epilogue rounds the accumulators, TMA stores); no split-K,
- *                               no accumulate -- th.matmul of GraphConv layer 1 (TrainingNeural.py:80).
+ *                               no accumulate -- th.matmul of GraphConv layer 1 (TrainingNeural.py:80).  Optional fp32
+ *                               bias[N] (N % 4 == 0) and ReLU in the epilogue (the whole first layer when the features
+ *                               are pre-aggregated, gmc_csr_preaggregate_bf16).
  * gmc_spmm_fused_skinny_bf16  : gmc_spmm_fused_skinny_f32 with a bf16 X and an fp32 (y_bf16 = 0) or bf16 (y_bf16 = 1) Y;
  *                               with a bf16 Y the projection T = Y W uses the rounded Y (what the backward pass reads).
  * gmc_skinny_bwd_bf16         : gmc_skinny_bwd_f32 with bf16 H and dHpre (ldh, lddh multiples of 4).
@@ -265,7 +275,7 @@ int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
  * gmc_skinny_fwd_bf16         : gmc_skinny_fwd_f32 with a bf16 H (n_out <= 4, n_in <= 512): the projection T = H1 W2
  *                               when the forward aggregation runs through the slab kernel. */
 int gmc_gemm_bf16_bf16out(int32_t op, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
-                          int64_t lda, int64_t ldb, int64_t ldc, void* stream);
+                          int64_t lda, int64_t ldb, int64_t ldc, const float* bias, int32_t relu, void* stream);
 int gmc_spmm_fused_skinny_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
                                const float* norm_src, const float* norm_dst, const void* X, void* Y, int32_t y_bf16,
                                int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy, const float* bias,

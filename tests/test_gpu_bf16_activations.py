@@ -169,6 +169,35 @@ def test_skinny_fwd_bf16(n_in, K, n):
         ops.skinny_fwd_bf16(Hb, torch.randn(n_in, 5, device=DEV))       # n_out > 4: not supported by this kernel
 
 
+def test_bf16_chain_on_a_ragged_batch():
+    """Graphs of different sizes and degrees in one batch (config 4 mixes d = 6, 7, 8; the reference's test sets mix
+    n = 50..500): slab SpMM, both skinny kernels and the fused row kernel on the same ragged block-diagonal batch."""
+    import networkx as nx
+    from gmc_b200.graph import CSRGraph
+    specs = [(130, 6, 1), (256, 7, 2), (1000, 7, 3), (128, 8, 4), (514, 7, 5), (300, 6, 6)]
+    graphs = []
+    for n, d, seed in specs:
+        g = nx.random_regular_graph(d=d, n=n, seed=seed)
+        nx.set_edge_attributes(g, 1, "weight")
+        graphs.append(CSRGraph.from_networkx(g))
+    batch = GraphBatch(graphs, device=DEV)
+    assert batch.build_plan()
+    C, K = 500, 3
+    torch.manual_seed(0)
+    X = torch.randn(batch.num_nodes, C)
+    bias, W = torch.randn(C) * 0.2, torch.randn(C, K) / C ** 0.5
+    Xb = ops.padded_empty_bf16(batch.num_nodes, C, DEV, zero=True)
+    ops.to_bf16(X.to(DEV), out=Xb)
+    want = torch.relu(ahat_times(batch, bf16_round(X)) + bias.double())
+    H = ops.spmm_bf16(batch, Xb, bias=bias.to(DEV), relu=True)
+    assert_bf16_close(H, want, extra=2e-6)
+    Hrow, Trow = ops.spmm_fused_skinny_bf16(batch, Xb, W.to(DEV), bias=bias.to(DEV), relu=True)
+    assert_bf16_close(Hrow, want, extra=2e-6)
+    T = ops.skinny_fwd_bf16(H, W.to(DEV))
+    assert float((T.double().cpu() - H.double().cpu() @ W.double()).abs().max()) < 2e-5
+    assert float((Trow.double().cpu() - Hrow.double().cpu() @ W.double()).abs().max()) < 2e-5
+
+
 def test_spmm_batched_bf16_needs_a_plan():
     from gmc_b200 import _lib
     import networkx as nx
@@ -253,6 +282,80 @@ def test_bf16_activation_forward_variants_agree(monkeypatch):
     assert relerr(res[True][0], res[False][0]) < 2e-3
     for a, b in zip(res[True][2], res[False][2]):
         assert relerr(a, b) < 1e-2
+
+
+def test_gemm_bf16_bf16out_bias_relu_epilogue():
+    torch.manual_seed(8)
+    M, N, K = 700, 500, 320
+    A, B, bias = torch.randn(M, K), torch.randn(K, N) / K ** 0.5, torch.randn(N)
+    Ab, Bb = ops.to_bf16(A.to(DEV)), ops.to_bf16(B.to(DEV))
+    want = torch.relu(bf16_round(A) @ bf16_round(B) + bias.double())
+    got = ops.gemm_bf16_bf16out("nn", Ab, Bb, bias=bias.to(DEV), relu=True)
+    assert_bf16_close(got, want, extra=1e-4)
+    got2 = ops.gemm_bf16_bf16out("nn", Ab, Bb, bias=bias.to(DEV))
+    assert_bf16_close(got2, bf16_round(A) @ bf16_round(B) + bias.double(), extra=1e-4)
+    full = got._base if got._base is not None else got
+    assert float(full[:, N:].abs().max()) == 0.0
+
+
+def test_preaggregated_features_equal_ahat_times_adjacency():
+    import networkx as nx
+    from gmc_b200.graph import CSRGraph
+    specs = [(130, 6, 1), (256, 7, 2), (60, 3, 3), (128, 8, 4)]
+    graphs = []
+    rng = np.random.default_rng(0)
+    for n, d, seed in specs:
+        g = nx.random_regular_graph(d=d, n=n, seed=seed)
+        for u, v in g.edges():
+            g[u][v]["weight"] = int(rng.integers(1, 4))
+        graphs.append(CSRGraph.from_networkx(g))
+    g = nx.barabasi_albert_graph(200, 3, seed=1)             # irregular degrees: no ELL plan needed for this path
+    nx.set_edge_attributes(g, 1, "weight")
+    graphs.append(CSRGraph.from_networkx(g))
+    batch = GraphBatch(graphs, device=DEV)
+    F = 264
+    X = ops.densify(batch, F)
+    want = ahat_times(batch, X.double().cpu())
+    XA = ops.preaggregate_features_bf16(batch, F)
+    assert_bf16_close(XA, want, extra=1e-7)
+    assert torch.equal(XA, ops.preaggregate_features_bf16(batch, F))          # fixed summation order
+    full = XA._base if XA._base is not None else XA
+    assert float(full[:, F:].abs().max()) == 0.0 if full.shape[1] > F else True
+
+
+def test_preaggregated_engine_matches_the_standard_bf16_step():
+    """preaggregate=True computes the same layer 1 with the aggregation applied to the features: probabilities, loss and
+    gradients agree with the standard bf16-activation step (and with fp32) to bf16 rounding; passing the features
+    through ops.PreaggregatedFeatures (built from the graph) or letting the engine aggregate a dense X is the same."""
+    from Training import TrainingNeural as T
+    batch = regular_batch(40, 256, 7, seed=21)
+    X = ops.densify(batch, 256)
+    out = {}
+    for name, kw in (("fp32", dict(precision="fp32")), ("std16", dict(precision="bf16", activations="bf16")),
+                     ("pre16", dict(precision="bf16", activations="bf16", preaggregate=True))):
+        cfg = T.TrainingConfig(n_nodes=256, dim_embedding=256, hidden_dim=128, loss_mode="soft")
+        torch.manual_seed(3)
+        net, embed, opt = T.setup_model_and_optimizer(cfg)
+        with torch.no_grad():
+            net.conv1.bias.normal_(0, 0.1)
+        eng = GCNEngine(net, opt, loss_mode="soft", **kw)
+        loss = eng.loss_and_grads(batch, X).cpu().clone()
+        rec = (loss, eng.P[: batch.num_nodes].cpu().clone(), [g.cpu().clone() for g in eng.grads()])
+        if name == "pre16":
+            XA = ops.PreaggregatedFeatures(ops.preaggregate_features_bf16(batch, 256))
+            loss2 = eng.loss_and_grads(batch, XA).cpu()
+            assert relerr(loss2, loss) < 1e-3
+            assert eng.bufA is None                              # no fp32 [N, hidden] buffer, and no SpMM over hidden columns
+            losses = [float(eng.train_step(batch, XA).sum()) for _ in range(4)]
+            assert all(np.isfinite(losses))
+        out[name] = rec
+    for ref in ("fp32", "std16"):
+        assert relerr(out["pre16"][0], out[ref][0]) < 1e-2
+        assert float((out["pre16"][1] - out[ref][1]).abs().max()) < 1e-2
+        for a, b in zip(out["pre16"][2], out[ref][2]):
+            assert relerr(a, b) < 3e-2
+    with pytest.raises(ValueError):
+        GCNEngine(net, opt, precision="bf16", activations="fp32", preaggregate=True)
 
 
 def test_bf16_activations_need_bf16_gemms_and_fall_back_without_a_plan():
