@@ -15,8 +15,12 @@ dense GEMMs on the tensor cores.  --precision picks their operand type: bf16 (de
 master weights / logits / loss / reductions / Adam stay fp32), tf32 (fp32 operands, one TF32 pass), tf32x3 and
 fp32 (fp32-grade parity paths).  With bf16 operands, --activations bf16 (default; ordinary mixed precision:
 bf16 storage, fp32 arithmetic) also STORES the four [nodes, hidden] layer-1 tensors T1, H1, dH1pre, dT1 in
-bf16; --activations fp32 keeps them fp32.  The default line also carries `alt_paths`: the same step with fp32
-activations, with TF32 GEMMs, and with layer 1 in aggregation form (--feature-source adjacency-sparse).
+bf16; --activations fp32 keeps them fp32.  --layer1 preaggregated (default with bf16 / bf16) evaluates GraphConv layer 1
+as relu((A_hat X) W1 + b1): the aggregation is applied to the features, which depend on the graph alone (resident input:
+A_hat X; end-to-end: rebuilt from every step's host CSR), so the step is one GEMM per direction with no hidden-width
+SpMM; --layer1 standard keeps relu(A_hat (X W1) + b1) with the slab SpMM forward and backward in every step.  The
+default line also carries `alt_paths`: the same step with the standard layer 1, with fp32 activations, with TF32 GEMMs,
+and with layer 1 in aggregation form (--feature-source adjacency-sparse).
 Other workloads: --workload config1 | config2 | config5, --feature-source embedding.
 
 Output: ONE JSON line on rank 0 (contract in the task statement) with `roofline`, `cpu_baseline`,

@@ -358,6 +358,33 @@ def test_preaggregated_engine_matches_the_standard_bf16_step():
         GCNEngine(net, opt, precision="bf16", activations="fp32", preaggregate=True)
 
 
+def test_training_api_with_the_throughput_configuration():
+    """TrainingConfig(gemm_precision='bf16', activations='bf16', preaggregate_features=True) through train_single_epoch
+    (batched steps, dataset produced by the mirror of graphExtender): epoch losses track the fp32 configuration."""
+    import contextlib, io
+    import networkx as nx
+    from DataGenerator import graphExtender as E
+    from Training import TrainingNeural as T
+    graphs = {i: nx.random_regular_graph(d=5 + i % 3, n=128 + 4 * (i % 5), seed=200 + i) for i in range(36)}
+    for g in graphs.values():
+        nx.set_edge_attributes(g, 1, "weight")
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds = E.process_graphs_from_folder(graphs, {i: [5 + i % 3, 40, 77] for i in range(36)}, max_nodes=160)
+    runs = {}
+    for name, kw in (("fp32", {}), ("std16", dict(gemm_precision="bf16", activations="bf16")),
+                     ("pre16", dict(gemm_precision="bf16", activations="bf16", preaggregate_features=True))):
+        cfg = T.TrainingConfig(n_nodes=160, dim_embedding=160, hidden_dim=64, batch_graphs=36, learning_rate=1e-3,
+                               loss_mode="soft", **kw)
+        torch.manual_seed(3)
+        net, embed, opt = T.setup_model_and_optimizer(cfg)
+        runs[name] = [T.train_single_epoch(ds, net, opt, embed, cfg) for _ in range(4)]
+        eng = T._engine_for(net, opt, cfg)
+        assert eng.preaggregate == (name == "pre16") and eng.activations == ("fp32" if name == "fp32" else "bf16")
+    np.testing.assert_allclose(runs["std16"], runs["fp32"], rtol=1e-2)
+    np.testing.assert_allclose(runs["pre16"], runs["fp32"], rtol=1e-2)
+    assert runs["fp32"][-1] < runs["fp32"][0]                # and it trains
+
+
 def test_bf16_activations_need_bf16_gemms_and_fall_back_without_a_plan():
     from Training import TrainingNeural as T
     import networkx as nx
