@@ -187,6 +187,13 @@ struct Params {
     int c_bf16;              // C is a bf16 matrix (tmC describes it): accumulators rounded to nearest even on the way out
     const float* bias;       // c_bf16 only: fp32 bias[N] added to every row before the rounding (nullable)
     int relu;                // c_bf16 only: max(., 0) after the bias
+    // c_bf16 only, optional skinny projection of the ROUNDED result: P[m, k] += sum_n bf16(C[m, n]) * projW[n][k], k < 4.
+    // projW is [N rounded up to 64][4] fp32 (zero padded), P [M, ldp] fp32 zeroed by the launcher; the (at most two)
+    // n-tiles of a row add their partial sums with atomics -- two addends into zero commute, so P is reproducible.
+    const float4* proj_w;
+    float* proj_out;
+    int64_t ldp;
+    int proj_k;
 };
 
 // Thread-block cluster of CLM x CLN CTAs (rank = rm + CLM * rn) that owns CLM consecutive m-tiles x CLN consecutive
@@ -370,6 +377,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.c_bf16) {
                 // bf16 output: 64 accumulator columns -> 32 packed words = one 128-byte staging row per lane, same swizzle
                 // and the same 32-row TMA store as the fp32 path (box 64 x 32 bf16); half the store traffic of the tile
+                float pj[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N / 64; ++c) {
                     const int n = n0 + 64 * c;
@@ -409,6 +417,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         wv[i] = pack_bf16x2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
                         wv[16 + i] = pack_bf16x2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
                     }
+                    if (p.proj_w) {                                // this row's 64 rounded values against projW[n .. n+63][0..3]
+                        const float4* w4 = p.proj_w + n;           // same address in every lane: broadcast, L1-resident
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float lo = __uint_as_float(wv[i] << 16), hi = __uint_as_float(wv[i] & 0xffff0000u);
+                            const float4 wa = __ldg(w4 + 2 * i), wb = __ldg(w4 + 2 * i + 1);
+                            pj[0] = fmaf(lo, wa.x, pj[0]); pj[1] = fmaf(lo, wa.y, pj[1]); pj[2] = fmaf(lo, wa.z, pj[2]); pj[3] = fmaf(lo, wa.w, pj[3]);
+                            pj[0] = fmaf(hi, wb.x, pj[0]); pj[1] = fmaf(hi, wb.y, pj[1]); pj[2] = fmaf(hi, wb.z, pj[2]); pj[3] = fmaf(hi, wb.w, pj[3]);
+                        }
+                    }
                     const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
                     if (lane == 0) bulk_wait_read<1>();
                     __syncwarp();
@@ -425,6 +443,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         bulk_commit();
                     }
                     ebuf ^= 1;
+                }
+                if (p.proj_w && m < p.M && m0 < p.M && n0 < p.N) {
+                    float* po = p.proj_out + m * p.ldp;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < p.proj_k) atomicAdd(po + k, pj[k]);
                 }
             } else {
 #pragma unroll 1
@@ -813,7 +837,8 @@ static int cluster_slots() {
 template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
 static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
-                  const float* bias = nullptr, int relu = 0) {
+                  const float* bias = nullptr, int relu = 0, const float* proj_w = nullptr, float* proj_out = nullptr,
+                  int64_t ldp = 0, int proj_k = 0) {
     constexpr int CL = CLM * CLN;
     constexpr int ELT = BF16 ? 2 : 4;
     constexpr int BK = 128 / ELT, MNC = 128 / ELT;                 // k elements per stage, m/n elements per MN-major chunk
@@ -879,6 +904,18 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
         }
         p.bias = bias;
         p.relu = relu;
+        if (proj_w) {
+            if (!proj_out || proj_k < 1 || proj_k > 4 || ldp < proj_k || N > 2 * BLOCK_N || !aligned16(proj_w)) {
+                set_error("gmc_gemm_bf16_bf16out: the fused projection needs 1 <= n_proj <= 4, ldp >= n_proj, N <= 512 and a "
+                          "16-byte aligned padded weight matrix");
+                return GMC_ERR_INVALID_ARG;
+            }
+            GMC_CUDA(cudaMemset2DAsync(proj_out, (size_t)ldp * sizeof(float), 0, (size_t)proj_k * sizeof(float), (size_t)M, s));
+            p.proj_w = reinterpret_cast<const float4*>(proj_w);
+            p.proj_out = proj_out;
+            p.ldp = ldp;
+            p.proj_k = proj_k;
+        }
     } else if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
         rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
         if (rc) return rc;
@@ -899,15 +936,16 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
 template <bool A_MN, bool B_MN, bool BF16 = false>
 static int launch_cl(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                      int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
-                     const float* bias = nullptr, int relu = 0) {
+                     const float* bias = nullptr, int relu = 0, const float* proj_w = nullptr, float* proj_out = nullptr,
+                     int64_t ldp = 0, int proj_k = 0) {
     int clm, cln;
     cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln, BF16);
 #define GMC_GEMM_CASE(CM, CN)                                                                                       \
     if (clm == CM && cln == CN)                                                                                     \
-        return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
+        return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
     GMC_GEMM_CASE(1, 1) GMC_GEMM_CASE(2, 1) GMC_GEMM_CASE(4, 1) GMC_GEMM_CASE(8, 1) GMC_GEMM_CASE(2, 2) GMC_GEMM_CASE(4, 2)
 #undef GMC_GEMM_CASE
-    return launch<A_MN, B_MN, 4, 1, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
+    return launch<A_MN, B_MN, 4, 1, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
 }
 
 static bool use_two_cta() {
@@ -1121,7 +1159,7 @@ size_t tc_bf16_workspace_bytes(int op, int64_t M, int64_t N, int64_t K) { return
 
 int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                  int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16,
-                 const float* bias, int relu) {
+                 const float* bias, int relu, const float* proj_w, float* proj_out, int64_t ldp, int proj_k) {
     GMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B),
                 "gmc_gemm_bf16: TMA needs 16-byte aligned bases and leading dimensions that are multiples of 8 elements");
     GMC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gmc_gemm_bf16: dimension exceeds int32 TMA coordinates");
@@ -1133,9 +1171,9 @@ int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64
     }
     float* Cf = reinterpret_cast<float*>(C);                       // reinterpreted by the kernel when c_bf16 is set
     switch (op) {
-        case 0: return tc::launch_cl<false, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
-        case 1: return tc::launch_cl<false, false, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
-        case 2: return tc::launch_cl<true, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu);
+        case 0: return tc::launch_cl<false, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
+        case 1: return tc::launch_cl<false, false, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
+        case 2: return tc::launch_cl<true, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
     }
     set_error("gmc_gemm_bf16: bad op %d", op);
     return GMC_ERR_INVALID_ARG;

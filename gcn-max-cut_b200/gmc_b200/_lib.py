@@ -51,7 +51,8 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_gemm_bf16_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64]),
     "gmc_gemm_bf16": (c_int, [c_int32, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, P,
                               c_size_t, P]),
-    "gmc_gemm_bf16_bf16out": (c_int, [c_int32, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, P, c_int32, P]),
+    "gmc_gemm_bf16_bf16out": (c_int, [c_int32, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, P, c_int32,
+                                      P, P, c_int64, c_int32, P]),
     "gmc_spmm_fused_skinny_bf16": (c_int, [P, P, P, P, P, P, P, c_int32, c_int64, c_int32, c_int64, c_int64, P, c_int32,
                                            P, c_int32, P, c_int64, P]),
     "gmc_skinny_bwd_bf16": (c_int, [P, c_int64, P, P, c_int64, P, c_int64, P, P, c_int64, c_int32, c_int32, P, c_size_t, P]),

@@ -40,6 +40,8 @@ _FWD_SLAB = os.environ.get("GMC_FWD_SLAB", "0") == "1"
 # bf16 activations: GMC_FWD16 = 'slab' (default: bf16 slab SpMM + bf16 skinny projection, 2.4 + 1.3 ms at config 3) |
 # 'row' (fused row kernel with bf16 gathers, 4.95 ms: ~775 warp instructions per row, issue-bound)
 _FWD16_SLAB = os.environ.get("GMC_FWD16", "slab") == "slab"
+# pre-aggregated layer 1: T2 = H1 W2 folded into the GEMM epilogue (GMC_FUSE_PROJ=0: separate skinny_fwd pass over H1)
+_FUSE_PROJ = os.environ.get("GMC_FUSE_PROJ", "1") == "1"
 
 
 def _pad4(n: int) -> int:
@@ -141,6 +143,7 @@ class GCNEngine:
         self.W1b = ops.padded_empty_bf16(self.F, self.H, self.device, zero=True) if precision == "bf16" else None
         self._xb_cache: Dict[tuple, torch.Tensor] = {}
         self._xa_cache: Dict[tuple, torch.Tensor] = {}
+        self._w2p = None
         self.bufB16 = None
         self.bufA16 = None
         self._cap_nodes = 0
@@ -264,9 +267,18 @@ class GCNEngine:
             self._ensure(N, batch.num_graphs, b16=True)
             B16 = self.bufB16[:N]
             ops.to_bf16(W1.data, out=self.W1b)
-            # the whole first layer: H1 = relu(XA W1 + b1), bias and ReLU in the GEMM epilogue, bf16 out
-            self._op("gemm_nn_layer1", 1, ops.gemm_bf16_bf16out, "nn", XA, self.W1b, out=B16, bias=b1.data, relu=True)
-            self._op("skinny_fwd", 1, ops.skinny_fwd_bf16, B16, W2.data, out=self.T2[:N])
+            if _FUSE_PROJ and self.H <= 512:
+                # the whole first layer AND the projection of the second: H1 = relu(XA W1 + b1) and T2 = H1 W2 in one
+                # GEMM (bias / ReLU / rounding / projection of the rounded rows in the epilogue): H1 is not read again
+                if self._w2p is None:
+                    self._w2p = torch.zeros(((self.H + 63) // 64 * 64, 4), dtype=torch.float32, device=self.device)
+                ops.pad_proj_weights(W2.data, out=self._w2p)
+                self._op("gemm_nn_layer1", 1, ops.gemm_bf16_bf16out, "nn", XA, self.W1b, out=B16, bias=b1.data, relu=True,
+                         proj_w=self._w2p, proj_out=self.T2[:N], n_proj=self.K)
+            else:
+                # the whole first layer: H1 = relu(XA W1 + b1), bias and ReLU in the GEMM epilogue, bf16 out
+                self._op("gemm_nn_layer1", 1, ops.gemm_bf16_bf16out, "nn", XA, self.W1b, out=B16, bias=b1.data, relu=True)
+                self._op("skinny_fwd", 1, ops.skinny_fwd_bf16, B16, W2.data, out=self.T2[:N])
             self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
             return self.Z[:N]
         X = self._features(batch, X)

@@ -336,10 +336,27 @@ def gemm_bf16(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Ten
 
 
 # ---------------------------------------------------------------- bf16 layer-1 activations
+def pad_proj_weights(W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n_in, n_out <= 4] fp32 -> zero-padded [n_in rounded up to 64, 4] (the layout of the fused GEMM projection)."""
+    W = _f32(W, "W")
+    n_in, n_out = W.shape
+    if n_out > 4:
+        raise ValueError("the fused projection takes at most 4 output columns")
+    rows = (n_in + 63) // 64 * 64
+    if out is None:
+        out = torch.zeros((rows, 4), dtype=torch.float32, device=W.device)
+    if out.shape != (rows, 4) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous fp32 [{rows}, 4] tensor")
+    copy2d(out[:n_in, :n_out], W.contiguous())
+    return out
+
+
 def gemm_bf16_bf16out(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None,
-                      bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+                      bias: Optional[torch.Tensor] = None, relu: bool = False, proj_w: Optional[torch.Tensor] = None,
+                      proj_out: Optional[torch.Tensor] = None, n_proj: int = 0) -> torch.Tensor:
     """gemm_bf16 whose result is rounded to bf16 in the epilogue (no split-K, no accumulate); optional fp32 bias
-    over the columns and ReLU before the rounding."""
+    over the columns and ReLU before the rounding; optional fused projection proj_out = bf16(C) @ W for a padded weight
+    matrix from pad_proj_weights (proj_out [M, >= n_proj] fp32 is overwritten)."""
     A, lda = _bf16_rowmajor(A, "A")
     B, ldb = _bf16_rowmajor(B, "B")
     if op == "nn":
@@ -357,8 +374,19 @@ def gemm_bf16_bf16out(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[t
     out, ldc = _bf16_rowmajor(out, "out")
     if bias is not None and (_f32(bias, "bias").numel() != N or not bias.is_contiguous()):
         raise ValueError(f"bias must be a contiguous fp32 vector of {N} elements")
+    ldp = 0
+    if proj_w is not None:
+        rows = (N + 63) // 64 * 64
+        if proj_w.shape != (rows, 4) or proj_w.dtype != torch.float32 or not proj_w.is_contiguous():
+            raise ValueError(f"proj_w must come from pad_proj_weights: contiguous fp32 [{rows}, 4]")
+        if proj_out is None or not 1 <= n_proj <= 4:
+            raise ValueError("the fused projection needs proj_out and 1 <= n_proj <= 4")
+        proj_out, ldp = _rowmajor(proj_out, "proj_out")
+        if proj_out.shape[0] != M or proj_out.shape[1] < n_proj:
+            raise ValueError(f"proj_out must be [{M}, >= {n_proj}]")
     check(lib().gmc_gemm_bf16_bf16out(_OPS[op], A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
-                                      _ptr(bias), int(relu), _stream()), "gmc_gemm_bf16_bf16out")
+                                      _ptr(bias), int(relu), _ptr(proj_w), _ptr(proj_out), ldp, int(n_proj), _stream()),
+          "gmc_gemm_bf16_bf16out")
     return out
 
 

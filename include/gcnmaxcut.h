@@ -267,7 +267,10 @@ int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, cons
  * gmc_gemm_bf16_bf16out       : gmc_gemm_bf16 with a bf16 C (epilogue rounds the accumulators, TMA stores); no split-K,
  *                               no accumulate -- th.matmul of GraphConv layer 1 (TrainingNeural.py:80).  Optional fp32
  *                               bias[N] (N % 4 == 0) and ReLU in the epilogue (the whole first layer when the features
- *                               are pre-aggregated, gmc_csr_preaggregate_bf16).
+ *                               are pre-aggregated, gmc_csr_preaggregate_bf16).  Optional fused projection
+ *                               P = bf16(C) projW (projW [N rounded up to 64][4] fp32 zero padded, n_proj <= 4,
+ *                               N <= 512; P is zeroed by the call): T2 = H1 W2 (TrainingNeural.py:83) without a second
+ *                               pass over H1.
  * gmc_spmm_fused_skinny_bf16  : gmc_spmm_fused_skinny_f32 with a bf16 X and an fp32 (y_bf16 = 0) or bf16 (y_bf16 = 1) Y;
  *                               with a bf16 Y the projection T = Y W uses the rounded Y (what the backward pass reads).
  * gmc_skinny_bwd_bf16         : gmc_skinny_bwd_f32 with bf16 H and dHpre (ldh, lddh multiples of 4).
@@ -275,7 +278,8 @@ int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, cons
  * gmc_skinny_fwd_bf16         : gmc_skinny_fwd_f32 with a bf16 H (n_out <= 4, n_in <= 512): the projection T = H1 W2
  *                               when the forward aggregation runs through the slab kernel. */
 int gmc_gemm_bf16_bf16out(int32_t op, const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
-                          int64_t lda, int64_t ldb, int64_t ldc, const float* bias, int32_t relu, void* stream);
+                          int64_t lda, int64_t ldb, int64_t ldc, const float* bias, int32_t relu, const float* proj_w,
+                          float* proj_out, int64_t ldp, int32_t n_proj, void* stream);
 int gmc_spmm_fused_skinny_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
                                const float* norm_src, const float* norm_dst, const void* X, void* Y, int32_t y_bf16,
                                int64_t n_rows, int32_t n_cols, int64_t ldx, int64_t ldy, const float* bias,

@@ -296,6 +296,38 @@ def test_gemm_bf16_bf16out_bias_relu_epilogue():
     assert_bf16_close(got2, bf16_round(A) @ bf16_round(B) + bias.double(), extra=1e-4)
     full = got._base if got._base is not None else got
     assert float(full[:, N:].abs().max()) == 0.0
+    # fused skinny projection of the rounded result: P = bf16(C) @ W, reproducible (two n-tiles: two addends commute)
+    for n_proj in (3, 1, 4):
+        W = torch.randn(N, n_proj) / N ** 0.5
+        Wp = ops.pad_proj_weights(W.to(DEV))
+        P = torch.full((M, n_proj), 7.0, device=DEV)                       # overwritten, not accumulated
+        got3 = ops.gemm_bf16_bf16out("nn", Ab, Bb, bias=bias.to(DEV), relu=True, proj_w=Wp, proj_out=P, n_proj=n_proj)
+        assert torch.equal(got3, got)
+        wantP = got.double().cpu() @ W.double()
+        assert float((P.double().cpu() - wantP).abs().max()) < 2e-5 * max(1.0, float(wantP.abs().max()))
+        P2 = torch.empty_like(P)
+        ops.gemm_bf16_bf16out("nn", Ab, Bb, bias=bias.to(DEV), relu=True, proj_w=Wp, proj_out=P2, n_proj=n_proj)
+        assert torch.equal(P, P2)
+
+
+def test_fused_projection_engine_equals_separate_pass(monkeypatch):
+    from Training import TrainingNeural as T
+    from gmc_b200 import engine as E
+    batch = regular_batch(36, 256, 7, seed=33)
+    XA = ops.PreaggregatedFeatures(ops.preaggregate_features_bf16(batch, 256))
+    cfg = T.TrainingConfig(n_nodes=256, dim_embedding=256, hidden_dim=128, loss_mode="soft")
+    torch.manual_seed(2)
+    net, embed, opt = T.setup_model_and_optimizer(cfg)
+    res = {}
+    for fused in (True, False):
+        monkeypatch.setattr(E, "_FUSE_PROJ", fused)
+        eng = GCNEngine(net, None, loss_mode="soft", precision="bf16", activations="bf16", preaggregate=True)
+        loss = eng.loss_and_grads(batch, XA).cpu().clone()
+        res[fused] = (loss, eng.Z[: batch.num_nodes].cpu().clone(), [g.cpu().clone() for g in eng.grads()])
+    assert relerr(res[True][1], res[False][1]) < 1e-5          # same rounded H1, fp32 projection in a different order
+    assert relerr(res[True][0], res[False][0]) < 1e-5
+    for a, b in zip(res[True][2], res[False][2]):
+        assert relerr(a, b) < 1e-4
 
 
 def test_preaggregated_features_equal_ahat_times_adjacency():
