@@ -127,8 +127,37 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.rows = []
         self._stop_evt = threading.Event()
+        # NVML in-process (a sample costs microseconds: ~10 ms period, so even a 0.2 s timed region gets ~20 samples);
+        # one nvidia-smi process per sample (~100 ms each) remains the fallback
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+            self.period = min(period, 0.01)
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = (0x8, 0x40, 0x20, 0x4)                 # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        return [str(sm), str(mx), f"{pw:.2f}"] + ["Active" if mask & b else "Not Active" for b in bits]
 
     def run(self):
+        while self._nvml is not None and not self._stop_evt.is_set():
+            try:
+                self.rows.append(self._sample_nvml())
+            except Exception:
+                self._nvml = None                      # fall through to the nvidia-smi loop
+                break
+            self._stop_evt.wait(self.period)
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
