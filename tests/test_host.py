@@ -395,3 +395,43 @@ def test_data_parallel_allreduce_world2_gloo():
     want = (torch.arange(8, dtype=torch.float32) * sum(range(1, 12))).tolist()
     for _, flat, loss, mx in res:
         assert flat == want and loss == float(sum(range(11))) and mx == 1.0
+
+
+# ------------------------------------------------------------------ bench.py argument rules / config fields
+def _bench_args(argv, monkeypatch):
+    import importlib
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    for k in ("GMC_BENCH_PRECISION", "GMC_BENCH_ACTIVATIONS", "GMC_BENCH_LAYER1"):
+        monkeypatch.delenv(k, raising=False)
+    return bench.parse_args()
+
+
+def test_bench_defaults_name_the_throughput_configuration(monkeypatch):
+    a = _bench_args([], monkeypatch)
+    assert (a.gpus, a.steps, a.warmup) == (1, 20, 3) and a.warmup >= 3
+    assert (a.precision, a.activations, a.layer1, a.workload) == ("bf16", "bf16", "preaggregated", "config3")
+    assert (a.graphs_per_gpu, a.nodes, a.degree, a.features, a.hidden, a.classes) == (4096, 1000, 7, 1000, 500, 3)
+
+
+@pytest.mark.parametrize("argv,want", [
+    (["--precision", "tf32"], ("tf32", "fp32", "standard")),            # bf16 storage needs bf16 GEMM operands
+    (["--activations", "fp32"], ("bf16", "fp32", "standard")),          # pre-aggregation is built on the bf16 chain
+    (["--layer1", "standard"], ("bf16", "bf16", "standard")),
+    (["--feature-source", "embedding"], ("bf16", "fp32", "standard")),  # trainable features cannot be pre-aggregated
+    (["--precision", "fp32", "--layer1", "preaggregated"], ("fp32", "fp32", "standard")),
+])
+def test_bench_option_rules(argv, want, monkeypatch):
+    a = _bench_args(argv, monkeypatch)
+    assert (a.precision, a.activations, a.layer1) == want
+
+
+def test_training_config_extension_fields_default_to_reference_behaviour():
+    from Training import TrainingNeural as T
+    cfg = T.TrainingConfig()
+    assert (cfg.batch_graphs, cfg.gemm_precision, cfg.activations, cfg.preaggregate_features,
+            cfg.adjacency_kernels, cfg.loss_mode, cfg.feature_source) == (1, "fp32", "fp32", False, False, "ste", "adjacency")
+    blob = pickle.dumps(T.TrainingConfig(activations="bf16", gemm_precision="bf16", preaggregate_features=True))
+    back = pickle.loads(blob)
+    assert back.activations == "bf16" and back.preaggregate_features is True

@@ -247,3 +247,29 @@ def test_extender_fixture_shapes():
         assert X.shape == (12, 16)
         assert int(z[f"{name}_nnz"]) == 2 * len(z[f"{name}_edges_out"])
         assert X[:, 12:].sum() == 0 and np.array_equal(X[:, :12], X[:, :12].T)
+
+
+def test_preaggregated_layer1_is_the_same_function_as_the_reference_order():
+    """The identity the B200 throughput path rests on (GCNEngine(preaggregate=True)), checked on the ORACLE in float64:
+    GraphConv layer 1 is relu(A_hat (X W1) + b1) in the reference order (TrainingNeural.py:80, DGL multiplies by W first
+    because in_feats > out_feats); with XA = A_hat X it is relu(XA W1 + b1), and its weight gradient
+    X^T (A_hat dH1pre) equals XA^T dH1pre because A_hat is symmetric.  Also on the reference-generated step fixture."""
+    g = nx.random_regular_graph(d=5, n=40, seed=7)
+    nx.set_edge_attributes(g, 1, "weight")
+    csr = rs.csr_from_networkx(g)
+    X = rs.dense_adjacency(csr, 48, dtype=torch.float64)
+    torch.manual_seed(0)
+    p = rs.GCNParams(torch.randn(48, 20, dtype=torch.float64) * 0.2, torch.randn(20, dtype=torch.float64) * 0.1,
+                     torch.randn(20, 3, dtype=torch.float64) * 0.3, torch.randn(3, dtype=torch.float64) * 0.1)
+    fwd = rs.gcn_forward(csr, X, p)
+    deg = torch.from_numpy(csr.degrees()).double()
+    norm = deg.clamp(min=1).pow(-0.5).unsqueeze(1)
+    XA = rs._aggregate(csr, X * norm) * norm                         # A_hat X
+    H1_pre = torch.relu(XA @ p.W1 + p.b1)
+    assert float((H1_pre - fwd["H1"]).abs().max()) < 1e-12
+    dZ = torch.randn(40, 3, dtype=torch.float64)
+    grads = rs.gcn_backward(csr, X, p, fwd, dZ)
+    dT2 = rs._aggregate(csr, dZ * norm) * norm
+    dH1pre = (dT2 @ p.W2.t()) * (fwd["pre1"] > 0).double()
+    assert float((XA.t() @ dH1pre - grads["W1"]).abs().max()) < 1e-12
+    assert float((dH1pre.sum(0) - grads["b1"]).abs().max()) < 1e-12
