@@ -1,6 +1,7 @@
 // graph_ops.cu -- per-batch graph preparation: degree norms, A_hat edge coefficients,
 // dense padded adjacency rows (device-side graphExtender).  HBM-bound integer/float work.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kPreaggWarps * 32)
 preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                          const float* __restrict__ coef, const float* __restrict__ vals,
                          const int32_t* __restrict__ graph_ptr, int n_graphs, int64_t n_rows, int n_cols, int ncp,
-                         __nv_bfloat16* __restrict__ X, int64_t ldx) {
+                         __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ only) {
     extern __shared__ __align__(16) float preagg_rows[];              // kPreaggWarps x ncp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* buf = preagg_rows + warp * ncp;
@@ -138,6 +139,7 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     //   other rows = neighbours one after the other in CSR order, lanes over N(u) (distinct columns): fixed order.
     // Config 3 (4.1 M rows, 8.4 GB written): 3.0 ms.
     for (int64_t row = (int64_t)blockIdx.x * kPreaggWarps + warp; row < n_rows; row += stride) {
+        if (only && !__ldg(only + row)) continue;                      // second pass: rows the counting kernel left
         for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
         const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
         int g = (int)(((float)row + 0.5f) * inv_n0);
@@ -206,6 +208,79 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
             *reinterpret_cast<uint4*>(xr + c8 * 8) = *reinterpret_cast<const uint4*>(o);
         }
         __syncwarp();
+    }
+}
+
+// Counting form of the fast rows (unit weights, <= 8 neighbours which all have one degree D <= 8 and one coefficient
+// c): every 2-hop addend is the same c, so a row of A_hat X is c x (number of 2-hop paths into each column).  Eight
+// lanes own a row and count the paths in BYTES (1 KB per row instead of a 4 KB fp32 buffer: 32 rows per CTA, ~190 rows
+// in flight per SM instead of 48, which is what the dependent loads of a row need), then map counts to bf16 through a
+// 65-entry table k -> bf16(k c) and write the row whole.  Rows that do not qualify are flagged in `slow` and left to
+// preaggregate_bf16_kernel (second launch, masked).
+constexpr int kPcLanes = 8, kPcRows = 32, kPcLut = 72;
+
+__global__ void __launch_bounds__(kPcLanes * kPcRows)
+preaggregate_counts_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                           const float* __restrict__ coef, const int32_t* __restrict__ graph_ptr, int n_graphs,
+                           int64_t n_rows, int n_cols, int ncp, __nv_bfloat16* __restrict__ X, int64_t ldx,
+                           uint8_t* __restrict__ slow) {
+    extern __shared__ __align__(16) uint32_t pc_smem[];               // kPcRows x wstride count words, then the tables
+    const int wstride = ((ncp >> 2) + 3) & ~3;                         // words per row, 16-byte multiple
+    const int sub = threadIdx.x & (kPcLanes - 1), grp = threadIdx.x / kPcLanes;
+    uint32_t* cnt = pc_smem + grp * wstride;
+    uint16_t* lut = reinterpret_cast<uint16_t*>(pc_smem + kPcRows * wstride) + grp * kPcLut;
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kPcLanes - 1));
+    const int n0 = __ldg(graph_ptr + 1) - __ldg(graph_ptr);
+    const float inv_n0 = n0 > 0 ? 1.0f / (float)n0 : 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * kPcRows + grp; row < n_rows; row += (int64_t)gridDim.x * kPcRows) {
+        for (int w = sub * 4; w < wstride; w += kPcLanes * 4) *reinterpret_cast<uint4*>(cnt + w) = make_uint4(0u, 0u, 0u, 0u);
+        const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+        int g = (int)(((float)row + 0.5f) * inv_n0);
+        if (g >= n_graphs) g = n_graphs - 1;
+        int base = __ldg(graph_ptr + g);
+        if (n0 <= 0 || (int64_t)base > row || row >= (int64_t)__ldg(graph_ptr + g + 1))
+            base = __ldg(graph_ptr + find_graph(graph_ptr, n_graphs, row));
+        const int deg = e1 - e0;
+        int my_f0 = 0, my_deg = 0;
+        float my_c = 0.f;
+        if (sub < min(deg, kPcLanes)) {
+            const int u = __ldg(colidx + e0 + sub);
+            my_c = __ldg(coef + e0 + sub);
+            my_f0 = __ldg(rowptr + u);
+            my_deg = __ldg(rowptr + u + 1) - my_f0;
+        }
+        const int D0 = __shfl_sync(gmask, my_deg, 0, kPcLanes);
+        const float c0 = __shfl_sync(gmask, my_c, 0, kPcLanes);
+        const bool mine_ok = sub >= deg || (my_deg == D0 && my_c == c0);
+        const bool fast = deg <= kPcLanes && D0 <= kPcLanes && (__ballot_sync(gmask, mine_ok) & gmask) == gmask;
+        if (!fast) {                                                   // group-uniform
+            if (sub == 0) slow[row] = 1;
+            __syncwarp(gmask);
+            continue;
+        }
+        __syncwarp(gmask);                                             // the count row is zero
+#pragma unroll
+        for (int q = 0; q < kPcLanes; ++q) {
+            const int f0 = __shfl_sync(gmask, my_f0, q, kPcLanes);
+            if (q < deg && sub < D0) {
+                const int local = __ldg(colidx + f0 + sub) - base;
+                if (local >= 0 && local < n_cols) atomicAdd(cnt + (local >> 2), 1u << ((local & 3) * 8));
+            }
+        }
+        for (int k = sub; k < kPcLut; k += kPcLanes) lut[k] = __bfloat16_as_ushort(__float2bfloat16_rn((float)k * c0));
+        __syncwarp(gmask);
+        __nv_bfloat16* xr = X + row * ldx;
+        for (int c8 = sub; c8 * 8 < ncp; c8 += kPcLanes) {
+            const uint2 w = *reinterpret_cast<const uint2*>(cnt + c8 * 2);
+            uint4 o;
+            o.x = (uint32_t)lut[w.x & 0xffu] | ((uint32_t)lut[(w.x >> 8) & 0xffu] << 16);
+            o.y = (uint32_t)lut[(w.x >> 16) & 0xffu] | ((uint32_t)lut[w.x >> 24] << 16);
+            o.z = (uint32_t)lut[w.y & 0xffu] | ((uint32_t)lut[(w.y >> 8) & 0xffu] << 16);
+            o.w = (uint32_t)lut[(w.y >> 16) & 0xffu] | ((uint32_t)lut[w.y >> 24] << 16);
+            *reinterpret_cast<uint4*>(xr + c8 * 8) = o;
+        }
+        if (sub == 0) slow[row] = 0;
+        __syncwarp(gmask);                                             // counts and table are free for the next row
     }
 }
 
@@ -315,9 +390,11 @@ int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
 // A_hat given by its per-edge values `coef` (gmc_edge_coef_f32): the features of the pre-aggregated first layer,
 // H1 = relu(XA W1 + b1) == relu(A_hat (X W1) + b1) (TrainingNeural.py:80-81).  Every row is written whole (ldx % 8 == 0,
 // 16-byte aligned base); rows are built in a fixed order, so the result is bitwise reproducible.
+size_t gmc_csr_preaggregate_workspace_bytes(int64_t n_rows) { return n_rows > 0 ? (size_t)n_rows : 0; }
+
 int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
                               const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
-                              int64_t ldx, void* stream) {
+                              int64_t ldx, void* workspace, size_t workspace_bytes, void* stream) {
     GMC_REQUIRE(rowptr && colidx && coef && graph_ptr && X, "gmc_csr_preaggregate_bf16: null pointer");
     GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0 && n_cols > 0 && ldx >= n_cols, "gmc_csr_preaggregate_bf16: bad sizes");
     const int ncp = (n_cols + 7) & ~7;
@@ -325,6 +402,32 @@ int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, cons
                 "gmc_csr_preaggregate_bf16: needs ldx %% 8 == 0 covering n_cols rounded up to 8, a 16-byte aligned X and "
                 "n_cols <= 6144");
     if (n_rows == 0) return GMC_OK;
+    cudaStream_t s = gmc::as_stream(stream);
+    __nv_bfloat16* Xb = reinterpret_cast<__nv_bfloat16*>(X);
+    // counting kernel first when the caller passes the row-mask workspace (unit weights and a count row that fits): it
+    // flags the rows it leaves.  Measured at config 3: 3.24 ms for the pair of launches against 3.00 ms for the general
+    // kernel alone -- byte counters lift the occupancy limit (160 rows in flight per SM instead of 48) without making
+    // the kernel faster, so the Python wrapper does not pass a workspace by default.
+    const uint8_t* only = nullptr;
+    const int wstride = ((ncp >> 2) + 3) & ~3;
+    const size_t pc_smem = (size_t)gmc::kPcRows * wstride * 4 + (size_t)gmc::kPcRows * gmc::kPcLut * 2;
+    if (!vals && workspace && workspace_bytes >= (size_t)n_rows && pc_smem <= 100 * 1024) {
+        static bool attr2 = false;
+        if (!attr2) {
+            GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr2 = true;
+        }
+        int per_sm = (int)((220 * 1024) / (pc_smem + 1024));
+        if (per_sm > 8) per_sm = 8;
+        int64_t blocks = gmc::ceil_div<int64_t>(n_rows, gmc::kPcRows);
+        const int64_t cap = (int64_t)gmc::sm_count() * per_sm;
+        if (blocks > cap) blocks = cap;
+        uint8_t* slow = reinterpret_cast<uint8_t*>(workspace);
+        gmc::preaggregate_counts_kernel<<<(unsigned)blocks, gmc::kPcLanes * gmc::kPcRows, pc_smem, s>>>(
+            rowptr, colidx, coef, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, slow);
+        GMC_LAUNCH_CHECK();
+        only = slow;
+    }
     const size_t smem = (size_t)gmc::kPreaggWarps * ncp * sizeof(float);
     static bool attr = false;
     if (!attr) {
@@ -337,8 +440,8 @@ int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, cons
     int64_t blocks = gmc::ceil_div<int64_t>(n_rows, gmc::kPreaggWarps);
     const int64_t cap = (int64_t)gmc::sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
-    gmc::preaggregate_bf16_kernel<<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, gmc::as_stream(stream)>>>(
-        rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, reinterpret_cast<__nv_bfloat16*>(X), ldx);
+    gmc::preaggregate_bf16_kernel<<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, s>>>(
+        rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
 }

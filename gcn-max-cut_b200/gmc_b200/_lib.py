@@ -61,7 +61,8 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_f32_to_bf16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, P]),
     "gmc_csr_densify_bf16": (c_int, [P, P, P, P, c_int32, c_int64, c_int32, P, c_int64, P]),
     "gmc_csr_scatter_bf16": (c_int, [P, P, P, P, c_int32, c_int64, c_int32, P, c_int64, c_int32, P]),
-    "gmc_csr_preaggregate_bf16": (c_int, [P, P, P, P, P, c_int32, c_int64, c_int32, P, c_int64, P]),
+    "gmc_csr_preaggregate_workspace_bytes": (c_size_t, [c_int64]),
+    "gmc_csr_preaggregate_bf16": (c_int, [P, P, P, P, P, c_int32, c_int64, c_int32, P, c_int64, P, c_size_t, P]),
     "gmc_adj_features_fwd_f32": (c_int, [P, P, c_int32, c_int32, P, c_int64, c_int32, P, c_int64, c_int64, c_int32, P]),
     "gmc_adj_features_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "gmc_adj_features_bwd_f32": (c_int, [P, P, c_int32, c_int32, P, c_int64, c_int64, c_int32, P, c_int64, c_int32, P,

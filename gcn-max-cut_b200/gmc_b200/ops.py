@@ -278,7 +278,8 @@ class PreaggregatedFeatures:
         self.tensor = tensor
 
 
-def preaggregate_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def preaggregate_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None,
+                               workspace: Optional[Workspace] = None, counting: bool = False) -> torch.Tensor:
     """XA = A_hat X in bf16 for X = the zero-padded adjacency rows of the batch, straight from the graph (the dense X
     is never formed)."""
     if out is None:
@@ -286,9 +287,13 @@ def preaggregate_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] =
     out, ld = _bf16_rowmajor(out, "out")
     if out.shape[0] != batch.num_nodes or out.shape[1] != n_cols:
         raise ValueError(f"out must be [{batch.num_nodes}, {n_cols}]")
+    wptr, wbytes = None, 0
+    if counting:        # byte-counting kernel for the regular rows + masked general kernel (no faster at config 3: opt-in)
+        ws = workspace or _default_ws
+        wptr, wbytes = ws.get(lib().gmc_csr_preaggregate_workspace_bytes(batch.num_nodes), batch.device)
     check(lib().gmc_csr_preaggregate_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(),
                                           _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(), batch.num_graphs,
-                                          batch.num_nodes, n_cols, out.data_ptr(), ld, _stream()),
+                                          batch.num_nodes, n_cols, out.data_ptr(), ld, wptr, wbytes, _stream()),
           "gmc_csr_preaggregate_bf16")
     return out
 

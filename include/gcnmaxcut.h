@@ -252,10 +252,14 @@ int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
  * given by `coef` (gmc_edge_coef_f32).  A_hat (X W1) = (A_hat X) W1 and X depends on the graph alone, so GraphConv
  * layer 1's aggregation (TrainingNeural.py:80) moves from the activations (every step, forward and backward) to the
  * features (once per graph): H1 = relu(XA W1 + b1) is then one GEMM with a bias/ReLU epilogue and
- * dW1 = XA^T dH1pre one GEMM.  ldx % 8 == 0, n_cols <= 6144; rows are written whole; bitwise reproducible. */
+ * dW1 = XA^T dH1pre one GEMM.  ldx % 8 == 0, n_cols <= 6144; rows are written whole; bitwise reproducible.
+ * `workspace` (nullable, gmc_csr_preaggregate_workspace_bytes = one byte per row) enables the counting kernel for rows
+ * with unit weights and <= 8 neighbours of one degree and coefficient (every graph the reference generates); the
+ * other rows, or all rows without a workspace, take the general kernel. */
+size_t gmc_csr_preaggregate_workspace_bytes(int64_t n_rows);
 int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
                               const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
-                              int64_t ldx, void* stream);
+                              int64_t ldx, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- bf16 layer-1 activations (engine option activations='bf16', on top of the bf16 GEMM operands) ----------------
  * T1 = X W1, H1 = relu(A_hat T1 + b1), dH1pre and dT1 are [n_nodes, hidden] matrices that are each written once and

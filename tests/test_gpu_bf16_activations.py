@@ -355,6 +355,34 @@ def test_preaggregated_features_equal_ahat_times_adjacency():
     assert float(full[:, F:].abs().max()) == 0.0 if full.shape[1] > F else True
 
 
+def test_preaggregate_counting_kernel_and_masked_fallback():
+    """Unit weights: rows with <= 8 neighbours of one degree take the byte-counting kernel, the irregular graph's rows
+    (and a 12-regular graph's) are flagged and finished by the general kernel in the same call (counting=True; opt-in --
+    it measured no faster than the general kernel alone, which is the default and is checked beside it)."""
+    import networkx as nx
+    from gmc_b200.graph import CSRGraph
+    graphs = []
+    for n, d, seed in [(130, 6, 1), (1000, 7, 2), (256, 8, 3), (64, 12, 4), (50, 3, 5)]:
+        g = nx.random_regular_graph(d=d, n=n, seed=seed)
+        nx.set_edge_attributes(g, 1, "weight")
+        graphs.append(CSRGraph.from_networkx(g))
+    g = nx.barabasi_albert_graph(300, 4, seed=9)
+    nx.set_edge_attributes(g, 1, "weight")
+    graphs.append(CSRGraph.from_networkx(g))
+    batch = GraphBatch(graphs, device=DEV)
+    assert batch.wts_f32 is None                                 # unit weights: the counting kernel is eligible
+    F = 1000
+    want = ahat_times(batch, ops.densify(batch, F).double().cpu())
+    XA = ops.preaggregate_features_bf16(batch, F, counting=True)
+    assert_bf16_close(XA, want, extra=1e-7)
+    assert torch.equal(XA, ops.preaggregate_features_bf16(batch, F, counting=True))
+    full = XA._base if XA._base is not None else XA
+    assert float(full[:, F:].abs().max()) == 0.0
+    XG = ops.preaggregate_features_bf16(batch, F)                # general kernel alone: k c versus c + c + ... (one ulp)
+    assert_bf16_close(XG, want, extra=1e-7)
+    assert float((XG.float() - XA.float()).abs().max()) <= BF16_ULP * float(want.abs().max())
+
+
 def test_preaggregated_engine_matches_the_standard_bf16_step():
     """preaggregate=True computes the same layer 1 with the aggregation applied to the features: probabilities, loss and
     gradients agree with the standard bf16-activation step (and with fp32) to bf16 rounding; passing the features
