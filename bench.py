@@ -91,14 +91,16 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(--steps, 10)")
     args = ap.parse_args()
-    if args.precision != "bf16" or args.feature_source != "adjacency":
-        args.activations = "fp32"
-    if args.activations != "bf16":
-        args.layer1 = "standard"
     if args.workload == "config5":
         args.graphs_per_gpu, args.nodes, args.degree, args.features, args.hidden = 1, 1000000, 7, 256, 128
         args.feature_source = "embedding"
         args.no_cpu_baseline = True          # the per-graph reference step at n = 1M is not a bounded sample
+    if args.feature_source == "embedding" and args.precision == "bf16":
+        args.precision = "tf32"              # trainable features need dL/dX = dT1 W1^T, which has no bf16-operand path
+    if args.precision != "bf16" or args.feature_source != "adjacency":
+        args.activations = "fp32"
+    if args.activations != "bf16":
+        args.layer1 = "standard"
     return args
 
 
