@@ -463,3 +463,34 @@ def test_bf16_activations_need_bf16_gemms_and_fall_back_without_a_plan():
     a = GCNEngine(net, None, loss_mode="soft", precision="bf16", activations="bf16").loss_and_grads(batch, X).cpu()
     b = GCNEngine(net, None, loss_mode="soft", precision="bf16", activations="fp32").loss_and_grads(batch, X).cpu()
     assert torch.equal(a, b)
+
+
+def test_empty_and_bad_inputs_through_the_raw_abi():
+    """n_rows = 0 is a no-op for every entry point of the bf16 chain; null pointers and misaligned leading dimensions are
+    argument errors (negative codes), never launches."""
+    import ctypes
+    from gmc_b200 import _lib
+    L = _lib.lib()
+    z = ctypes.c_void_p(0)
+    b16 = torch.zeros(64, dtype=torch.bfloat16, device=DEV)
+    f32 = torch.zeros(64, device=DEV)
+    i32 = torch.zeros(8, dtype=torch.int32, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert L.gmc_gemm_bf16_bf16out(0, p(b16), p(b16), p(b16), 0, 8, 8, 8, 8, 8, z, 0, z, z, 0, 0, z) == 0
+    assert L.gmc_spmm_fused_skinny_bf16(p(i32), p(i32), z, z, z, p(b16), p(b16[32:]), 1, 0, 16, 16, 16, z, 0, p(f32), 3,
+                                        p(f32), 3, z) == 0
+    assert L.gmc_skinny_fwd_bf16(p(b16), 16, p(f32), p(f32), 3, 0, 16, 3, z) == 0
+    ws = torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)
+    assert L.gmc_skinny_bwd_bf16(p(f32), 3, p(f32), p(b16), 16, p(b16[32:]), 16, p(f32), p(f32[48:]), 0, 16, 3, p(ws),
+                                 ws.numel(), z) == 0
+    assert L.gmc_spmm_batched_bf16(p(i32), 0, 0, z, p(b16), p(b16[32:]), 0, 16, 16, 16, z, 0, z) == 0
+    assert L.gmc_csr_scatter_bf16(p(i32), p(i32), z, p(i32), 0, 0, 16, p(b16), 16, 0, z) == 0
+    assert L.gmc_csr_preaggregate_bf16(p(i32), p(i32), p(f32), z, p(i32), 0, 0, 16, p(b16), 16, z, 0, z) == 0
+    assert L.gmc_csr_preaggregate_workspace_bytes(0) == 0 and L.gmc_csr_preaggregate_workspace_bytes(77) == 77
+    # argument errors
+    assert L.gmc_gemm_bf16_bf16out(0, z, p(b16), p(b16), 8, 8, 8, 8, 8, 8, z, 0, z, z, 0, 0, z) < 0            # null A
+    assert L.gmc_gemm_bf16_bf16out(0, p(b16), p(b16), p(b16), 8, 8, 8, 8, 8, 12, z, 0, z, z, 0, 0, z) < 0      # ldc % 8 != 0
+    assert L.gmc_skinny_fwd_bf16(p(b16), 16, p(f32), p(f32), 5, 4, 16, 5, z) < 0                               # n_out > 4
+    assert L.gmc_csr_preaggregate_bf16(p(i32), p(i32), p(f32), z, p(i32), 1, 4, 16, p(b16), 12, z, 0, z) < 0   # ldx % 8 != 0
+    assert "gmc_csr_preaggregate_bf16" in _lib.last_error()
+    torch.cuda.synchronize()
