@@ -637,7 +637,7 @@ def run_b200_arm(args):
                            "aggregation moved from the activations (every step) to the features (once per graph; every step "
                            "in e2e)" if preagg else "standard: relu(A_hat (X W1) + b1), SpMM forward and backward every step"),
                 "spmm_bytes_form": "compulsory" if n * H * 4 <= 32 * 2 ** 20 else "gather",
-                "model": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
+                "gcn": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
                 "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",
                 "gemm_precision": args.precision, "parallelism": f"dp{world}",
                 "activations": ("bf16 storage of T1 / H1 / dH1pre / dT1 (fp32 arithmetic, logits, loss, gradients, Adam)"
