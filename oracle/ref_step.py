@@ -142,6 +142,37 @@ def gcn_forward(csr: HostCSR, X: torch.Tensor, p: GCNParams) -> Dict[str, torch.
     return {"pre1": pre1, "H1": H1, "Z": Z, "P": P}
 
 
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round to nearest even bf16 and back (what cvt.rn.bf16x2.f32 / torch's .to(bfloat16) do), keeping the dtype."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def gcn_forward_bf16_storage(csr: HostCSR, X: torch.Tensor, p: GCNParams, preaggregated: bool = True) -> Dict[str, torch.Tensor]:
+    """GCNSoftmax.forward (TrainingNeural.py:79-85) with the STORAGE roundings of the B200 throughput configuration
+    applied at exactly the points where its kernels store bf16, all arithmetic in the dtype of X (use float64):
+      preaggregated: XA = bf16(A_hat X), W1b = bf16(W1), H1 = bf16(relu(XA W1b + b1)), T2 = H1 W2, Z = A_hat T2 + b2
+      standard     : Xb = bf16(X), W1b = bf16(W1), T1 = bf16(Xb W1b), H1 = bf16(relu(A_hat T1 + b1)), T2 = H1 W2, ...
+    TEST INFRASTRUCTURE: lets the GPU tests pin the bf16 paths to ~1e-3 instead of comparing them with fp32 at 1e-2."""
+    dt = X.dtype
+    deg = torch.from_numpy(csr.degrees())
+    norm = deg.to(dt).clamp(min=1).pow(-0.5).unsqueeze(1)
+
+    def ahat(h):
+        return _aggregate(csr, h * norm) * norm
+
+    W1b = _bf16(p.W1.to(dt))
+    if preaggregated:
+        XA = _bf16(ahat(X))
+        pre1 = XA @ W1b + p.b1.to(dt)
+    else:
+        T1 = _bf16(_bf16(X) @ W1b)
+        pre1 = ahat(T1) + p.b1.to(dt)
+    H1 = _bf16(torch.relu(pre1))
+    T2 = H1 @ p.W2.to(dt)
+    Z = ahat(T2) + p.b2.to(dt)
+    return {"pre1": pre1, "H1": H1, "Z": Z, "P": torch.softmax(Z, dim=1)}
+
+
 def hard_labels(P: torch.Tensor, override_terminals: bool = True) -> torch.Tensor:
     """argmax rows (first max on ties, torch.argmax; TrainingNeural.py:96-106) with
     rows 0,1,2 forced to classes 0,1,2 (override_fixed_nodes, :87-94)."""
