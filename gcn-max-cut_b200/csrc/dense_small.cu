@@ -253,6 +253,86 @@ skinny_bwd_b16_kernel(const float* __restrict__ dT, int64_t lddt, const float* _
     }
 }
 
+// fp32-grade form for the split-operand weight-gradient GEMM (split.cu): H stays fp32, and dHpre leaves as NS stacked
+// bf16 parts (hi, lo [, lo2]) of row_scale[v] * dHpre[v, :] -- part s at rows [s * split_rows, s * split_rows + n_rows)
+// of dH -- the B operand of dW1 = XI^T (s . dH1pre).  dW and dbias are sums of the UNSCALED fp32 values.
+template <int NOUT, int NS>
+__global__ void __launch_bounds__(128)
+skinny_bwd_split_kernel(const float* __restrict__ dT, int64_t lddt, const float* __restrict__ W, const float* __restrict__ H,
+                        int64_t ldh, const float* __restrict__ row_scale, uint2* __restrict__ dH, int64_t lddh4,
+                        int64_t split_rows, int64_t n_rows, int n_in, float* __restrict__ ws) {
+    const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per;
+    const int64_t r1 = min(n_rows, r0 + rows_per);
+    float* my_ws = ws + (int64_t)blockIdx.x * n_in * (NOUT + 1);
+    for (int j0 = threadIdx.x * 4; j0 < n_in; j0 += blockDim.x * 4) {
+        const int j4 = j0 >> 2;
+        float w[4][NOUT], dw[4][NOUT], db[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            db[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) {
+                w[i][k] = (j0 + i < n_in) ? __ldg(W + (int64_t)(j0 + i) * NOUT + k) : 0.f;
+                dw[i][k] = 0.f;
+            }
+        }
+        auto row = [&](const float (&t)[NOUT], const float4 h4, float rs, int64_t v) {
+            const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) { s = fmaf(t[k], w[i][k], s); dw[i][k] = fmaf(h[i], t[k], dw[i][k]); }
+                s = h[i] > 0.f ? s : 0.f;
+                db[i] += s;
+                o[i] = s * rs;
+            }
+#pragma unroll
+            for (int sp = 0; sp < NS; ++sp) {
+                uint2 pk;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
+                dH[((int64_t)sp * split_rows + v) * lddh4 + j4] = pk;
+                if (sp + 1 < NS) {                                 // exact residuals: what the next part has to carry
+                    o[0] -= __uint_as_float(pk.x << 16); o[1] -= __uint_as_float(pk.x & 0xffff0000u);
+                    o[2] -= __uint_as_float(pk.y << 16); o[3] -= __uint_as_float(pk.y & 0xffff0000u);
+                }
+            }
+        };
+        int64_t v = r0;
+        for (; v + 4 <= r1; v += 4) {
+            float t[4][NOUT], rs[4];
+            float4 h[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) h[r] = ldg_stream4(reinterpret_cast<const float4*>(H + (v + r) * ldh + j0));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                rs[r] = row_scale ? __ldg(row_scale + v + r) : 1.f;
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) t[r][k] = __ldg(dT + (v + r) * lddt + k);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) row(t[r], h[r], rs[r], v + r);
+        }
+        for (; v < r1; ++v) {
+            float t[NOUT];
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) t[k] = __ldg(dT + v * lddt + k);
+            row(t, __ldg(reinterpret_cast<const float4*>(H + v * ldh + j0)), row_scale ? __ldg(row_scale + v) : 1.f, v);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (j0 + i < n_in) {
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k) my_ws[(int64_t)(j0 + i) * (NOUT + 1) + k] = dw[i][k];
+                my_ws[(int64_t)(j0 + i) * (NOUT + 1) + NOUT] = db[i];
+            }
+        }
+    }
+}
+
 // ---- TMA-streamed forms of the two bf16 skinny kernels -----------------------------------------------------------
 // The register-staged kernels above are latency-bound (ncu, profiles/r01c_*: 8-10 warps stalled on the long scoreboard
 // per issue, 0.50-0.60 of the HBM roofline): the bytes in flight are capped by the registers that hold them.  Here the
@@ -715,6 +795,49 @@ int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const voi
     }
 #define GMC_CASE(K) case K: skinny_bwd_b16_kernel<K><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H2, ldh / 4, dH2, lddh / 4, n_rows, n_in, ws); break;
     switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
+#undef GMC_CASE
+    GMC_LAUNCH_CHECK();
+    const int total = n_in * (n_out + 1);
+    skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
+// gmc_skinny_bwd_f32 whose dHpre leaves as n_split (2 or 3) stacked bf16 parts of row_scale[v] * dHpre[v, :] (row_scale
+// nullable = 1): part s occupies rows [s * split_rows, s * split_rows + n_rows) of the bf16 matrix dH_split (lddh in
+// elements, multiple of 4).  H is fp32.  Feeds gmc_gemm_bf16_split (op tn) -- autograd of TrainingNeural.py:80-83 at fp32
+// grade on bf16 tensor cores.  Same workspace as gmc_skinny_bwd_f32.
+int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh, const float* row_scale,
+                         void* dH_split, int64_t lddh, int64_t split_rows, int32_t n_split, float* dW, float* dbias,
+                         int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(dT && W && H && dH_split && dW, "gmc_skinny_bwd_split: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_in > 0 && n_out >= 1 && n_out <= 4 && ldh >= n_in && lddh >= n_in && lddt >= n_out,
+                "gmc_skinny_bwd_split: bad sizes (n_out must be 1..4)");
+    GMC_REQUIRE((n_split == 2 || n_split == 3) && split_rows >= n_rows, "gmc_skinny_bwd_split: n_split must be 2 or 3 and split_rows >= n_rows");
+    GMC_REQUIRE(n_in % 4 == 0 && ldh % 4 == 0 && lddh % 4 == 0 && aligned16(H) && (reinterpret_cast<uintptr_t>(dH_split) & 7u) == 0,
+                "gmc_skinny_bwd_split: n_in and leading dimensions must be multiples of 4 with aligned bases");
+    int n_ctas = reduce_ctas() * 2;
+    if ((int64_t)n_ctas > n_rows) n_ctas = (int)(n_rows > 0 ? n_rows : 1);
+    const size_t need = (size_t)n_ctas * n_in * (n_out + 1) * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+        set_error("gmc_skinny_bwd_split: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return GMC_ERR_WORKSPACE;
+    }
+    cudaStream_t s = as_stream(stream);
+    float* ws = reinterpret_cast<float*>(workspace);
+    if (n_rows == 0) {
+        GMC_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * n_in * n_out, s));
+        if (dbias) GMC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * n_in, s));
+        return GMC_OK;
+    }
+    uint2* dH2 = reinterpret_cast<uint2*>(dH_split);
+#define GMC_CASE(K)                                                                                                           \
+    case K:                                                                                                                   \
+        if (n_split == 2) skinny_bwd_split_kernel<K, 2><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws); \
+        else skinny_bwd_split_kernel<K, 3><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws); \
+        break;
+    switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) }
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();
     const int total = n_in * (n_out + 1);

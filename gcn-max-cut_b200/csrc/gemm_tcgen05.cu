@@ -166,11 +166,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, bool bf16 = false) {
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, bool bf16 = false, int mma_n = BLOCK_N) {
     return (1u << 4)                              // D format  : F32
          | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10)   // A/B format: TF32 = 2 (kind::tf32), BF16 = 1 (kind::f16)
          | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
-         | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+         | ((uint32_t)(mma_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
 struct Params {
@@ -194,6 +194,11 @@ struct Params {
     float* proj_out;
     int64_t ldp;
     int proj_k;
+    // split-operand GEMMs (NS > 1): B is NS stacked bf16 matrices (hi, lo [, lo2] parts of an fp32 operand), part s
+    // starting b_split_rows rows below part 0; the MMA sees them side by side along N and the epilogue adds them up
+    int64_t b_split_rows;
+    // fp32 epilogue (direct, non split-K outputs): C[m, n] = act(row_scale[m] * acc + bias[n]); each nullable / 0
+    const float* row_scale;
 };
 
 // Thread-block cluster of CLM x CLN CTAs (rank = rm + CLM * rn) that owns CLM consecutive m-tiles x CLN consecutive
@@ -204,11 +209,22 @@ struct Params {
 // slower).  SM reads per output scale with 1/(256 CLN) + 1/(128 CLM).  A stage may be refilled only when every CTA
 // that receives one of this CTA's multicasts has consumed it, and symmetrically, so each MMA warp multicasts its
 // tcgen05.commit to its row and column (arrival count CLM + CLN - 1).
-template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
+//
+// NS > 1 (bf16, MN-major B only): fp32-grade product with a SPLIT B operand.  B = B_0 + B_1 [+ B_2] with bf16 parts
+// (hi / lo / lo2 of an fp32 matrix, 8 mantissa bits each), A exact in bf16 (small integers).  A tile covers RN = BN / NS
+// real output columns; its B stage holds the NS parts of those columns side by side (BN = 256 for NS = 2, 192 for NS = 3),
+// ONE MMA per k-step multiplies the A tile with all parts (the A tile is loaded once for NS products) and the epilogue
+// adds the NS accumulator column groups.  Everything else -- ring, barriers, multicast, split-K -- is unchanged.
+template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16, int NS = 1>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const Params p) {
+    static_assert(NS == 1 || (BF16 && B_MN && CLN == 1), "split operands: bf16, MN-major B, 1-D clusters");
     constexpr int CL = CLM * CLN;
+    constexpr int BN = NS == 3 ? 192 : BLOCK_N;                    // MMA N = columns of the B stage
+    constexpr int RN = BN / NS;                                    // real output columns per tile
+    constexpr int B_BYTES_T = BN * 128;                            // B stage bytes (BN columns x 128 B of k)
+    constexpr int STAGE_T = A_BYTES + B_BYTES_T;
     // element-size dependent geometry; everything in BYTES is the same for fp32 (tf32) and bf16 operands: a stage row
     // is 128 B = 32 fp32 or 64 bf16 along k (K-major) or along m/n (MN-major chunk), one MMA eats 32 B of k
     constexpr int ELT = BF16 ? 2 : 4;
@@ -219,7 +235,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
-    const uint32_t epi = tiles + STAGES * STAGE_BYTES;             // epilogue staging: 4 warps x 2 x 4 KB, 1024-aligned
+    const uint32_t epi = tiles + STAGES * STAGE_T;                 // epilogue staging: 4 warps x 2 x 4 KB, 1024-aligned
     const uint32_t bars = epi + EPI_BYTES;
     const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
     const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 8 * ACC_STAGES;
@@ -266,14 +282,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int split = (int)(w / tiles_gn);
                 const int64_t rem = w - (int64_t)split * tiles_gn;
                 const int m0 = ((int)(rem / p.ng_tiles) * CLM + (int)rm) * BLOCK_M;
-                const int n0 = ((int)(rem % p.ng_tiles) * CLN + (int)rn) * BLOCK_N;
+                const int n0 = ((int)(rem % p.ng_tiles) * CLN + (int)rn) * RN;
                 const int64_t kb = (int64_t)split * p.k_per_split;
                 const int64_t ke = min(p.K, kb + p.k_per_split);
                 for (int64_t k0 = kb; k0 < ke; k0 += BK) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                    const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint32_t sa = tiles + stage * STAGE_T, sb = sa + A_BYTES;
                     const uint32_t fb = full_bar + 8 * stage;
-                    mbar_expect_tx(fb, STAGE_BYTES);
+                    mbar_expect_tx(fb, STAGE_T);
                     if (CLN == 1) {
                         if (A_MN) {
 #pragma unroll
@@ -292,19 +308,26 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         constexpr int ROWS = BLOCK_M / CLN;
                         tma_load_2d_mc(sa + rn * (ROWS * 128), &tmA, (int)k0, m0 + (int)rn * ROWS, fb, MASK_A);
                     }
+                    // chunk j of the B stage = column chunk (j % CPS) of split part (j / CPS): part s lives b_split_rows * s
+                    // rows below part 0 in the stacked operand (NS == 1: CPS = all chunks, part 0 only)
+                    constexpr int NCH = BN / MNC, CPS = NCH / NS;
                     if (CLM == 1) {
                         if (B_MN) {
 #pragma unroll
-                            for (int j = 0; j < BLOCK_N / MNC; ++j) tma_load_2d(sb + j * CHUNK, &tmB, n0 + MNC * j, (int)k0, fb);
+                            for (int j = 0; j < NCH; ++j)
+                                tma_load_2d(sb + j * CHUNK, &tmB, n0 + MNC * (j % CPS),
+                                            (int)(k0 + (NS > 1 ? (int64_t)(j / CPS) * p.b_split_rows : 0)), fb);
                         } else {
                             tma_load_2d(sb, &tmB, (int)k0, n0, fb);
                         }
-                    } else if (B_MN) {                             // my share of the 8 column chunks, to my cluster column
-                        constexpr int PER = BLOCK_N / MNC / CLM;
+                    } else if (B_MN) {                             // my share of the column chunks, to my cluster column
+                        static_assert(NS == 1 || NCH % CLM == 0, "B chunks must divide over the cluster column");
+                        constexpr int PER = NCH / CLM;
 #pragma unroll
                         for (int jj = 0; jj < PER; ++jj) {
                             const int j = (int)rm * PER + jj;
-                            tma_load_2d_mc(sb + j * CHUNK, &tmB, n0 + MNC * j, (int)k0, fb, MASK_B);
+                            tma_load_2d_mc(sb + j * CHUNK, &tmB, n0 + MNC * (j % CPS),
+                                           (int)(k0 + (NS > 1 ? (int64_t)(j / CPS) * p.b_split_rows : 0)), fb, MASK_B);
                         }
                     } else {                                       // K-major B: my BLOCK_N / CLM rows, to my cluster column
                         constexpr int ROWS = BLOCK_N / CLM;
@@ -316,7 +339,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BF16);
+        constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BF16, BN);
         // K-major : SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1 = CUTLASS convention)
         // MN-major: SWIZZLE_128B_BASE32B, 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart (SBO)
         // 16-bit MN-major: plain SWIZZLE_128B, 64-element chunks CHUNK apart (LBO), 8-k-row atoms 1024 B apart (SBO)
@@ -341,7 +364,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 __syncwarp();
                 if (elect_one()) {
-                    const uint32_t sa = tiles + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint32_t sa = tiles + stage * STAGE_T, sb = sa + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint64_t ad = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
@@ -368,13 +391,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int split = (int)(w / tiles_gn);
             const int64_t rem = w - (int64_t)split * tiles_gn;
             const int64_t m0 = ((rem / p.ng_tiles) * CLM + rm) * BLOCK_M;
-            const int n0 = ((int)(rem % p.ng_tiles) * CLN + (int)rn) * BLOCK_N;
+            const int n0 = ((int)(rem % p.ng_tiles) * CLN + (int)rn) * RN;
             float* Cs = p.C + (int64_t)split * p.split_stride;
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const int64_t m = m0 + 32 * q + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BLOCK_N;
-            if (p.c_bf16) {
+            if (NS == 1 && p.c_bf16) {
                 // bf16 output: 64 accumulator columns -> 32 packed words = one 128-byte staging row per lane, same swizzle
                 // and the same 32-row TMA store as the fp32 path (box 64 x 32 bf16); half the store traffic of the tile
                 float pj[4] = {0.f, 0.f, 0.f, 0.f};
@@ -452,11 +475,45 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             } else {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = 0; c < RN / 32; ++c) {
                 const int n = n0 + 32 * c;
                 if (n >= p.N || m0 >= p.M) break;                  // warp-uniform
                 uint32_t r[32];
-                tmem_ld32(t_row + 32 * c, r);
+                if (NS == 1) {
+                    tmem_ld32(t_row + 32 * c, r);
+                } else {
+                    // split operand: column n of the product = sum of the NS accumulator groups (low-order parts first)
+                    uint32_t r2[32];
+                    tmem_ld32(t_row + (NS - 1) * RN + 32 * c, r);
+#pragma unroll
+                    for (int sp = NS - 2; sp >= 0; --sp) {
+                        tmem_ld32(t_row + sp * RN + 32 * c, r2);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                    }
+                }
+                if (p.row_scale) {
+                    const float rs = m < p.M ? __ldg(p.row_scale + m) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
+                }
+                if (p.bias) {                                      // same address in every lane: broadcast loads
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (n + 4 * i < p.N) {                     // N % 4 == 0 (checked by the launcher)
+                            const float4 b = __ldg(b4 + i);
+                            r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + b.x);
+                            r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b.y);
+                            r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b.z);
+                            r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b.w);
+                        }
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
+                }
                 if (p.tma_store) {
                     // registers -> 128B-swizzled staging block (lane = row, 16-byte chunk i at i ^ (row & 7): conflict-free
                     // STS.128) -> one TMA store of 32 full 128-byte row segments; rows / columns beyond M / N are clipped
@@ -805,12 +862,12 @@ static bool no_tma_store() {
 }
 
 // co-resident clusters of the kernel on this device: the GPC geometry may admit fewer than SMs / CL
-template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
+template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16, int NS = 1>
 static int cluster_slots() {
     constexpr int CL = CLM * CLN;
     static int cached = -1;
     if (cached < 0) {
-        cudaFuncSetAttribute(gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         cached = sm_count() / CL;
         if (CL > 1) {
             cudaLaunchConfig_t probe = {};
@@ -823,7 +880,7 @@ static int cluster_slots() {
             probe.attrs = attr;
             probe.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16>, &probe) == cudaSuccess && n > 0) {
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16, NS>, &probe) == cudaSuccess && n > 0) {
                 if (n < cached) cached = n;
             } else {
                 cudaGetLastError();
@@ -834,20 +891,22 @@ static int cluster_slots() {
     return cached;
 }
 
-template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16>
+template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16, int NS = 1>
 static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
                   const float* bias = nullptr, int relu = 0, const float* proj_w = nullptr, float* proj_out = nullptr,
-                  int64_t ldp = 0, int proj_k = 0) {
+                  int64_t ldp = 0, int proj_k = 0, int64_t b_split_rows = 0, const float* row_scale = nullptr) {
     constexpr int CL = CLM * CLN;
     constexpr int ELT = BF16 ? 2 : 4;
     constexpr int BK = 128 / ELT, MNC = 128 / ELT;                 // k elements per stage, m/n elements per MN-major chunk
+    constexpr int RN = (NS == 3 ? 192 : BLOCK_N) / NS;             // real output columns per tile
     CUtensorMap tmA, tmB;
     int rc;
     if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, MNC, BK, true, ELT);       // A[K rows, M cols]
     else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BLOCK_M / CLN, false, ELT);  // A[M rows, K cols]
     if (rc) return rc;
-    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, MNC, BK, true, ELT);       // B[K rows, N cols]
+    // split operand: NS stacked [b_split_rows, N] parts; the last part ends at row (NS - 1) * b_split_rows + K
+    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)((NS - 1) * b_split_rows + K), (uint64_t)ldb, MNC, BK, true, ELT);  // B[K rows, N cols]
     else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BLOCK_N / CLM, false, ELT);  // B[N rows, K cols]
     if (rc) return rc;
 
@@ -860,16 +919,18 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const int slots = cluster_slots<A_MN, B_MN, CLM, CLN, BF16>();  // co-resident clusters (GPC geometry), <= SMs / CL
+    const int slots = cluster_slots<A_MN, B_MN, CLM, CLN, BF16, NS>();  // co-resident clusters (GPC geometry), <= SMs / CL
 
     Params p = {};
     p.M = M; p.N = N; p.K = K;
+    p.b_split_rows = b_split_rows;
     p.m_tiles = (int)ceil_div<int64_t>(M, BLOCK_M);
-    p.n_tiles = (int)ceil_div<int64_t>(N, BLOCK_N);
+    p.n_tiles = (int)ceil_div<int64_t>(N, RN);
     p.mg_tiles = ceil_div(p.m_tiles, CLM);
     p.ng_tiles = ceil_div(p.n_tiles, CLN);
     const int64_t ctiles = (int64_t)p.mg_tiles * p.ng_tiles;
-    int splits = c_bf16 ? 1 : pick_splits_cl(ctiles, K, slots);   // a bf16 C leaves straight from the accumulators
+    const bool fused_epilogue = c_bf16 || row_scale || bias || relu;   // these leave straight from the accumulators
+    int splits = fused_epilogue ? 1 : pick_splits_cl(ctiles, K, slots);
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
         if (splits < 1) splits = 1;
@@ -916,15 +977,27 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
             p.ldp = ldp;
             p.proj_k = proj_k;
         }
-    } else if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
-        rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
-        if (rc) return rc;
-        p.tma_store = 1;
+    } else {
+        if (fused_epilogue) {
+            if (accumulate || (bias && (N % 4 != 0 || !aligned16(bias)))) {
+                set_error("gmc_gemm: an fp32 epilogue (row scale / bias / ReLU) needs accumulate = 0 and, with a bias, "
+                          "N %% 4 == 0 and a 16-byte aligned bias");
+                return GMC_ERR_INVALID_ARG;
+            }
+            p.row_scale = row_scale;
+            p.bias = bias;
+            p.relu = relu;
+        }
+        if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
+            rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
+            if (rc) return rc;
+            p.tma_store = 1;
+        }
     }
     const int64_t n_work = ctiles * splits;
     const int grid = (int)(n_work < slots ? n_work : slots) * CL;
     cfg.gridDim = dim3(grid);
-    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16>, tmA, tmB, tmC, p));
+    GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16, NS>, tmA, tmB, tmC, p));
     if (splits > 1) {
         const int64_t MN = M * N;
         tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
@@ -940,6 +1013,7 @@ static int launch_cl(const void* A, const void* B, float* C, int64_t M, int64_t 
                      int64_t ldp = 0, int proj_k = 0) {
     int clm, cln;
     cluster_shape(A_MN, ceil_div<int64_t>(N, BLOCK_N), &clm, &cln, BF16);
+    if (BF16 && B_MN && clm == 8) clm = 4;                         // a bf16 MN-major B stage has four chunks to share out
 #define GMC_GEMM_CASE(CM, CN)                                                                                       \
     if (clm == CM && cln == CN)                                                                                     \
         return launch<A_MN, B_MN, CM, CN, BF16>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
@@ -1177,6 +1251,65 @@ int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64
     }
     set_error("gmc_gemm_bf16: bad op %d", op);
     return GMC_ERR_INVALID_ARG;
+}
+
+// ---- split-operand bf16 GEMM: fp32-grade products at bf16 tensor-core rates ---------------------------------------
+// C = op(A) * (B_0 + ... + B_{NS-1}): A exact in bf16 (the integer path counts d * A_hat X of a regular graph), B an fp32
+// matrix split into NS bf16 parts by gmc_f32_split_bf16 (NS = 2: 16 mantissa bits, NS = 3: 24 = all of fp32), products
+// accumulated in fp32 TMEM and added up in the epilogue.  op 0 (nn) and 2 (tn): B is MN-major in both.
+namespace tc {
+static void split_cluster(int ns, int* clm) {
+    // NS = 2: four 64-column chunks per stage -> 2x1 clusters share them (the plain bf16 default); NS = 3: three chunks,
+    // no even share -> single CTAs (the bf16 nn kernel is insensitive to the cluster shape, profiles/r01_gemm_notes.md)
+    *clm = ns == 2 ? 2 : 1;
+    const char* e = getenv("GMC_GEMM_SPLIT_CLUSTER");
+    if (e && e[0] == '1') *clm = 1;
+}
+
+static int64_t split_tiles(int ns, int64_t M, int64_t N, int clm) {
+    const int rn = (ns == 3 ? 192 : BLOCK_N) / ns;
+    return ceil_div<int64_t>(ceil_div<int64_t>(M, BLOCK_M), clm) * ceil_div<int64_t>(N, rn);
+}
+}  // namespace tc
+
+size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int n_split) {
+    (void)op;
+    if (n_split < 2 || n_split > 3) return 0;
+    int clm;
+    tc::split_cluster(n_split, &clm);
+    const int splits = tc::pick_splits_cl(tc::split_tiles(n_split, M, N, clm), K, sm_count() / clm);
+    return splits > 1 ? (((size_t)splits * M * N * sizeof(float) + 255) & ~(size_t)255) : 0;
+}
+
+int tc_gemm_bf16_split(int op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                       int64_t ldb, int64_t ldc, int n_split, int64_t b_split_rows, const float* row_scale,
+                       const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    GMC_REQUIRE(op == 0 || op == 2, "gmc_gemm_bf16_split: op must be 0 (nn) or 2 (tn): the split operand is MN-major");
+    GMC_REQUIRE(n_split == 2 || n_split == 3, "gmc_gemm_bf16_split: n_split must be 2 or 3");
+    GMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B),
+                "gmc_gemm_bf16_split: TMA needs 16-byte aligned bases and leading dimensions that are multiples of 8 elements");
+    GMC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && (int64_t)(n_split - 1) * b_split_rows + K < (1ll << 31),
+                "gmc_gemm_bf16_split: dimension exceeds int32 TMA coordinates");
+    GMC_REQUIRE(b_split_rows >= (K + 63) / 64 * 64, "gmc_gemm_bf16_split: b_split_rows must cover K rounded up to 64 "
+                "(the rows between K and b_split_rows of every part must be zero)");
+    if (M == 0 || N == 0) return GMC_OK;
+    if (K == 0) {
+        GMC_REQUIRE(!row_scale && !bias && !relu, "gmc_gemm_bf16_split: K = 0 with an epilogue");
+        if (!accumulate) GMC_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, s));
+        return GMC_OK;
+    }
+    int clm;
+    tc::split_cluster(n_split, &clm);
+#define GMC_SPLIT_CASE(AMN, CM, NSV)                                                                                  \
+    return tc::launch<AMN, true, CM, 1, true, NSV>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, 0, \
+                                                   bias, relu, nullptr, nullptr, 0, 0, b_split_rows, row_scale);
+    if (op == 0) {
+        if (n_split == 2) { if (clm == 2) { GMC_SPLIT_CASE(false, 2, 2) } else { GMC_SPLIT_CASE(false, 1, 2) } }
+        GMC_SPLIT_CASE(false, 1, 3)
+    }
+    if (n_split == 2) { if (clm == 2) { GMC_SPLIT_CASE(true, 2, 2) } else { GMC_SPLIT_CASE(true, 1, 2) } }
+    GMC_SPLIT_CASE(true, 1, 3)
+#undef GMC_SPLIT_CASE
 }
 
 }  // namespace gmc

@@ -96,12 +96,23 @@ __device__ __forceinline__ int sampled_label(const float* __restrict__ P, int64_
                                              const double* __restrict__ Ug, int64_t per_iter, int it, int cmp_f32) {
     if (i < 3) return i;
     const double r = __ldg(Ug + (int64_t)it * per_iter + (i - 3));
-    const float rf = (float)r;
-    float cum = 0.0f;
+    if (cmp_f32) {
+        // numpy >= 2 (NEP 50): `0 + np.float32` stays float32 and the Python-float uniform is "weak": float32 running
+        // sum, float32 comparison
+        const float rf = (float)r;
+        float cum = 0.0f;
+        for (int k = 0; k < K; ++k) {
+            cum = __fadd_rn(cum, __ldg(P + v * ldp + k));     // no contraction
+            if (rf < cum) return k;
+        }
+        return K - 1;
+    }
+    // numpy 1.x (legacy promotion): the Python int 0 plus a float32 SCALAR promotes to float64, so the running sum is the
+    // float64 sum of the float32 probabilities and the comparison is float64
+    double cum = 0.0;
     for (int k = 0; k < K; ++k) {
-        cum = __fadd_rn(cum, __ldg(P + v * ldp + k));     // float32 running sum, no contraction
-        const bool hit = cmp_f32 ? (rf < cum) : (r < (double)cum);
-        if (hit) return k;
+        cum = __dadd_rn(cum, (double)__ldg(P + v * ldp + k));
+        if (r < cum) return k;
     }
     return K - 1;
 }

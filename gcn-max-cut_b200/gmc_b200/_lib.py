@@ -19,7 +19,8 @@ GMC_LOSS_STE, GMC_LOSS_SOFT = 0, 1
 PRECISIONS = {"fp32": GMC_GEMM_FP32, "tf32": GMC_GEMM_TF32, "tf32x3": GMC_GEMM_TF32X3}
 # engine-level precision (GCNEngine / TrainingConfig.gemm_precision): the three above plus "bf16" (bf16 operands
 # through gmc_gemm_bf16; not a gmc_gemm_* precision code because its operands are a different type)
-ENGINE_PRECISIONS = tuple(PRECISIONS) + ("bf16",)
+# and "bf16x2" / "bf16x3" (fp32-grade: exact integer features x an fp32 operand split into 2 / 3 bf16 parts, csrc/split.cu)
+ENGINE_PRECISIONS = tuple(PRECISIONS) + ("bf16", "bf16x2", "bf16x3")
 LOSS_MODES = {"ste": GMC_LOSS_STE, "soft": GMC_LOSS_SOFT}
 
 
@@ -67,6 +68,13 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_adj_features_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "gmc_adj_features_bwd_f32": (c_int, [P, P, c_int32, c_int32, P, c_int64, c_int64, c_int32, P, c_int64, c_int32, P,
                                          c_size_t, P]),
+    "gmc_f32_split_bf16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int64, P]),
+    "gmc_row_scale_f32": (c_int, [P, P, c_int64, P, P, P]),
+    "gmc_gemm_bf16_split_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int32]),
+    "gmc_gemm_bf16_split": (c_int, [c_int32, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_int64,
+                                    P, P, c_int32, c_int32, P, c_size_t, P]),
+    "gmc_skinny_bwd_split": (c_int, [P, c_int64, P, P, c_int64, P, P, c_int64, c_int64, c_int32, P, P, c_int64, c_int32,
+                                     c_int32, P, c_size_t, P]),
     "gmc_gemm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int32]),
     "gmc_gemm_nn": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_size_t, P]),
     "gmc_gemm_nt": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_size_t, P]),

@@ -82,7 +82,7 @@ class GCNEngine:
     def __init__(self, net, optimizer: Optional[FusedAdam] = None, *, C: float = 1.0, loss_mode: str = "ste",
                  override_terminals: bool = True, penalty: float = 0.0, precision: str = "fp32",
                  process_group=None, adjacency_kernels: bool = False, activations: str = "fp32",
-                 preaggregate: bool = False):
+                 preaggregate: bool = False, adjacency_features: bool = False):
         self.device = _lib.require_cuda()
         self.net = net
         self.optimizer = optimizer
@@ -92,6 +92,22 @@ class GCNEngine:
         if precision not in _lib.ENGINE_PRECISIONS:
             raise ValueError(f"unknown precision {precision!r}")
         self.precision = precision
+        # precision 'bf16x3' / 'bf16x2' -- the fp32-GRADE tensor-core path (csrc/split.cu).  Layer 1 runs pre-aggregated on
+        # the integer features XI (2-step path counts, exact in bf16; A_hat X = s . XI with one scale per row), and the
+        # fp32 operand of each GEMM is split into bf16 parts: W1 into 3 (2) parts forward -- all 24 (16) mantissa bits --
+        # and s . dH1pre into 2 parts backward (16 bits: 4e-6 relative per element, far inside the 1e-4 parity bar; the
+        # forward decides the hard labels, so it gets the exact operand).  H1, logits, loss, gradients, Adam: fp32.
+        # Needs adjacency features (IntegerFeatures, or adjacency_features=True: the caller guarantees that the
+        # features are the zero-padded 0/1 adjacency rows, as _prepare verifies) and one A_hat coefficient per row
+        # (regular graphs); other batches take the standard layer 1 with tf32x3 GEMMs (also fp32-grade).
+        self.split_fwd = {"bf16x2": 2, "bf16x3": 3}.get(precision, 0)
+        self.split_bwd = int(os.environ.get("GMC_SPLIT_BWD", "2")) if self.split_fwd else 0
+        if self.split_bwd not in (0, 2, 3):
+            raise ValueError("GMC_SPLIT_BWD must be 2 or 3")
+        self.adjacency_features = bool(adjacency_features)
+        self._std_precision = "tf32x3" if self.split_fwd else precision
+        self.W1s = None
+        self.bufS = None
         # activations='bf16' (needs precision='bf16'): the four [n_nodes, hidden] layer-1 tensors -- T1 = X W1,
         # H1 = relu(A_hat T1 + b1), dH1pre, dT1 -- are STORED in bf16 (standard mixed-precision practice: bf16 storage,
         # fp32 arithmetic).  Each is written once and read once (T1: d times by the gather), so every layer-1 pass
@@ -148,6 +164,9 @@ class GCNEngine:
         self.bufA16 = None
         self._cap_nodes = 0
         self._cap_graphs = 0
+        # bumped whenever _ensure replaces an engine buffer: captured CUDA graphs bake raw addresses in, so a graph
+        # captured under an older generation (or an older workspace allocation) must never be replayed
+        self._buffer_generation = 0
         self.bufA = self.bufB = self.T2 = self.Z = self.P = self.dZ = self.dT2 = None
         self.loss = None
         self.timer: Optional[OpTimer] = None
@@ -175,7 +194,7 @@ class GCNEngine:
     def grads(self) -> List[torch.Tensor]:
         return [self.gW1, self.gb1, self.gW2, self.gb2]
 
-    def _ensure(self, n_nodes: int, n_graphs: int, b16: bool = False) -> None:
+    def _ensure(self, n_nodes: int, n_graphs: int, b16: bool = False, split: bool = False) -> None:
         dev, f32 = self.device, torch.float32
         if n_nodes > self._cap_nodes:
             cap = n_nodes
@@ -185,19 +204,56 @@ class GCNEngine:
             self.dZ = torch.empty((cap, self.K), dtype=f32, device=dev)
             self.dT2 = torch.empty((cap, self.K), dtype=f32, device=dev)
             self._cap_nodes = cap
-        if not b16 and (self.bufA is None or self.bufA.shape[0] < n_nodes):
+            self._buffer_generation += 1
+        if split:
+            # split-operand path: H1 fp32 in bufB, the stacked bf16 parts of s . dH1pre in bufS (zeroed: its pad rows
+            # must stay finite)
+            if self.bufB is None or self.bufB.shape[0] < n_nodes:
+                self.bufB = ops.padded_empty(n_nodes, self.H, dev)
+                self._buffer_generation += 1
+            need = self.split_bwd * ops.split_rows_for(n_nodes)
+            if self.bufS is None or self.bufS.shape[0] < need:
+                self.bufS = ops.padded_empty_bf16(need, self.H, dev, zero=True)
+                self._buffer_generation += 1
+        elif not b16 and (self.bufA is None or self.bufA.shape[0] < n_nodes):
             # row pitch padded to 128 B: TMA boxes / 128-bit gathers never straddle cache lines
             self.bufA = ops.padded_empty(n_nodes, self.H, dev)
             self.bufB = ops.padded_empty(n_nodes, self.H, dev)
+            self._buffer_generation += 1
         if self.precision == "bf16" and (self.bufB16 is None or self.bufB16.shape[0] < n_nodes):
             # zero-initialised: the pad columns (hidden .. pitch) stay zero, every kernel that writes it preserves that
             self.bufB16 = ops.padded_empty_bf16(n_nodes, self.H, dev, zero=True)
+            self._buffer_generation += 1
         if b16 and (self.bufA16 is None or self.bufA16.shape[0] < n_nodes):
             # bf16 activations: two bf16 buffers carry the whole layer-1 chain (A16 = T1 then dH1pre, B16 = H1 then dT1)
             self.bufA16 = ops.padded_empty_bf16(n_nodes, self.H, dev, zero=True)
+            self._buffer_generation += 1
         if n_graphs > self._cap_graphs:
             self.loss = torch.empty(n_graphs, dtype=torch.float64, device=self.device)
             self._cap_graphs = n_graphs
+            self._buffer_generation += 1
+
+    def _integer_features(self, batch: GraphBatch, X) -> Optional["ops.IntegerFeatures"]:
+        """IntegerFeatures of the batch for the split-operand path, or None when the batch / features do not qualify
+        (the caller then runs the standard tf32x3 layer 1)."""
+        if not self.split_fwd:
+            return None
+        if isinstance(X, ops.IntegerFeatures):
+            if X.tensor.shape[0] != batch.num_nodes or X.tensor.shape[1] != self.F:
+                raise ValueError(f"integer features must be [{batch.num_nodes}, {self.F}], got {tuple(X.tensor.shape)}")
+            return X
+        if not (X is None or self.adjacency_features):
+            return None
+        hit = getattr(batch, "_xi", None)
+        if hit is None or hit[0] != self.F:
+            xi = None
+            if batch.unit_weights and batch.max_nodes <= self.F and self.H % 4 == 0 and self.K <= 4:
+                scale, bad = ops.row_scale(batch)
+                if bad == 0:
+                    xi = ops.IntegerFeatures(ops.integer_features_bf16(batch, self.F), scale)
+            hit = (self.F, xi)
+            batch._xi = hit
+        return hit[1]
 
     def _sparse_layer1(self, batch: GraphBatch) -> bool:
         return self.adjacency_kernels and ops.adjacency_kernels_apply(batch, self.F)
@@ -217,14 +273,16 @@ class GCNEngine:
         X = self._features(batch, X)
         key = (id(batch), X.data_ptr(), tuple(X.shape), X.stride(0), X._version, X.dtype)
         hit = self._xa_cache.get(key)
-        if hit is None:
+        # the entry holds the batch AND the tensor it was computed from: a freed X whose address the caching allocator
+        # hands to the next batch's features (same shape, _version 0) must not hit
+        if hit is None or hit[0] is not batch or hit[1] is not X:
             if len(self._xa_cache) >= 64:
                 self._xa_cache.clear()
             X32 = X.float() if X.dtype == torch.bfloat16 else X
-            hit = (batch, ops.to_bf16(ops.spmm(batch, X32)))      # the batch is kept alive with its entry (id reuse)
+            hit = (batch, X, ops.to_bf16(ops.spmm(batch, X32)))
             del X32
             self._xa_cache[key] = hit
-        return hit[1]
+        return hit[2]
 
     def _features(self, batch: GraphBatch, X: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if X is None:
@@ -248,12 +306,18 @@ class GCNEngine:
             return X
         key = (X.data_ptr(), tuple(X.shape), X.stride(0), X._version)
         hit = self._xb_cache.get(key)
-        if hit is None:
+        if hit is None or hit[0] is not X:                  # identity, not address: see _preaggregated
             if len(self._xb_cache) >= 64:
                 self._xb_cache.clear()
-            hit = ops.to_bf16(X)
+            hit = (X, ops.to_bf16(X))
             self._xb_cache[key] = hit
-        return hit
+        return hit[1]
+
+    def invalidate_feature_caches(self) -> None:
+        """Forget every derived copy of feature tensors (bf16 copies, A_hat X).  Call after writing features through
+        raw pointers (gmc_* kernels such as ops.densify(out=X) do not bump torch's version counter)."""
+        self._xb_cache.clear()
+        self._xa_cache.clear()
 
     # ------------------------------------------------------------------ forward
     def forward_logits(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
@@ -281,6 +345,19 @@ class GCNEngine:
                 self._op("skinny_fwd", 1, ops.skinny_fwd_bf16, B16, W2.data, out=self.T2[:N])
             self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
             return self.Z[:N]
+        XI = self._integer_features(batch, X)
+        if XI is not None:
+            # fp32-grade layer 1 on the tensor cores: H1 = relu(s . (XI (W1_hi + W1_lo + W1_lo2)) + b1), fp32 out
+            self._ensure(N, batch.num_graphs, split=True)
+            Bf = self.bufB[:N]
+            if self.W1s is None:
+                self.W1s = ops.split_empty(self.F, self.H, self.split_fwd, self.device)
+            ops.f32_split_bf16(W1.data, self.split_fwd, out=self.W1s)
+            self._op("gemm_nn_layer1", 1, ops.gemm_bf16_split, "nn", XI.tensor, self.W1s, self.split_fwd, self.F, out=Bf,
+                     row_scale=XI.scale, bias=b1.data, relu=True, workspace=self.ws)
+            self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
+            self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
+            return self.Z[:N]
         X = self._features(batch, X)
         if self._b16_activations(batch):
             self._ensure(N, batch.num_graphs, b16=True)
@@ -305,7 +382,7 @@ class GCNEngine:
             ops.to_bf16(W1.data, out=self.W1b)
             self._op("gemm_nn_xw1", 1, ops.gemm_bf16, "nn", self._bf16_features(X), self.W1b, out=A, workspace=self.ws)
         else:
-            self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, self.W1p, out=A, precision=self.precision, workspace=self.ws)
+            self._op("gemm_nn_xw1", 1, ops.gemm, "nn", X, self.W1p, out=A, precision=self._std_precision, workspace=self.ws)
         if 16 <= self.H <= 512 and self.H % 4 == 0 and not (_FWD_SLAB and getattr(batch, "plan", None) is not None):
             # aggregation + bias + ReLU + the skinny projection H1 W2 in one pass over the row
             self._op("spmm_h_fused", 1, ops.spmm_fused_skinny, batch, A, W2.data, out=Bf, proj=self.T2[:N],
@@ -337,7 +414,7 @@ class GCNEngine:
             if dX is not None:
                 raise ValueError("preaggregate=True folds the aggregation into fixed features; trainable features (dX) "
                                  "need the standard path")
-        else:
+        elif self._integer_features(batch, X) is None:
             X = self._features(batch, X)
         if dX is not None and self._sparse_layer1(batch):
             raise ValueError("adjacency_kernels promises fixed adjacency features; trainable features need the dense path")
@@ -355,6 +432,16 @@ class GCNEngine:
             self._op("skinny_bwd", 2, ops.skinny_bwd_bf16, self.dT2[:N], W2.data, B16, dH=A16, dW=self.gW2,
                      dbias=self.gb1, workspace=self.ws)                                              # dH1pre, bf16
             self._op("gemm_tn_dw1", 2, ops.gemm_bf16, "tn", XA, A16, out=self.gW1, workspace=self.ws)  # (A_hat X)^T dH1pre
+            return loss
+        XI = self._integer_features(batch, X)
+        if XI is not None:
+            if dX is not None:
+                raise ValueError("the integer-feature path has fixed adjacency features; trainable features need tf32 / fp32")
+            ns = self.split_bwd
+            S = self.bufS[: ns * ops.split_rows_for(N)]
+            self._op("skinny_bwd", 2, ops.skinny_bwd_split, self.dT2[:N], W2.data, self.bufB[:N], ns, S,
+                     row_scale=XI.scale, dW=self.gW2, dbias=self.gb1, workspace=self.ws)             # s . dH1pre, bf16 parts
+            self._op("gemm_tn_dw1", 2, ops.gemm_bf16_split, "tn", XI.tensor, S, ns, N, out=self.gW1, workspace=self.ws)
             return loss
         if self._b16_activations(batch):
             if dX is not None:
@@ -378,9 +465,9 @@ class GCNEngine:
         if self._sparse_layer1(batch):
             self._op("adj_bwd_dw1", 2, ops.adj_features_bwd, batch, Bf, out=self.gW1, workspace=self.ws)
         else:
-            self._op("gemm_tn_dw1", 2, ops.gemm, "tn", X, Bf, out=self.gW1, precision=self.precision, workspace=self.ws)
+            self._op("gemm_tn_dw1", 2, ops.gemm, "tn", X, Bf, out=self.gW1, precision=self._std_precision, workspace=self.ws)
         if dX is not None:
-            self._op("gemm_nt_dx", 1, ops.gemm, "nt", Bf, self.W1p, out=dX, precision=self.precision,
+            self._op("gemm_nt_dx", 1, ops.gemm, "nt", Bf, self.W1p, out=dX, precision=self._std_precision,
                      workspace=self.ws)
         return loss
 
@@ -435,12 +522,19 @@ class GCNEngine:
                                                              and dist.get_world_size() > 1):
             return self.train_step(batch, X)
         params, group, states = self._adam_state()
-        key = (id(batch), X.data_ptr(), tuple(X.shape), group["lr"], tuple(group["betas"]), group["eps"])
+        xkey = (X.data_ptr(), tuple(X.shape)) if torch.is_tensor(X) else id(X)     # feature wrappers / None: identity
+        key = (id(batch), xkey, group["lr"], tuple(group["betas"]), group["eps"])
         entry = self._graphs.get(key)
-        if entry is None:
+        if entry is None or entry["batch"] is not batch or entry["X"] is not X:
             if len(self._graphs) >= 4096:
                 self._graphs.clear()
             self._graphs[key] = {"batch": batch, "X": X, "graph": None, "loss": None}   # keeps both alive
+            return self.train_step(batch, X)
+        generation = (self._buffer_generation, self.ws.generation)
+        if entry["graph"] is not None and entry["generation"] != generation:
+            # an engine buffer or the workspace was reallocated since the capture (a larger batch came by): the graph
+            # holds freed addresses -- drop it; this visit runs eagerly (it may grow buffers again), the next re-captures
+            entry["graph"], entry["loss"] = None, None
             return self.train_step(batch, X)
         if entry["graph"] is None:
             steps = {int(s["step"].item()) for s in states}
@@ -454,6 +548,7 @@ class GCNEngine:
             with torch.cuda.graph(graph):
                 entry["loss"] = self._train_step_capturable(batch, X)
             entry["graph"], entry["launches"] = graph, self.launch_count - launches
+            entry["generation"] = (self._buffer_generation, self.ws.generation)
             self.launch_count = launches
         # eager steps (first visits of other items) advance only the host counters: resynchronise the device one
         host_step = int(states[0]["step"].item())
@@ -466,6 +561,13 @@ class GCNEngine:
         for st in states:
             st["step"] += 1
         return entry["loss"]
+
+    def train_step_empty(self) -> None:
+        """The optimiser step of a rank whose shard of the step's graphs is empty (data parallel, fewer graphs than
+        ranks in the last chunk): zero gradients into the all-reduce, then the same Adam update as everyone else."""
+        self.grads_flat.zero_()
+        self.allreduce_grads()
+        self.apply_adam()
 
     def train_step(self, batch: GraphBatch, X: torch.Tensor, feature_param: Optional[torch.Tensor] = None,
                    feature_grad: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -112,6 +112,58 @@ class CSRGraph:
         return CSRGraph.from_edges(n, e, w)
 
 
+class AdjacencyFeatures:
+    """Stand-in for element [1] of a dataset item (`[graph, X, nx_graph, terminals]`, graphExtender.py:114) whose
+    features are the zero-padded adjacency rows of its graph -- what graphExtender always writes -- without holding
+    the dense [n, max_nodes] matrix (4 MB per graph at max_nodes = 1000).  `process_graphs_from_folder(...,
+    dense_features=False)` produces it; `.dense()` materialises the reference's tensor on demand."""
+    __slots__ = ("graph", "n_cols")
+
+    def __init__(self, graph: CSRGraph, n_cols: int):
+        self.graph, self.n_cols = graph, int(n_cols)
+
+    @property
+    def shape(self):
+        return (self.graph.n, self.n_cols)
+
+    def dense(self):
+        import torch
+        g = self.graph
+        out = torch.zeros(g.n, self.n_cols, dtype=torch.float32)
+        rows = np.repeat(np.arange(g.n), np.diff(g.rowptr))
+        out[torch.from_numpy(rows), torch.from_numpy(g.colidx.astype(np.int64))] = torch.from_numpy(g.weights)
+        return out
+
+
+NOT_ADJACENCY = ("dataset features are not the zero-padded adjacency rows of the graph; "
+                  "the fused max-cut loss takes its edge weights from the graph structure")
+
+
+def check_adjacency_features(handle: CSRGraph, X) -> int:
+    """The reference's loss reads its weights from `adjacency_matrix` (= the features, :380); the fused kernel reads
+    them from the graph, which is the same thing for every dataset graphExtender produces.  Verified per item where the
+    item lives (host tensors on the host), against the graph's own nnz entries: every edge position holds its weight
+    and nothing else is non-zero.  Anything else is refused rather than silently diverging.  Returns the feature width."""
+    if isinstance(X, AdjacencyFeatures):
+        if X.graph is not handle and (X.graph.n != handle.n or not np.array_equal(X.graph.colidx, handle.colidx)
+                                      or not np.array_equal(X.graph.rowptr, handle.rowptr)):
+            raise NotImplementedError(NOT_ADJACENCY)
+        return X.n_cols
+    import torch
+    if not torch.is_tensor(X) or X.dim() != 2 or X.shape[0] != handle.n:
+        raise NotImplementedError(NOT_ADJACENCY)
+    nnz = handle.number_of_edges()
+    if nnz and int(handle.colidx.max()) >= X.shape[1]:
+        raise NotImplementedError(NOT_ADJACENCY)
+    rows = torch.from_numpy(np.repeat(np.arange(handle.n), np.diff(handle.rowptr))).to(X.device)
+    cols = torch.from_numpy(handle.colidx.astype(np.int64)).to(X.device)
+    want = torch.from_numpy(handle.weights).to(device=X.device, dtype=X.dtype)
+    # duplicate-free CSR: nnz matching entries + exactly count_nonzero(weights) non-zeros overall == equality
+    if not torch.equal(X[rows, cols], want) or int(torch.count_nonzero(X)) != int(np.count_nonzero(handle.weights)):
+        raise NotImplementedError(NOT_ADJACENCY)
+    return int(X.shape[1])
+
+
 def from_networkx(nx_graph, **_ignored) -> CSRGraph:
     """Module-level spelling so that `dgl.from_networkx(nx_graph=...)` call sites keep working."""
     return CSRGraph.from_networkx(nx_graph)
@@ -172,6 +224,28 @@ class GraphBatch:
         w = np.ones(self.nnz, dtype=np.float32) if weights is None else np.asarray(weights, dtype=np.float32)
         self._finish(np.asarray(rowptr, dtype=np.int32), np.asarray(colidx, dtype=np.int32), w,
                      graph_ptr.astype(np.int32), check_degrees)
+        return self
+
+    @classmethod
+    def from_device_arrays(cls, rowptr, colidx, graph_ptr, sizes, max_nodes: Optional[int] = None,
+                           norm=None, coef=None) -> "GraphBatch":
+        """Adopt block-diagonal CSR arrays that already live on the device (a streamed batch: the arrays were copied
+        from pinned host memory on a copy stream).  Unit edge weights; degrees must have been validated by the caller
+        (no zero-degree rows) -- nothing here synchronises with the host.  `norm` / `coef` are optional preallocated
+        outputs.  No ELL plan is built (its construction reads a flag back)."""
+        from . import ops
+        self = cls.__new__(cls)
+        self.device = rowptr.device
+        self.sizes = np.asarray(sizes, dtype=np.int64)
+        self.num_graphs = int(self.sizes.shape[0])
+        self.num_nodes = int(self.sizes.sum())
+        self.nnz = int(colidx.numel())
+        self.rowptr, self.colidx, self.graph_ptr = rowptr, colidx, graph_ptr
+        self.unit_weights, self.wts_f32, self.wts_i32, self.integer_weights = True, None, None, True
+        self.norm, _ = ops.degree_norm(rowptr, self.num_nodes, count_zero=False, out=norm)
+        self.coef = ops.edge_coef(rowptr, colidx, None, self.norm, self.norm, self.num_nodes, out=coef)
+        self.max_nodes = int(max_nodes if max_nodes is not None else (self.sizes.max() if self.num_graphs else 0))
+        self.plan = None
         return self
 
     def _finish(self, rowptr, colidx, weights, graph_ptr, check_degrees):

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .graph import CSRGraph, GraphBatch
+from .graph import AdjacencyFeatures, CSRGraph, GraphBatch
 
 GraphLike = Union[CSRGraph, GraphBatch]
 
@@ -40,6 +40,17 @@ def as_batch(g: GraphLike) -> GraphBatch:
 
 def to_device_features(x: torch.Tensor, device) -> torch.Tensor:
     """Reference datasets hold CPU float32 tensors (graphExtender.py:110-114); upload once and cache."""
+    if isinstance(x, AdjacencyFeatures):
+        # implied features (graphExtender dense_features=False): densified on the device from the graph
+        key = ("adjacency", id(x))
+        hit = _FEATURE_CACHE.get(key)
+        if hit is None or hit[0] is not x:
+            if len(_FEATURE_CACHE) > 1024:
+                _FEATURE_CACHE.clear()
+            batch = as_batch(x.graph)
+            hit = (x, ops.densify(batch, x.n_cols, out=ops.padded_empty(batch.num_nodes, x.n_cols, batch.device)))
+            _FEATURE_CACHE[key] = hit
+        return hit[1]
     if x.is_cuda:
         return x if x.dtype == torch.float32 else x.float()
     key = (x.data_ptr(), tuple(x.shape), x._version)
@@ -176,7 +187,8 @@ class GCNSoftmax(nn.Module):
             raise ValueError(f"unknown precision {precision!r}")
         # 'bf16' is an engine (training-step) mode with resident bf16 operands; this generic autograd path keeps fp32
         # operands and runs them through the one-pass TF32 kernel instead
-        generic = "tf32" if precision == "bf16" else precision
+        # ('bf16x3' / 'bf16x2' are fp32-grade engine modes on integer features: the generic path uses tf32x3 for them)
+        generic = {"bf16": "tf32", "bf16x3": "tf32x3", "bf16x2": "tf32x3"}.get(precision, precision)
         self.conv1.gemm_precision = generic
         self.conv2.gemm_precision = generic
 

@@ -49,12 +49,14 @@ class Workspace:
 
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
+        self.generation = 0          # bumped on every reallocation (captured CUDA graphs hold the old address)
 
     def get(self, nbytes: int, device) -> Tuple[Optional[int], int]:
         if nbytes == 0:
             return None, 0
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
             self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self.generation += 1
         return self.buf.data_ptr(), self.buf.numel()
 
 
@@ -66,16 +68,22 @@ _SLAB_FUSED = os.environ.get("GMC_SLAB_FUSED", "0") == "1"
 
 
 # ---------------------------------------------------------------- graph preparation
-def degree_norm(rowptr: torch.Tensor, n_rows: int) -> Tuple[torch.Tensor, int]:
-    norm = torch.empty(n_rows, dtype=torch.float32, device=rowptr.device)
+def degree_norm(rowptr: torch.Tensor, n_rows: int, count_zero: bool = True,
+                out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[int]]:
+    """(norm, zero-degree rows).  count_zero=False skips the count and its host read-back (no synchronisation: for
+    callers that validated the degrees on the host already)."""
+    norm = out if out is not None else torch.empty(n_rows, dtype=torch.float32, device=rowptr.device)
+    if not count_zero:
+        check(lib().gmc_degree_norm_f32(rowptr.data_ptr(), n_rows, norm.data_ptr(), None, _stream()), "gmc_degree_norm_f32")
+        return norm, None
     zero = torch.zeros(1, dtype=torch.int32, device=rowptr.device)
     check(lib().gmc_degree_norm_f32(rowptr.data_ptr(), n_rows, norm.data_ptr(), zero.data_ptr(), _stream()),
           "gmc_degree_norm_f32")
     return norm, int(zero.item())
 
 
-def edge_coef(rowptr, colidx, vals, norm_src, norm_dst, n_rows: int) -> torch.Tensor:
-    coef = torch.empty(colidx.numel(), dtype=torch.float32, device=colidx.device)
+def edge_coef(rowptr, colidx, vals, norm_src, norm_dst, n_rows: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    coef = out if out is not None else torch.empty(colidx.numel(), dtype=torch.float32, device=colidx.device)
     check(lib().gmc_edge_coef_f32(rowptr.data_ptr(), colidx.data_ptr(), _ptr(vals), _ptr(norm_src), _ptr(norm_dst),
                                   n_rows, coef.data_ptr(), _stream()), "gmc_edge_coef_f32")
     return coef
@@ -338,6 +346,151 @@ def gemm_bf16(op: str, A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Ten
     check(lib().gmc_gemm_bf16(_OPS[op], A.data_ptr(), B.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
                               int(accumulate), wptr, wbytes, _stream()), "gmc_gemm_bf16")
     return out
+
+
+# ---------------------------------------------------------------- fp32-grade split-operand path (csrc/split.cu)
+def split_rows_for(k: int) -> int:
+    """Row stride between the stacked bf16 parts of a K-row operand (K rounded up to the 64-row k-block)."""
+    return (int(k) + 63) // 64 * 64
+
+
+def split_empty(rows: int, cols: int, n_split: int, device) -> torch.Tensor:
+    """Zeroed [n_split * split_rows_for(rows), cols] bf16 buffer (128-byte row pitch) for a split operand."""
+    return padded_empty_bf16(n_split * split_rows_for(rows), cols, device, zero=True)
+
+
+def f32_split_bf16(src: torch.Tensor, n_split: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [K, N] -> n_split stacked bf16 parts hi, lo [, lo2] with src = sum of the parts up to 2^-(8 n_split + 1)
+    relative; part p at rows [p * split_rows_for(K), ...); the pad rows of every part are written as zeros."""
+    src, lds = _rowmajor(src, "src")
+    k, n = src.shape
+    sr = split_rows_for(k)
+    if out is None:
+        out = split_empty(k, n, n_split, src.device)
+    out, ldd = _bf16_rowmajor(out, "out")
+    if out.shape[0] != n_split * sr or out.shape[1] != n:
+        raise ValueError(f"out must be [{n_split * sr}, {n}]")
+    check(lib().gmc_f32_split_bf16(src.data_ptr(), lds, out.data_ptr(), ldd, k, n, n_split, sr, _stream()),
+          "gmc_f32_split_bf16")
+    return out
+
+
+def row_scale(batch, count_nonuniform: bool = True, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[int]]:
+    """(s, nonuniform): s[v] = the A_hat coefficient of row v's edges, nonuniform = rows whose edges differ (such a
+    batch cannot take the integer-feature path).  count_nonuniform=False skips the count and its host read-back."""
+    s = out if out is not None else torch.empty(batch.num_nodes, dtype=torch.float32, device=batch.device)
+    if not count_nonuniform:
+        check(lib().gmc_row_scale_f32(batch.rowptr.data_ptr(), batch.coef.data_ptr(), batch.num_nodes, s.data_ptr(),
+                                      None, _stream()), "gmc_row_scale_f32")
+        return s, None
+    bad = torch.zeros(1, dtype=torch.int32, device=batch.device)
+    check(lib().gmc_row_scale_f32(batch.rowptr.data_ptr(), batch.coef.data_ptr(), batch.num_nodes, s.data_ptr(),
+                                  bad.data_ptr(), _stream()), "gmc_row_scale_f32")
+    return s, int(bad.item())
+
+
+def integer_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None,
+                          ones: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """XI = sum over neighbours of the zero-padded 0/1 adjacency rows (2-step path counts): (A_hat X) = s . XI for a
+    batch with one coefficient per row; small integers, exact in bf16.  Unit edge weights only.  `ones` is an optional
+    caller-owned fp32 vector of >= nnz ones (streamed batches reuse one instead of allocating per step)."""
+    if not batch.unit_weights:
+        raise ValueError("integer features need unit edge weights")
+    if ones is None:
+        ones = getattr(batch, "_unit_coef", None)
+        if ones is None or ones.numel() != batch.nnz:
+            ones = torch.ones(batch.nnz, dtype=torch.float32, device=batch.device)
+            batch._unit_coef = ones
+    elif ones.numel() < batch.nnz or ones.dtype != torch.float32:
+        raise ValueError("ones must be an fp32 vector with at least nnz entries")
+    if out is None:
+        out = padded_empty_bf16(batch.num_nodes, n_cols, batch.device, zero=True)
+    out, ld = _bf16_rowmajor(out, "out")
+    check(lib().gmc_csr_preaggregate_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), ones.data_ptr(), None,
+                                          batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
+                                          out.data_ptr(), ld, None, 0, _stream()), "gmc_csr_preaggregate_bf16")
+    return out
+
+
+class IntegerFeatures:
+    """XI (bf16 integers) + the per-row scale s with A_hat X = s . XI, for GCNEngine(precision='bf16x2' | 'bf16x3')."""
+    __slots__ = ("tensor", "scale")
+
+    def __init__(self, tensor: torch.Tensor, scale: torch.Tensor):
+        _bf16_rowmajor(tensor, "XI")
+        if scale.dtype != torch.float32 or scale.numel() != tensor.shape[0] or not scale.is_contiguous():
+            raise ValueError("scale must be a contiguous fp32 vector with one entry per row")
+        self.tensor, self.scale = tensor, scale
+
+    @classmethod
+    def from_batch(cls, batch, n_cols: int) -> "IntegerFeatures":
+        s, bad = row_scale(batch)
+        if bad:
+            raise ValueError(f"{bad} rows have neighbours of different degrees: no single A_hat coefficient per row")
+        return cls(integer_features_bf16(batch, n_cols), s)
+
+
+def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: int, k: int,
+                    out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+                    bias: Optional[torch.Tensor] = None, relu: bool = False, accumulate: bool = False,
+                    workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """C = op(A) (B_0 + ... + B_{n_split-1}) with bf16 A (exact) and the stacked bf16 parts of an fp32 B [k, N]
+    (f32_split_bf16 / skinny_bwd_split); fp32 accumulation and output.  op 'nn': A [M, k]; 'tn': A [k, M].
+    Optional fp32 epilogue C[m, n] = act(row_scale[m] * acc + bias[n])."""
+    A, lda = _bf16_rowmajor(A, "A")
+    B_split, ldb = _bf16_rowmajor(B_split, "B_split")
+    if op == "nn":
+        M, K = A.shape
+    elif op == "tn":
+        K, M = A.shape
+    else:
+        raise ValueError("gemm_bf16_split: op must be 'nn' or 'tn'")
+    if K != k:
+        raise ValueError(f"gemm_bf16_split {op}: inner dimensions differ ({K} vs {k})")
+    sr = split_rows_for(k)
+    if B_split.shape[0] < n_split * sr:
+        raise ValueError(f"B_split must hold {n_split} parts of {sr} rows")
+    N = B_split.shape[1]
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs an output tensor")
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    out, ldc = _rowmajor(out, "out")
+    if row_scale is not None and (_f32(row_scale, "row_scale").numel() != M or not row_scale.is_contiguous()):
+        raise ValueError(f"row_scale must be a contiguous fp32 vector of {M} elements")
+    if bias is not None and (_f32(bias, "bias").numel() != N or not bias.is_contiguous()):
+        raise ValueError(f"bias must be a contiguous fp32 vector of {N} elements")
+    ws = workspace or _default_ws
+    wptr, wbytes = ws.get(lib().gmc_gemm_bf16_split_workspace_bytes(_OPS[op], M, N, K, n_split), A.device)
+    check(lib().gmc_gemm_bf16_split(_OPS[op], A.data_ptr(), B_split.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
+                                    n_split, sr, _ptr(row_scale), _ptr(bias), int(relu), int(accumulate), wptr, wbytes,
+                                    _stream()), "gmc_gemm_bf16_split")
+    return out
+
+
+def skinny_bwd_split(dT: torch.Tensor, W: torch.Tensor, H: torch.Tensor, n_split: int, dH_split: torch.Tensor,
+                     row_scale: Optional[torch.Tensor] = None, dW: Optional[torch.Tensor] = None,
+                     dbias: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None):
+    """skinny_bwd with an fp32 H whose dHpre leaves as n_split stacked bf16 parts of row_scale . dHpre."""
+    dT, lddt = _rowmajor(dT, "dT")
+    H, ldh = _rowmajor(H, "H")
+    W = _f32(W, "W").contiguous()
+    n, n_in = H.shape
+    n_out = W.shape[1]
+    dH_split, lddh = _bf16_rowmajor(dH_split, "dH_split")
+    sr = split_rows_for(n)
+    if dH_split.shape[0] < n_split * sr or dH_split.shape[1] != n_in:
+        raise ValueError(f"dH_split must be [>= {n_split * sr}, {n_in}]")
+    if dW is None:
+        dW = torch.empty((n_in, n_out), dtype=torch.float32, device=H.device)
+    if dbias is None:
+        dbias = torch.empty(n_in, dtype=torch.float32, device=H.device)
+    ws = workspace or _default_ws
+    wptr, wbytes = ws.get(lib().gmc_skinny_bwd_workspace_bytes(n_in, n_out), H.device)
+    check(lib().gmc_skinny_bwd_split(dT.data_ptr(), lddt, W.data_ptr(), H.data_ptr(), ldh, _ptr(row_scale),
+                                     dH_split.data_ptr(), lddh, sr, n_split, dW.data_ptr(), dbias.data_ptr(), n, n_in,
+                                     n_out, wptr, wbytes, _stream()), "gmc_skinny_bwd_split")
+    return dH_split, dW, dbias
 
 
 # ---------------------------------------------------------------- bf16 layer-1 activations

@@ -20,6 +20,8 @@ from typing import Dict, List, Optional, Tuple  # noqa: F401
 
 import torch
 
+from gmc_b200.graph import AdjacencyFeatures
+
 TORCH_DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 TORCH_DTYPE = torch.float32
 
@@ -66,8 +68,11 @@ def _terminal_swap_plan(terminals: List[int]) -> Optional[Dict[int, int]]:
 
 def process_graphs_from_folder(all_graphs: Dict, all_terminals: Dict, max_nodes: int,
                                save_batch_size: Optional[int] = None,
-                               output_filename_prefix: str = "processed_graphs") -> Dict:
-    """Normalise terminals to nodes 0,1,2 and emit dataset tuples (reference :50-132)."""
+                               output_filename_prefix: str = "processed_graphs", dense_features: bool = True) -> Dict:
+    """Normalise terminals to nodes 0,1,2 and emit dataset tuples (reference :50-132).
+    dense_features=False (extension) puts an AdjacencyFeatures stand-in into slot [1] instead of the dense
+    [n, max_nodes] tensor (4 MB per graph at max_nodes = 1000): same 4-tuple format, the training / testing entry
+    points rebuild the features on the device from the graph, `.dense()` yields the reference's tensor."""
     datasetItem = {}
     i = 0
     skipped = 0
@@ -83,7 +88,12 @@ def process_graphs_from_folder(all_graphs: Dict, all_terminals: Dict, max_nodes:
             print(f"Terminal swapped {i}")
 
             handle = dgl.from_networkx(nx_graph=graph).to(TORCH_DEVICE)
-            full_matrix = adjacency_tensor(graph, max_nodes, TORCH_DTYPE)
+            if dense_features:
+                full_matrix = adjacency_tensor(graph, max_nodes, TORCH_DTYPE)
+            else:
+                if max_nodes < graph.number_of_nodes():
+                    raise ValueError("N should be greater than or equal to the original matrix size.")
+                full_matrix = AdjacencyFeatures(handle, max_nodes)
 
             datasetItem[i] = [handle, full_matrix, graph, [0, 1, 2]]
             i += 1

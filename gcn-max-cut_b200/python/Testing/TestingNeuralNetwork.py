@@ -281,8 +281,19 @@ def test_multiple_graphs_batched(model, processed_graphs: Dict, graph_sizes: Lis
         return [], results_by_size
     handles = [h if isinstance(h, CSRGraph) else CSRGraph.from_networkx(g) for _, _, h, _, g, _ in chosen]
     batch = GraphBatch(handles, device=dev)
-    feats = [to_device_features(X, dev) for _, _, _, X, _, _ in chosen]
-    X_all = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+    # features are verified per item to be the adjacency rows of their graph and then rebuilt on the device from the
+    # batch (no concatenation of the items' dense host tensors); anything else keeps the uploaded tensors
+    from gmc_b200.graph import check_adjacency_features
+    try:
+        widths = {check_adjacency_features(h, X) for h, (_, _, _, X, _, _) in zip(handles, chosen)}
+    except NotImplementedError:
+        widths = set()
+    if len(widths) == 1:
+        width = widths.pop()
+        X_all = _ops.densify(batch, width, out=_ops.padded_empty(batch.num_nodes, width, dev))
+    else:
+        feats = [to_device_features(X, dev) for _, _, _, X, _, _ in chosen]
+        X_all = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
     engine = GCNEngine(model, None, precision=getattr(model.conv1, "gemm_precision", "fp32"))
     with torch.no_grad():
         probs = engine.forward(batch, X_all).clone()

@@ -11,7 +11,11 @@ Opt-in extensions (defaults reproduce the reference exactly):
     TrainingConfig.batch_graphs      graphs per optimiser step (1 = the reference's sequential
                                      per-graph Adam steps; >1 = block-diagonal mini-batches with
                                      loss = sum of per-graph losses)
-    TrainingConfig.gemm_precision    'fp32' (FFMA, parity) | 'tf32' | 'tf32x3' (tcgen05)
+    TrainingConfig.gemm_precision    'fp32' (FFMA, parity) | 'tf32' | 'tf32x3' (tcgen05) | 'bf16x3' / 'bf16x2' (fp32-grade on
+                                     bf16 tensor cores: exact integer features x split weights, csrc/split.cu) | 'bf16'
+    TrainingConfig.stream_dataset    upload every step's graphs from pinned host memory (the reference moves each graph
+                                     to the device inside its loop, :371-373) instead of caching device batches
+    TrainingConfig.eval_batch_graphs graphs per block-diagonal forward pass in evaluate_model
     TrainingConfig.loss_mode         'ste' (reference live path) | 'soft' (north-star objective)
     TrainingConfig.use_terminal_penalty   enable the penalty the reference left commented (:308)
     TrainingConfig.adjacency_kernels  with feature_source='adjacency' and batch_graphs >= 32: the dataset features are
@@ -42,7 +46,8 @@ import torch.nn.functional as F  # noqa: F401
 
 from gmc_b200 import _lib as _gmc_lib
 from gmc_b200.engine import GCNEngine
-from gmc_b200.graph import CSRGraph, GraphBatch
+from gmc_b200.graph import NOT_ADJACENCY as _NOT_ADJACENCY
+from gmc_b200.graph import AdjacencyFeatures, CSRGraph, GraphBatch, check_adjacency_features
 from gmc_b200.model import GCNSoftmax, to_device_features
 from gmc_b200.optim import FusedAdam
 
@@ -87,6 +92,9 @@ class TrainingConfig:
     adjacency_kernels: bool = False          # batched steps only: X W1 / X^T dT1 as aggregations (csrc/spmm_adj.cu)
     activations: str = "fp32"                # 'bf16' (with gemm_precision='bf16'): layer-1 activations stored in bf16
     preaggregate_features: bool = False      # with bf16 / bf16: layer 1 as relu((A_hat X) W1 + b1), A_hat X built once
+    stream_dataset: bool = False             # keep the dataset in pinned host memory and upload every step's graphs (H2D on a
+                                             # copy stream, one step ahead) instead of caching device-resident batches
+    eval_batch_graphs: int = 64              # evaluate_model: graphs per block-diagonal forward pass
 
     def __post_init__(self):
         if self.feature_source not in ("adjacency", "embedding"):
@@ -224,22 +232,23 @@ def setup_model_and_optimizer(config: TrainingConfig):
 
 
 def _engine_for(net, optimizer, config: TrainingConfig) -> GCNEngine:
+    precision = getattr(config, "gemm_precision", "fp32")
+    adjacency = getattr(config, "feature_source", "adjacency") == "adjacency"
     key = (id(optimizer), float(config.C), getattr(config, "loss_mode", "ste"),
-           bool(getattr(config, "use_terminal_penalty", False)), float(config.penalty),
-           getattr(config, "gemm_precision", "fp32"),
-           bool(getattr(config, "adjacency_kernels", False))
-           and getattr(config, "feature_source", "adjacency") == "adjacency",
+           bool(getattr(config, "use_terminal_penalty", False)), float(config.penalty), precision,
+           bool(getattr(config, "adjacency_kernels", False)) and adjacency,
            getattr(config, "activations", "fp32"),
-           bool(getattr(config, "preaggregate_features", False))
-           and getattr(config, "feature_source", "adjacency") == "adjacency")
+           bool(getattr(config, "preaggregate_features", False)) and adjacency)
     cached = _ENGINES.get(net)
     if cached is not None and cached[0] == key:
         return cached[1]
     if optimizer is not None and not isinstance(optimizer, FusedAdam):
         raise TypeError("the B200 training loop needs the FusedAdam returned by setup_model_and_optimizer")
+    # adjacency_features: _prepare verifies that every item's features ARE the zero-padded adjacency rows of its graph
+    # before a batch reaches the engine, which is what the integer-feature GEMM path ('bf16x2' / 'bf16x3') relies on
     engine = GCNEngine(net, optimizer, C=config.C, loss_mode=key[2], override_terminals=True,
-                       penalty=config.penalty if key[3] else 0.0, precision=key[5], adjacency_kernels=key[6],
-                       activations=key[7], preaggregate=key[8])
+                       penalty=config.penalty if key[3] else 0.0, precision=precision, adjacency_kernels=key[6],
+                       activations=key[7], preaggregate=key[8], adjacency_features=adjacency)
     _ENGINES[net] = (key, engine)
     return engine
 
@@ -248,10 +257,11 @@ _ENGINES = weakref.WeakKeyDictionary()     # net -> (settings key, GCNEngine); n
 
 
 class _PreparedItem:
-    __slots__ = ("batch", "X")
+    __slots__ = ("batch", "X", "host", "n_graphs")
 
-    def __init__(self, batch, X):
-        self.batch, self.X = batch, X
+    def __init__(self, batch, X, host=None, n_graphs=None):
+        self.batch, self.X, self.host = batch, X, host
+        self.n_graphs = n_graphs if n_graphs is not None else (batch.num_graphs if batch is not None else 0)
 
 
 def _graph_handle(item) -> CSRGraph:
@@ -263,64 +273,282 @@ def _graph_handle(item) -> CSRGraph:
     return from_networkx(nx_graph)  # foreign handle (e.g. legacy DGL object): rebuild from networkx
 
 
+_check_item_features = check_adjacency_features
+
+
 def _check_features_are_adjacency(batch: GraphBatch, X: torch.Tensor) -> None:
-    """The reference's loss reads its weights from `adjacency_matrix` (= the features, :380).  The
-    fused kernel reads them from the graph instead, which is the same thing for every dataset
-    graphExtender produces; refuse anything else rather than silently diverge."""
+    """Device-side form of the same check for an already batched dense X (kept for callers that hold one)."""
     from gmc_b200 import ops
     want = ops.densify(batch, X.shape[1])
     if not torch.equal(want, X):
-        raise NotImplementedError("dataset features are not the zero-padded adjacency rows of the graph; "
-                                  "the fused max-cut loss takes its edge weights from the graph structure")
+        raise NotImplementedError(_NOT_ADJACENCY)
 
 
-def _prepare(dataset: Dict, batch_graphs: int, device) -> List[_PreparedItem]:
-    """Device-resident (GraphBatch, X) per optimiser step, cached on the dataset dict's identity."""
+def _engine_mode(engine: Optional[GCNEngine]) -> tuple:
+    if engine is None:
+        return ("dense", None)
+    if engine.split_fwd:
+        return ("integer", engine.F)
+    if engine.preaggregate:
+        return ("preaggregated", engine.F)
+    if engine.adjacency_kernels:
+        return ("sparse", engine.F)
+    return ("dense", None)
+
+
+def _device_features(batch: GraphBatch, width: int, engine: Optional[GCNEngine], mode: tuple):
+    """The step's feature operand, REBUILT on the device from the (verified) graph structure in the form the engine's
+    layer 1 wants -- never a concatenation of the items' dense host tensors."""
+    from gmc_b200 import ops
+    kind = mode[0]
+    if kind == "integer":
+        xi = engine._integer_features(batch, None)
+        if xi is not None:
+            return xi
+    elif kind == "preaggregated":
+        return ops.PreaggregatedFeatures(ops.preaggregate_features_bf16(batch, width))
+    elif kind == "sparse" and ops.adjacency_kernels_apply(batch, width):
+        return None
+    return ops.densify(batch, width, out=ops.padded_empty(batch.num_nodes, width, batch.device))
+
+
+def _dist_world() -> Tuple[int, int]:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _prepare(dataset: Dict, batch_graphs: int, device, engine: Optional[GCNEngine] = None,
+             stream: bool = False) -> List[_PreparedItem]:
+    """One (GraphBatch, features) pair per optimiser step, cached on the dataset dict's identity.
+
+    * every item's features are verified to be the adjacency rows of its graph (host-side, O(nnz) gather + one
+      count_nonzero); the device operand is then rebuilt from the graph (`_device_features`);
+    * under torch.distributed each step's chunk of `batch_graphs` graphs is sharded contiguously over the ranks
+      (gmc_b200.dist.shard_bounds): `batch_graphs` is the GLOBAL batch, so N ranks take the same optimiser steps as one;
+    * stream=True keeps each step's block-diagonal CSR in PINNED HOST memory instead (uploaded every step by
+      train_single_epoch, as the reference moves every graph to the device inside its loop, :371-373)."""
+    from gmc_b200 import dist as gdist
+    rank, world = _dist_world()
+    mode = _engine_mode(engine)
     cache = _PREPARED.get(id(dataset))
     keys = list(dataset.keys())
-    if cache is not None and cache[0] is dataset and cache[1] == (keys, batch_graphs):
+    sig = (keys, batch_graphs, mode, rank, world, bool(stream))
+    if cache is not None and cache[0] is dataset and cache[1] == sig:
         return cache[2]
     items = [dataset[k] for k in keys]
     steps: List[_PreparedItem] = []
-    for lo in range(0, len(items), max(1, batch_graphs)):
-        chunk = items[lo: lo + max(1, batch_graphs)]
+    bg = max(1, batch_graphs)
+    for lo in range(0, len(items), bg):
+        chunk = items[lo: lo + bg]
+        if world > 1:
+            a, b = gdist.shard_bounds(len(chunk), rank, world)
+            chunk = chunk[a:b]
+        if not chunk:
+            steps.append(_PreparedItem(None, None, n_graphs=0))        # this rank only joins the step's all-reduce
+            continue
         handles = [_graph_handle(it) for it in chunk]
+        widths = {_check_item_features(h, it[1]) for h, it in zip(handles, chunk)}
+        if len(widths) != 1:
+            raise ValueError(f"items of one step have different feature widths: {sorted(widths)}")
+        width = widths.pop()
+        if stream:
+            steps.append(_PreparedItem(None, None, host=_HostBatch(handles, width), n_graphs=len(handles)))
+            continue
         batch = GraphBatch(handles, device=device)
-        feats = [to_device_features(it[1], device) for it in chunk]
-        X = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
-        _check_features_are_adjacency(batch, X)
-        steps.append(_PreparedItem(batch, X))
+        steps.append(_PreparedItem(batch, _device_features(batch, width, engine, mode)))
     if len(_PREPARED) > 8:
         _PREPARED.clear()
-    _PREPARED[id(dataset)] = (dataset, (keys, batch_graphs), steps)
+    _PREPARED[id(dataset)] = (dataset, sig, steps)
     return steps
 
 
 _PREPARED: Dict[int, tuple] = {}
 
 
+class _HostBatch:
+    """Block-diagonal CSR of one step's graphs in pinned host memory (unit weights, degrees validated here so the
+    device side never has to read a flag back)."""
+
+    def __init__(self, handles: List[CSRGraph], width: int):
+        sizes = np.asarray([h.n for h in handles], dtype=np.int64)
+        nnzs = np.asarray([h.number_of_edges() for h in handles], dtype=np.int64)
+        gp = np.zeros(len(handles) + 1, dtype=np.int64)
+        np.cumsum(sizes, out=gp[1:])
+        ep = np.zeros(len(handles) + 1, dtype=np.int64)
+        np.cumsum(nnzs, out=ep[1:])
+        if gp[-1] >= 2 ** 31 - 1 or ep[-1] >= 2 ** 31 - 1:
+            raise ValueError("batch too large for int32 CSR indices; lower batch_graphs")
+        self.rowptr = torch.empty(int(gp[-1]) + 1, dtype=torch.int32).pin_memory()
+        self.colidx = torch.empty(int(ep[-1]), dtype=torch.int32).pin_memory()
+        self.graph_ptr = torch.from_numpy(gp.astype(np.int32)).pin_memory()
+        rp, ci = self.rowptr.numpy(), self.colidx.numpy()
+        rp[0] = 0
+        uniform = True
+        for i, h in enumerate(handles):
+            if not np.all(h.weights == 1.0):
+                raise NotImplementedError("stream_dataset=True supports unit edge weights (what GraphCreator writes)")
+            deg = np.diff(h.rowptr)
+            if h.n and deg.min() == 0:
+                from gmc_b200.graph import ZeroDegreeError
+                raise ZeroDegreeError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid.")
+            uniform = uniform and (h.n == 0 or deg.min() == deg.max())
+            rp[gp[i] + 1: gp[i + 1] + 1] = h.rowptr[1:] + ep[i]
+            ci[ep[i]: ep[i + 1]] = h.colidx + gp[i]
+        self.sizes, self.width = sizes, int(width)
+        self.num_nodes, self.nnz = int(gp[-1]), int(ep[-1])
+        self.max_nodes = int(sizes.max()) if len(handles) else 0
+        self.regular = bool(uniform)                  # every graph regular => one A_hat coefficient per row
+        self.nbytes = (self.rowptr.numel() + self.colidx.numel() + self.graph_ptr.numel()) * 4
+
+
+class _Streamer:
+    """Double-buffered upload of _HostBatch steps: the H2D copy of step i+1 runs on a copy stream while step i
+    computes; device buffers are reused across steps and epochs (no allocation in the loop)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slots = [dict(cap=(0, 0, 0)), dict(cap=(0, 0, 0))]
+        self.ones = None
+        self.feat = None
+        self.loss_host = None
+        self.stats = {"h2d_bytes": 0, "d2h_bytes": 0, "steps": 0}
+
+    def _slot(self, i: int, hb: _HostBatch) -> dict:
+        sl = self.slots[i]
+        need = (hb.rowptr.numel(), hb.colidx.numel(), hb.graph_ptr.numel())
+        if any(n > c for n, c in zip(need, sl["cap"])):
+            dev, i32, f32 = self.device, torch.int32, torch.float32
+            cap = tuple(max(n, c) for n, c in zip(need, sl["cap"]))
+            sl.update(cap=cap, rowptr=torch.empty(cap[0], dtype=i32, device=dev), colidx=torch.empty(cap[1], dtype=i32, device=dev),
+                      graph_ptr=torch.empty(cap[2], dtype=i32, device=dev), norm=torch.empty(cap[0], dtype=f32, device=dev),
+                      coef=torch.empty(cap[1], dtype=f32, device=dev), scale=torch.empty(cap[0], dtype=f32, device=dev),
+                      copied=torch.cuda.Event(), consumed=None)
+        return sl
+
+    def issue(self, i: int, hb: _HostBatch) -> None:
+        sl = self._slot(i, hb)
+        with torch.cuda.stream(self.copy_stream):
+            if sl["consumed"] is not None:
+                self.copy_stream.wait_event(sl["consumed"])          # the step that last read this slot has finished
+            sl["rowptr"][: hb.rowptr.numel()].copy_(hb.rowptr, non_blocking=True)
+            sl["colidx"][: hb.colidx.numel()].copy_(hb.colidx, non_blocking=True)
+            sl["graph_ptr"][: hb.graph_ptr.numel()].copy_(hb.graph_ptr, non_blocking=True)
+            sl["copied"].record(self.copy_stream)
+        self.stats["h2d_bytes"] += hb.nbytes
+
+    def batch(self, i: int, hb: _HostBatch) -> GraphBatch:
+        sl = self.slots[i]
+        torch.cuda.current_stream().wait_event(sl["copied"])
+        n, nnz = hb.num_nodes, hb.nnz
+        return GraphBatch.from_device_arrays(sl["rowptr"][: n + 1], sl["colidx"][:nnz], sl["graph_ptr"][: len(hb.sizes) + 1],
+                                             hb.sizes, hb.max_nodes, norm=sl["norm"][:n], coef=sl["coef"][:nnz])
+
+    def features(self, i: int, hb: _HostBatch, batch: GraphBatch, engine: GCNEngine, mode: tuple):
+        from gmc_b200 import ops
+        kind = mode[0]
+        if kind in ("integer", "preaggregated"):
+            if self.feat is None or self.feat.shape[0] < hb.num_nodes or self.feat.shape[1] != hb.width:
+                self.feat = ops.padded_empty_bf16(hb.num_nodes, hb.width, self.device, zero=True)
+        if kind == "integer" and hb.regular and hb.max_nodes <= hb.width and engine.H % 4 == 0 and engine.K <= 4:
+            if self.ones is None or self.ones.numel() < hb.nnz:
+                self.ones = torch.ones(hb.nnz, dtype=torch.float32, device=self.device)
+            scale, _ = ops.row_scale(batch, count_nonuniform=False, out=self.slots[i]["scale"][: hb.num_nodes])
+            xi = ops.integer_features_bf16(batch, hb.width, out=self.feat[: hb.num_nodes], ones=self.ones)
+            return ops.IntegerFeatures(xi, scale)
+        if kind == "preaggregated":
+            return ops.PreaggregatedFeatures(ops.preaggregate_features_bf16(batch, hb.width, out=self.feat[: hb.num_nodes]))
+        if self.feat is None or self.feat.dtype != torch.float32 or self.feat.shape[0] < hb.num_nodes or self.feat.shape[1] != hb.width:
+            self.feat = ops.padded_empty(hb.num_nodes, hb.width, self.device)
+        return ops.densify(batch, hb.width, out=self.feat[: hb.num_nodes])
+
+    def done(self, i: int) -> None:
+        ev = torch.cuda.Event()
+        ev.record()
+        self.slots[i]["consumed"] = ev
+
+    def read_loss(self, losses: torch.Tensor, out: List[torch.Tensor]) -> None:
+        """D2H of the step's per-graph losses into pinned memory (asynchronous; summed after the epoch's sync)."""
+        host = torch.empty(losses.numel(), dtype=losses.dtype).pin_memory()
+        host.copy_(losses, non_blocking=True)
+        out.append(host)
+        self.stats["d2h_bytes"] += losses.numel() * losses.element_size()
+        self.stats["steps"] += 1
+
+
+_STREAMERS = weakref.WeakKeyDictionary()      # GCNEngine -> _Streamer
+
+
+def _train_epoch_streamed(engine: GCNEngine, steps: List[_PreparedItem], device) -> float:
+    st = _STREAMERS.get(engine)
+    if st is None:
+        st = _Streamer(device)
+        _STREAMERS[engine] = st
+    mode = _engine_mode(engine)
+    live = [s for s in steps if s.host is not None]
+    host_losses: List[torch.Tensor] = []
+    if live:
+        st.issue(0, live[0].host)
+    j = 0
+    for step in steps:
+        if step.host is None:
+            engine.train_step_empty()
+            continue
+        slot = j & 1
+        if j + 1 < len(live):
+            st.issue(slot ^ 1, live[j + 1].host)
+        batch = st.batch(slot, step.host)
+        feats = st.features(slot, step.host, batch, engine, mode)
+        losses = engine.train_step(batch, feats)
+        st.read_loss(losses, host_losses)
+        st.done(slot)
+        j += 1
+    torch.cuda.current_stream().synchronize()
+    return float(sum(float(h.sum()) for h in host_losses))
+
+
 def train_single_epoch(dataset: Dict, net, optimizer, embed, config: TrainingConfig,
                        dataset_files: Optional[List[str]] = None) -> float:
     """One pass over the dataset: forward, override, STE, loss, backward, Adam per graph, in dict
     order (reference :341-390).  Returns the summed loss.  The per-graph `.item()` host sync of the
-    reference (:388) is replaced by one device-side accumulation read back once per epoch."""
+    reference (:388) is replaced by one device-side accumulation read back once per epoch.
+    Under torch.distributed every rank trains its shard of each step's graphs and the returned loss
+    is the sum over all ranks."""
     device = _gmc_lib.require_cuda()
     net.train()
+    if float(getattr(net, "dropout_frac", 0.0) or 0.0) > 0.0:
+        raise NotImplementedError(
+            "TrainingConfig.dropout > 0: the fused training step has no dropout between the GraphConv layers "
+            "(reference :82 applies F.dropout in training mode); train through the autograd path "
+            "(loss = compute_loss(apply_max_to_one_hot(override_fixed_nodes(net(g, x))), ...); loss.backward(); "
+            "optimizer.step()), which honours it, or set dropout=0.0 (the reference default)")
     engine = _engine_for(net, optimizer, config)
     if dataset_files is None:
         dataset_files = ["./nx_test_generated_graph_n200_300_d8_12_t500.pkl"]
+    rank, world = _dist_world()
+    embedding_mode = getattr(config, "feature_source", "adjacency") == "embedding"
+    streamed = bool(getattr(config, "stream_dataset", False)) and not embedding_mode
     total = torch.zeros((), dtype=torch.float64, device=device)
     for dataset_file in dataset_files:
         current = dataset if isinstance(dataset, dict) else open_file(dataset_file)
-        embedding_mode = getattr(config, "feature_source", "adjacency") == "embedding"
-        for step in _prepare(current, int(getattr(config, "batch_graphs", 1)), device):
-            if embedding_mode:
-                losses = _embedding_step(engine, step, embed)
+        steps = _prepare(current, int(getattr(config, "batch_graphs", 1)), device, engine, stream=streamed)
+        if streamed:
+            total += _train_epoch_streamed(engine, steps, device)
+            continue
+        for step in steps:
+            if step.batch is None:
+                engine.train_step_empty()
+            elif embedding_mode:
+                total += _embedding_step(engine, step, embed).sum()
             elif _USE_CUDA_GRAPHS:
-                losses = engine.train_step_graphed(step.batch, step.X)   # launch-bound per-graph steps: graph replay
+                total += engine.train_step_graphed(step.batch, step.X).sum()   # launch-bound per-graph steps: graph replay
             else:
-                losses = engine.train_step(step.batch, step.X)
-            total += losses.sum()
+                total += engine.train_step(step.batch, step.X).sum()
+    if world > 1:
+        from gmc_b200 import dist as gdist
+        gdist.all_reduce_sum_(total)
     return float(total.item())
 
 
@@ -440,12 +668,42 @@ def evaluate_model(model, dataset: Dict, config: TrainingConfig) -> Dict:
     engine = cached[1] if cached is not None else _engine_for(model, None, config)
     total = torch.zeros((), dtype=torch.float64, device=device)
     num_samples = 0
-    for step in _prepare(dataset, 1, device):
+    # block-diagonal batches: per-graph losses are independent of their batch mates, so the sums equal the reference's
+    # per-graph loop (:553-562); never sharded -- every rank evaluates the whole dataset, as the reference would
+    per_batch = max(1, int(getattr(config, "eval_batch_graphs", 64)))
+    for step in _prepare_eval(dataset, per_batch, device, engine):
         total += engine.evaluate(step.batch, step.X).sum()
         num_samples += step.batch.num_graphs
     total_loss = float(total.item())
     return {"average_loss": total_loss / num_samples if num_samples > 0 else 0,
             "total_loss": total_loss, "num_samples": num_samples}
+
+
+def _prepare_eval(dataset: Dict, per_batch: int, device, engine: GCNEngine) -> List[_PreparedItem]:
+    """_prepare without data-parallel sharding (cached separately from the training steps)."""
+    mode = _engine_mode(engine)
+    keys = list(dataset.keys())
+    sig = (keys, per_batch, mode)
+    cache = _PREPARED_EVAL.get(id(dataset))
+    if cache is not None and cache[0] is dataset and cache[1] == sig:
+        return cache[2]
+    items = [dataset[k] for k in keys]
+    steps: List[_PreparedItem] = []
+    for lo in range(0, len(items), per_batch):
+        chunk = items[lo: lo + per_batch]
+        handles = [_graph_handle(it) for it in chunk]
+        widths = {_check_item_features(h, it[1]) for h, it in zip(handles, chunk)}
+        if len(widths) != 1:
+            raise ValueError(f"items of one evaluation batch have different feature widths: {sorted(widths)}")
+        batch = GraphBatch(handles, device=device)
+        steps.append(_PreparedItem(batch, _device_features(batch, widths.pop(), engine, mode)))
+    if len(_PREPARED_EVAL) > 8:
+        _PREPARED_EVAL.clear()
+    _PREPARED_EVAL[id(dataset)] = (dataset, sig, steps)
+    return steps
+
+
+_PREPARED_EVAL: Dict[int, tuple] = {}
 
 
 def load_neural_model(model_path: str, config: TrainingConfig):

@@ -316,6 +316,34 @@ int gmc_adj_features_bwd_f32(const void* plan, const int32_t* graph_ptr, int32_t
                              int64_t lddw, int32_t n_w_rows, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/* ---- (b'') fp32-grade layer-1 transforms at bf16 tensor-core rates (engine precision 'bf16x3') ----------------
+ * The reference computes both GraphConv layers in fp32 (TORCH_DTYPE, TrainingNeural.py:33-34; th.matmul of layer 1 at
+ * :80 through dgl GraphConv).  For a batch whose rows have ONE normalisation coefficient each (every regular graph) the
+ * pre-aggregated features factor as (A_hat X)[v,:] = s_v * XI[v,:] with XI = sum over neighbours of the 0/1 adjacency
+ * rows: small integers, exact in bf16 (gmc_csr_preaggregate_bf16 with unit coefficients builds XI; gmc_row_scale_f32
+ * yields s and counts rows whose coefficients differ).  The remaining fp32 operand -- W1 forward, s . dH1pre backward --
+ * is split into n_split bf16 parts hi + lo (+ lo2) (8 mantissa bits each: 16 / 24 bits), stored as stacked matrices
+ * (part p at rows [p * split_rows, p * split_rows + n_rows); rows up to split_rows must be zero, split_rows >= K
+ * rounded up to 64).  gmc_gemm_bf16_split multiplies the exact A tile with all parts in one tcgen05.mma per k-step
+ * (A is staged once for n_split products), accumulates in fp32 TMEM and adds the partial accumulators in the epilogue:
+ *   op 0 (nn): C[M,N] = act(row_scale[m] * (A[M,K] (B_0 + B_1 [+ B_2])) + bias[n])      H1 = relu(s . (XI W1) + b1)
+ *   op 2 (tn): C[M,N] (+)= A[K,M]^T (B_0 + B_1 [+ B_2]), split-K over the workspace      dW1 = XI^T (s . dH1pre)
+ * row_scale / bias (N % 4 == 0) / relu are nullable / 0 and need accumulate == 0 (they disable split-K).
+ * gmc_skinny_bwd_split is gmc_skinny_bwd_f32 (fp32 H) whose dHpre leaves as those stacked parts, pre-scaled by s. */
+int gmc_f32_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t n_rows, int32_t n_cols,
+                       int32_t n_split, int64_t split_rows, void* stream);
+int gmc_row_scale_f32(const int32_t* rowptr, const float* coef, int64_t n_rows, float* row_scale,
+                      int32_t* nonuniform_count /* device, nullable, incremented */, void* stream);
+size_t gmc_gemm_bf16_split_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t n_split);
+int gmc_gemm_bf16_split(int32_t op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K,
+                        int64_t lda, int64_t ldb, int64_t ldc, int32_t n_split, int64_t b_split_rows,
+                        const float* row_scale, const float* bias, int32_t relu, int32_t accumulate, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh,
+                         const float* row_scale, void* dH_split, int64_t lddh, int64_t split_rows, int32_t n_split,
+                         float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- (e) integer post-processing ------------------------------------------------------ */
 
 /* labels[v] = first argmax_k P[v,k]; the first min(3,n_g) nodes of each graph are forced to

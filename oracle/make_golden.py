@@ -253,6 +253,116 @@ def gen_testing(ref):
     np.savez_compressed(os.path.join(OUT, "testing.npz"), **out)
 
 
+def w1_digest(W: np.ndarray) -> dict:
+    """Compact but covering summary of a [1000, 500] matrix (2 MB in full): every 16th row verbatim, all row sums, all
+    column sums and the Frobenius norm -- each entry enters two of the linear functionals."""
+    W = np.asarray(W, dtype=np.float64)
+    return {"rows16": W[::16].astype(np.float32), "rowsum": W.sum(1), "colsum": W.sum(0),
+            "fro": np.float64(np.sqrt((W * W).sum()))}
+
+
+def gen_baseline_shapes(ref):
+    """BASELINE.json config 1 at its real shapes, executed by the reference itself: n = 500, 1000 features, hidden 500.
+    (a) one graph: forward, override + STE loss, autograd gradients (TrainingNeural.py:371-385);
+    (b) the 20-graph pipeline of complete_training_pipeline.ipynb cell 15 for two epochs through train_model
+        (:392-484): loss history + final weights;
+    (c) config 2: test_multiple_graphs with 200 post-processing iterations on one graph per size 50 .. 500
+        (TestingNeuralNetwork.py:188-295) with the model (b) trained.
+    Weights are numpy-seeded (set_weights with default_rng(seed)); the tests regenerate them from the same seeds, so
+    only outputs and the (swapped) edge lists are stored."""
+    T, Te = ref.training, ref.testing
+    out = {}
+    # ---- (a) single step
+    rng = np.random.default_rng(101)
+    out["a_weight_seed"] = np.int64(101)
+    g = ref.creator.generate_graph(n=500, d=7, graph_type="reg", random_seed=1000)
+    with quiet():
+        ds = ref.extender.process_graphs_from_folder({0: g}, {0: [17, 250, 433]}, max_nodes=1000)
+    dgl_g, X, nx_g, _ = ds[0]
+    cfg = T.TrainingConfig(n_nodes=1000, dim_embedding=1000, hidden_dim=500, learning_rate=1e-3)
+    net, embed, opt = T.setup_model_and_optimizer(cfg)
+    set_weights(net, rng)
+    net.train()
+    P = net(dgl_g, X)
+    s = T.apply_max_to_one_hot(T.override_fixed_nodes(P))
+    loss = T.compute_loss(s, X, cfg.A, cfg.C, cfg.penalty)
+    opt.zero_grad()
+    loss.backward()
+    out["a_edges"] = edges_of(nx_g).astype(np.int16)
+    out["a_P"] = P.detach().numpy().copy()
+    out["a_loss"] = np.float64(loss.item())
+    for k, prm in net.named_parameters():
+        if k == "conv1.weight":
+            for kk, v in w1_digest(prm.grad.numpy()).items():
+                out[f"a_grad_{k}_{kk}"] = v
+        else:
+            out[f"a_grad_{k}"] = prm.grad.numpy().copy()
+    # ---- (b) 20 graphs x 2 epochs
+    random.seed(0)
+    graphs, terms = {}, {}
+    for i in range(20):
+        graphs[i] = ref.creator.generate_graph(n=500, d=random.randint(6, 8), graph_type="reg", random_seed=1000 + i)
+        terms[i] = ref.creator.generate_unique_terminals(500, 3)
+    with quiet():
+        ds = ref.extender.process_graphs_from_folder(graphs, terms, max_nodes=1000)
+    out["b_num_graphs"] = np.int32(len(ds))
+    for i, item in ds.items():
+        out[f"b_g{i}_edges"] = edges_of(item[2]).astype(np.int16)
+    cfg = T.TrainingConfig(n_nodes=1000, dim_embedding=1000, hidden_dim=500, learning_rate=1e-3, number_epochs=2,
+                           patience=20, save_directory=None)
+    rng_b = np.random.default_rng(202)
+    out["b_weight_seed"] = np.int64(202)
+    real_setup = T.setup_model_and_optimizer
+
+    def patched(config):
+        net, embed, opt = real_setup(config)
+        set_weights(net, rng_b)
+        return net, embed, opt
+
+    T.setup_model_and_optimizer = patched
+    try:
+        with quiet():
+            net, best_loss, epoch, inputs, hist = T.train_model(ds, cfg)
+    finally:
+        T.setup_model_and_optimizer = real_setup
+    out["b_loss_history"] = np.asarray(hist, dtype=np.float64)
+    out["b_best_loss"] = np.float64(best_loss)
+    for k, prm in net.named_parameters():
+        if k == "conv1.weight":
+            for kk, v in w1_digest(prm.detach().numpy()).items():
+                out[f"b_final_{k}_{kk}"] = v
+        else:
+            out[f"b_final_{k}"] = prm.detach().numpy().copy()
+    with torch.no_grad():
+        ev = T.evaluate_model(net, ds, cfg)
+    out["b_eval_total"] = np.float64(ev["total_loss"])
+    # ---- (c) config 2 on the trained model: one graph per size, 200 iterations
+    sizes = [50, 100, 200, 300, 500]
+    random.seed(5)
+    tg, tt = {}, {}
+    for size in sizes:
+        name = f"test_n{size}_0"
+        tg[name] = ref.creator.generate_graph(n=size, d=random.randint(6, 8), graph_type="reg", random_seed=size * 1000)
+        tt[name] = ref.creator.generate_unique_terminals(size, 3)
+    with quiet():
+        tds = ref.extender.process_graphs_from_folder(tg, tt, max_nodes=1000)
+    net.eval()
+    np.random.seed(0)
+    with quiet():
+        results, _ = Te.test_multiple_graphs(net, tds, sizes, post_processing_iterations=200, verbose=False)
+    out["c_num_results"] = np.int32(len(results))
+    for i, r in enumerate(results):
+        out[f"c_r{i}_edges"] = edges_of(tds[i][2]).astype(np.int16)
+        out[f"c_r{i}_n"] = np.int32(r["nodes"])
+        out[f"c_r{i}_simple_cut"] = np.int64(r["simple_cut"])
+        out[f"c_r{i}_post_cut"] = np.int64(r["post_cut"])
+        out[f"c_r{i}_simple_assignment"] = np.asarray(r["simple_assignment"], dtype=np.int8)
+        out[f"c_r{i}_post_assignment"] = np.asarray(r["post_assignment"], dtype=np.int8)
+        out[f"c_r{i}_P"] = r["node_probabilities"].astype(np.float32)
+    out["c_rng_after"] = np.float64(np.random.rand())
+    np.savez_compressed(os.path.join(OUT, "baseline_shapes.npz"), **out)
+
+
 def main():
     if not ref_import.available():
         raise SystemExit("reference tree not available; fixtures can only be generated in the build container")
@@ -264,6 +374,7 @@ def main():
     gen_postproc(ref)
     gen_extender(ref)
     gen_testing(ref)
+    gen_baseline_shapes(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

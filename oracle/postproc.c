@@ -32,11 +32,12 @@ int64_t orc_cut_value(const int32_t* rowptr, const int32_t* colidx, const int32_
 /* python/Testing/TestingNeuralNetwork.py:18-46  assign_partitions.
  * Nodes 0,1,2 -> 0,1,2; every later node draws one uniform `r` and takes the first
  * class i with r < cumsum_i, else the last class.  The cumulative sum starts from
- * the Python int 0 and adds numpy float32 scalars, i.e. it is a float32 running
- * sum (0 + p0 == p0 exactly).  The comparison `rand_val < cumulative_prob` is
- * float64 under the reference's pinned numpy 1.x (legacy value-based promotion)
- * and float32 under numpy >= 2 (NEP 50: the Python float is "weak");
- * `compare_f32` selects which (last bullet). */
+ * the Python int 0 and adds numpy float32 scalars.  Under numpy >= 2 (NEP 50: Python
+ * scalars are "weak") the sum stays float32 and `rand_val < cumulative_prob` compares
+ * in float32; under the reference's pinned numpy 1.x (legacy promotion, scalar with
+ * scalar) `0 + np.float32` is float64, so the running sum is the float64 sum of the
+ * float32 probabilities and the comparison is float64.  `compare_f32` selects which
+ * (last bullet). */
 void orc_assign_partitions(const float* P, int32_t n, int32_t K, const double* U,
                            int32_t compare_f32, int32_t* out)
 {
@@ -45,10 +46,12 @@ void orc_assign_partitions(const float* P, int32_t n, int32_t K, const double* U
     for (int32_t v = 3; v < n; ++v) {
         double r = U[v - 3];
         volatile float cum = 0.0f;
+        volatile double cum64 = 0.0;
         int32_t pick = K - 1;
         for (int32_t i = 0; i < K; ++i) {
             cum = cum + P[(int64_t)v * K + i];
-            int hit = compare_f32 ? ((float)r < cum) : (r < (double)cum);
+            cum64 = cum64 + (double)P[(int64_t)v * K + i];
+            int hit = compare_f32 ? ((float)r < cum) : (r < cum64);
             if (hit) { pick = i; break; }
         }
         out[v] = pick;

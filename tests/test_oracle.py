@@ -118,6 +118,48 @@ def test_step_matches_reference_fixture(tag):
         np.testing.assert_allclose(t.numpy(), z[f"{tag}_step3_{name}"], rtol=1e-4, atol=1e-6)
 
 
+def test_single_step_at_baseline_shapes_matches_reference_fixture():
+    """BASELINE config 1 at its real shapes (n = 500, 1000 features, hidden 500): the restatement against the
+    reference's own forward, loss and autograd gradients (baseline_shapes.npz part a)."""
+    from golden_util import assert_w1_digest, gcn_shapes, seeded_weights
+    z = load("baseline_shapes.npz")
+    csr = rs.csr_from_networkx(graph_from_edges(z["a_edges"], 500))
+    X = rs.dense_adjacency(csr, 1000)
+    w = seeded_weights(np.random.default_rng(int(z["a_weight_seed"])), gcn_shapes(1000, 500))
+    p = rs.GCNParams(*[w[k] for k in ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias")])
+    fwd = rs.gcn_forward(csr, X, p)
+    np.testing.assert_allclose(fwd["P"].numpy(), z["a_P"], rtol=1e-4, atol=1e-7)
+    lg = rs.ste_loss_and_grads(csr, fwd["P"], C=1.0)
+    assert abs(float(lg["loss"]) - float(z["a_loss"])) <= 1e-4 * abs(float(z["a_loss"]))
+    grads = rs.gcn_backward(csr, X, p, fwd, lg["dZ"])
+    assert_w1_digest(grads["W1"].numpy(), z, "a_grad_conv1.weight", 1e-4)
+    for k, name in (("b1", "conv1.bias"), ("W2", "conv2.weight"), ("b2", "conv2.bias")):
+        ref = z[f"a_grad_{name}"]
+        assert np.abs(grads[k].numpy() - ref).max() <= 1e-4 * (np.abs(ref).max() + 1e-12), name
+
+
+def test_two_epochs_at_baseline_shapes_match_reference_fixture():
+    """The 20-graph pipeline of complete_training_pipeline.ipynb cell 15 for two epochs (40 sequential Adam steps at
+    n = 500, hidden 500): loss history and final weights of the restatement against the reference's train_model run."""
+    from golden_util import assert_w1_digest, gcn_shapes, seeded_weights
+    z = load("baseline_shapes.npz")
+    w = seeded_weights(np.random.default_rng(int(z["b_weight_seed"])), gcn_shapes(1000, 500))
+    p = rs.GCNParams(*[w[k] for k in ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias")])
+    st = rs.AdamState()
+    items = []
+    for i in range(int(z["b_num_graphs"])):
+        csr = rs.csr_from_networkx(graph_from_edges(z[f"b_g{i}_edges"], 500))
+        items.append((csr, rs.dense_adjacency(csr, 1000)))
+    hist = []
+    for _ in range(2):
+        hist.append(sum(rs.train_step_closed_form(csr, X, p, st) for csr, X in items))
+    np.testing.assert_allclose(hist, z["b_loss_history"], rtol=1e-4)
+    assert_w1_digest(p.W1.numpy(), z, "b_final_conv1.weight", 2e-4)
+    for t, name in ((p.b1, "conv1.bias"), (p.W2, "conv2.weight"), (p.b2, "conv2.bias")):
+        ref = z[f"b_final_{name}"]
+        assert np.abs(t.numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-12), name
+
+
 def test_faithful_port_matches_closed_form():
     g = nx.random_regular_graph(d=6, n=30, seed=3)
     csr = rs.csr_from_networkx(g)
