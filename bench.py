@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--hidden", type=int, default=500)
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "bf16"),
-                    choices=["fp32", "tf32", "tf32x3", "bf16"])
+                    choices=["fp32", "tf32", "tf32x3", "bf16", "bf16x3", "bf16x2"])
     ap.add_argument("--activations", default=os.environ.get("GMC_BENCH_ACTIVATIONS", "bf16"), choices=["fp32", "bf16"],
                     help="storage type of the four [nodes, hidden] layer-1 tensors (T1, H1, dH1pre, dT1); bf16 needs "
                          "--precision bf16.  Arithmetic is fp32 either way")
@@ -89,6 +89,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=8, help="graphs per reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short config 1 / config 2 runs of the default line")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(--steps, 10)")
     args = ap.parse_args()
     if args.workload == "config5":
@@ -278,18 +279,18 @@ def run_b200_arm(args):
     t_gen = time.perf_counter()
     rowptr, colidx, graph_ptr = synth.regular_batch_arrays(B, n, degs, seed=args.seed + 1000 * rank)
     t_gen = time.perf_counter() - t_gen
-    h_rowptr = torch.from_numpy(rowptr).pin_memory()
-    h_colidx = torch.from_numpy(colidx).pin_memory()
-    h_gptr = torch.from_numpy(graph_ptr).pin_memory()
     batch = GraphBatch.from_arrays(rowptr, colidx, graph_ptr, device=dev)
     N, nnz = batch.num_nodes, batch.nnz
     embedding = args.feature_source == "embedding"
     sparse_adj = args.feature_source == "adjacency-sparse"
+    split = args.precision in ("bf16x3", "bf16x2") and not embedding and not sparse_adj
     torch.manual_seed(args.seed)                        # identical initial weights on every rank
     cfg = T.TrainingConfig(n_nodes=n, dim_embedding=F, hidden_dim=H, number_classes=K, learning_rate=1e-3,
                            gemm_precision=args.precision, batch_graphs=B)
     net, embed, opt = T.setup_model_and_optimizer(cfg)
+    init_state = {k: v.detach().clone() for k, v in net.state_dict().items()}
     del embed
+    embed_api = torch.nn.Embedding(1, 1)                 # placeholder for the API's unused `embed` argument (:332-336)
     x_param = x_grad = None
     if embedding:
         # learned node embeddings: one [N, F] table per GPU (rows never leave the rank), 128-byte row pitch;
@@ -310,14 +311,18 @@ def run_b200_arm(args):
                              ">= 32 graphs, n <= 1024 <= features + 24)")
     elif args.precision == "bf16":
         X = ops.densify_bf16(batch, F)                   # dense padded adjacency rows in bf16 (0/1: exact), 128-byte pitch
+    elif split:
+        X = None                                         # integer features XI + row scale, built from the graph below
     else:
         X = ops.densify(batch, F, out=ops.padded_empty(N, F, dev))   # dense padded adjacency rows, 128-byte row pitch
     preagg = args.layer1 == "preaggregated" and args.workload == "config3"
     eng = GCNEngine(net, opt, precision=args.precision, adjacency_kernels=sparse_adj, activations=args.activations,
-                    preaggregate=preagg)
+                    preaggregate=preagg, adjacency_features=split)
     act16 = args.activations == "bf16" and (preagg or eng._b16_activations(batch))
     XA = None
-    if preagg:
+    if split:
+        feats = ops.IntegerFeatures.from_batch(batch, F)
+    elif preagg:
         # A_hat X straight from the graph (49 entries per row at d = 7), bf16, 128-byte pitch: the resident input of the step
         XA = ops.preaggregate_features_bf16(batch, F)
         feats = ops.PreaggregatedFeatures(XA)
@@ -361,90 +366,52 @@ def run_b200_arm(args):
     value = total_graphs * args.steps / (ms_max / 1000.0)
     last_loss = float(loss.sum().item())
 
-    # ---- end-to-end: host CSR buffers in, loss out, every step -------------------------------
+    # ---- end-to-end THROUGH THE DROP-IN API: a host dataset dict in graphExtender's 4-tuple format -> ---------------
+    # Training.TrainingNeural.train_single_epoch(dataset, net, optimizer, embed, config) with stream_dataset=True: every
+    # optimiser step uploads its graphs' CSR from pinned host memory (copy stream, one step ahead), rebuilds the degree
+    # norms / A_hat coefficients / layer-1 features on the device, trains, and reads the per-graph losses back
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not embedding and not sparse_adj:
         k_e2e = args.e2e_steps or min(args.steps, 10)
-        # two sets of device CSR buffers: the H2D copy of step i+1 (copy stream) overlaps the compute of step i --
-        # an input prefetch as any data loader does it; every step's inputs still cross PCIe inside the timed region
-        d_bufs = [(torch.empty_like(batch.rowptr), torch.empty_like(batch.colidx), torch.empty_like(batch.graph_ptr))
-                  for _ in range(2)]
-        copy_stream = torch.cuda.Stream()
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def issue_copy(slot):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[slot])               # the step that last read this slot has finished
-                d_bufs[slot][0].copy_(h_rowptr, non_blocking=True)
-                d_bufs[slot][1].copy_(h_colidx, non_blocking=True)
-                d_bufs[slot][2].copy_(h_gptr, non_blocking=True)
-                copied[slot].record(copy_stream)
-
-        def e2e_step(i, prefetch_next=True):
-            slot = i & 1
-            if prefetch_next:
-                issue_copy(slot ^ 1)
-            torch.cuda.current_stream().wait_event(copied[slot])
-            d_rowptr, d_colidx, d_gptr = d_bufs[slot]
-            b2 = GraphBatch.__new__(GraphBatch)
-            b2.device, b2.num_graphs, b2.sizes, b2.num_nodes, b2.nnz = dev, B, batch.sizes, N, nnz
-            b2.rowptr, b2.colidx, b2.graph_ptr, b2.max_nodes = d_rowptr, d_colidx, d_gptr, batch.max_nodes
-            b2.unit_weights, b2.wts_f32, b2.wts_i32, b2.integer_weights = True, None, None, True
-            b2.norm, _zero = ops.degree_norm(d_rowptr, N)            # includes the zero-degree check read-back
-            b2.coef = ops.edge_coef(d_rowptr, d_colidx, None, b2.norm, b2.norm, N)
-            if preagg:
-                # device-side graphExtender + layer-1 aggregation of the features, rebuilt from this step's graph
-                b2.plan = None
-                ops.preaggregate_features_bf16(b2, F, out=XA)
-                per_graph = train_step(b2, feats)
-                consumed[slot].record()
-                return per_graph.cpu()
-            b2.plan = (ops.spmm_plan(d_rowptr, d_colidx, b2.norm, b2.norm, d_gptr, B, N)
-                       if batch.plan is not None else None)   # slab-SpMM plan: a function of the graph, rebuilt per step
-            incremental = not embedding and not sparse_adj and X.dtype == torch.bfloat16
-            if incremental:                                          # device-side graphExtender on a reused all-zero buffer:
-                ops.scatter_features_bf16(b2, F, X)                  # write this step's nnz entries ...
-            elif not embedding and not sparse_adj:
-                ops.densify(b2, F, out=X)
-            per_graph = train_step(b2)
-            if incremental:
-                ops.scatter_features_bf16(b2, F, X, clear=True)      # ... and zero them again: no 8 GB memset per step
-            consumed[slot].record()
-            return per_graph.cpu()                                   # D2H of the step's result
-
-        def e2e_run(k):
-            issue_copy(0)                                            # k copies for k steps, all inside the caller's timing
-            out = None
-            for i in range(k):
-                out = e2e_step(i, prefetch_next=i + 1 < k)
-            torch.cuda.synchronize()
-            return out
-
-        x_incremental = not embedding and not sparse_adj and not preagg and X.dtype == torch.bfloat16
-        if x_incremental:
-            ops.scatter_features_bf16(batch, F, X, clear=True)       # the e2e steps start from (and leave) an all-zero X
-        e2e_run(3)
+        t_ds = time.perf_counter()
+        ds = synth.RegularGraphDataset(rowptr, colidx, graph_ptr, F, first_key=rank * B, total=B * world)
+        cfg_e2e = T.TrainingConfig(n_nodes=n, dim_embedding=F, hidden_dim=H, number_classes=K, learning_rate=1e-3,
+                                   gemm_precision=args.precision, activations=args.activations,
+                                   preaggregate_features=preagg, batch_graphs=B * world, stream_dataset=True)
+        eng_api = T._engine_for(net, opt, cfg_e2e)
+        eng_api.launch_count = 0
+        for _ in range(3):                                           # first call collates + pins the host batch (cached)
+            T.train_single_epoch(ds, net, opt, embed_api, cfg_e2e)
+        t_ds = time.perf_counter() - t_ds
+        streamer = T._STREAMERS[eng_api]
+        stats0 = dict(streamer.stats)
+        launches0 = eng_api.launch_count
         sync_all()
         t0 = time.perf_counter()
-        host_loss = e2e_run(k_e2e)
+        for _ in range(k_e2e):
+            api_loss = T.train_single_epoch(ds, net, opt, embed_api, cfg_e2e)
+        torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if x_incremental:
-            assert int(torch.count_nonzero(X[: n]).item()) == 0      # the buffer really is back to zero (first graph checked)
-            ops.scatter_features_bf16(batch, F, X)                   # resident features again, for the runs below
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         gdist.all_reduce_max_(t)
-        h2d = (h_rowptr.numel() + h_colidx.numel() + h_gptr.numel()) * 4
-        e2e = {"value": total_graphs * k_e2e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(B * 8 + 4), "steps": k_e2e,
-               "path": "pinned host CSR (rowptr, colidx, graph_ptr) -> H2D (copy stream, prefetched one step ahead) "
-                       "-> gmc_degree_norm/edge_coef/"
-                       + ("csr_preaggregate (device-side graphExtender with GraphConv layer 1's aggregation applied to "
-                          "the features: A_hat X rebuilt from every step's graph)" if preagg else
-                          "spmm_plan (embeddings are resident parameters)" if embedding else
-                          "csr_scatter (device-side graphExtender on a reused zero buffer: write nnz entries, clear them after the step)")
-                       + " -> GCNEngine.train_step -> per-graph loss D2H"}
-        del host_loss
+        steps_done = max(1, streamer.stats["steps"] - stats0["steps"])
+        e2e = {"value": total_graphs * k_e2e / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int((streamer.stats["h2d_bytes"] - stats0["h2d_bytes"]) / steps_done),
+               "d2h_bytes_per_step": int((streamer.stats["d2h_bytes"] - stats0["d2h_bytes"]) / steps_done) + 8,
+               "steps": k_e2e, "ms_per_step": 1000.0 * float(t.item()) / k_e2e,
+               "gpu_launches_per_step": (eng_api.launch_count - launches0) / k_e2e,
+               "dataset_build_s": t_ds, "loss_last_step": api_loss,
+               "path": "Training.TrainingNeural.train_single_epoch(dataset, net, optimizer, embed, TrainingConfig("
+                       f"batch_graphs={B * world}, gemm_precision='{args.precision}', activations='{args.activations}', "
+                       f"preaggregate_features={preagg}, stream_dataset=True)) on a host dataset dict of {B * world} items "
+                       "[CSRGraph, AdjacencyFeatures, nx.Graph, [0,1,2]] (graphExtender.py:114 format"
+                       + (f", this rank's shard of {B} materialised" if world > 1 else "") + "): per optimiser step "
+                       "pinned host CSR -> H2D (copy stream, one step ahead) -> gmc_degree_norm / gmc_edge_coef / "
+                       + ("gmc_csr_preaggregate_bf16 (A_hat X rebuilt from the step's graphs)" if preagg else
+                          "feature rebuild on the device")
+                       + " -> GCNEngine.train_step -> per-graph losses D2H (pinned) -> float returned per call"}
+        del ds
+        T._PREPARED.clear()
 
     # ---- the same workload on the other paths (reported beside the headline, never instead of it) ----------------
     def timed_alt(engine, feats, k):
@@ -464,7 +431,7 @@ def run_b200_arm(args):
 
     alt = None
     spmm_from_alt = None
-    if args.workload == "config3" and not embedding and not sparse_adj:
+    if args.workload == "config3" and not embedding and not sparse_adj and not split:
         alt = {}
         k_alt = min(args.steps, 10)
         if ops.adjacency_kernels_apply(batch, F):
@@ -505,10 +472,138 @@ def run_b200_arm(args):
             del eng_t, X32
             torch.cuda.empty_cache()
 
+    # ---- parity-grade path + label agreement ------------------------------------------------------------------------
+    # The headline step stores bf16.  The reference is fp32 everywhere (TrainingNeural.py:33-34), so the same workload is
+    # also timed on the fp32-GRADE tensor-core path ('bf16x3': exact integer features x W1 split into three bf16 parts --
+    # all 24 mantissa bits -- fp32 H1 / logits / loss / gradients; reproduces the reference fixtures at rel 1e-4,
+    # tests/test_gpu_api.py, tests/test_gpu_split.py), and both paths are run from the SAME initial weights for the same
+    # number of optimiser steps to compare the hard labels they end up with.
+    parity_grade = None
+    label_agreement = None
+    if args.workload == "config3" and not embedding and not sparse_adj and args.precision == "bf16":
+        import copy
+        k_pg = min(args.steps, 10)
+        xi = ops.IntegerFeatures.from_batch(batch, F)
+
+        def fresh(precision, **kw):
+            net_c = copy.deepcopy(net)
+            net_c.load_state_dict(init_state)
+            opt_c = type(opt)(net_c.parameters(), lr=1e-3)
+            return net_c, GCNEngine(net_c, opt_c, precision=precision, **kw)
+
+        net_pg, eng_pg = fresh("bf16x3", adjacency_features=True)
+        eng_pg.timer = OpTimer()
+        r_pg = timed_alt(eng_pg, xi, k_pg)
+        eng_pg.timer.collect()
+        t_pg = eng_pg.timer
+        eng_pg.timer = None
+        parity_grade = dict(r_pg, dtype="bf16x3 (fp32-grade)",
+            what="the same step on the fp32-grade tensor-core path (bench.py --precision bf16x3): H1 = relu(s . (XI (W1_hi + "
+                 "W1_lo + W1_lo2)) + b1) with XI = the integer 2-step path counts (exact in bf16) and W1 split into three bf16 "
+                 "parts (24 mantissa bits), dW1 = XI^T (s . dH1pre) with two parts; fp32 H1, logits, loss, gradients, Adam",
+            parity="rel 1e-4 on loss / logits / gradients / weights against reference-generated fixtures "
+                   "(tests/test_gpu_api.py::test_step_matches_reference_fixture[*-bf16x3], tests/test_gpu_split.py::"
+                   "test_two_epochs_at_baseline_shapes[bf16x3])",
+            ops_ms={k: t_pg.total_ms[k] / t_pg.calls[k] for k in t_pg.total_ms})
+        # label agreement: both paths from the same initial weights, same batch, same number of steps
+        net_a, eng_a = fresh("bf16", activations=args.activations, preaggregate=preagg)
+        net_b, eng_b = net_pg, eng_pg
+        net_b.load_state_dict(init_state)
+        for st_ in eng_b.optimizer.state.values():                   # restart Adam for the comparison run
+            st_["step"].zero_(); st_["exp_avg"].zero_(); st_["exp_avg_sq"].zero_()
+        k_la = args.steps
+        la_a = la_b = None
+        for _ in range(k_la):
+            la_a = eng_a.train_step(batch, feats)
+            la_b = eng_b.train_step(batch, xi)
+        loss_a, loss_b = float(la_a.sum().item()), float(la_b.sum().item())
+        eng_a.forward(batch, feats)
+        lab_a = ops.argmax_labels(batch, eng_a.P[:N]).clone()
+        eng_b.forward(batch, xi)
+        lab_b = ops.argmax_labels(batch, eng_b.P[:N]).clone()
+        same = int((lab_a == lab_b).sum().item())
+        cut_a, cut_b = ops.cut_value(batch, lab_a), ops.cut_value(batch, lab_b)
+        label_agreement = {
+            "steps_from_same_init": k_la, "nodes": N, "same_labels": same, "fraction": same / N,
+            "loss_last_step_headline": loss_a, "loss_last_step_parity_grade": loss_b,
+            "loss_rel_diff": abs(loss_a - loss_b) / max(abs(loss_b), 1.0),
+            "cut_sum_headline": int(cut_a.sum().item()), "cut_sum_parity_grade": int(cut_b.sum().item()),
+            "graphs_with_equal_cut": int((cut_a == cut_b).sum().item()), "graphs": B,
+            "what": "hard labels (argmax with terminal override) and integer cuts of the final models of the headline path and "
+                    "of the parity-grade path, each trained for the timed number of steps from the same initial weights"}
+        if not getattr(T, "_keep", False):
+            del eng_a, net_a, eng_b, net_b, eng_pg, net_pg, xi
+            torch.cuda.empty_cache()
+
+    # ---- data-parallel check (N > 1): same weights everywhere, and N ranks == one rank on the same global batch ----------
+    dp = None
+    if world > 1:
+        W1c = net.conv1.weight.detach().double()
+        chk = torch.stack([W1c.sum(), W1c.abs().sum(), net.conv2.weight.detach().double().sum()])
+        gathered = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        identical = all(torch.equal(g, gathered[0]) for g in gathered)
+        # small common batch: rank r owns graphs [r*S, (r+1)*S) of an S*world-graph batch; rank 0 also runs all of them alone
+        S = 32
+        import copy
+        net_d = copy.deepcopy(net)
+        net_d.load_state_dict(init_state)
+        opt_d = type(opt)(net_d.parameters(), lr=1e-3)
+        eng_d = GCNEngine(net_d, opt_d, precision=args.precision, activations=args.activations, preaggregate=preagg)
+        all_deg = [6 + (g % 3) for g in range(S * world)]
+        rp_s, ci_s, gp_s = synth.regular_batch_arrays(S, n, all_deg[rank * S:(rank + 1) * S], seed=args.seed + 555 + rank)
+        b_s = GraphBatch.from_arrays(rp_s, ci_s, gp_s, device=dev)
+        f_s = ops.PreaggregatedFeatures(ops.preaggregate_features_bf16(b_s, F)) if preagg else (
+            ops.densify_bf16(b_s, F) if args.precision == "bf16" else ops.densify(b_s, F, out=ops.padded_empty(b_s.num_nodes, F, dev)))
+        loss_s = eng_d.loss_and_grads(b_s, f_s).sum()
+        eng_d.allreduce_grads()
+        dist.all_reduce(loss_s)
+        g_dp = eng_d.grads_flat.clone()
+        rel = None
+        if rank == 0:
+            parts = [synth.regular_batch_arrays(S, n, all_deg[r * S:(r + 1) * S], seed=args.seed + 555 + r) for r in range(world)]
+            rp_chunks, nnz_off = [np.zeros(1, dtype=np.int64)], 0
+            for p_ in parts:
+                rp_chunks.append(p_[0][1:].astype(np.int64) + nnz_off)
+                nnz_off += len(p_[1])
+            rp_all = np.concatenate(rp_chunks).astype(np.int32)
+            ci_all = np.concatenate([p_[1].astype(np.int64) + i * S * n for i, p_ in enumerate(parts)]).astype(np.int32)
+            gp_all = (np.arange(S * world + 1, dtype=np.int64) * n).astype(np.int32)
+            b_all = GraphBatch.from_arrays(rp_all, ci_all, gp_all, device=dev)
+            f_all = ops.PreaggregatedFeatures(ops.preaggregate_features_bf16(b_all, F)) if preagg else (
+                ops.densify_bf16(b_all, F) if args.precision == "bf16" else ops.densify(b_all, F, out=ops.padded_empty(b_all.num_nodes, F, dev)))
+            net_1 = copy.deepcopy(net_d)
+            eng_1 = GCNEngine(net_1, type(opt)(net_1.parameters(), lr=1e-3), precision=args.precision,
+                              activations=args.activations, preaggregate=preagg)
+            eng_1.pg = None
+            loss_1 = eng_1.loss_and_grads(b_all, f_all).sum()
+            rel = float(((g_dp - eng_1.grads_flat).abs().max() / eng_1.grads_flat.abs().max()).item())
+            rel_loss = abs(float(loss_s.item()) - float(loss_1.item())) / max(abs(float(loss_1.item())), 1.0)
+            del eng_1, net_1, b_all, f_all
+        # per-rank timing attribution: step time and the all-reduce interval (contains the wait for slower ranks)
+        mine = torch.tensor([ms / args.steps, timer.total_ms.get("allreduce", 0.0) / max(1, timer.calls.get("allreduce", 1)),
+                             sum(v for k, v in timer.total_ms.items() if k != "allreduce") / args.steps],
+                            dtype=torch.float64, device=dev)
+        per_rank = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
+        if rank == 0:
+            dp = {"weights_identical_on_all_ranks": bool(identical),
+                  "n_ranks_vs_one_rank": {"graphs": S * world, "grad_rel_err": rel, "loss_rel_err": rel_loss, "tolerance": 1e-5,
+                                          "ok": bool(rel is not None and rel < 1e-5 and rel_loss < 1e-5),
+                                          "what": f"{world} ranks x {S} graphs, all-reduced gradients, against rank 0 running all "
+                                                  f"{S * world} graphs alone at the same weights"},
+                  "per_rank_ms_per_step": [float(p[0]) for p in per_rank],
+                  "per_rank_allreduce_ms": [float(p[1]) for p in per_rank],
+                  "per_rank_compute_ms": [float(p[2]) for p in per_rank],
+                  "note": "the all-reduce interval ends when the slowest rank's gradients arrive: it is 2 MB of NCCL latency plus "
+                          "the wait for slower ranks (ranks power-cap differently)"}
+        del eng_d, net_d, b_s, f_s
+        torch.cuda.empty_cache()
+
     # ---- rooflines ----------------------------------------------------------------------------
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0 if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"] / 2.0
-    if args.precision == "bf16":                         # bf16 operands: the measured bf16 figure itself
-        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    if args.precision in ("bf16", "bf16x3", "bf16x2"):   # bf16 operands: the measured bf16 figure itself (a split GEMM
+        tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])   # issues 2-3 MMAs per algorithmic flop)
     # compulsory form while one graph's source rows stay L2-resident (n*C*4 <= 32 MiB), else gather form
     def spmm_bytes(C):
         if n * C * 4 <= 32 * 2 ** 20:
@@ -524,6 +619,8 @@ def run_b200_arm(args):
         spmm_bytes_fused -= 4.0 * N * H
         spmm_bytes_h_bwd = spmm_bytes_h - 4.0 * N * H
         skinny_bwd_bytes -= 4.0 * N * H
+    if split:                                            # fp32 H1 in, two bf16 parts of s . dH1pre out
+        skinny_bwd_bytes = 4.0 * N * H + 2.0 * eng.split_bwd * N * H + 4.0 * N * K
     ldx = ops.pad_cols(F)
     gemm_flops = 2.0 * N * F * H
     algo = {
@@ -565,29 +662,23 @@ def run_b200_arm(args):
         if bound == "hbm":
             extra["frac_nominal_8TBs"] = achieved / 8000.0          # also against the nominal ~8 TB/s
         if act16 and name in ("spmm_h", "spmm_h_fwd", "spmm_h_fused"):
-            # SURVEY 8(d) states the SpMM bytes for fp32 columns (8 N C + indices); with 2-byte activations the kernel
-            # moves half of that, which is what `achieved` counts.  The fp32-form figure is the rate an fp32 kernel
-            # would need to finish in the same time.
-            fp32_form = spmm_bytes_h + (4.0 * N * K if name == "spmm_h_fused" else 0.0)
-            extra["algorithmic_bytes"] = work
-            extra["achieved_fp32_form"] = fp32_form / (avg_ms * 1e-3) / 1e9
-            extra["frac_fp32_form"] = extra["achieved_fp32_form"] / peaks["hbm_gbs"]
+            extra["algorithmic_bytes"] = work                       # 2-byte activations: the bytes the kernel moves
         ops_report[name] = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, **extra,
                             "frac": achieved / peak if peak else None, "avg_ms": avg_ms, "calls": calls,
                             "share_of_step": tot / ms,
                             # DRAM bytes per launch from the committed ncu --set full capture (per graph x graphs/GPU)
-                            "traffic": (traffic_db.get("per_graph_bytes_bf16_activations" if act16 else "per_graph_bytes",
-                                                       {}).get(name) or 0.0) * B or None}
+                            "traffic": ((traffic_db.get("config5_bytes_per_launch", {}).get(name) or None)
+                                        if args.workload == "config5" else
+                                        (traffic_db.get("per_graph_bytes_bf16_activations" if act16 else "per_graph_bytes",
+                                                        {}).get(name) or 0.0) * B or None)}
     spmm_standalone = None
     if spmm_from_alt is not None:
         # the pre-aggregated step has no [N, hidden] SpMM: the metric's "SpMM HBM GB/s" comes from the same bf16 slab
         # kernel timed inside the standard-layer-1 step that ran beside it (alt_paths.standard_layer1)
         a = spmm_bytes_h_bwd / (spmm_from_alt * 1e-3) / 1e9
-        a32 = spmm_bytes_h / (spmm_from_alt * 1e-3) / 1e9
         spmm_standalone = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": a / peaks["hbm_gbs"], "frac_nominal_8TBs": a / 8000.0, "avg_ms": spmm_from_alt,
-                           "algorithmic_bytes": spmm_bytes_h_bwd, "achieved_fp32_form": a32,
-                           "frac_fp32_form": a32 / peaks["hbm_gbs"],
+                           "algorithmic_bytes": spmm_bytes_h_bwd,
                            "where": "dT1 = A_hat dH1pre (bf16 slab SpMM) inside alt_paths.standard_layer1; the headline "
                                     "step applies this aggregation to the features instead",
                            "traffic": (traffic_db.get("per_graph_bytes_bf16_activations", {}).get("spmm_h") or 0.0) * B or None}
@@ -608,6 +699,27 @@ def run_b200_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run(args, 0, 1, min(4, args.cpu_sample), budget_s=args.cpu_seconds)
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    # ---- the other BASELINE.json configurations, short runs (rank 0, one GPU) -------------------------------------------
+    workloads = None
+    if rank == 0 and world == 1 and args.workload == "config3" and not args.no_workloads:
+        del eng, batch, feats, X, XA
+        torch.cuda.empty_cache()
+        workloads = {}
+        for name, fn, kw in (("config1", config1_line, dict(steps=5, warmup=3)), ("config2", config2_line, dict(steps=10, warmup=3))):
+            t0 = time.perf_counter()
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    w = fn(args, **kw)
+                w["wall_s"] = time.perf_counter() - t0
+                workloads[name] = {k: w[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config",
+                                                      "cpu_baseline", "e2e", "wall_s") if k in w}
+                for extra_key in ("ms_per_graph_step", "per_graph_loop", "avg_cut", "precisions"):
+                    if extra_key in w:
+                        workloads[name][extra_key] = w[extra_key]
+            except Exception as exc:                                 # a secondary workload never takes the headline down
+                workloads[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         clocks = sampler.summary()
@@ -630,20 +742,25 @@ def run_b200_arm(args):
                              f"pre-aggregated dense features A_hat X [{N},{F}] bf16 resident in HBM ({N * F * 2 / 1e9:.1f} "
                              "GB/GPU), X = the zero-padded adjacency rows: GraphConv layer 1 as relu((A_hat X) W1 + b1)"
                              if preagg else
+                             f"integer pre-aggregated features XI [{N},{F}] (2-step path counts, exact in bf16) + one A_hat "
+                             "scale per row, resident in HBM; W1 / s . dH1pre split into bf16 parts (fp32-grade)"
+                             if split else
                              f"dense zero-padded adjacency rows [{N},{F}] {'bf16' if args.precision == 'bf16' else 'fp32'} "
-                             f"resident in HBM ({N * F * (2 if args.precision == 'bf16' else 4) / 1e9:.1f} GB/GPU)"),
+                             f"resident in HBM ({N * F * (2 if args.precision.startswith('bf16') else 4) / 1e9:.1f} GB/GPU)"),
                 "layer1": ("preaggregated: H1 = relu((A_hat X) W1 + b1) -- one tcgen05 GEMM with bias / ReLU epilogue; "
                            "dW1 = (A_hat X)^T dH1pre -- one GEMM; identical to the reference's relu(A_hat (X W1) + b1), with the "
                            "aggregation moved from the activations (every step) to the features (once per graph; every step "
                            "in e2e)" if preagg else "standard: relu(A_hat (X W1) + b1), SpMM forward and backward every step"),
                 "spmm_bytes_form": "compulsory" if n * H * 4 <= 32 * 2 ** 20 else "gather",
+                "timed_regions": "value: CUDA events around the steps, inputs resident in HBM; e2e: wall clock around the API "
+                                 "calls (each returns the epoch loss as a float), host dataset in, H2D every step",
                 "gcn": f"GraphConv {F}->{H}->{K} + softmax, STE max-cut loss with terminal override, Adam lr=1e-3",
                 "step": "one optimiser step over the whole per-GPU batch; weight-gradient all-reduce (sum) over NCCL",
                 "gemm_precision": args.precision, "parallelism": f"dp{world}",
                 "activations": ("bf16 storage of T1 / H1 / dH1pre / dT1 (fp32 arithmetic, logits, loss, gradients, Adam)"
                                 if act16 else "fp32"),
                 "l2": (f"inputs larger than L2 (activations {2 * N * H * 4 / 1e9:.1f} GB)" if sparse_adj else
-                       f"inputs larger than L2 (X {N * F * (2 if args.precision == 'bf16' else 4) / 1e9:.1f} GB, "
+                       f"inputs larger than L2 (X {N * F * (2 if args.precision.startswith('bf16') else 4) / 1e9:.1f} GB, "
                        f"activations {2 * N * H * (2 if act16 else 4) / 1e9:.1f} GB)"),
                 "graph_generation_s": t_gen,
             },
@@ -654,6 +771,10 @@ def run_b200_arm(args):
             "e2e": e2e,
             "gpu_launches": launches,
             "alt_paths": alt,
+            "parity_grade": parity_grade,
+            "label_agreement": label_agreement,
+            "dp_check": dp,
+            "workloads": workloads,
             "node_epochs_per_s": value * n,
             "clocks": clocks,
             "loss_last_step": last_loss,
@@ -666,6 +787,10 @@ def run_b200_arm(args):
 
 # ----------------------------------------------------------------------------- config 1
 def run_config1(args):
+    print(json.dumps(config1_line(args)), flush=True)
+
+
+def config1_line(args, steps=None, warmup=None):
     """BASELINE.json configs[0]: the reference pipeline -- 20 random regular graphs n=500 (d in 6..8), 3 terminals,
     extended to n_nodes=1000, dim_embedding=1000, hidden_dim=500, Adam lr=1e-3, ONE optimiser step per graph in dict
     order (reference semantics), through the drop-in API (process_graphs_from_folder -> train_single_epoch).
@@ -689,23 +814,35 @@ def run_config1(args):
     with contextlib.redirect_stdout(io.StringIO()):
         ds = E.process_graphs_from_folder(graphs, terms, max_nodes=1000)
     t_extend = time.perf_counter() - t0
-    precision = "fp32" if args.precision == "fp32" else args.precision
-    cfg = T.TrainingConfig(n_nodes=1000, dim_embedding=1000, hidden_dim=500, learning_rate=1e-3, gemm_precision=precision)
-    torch.manual_seed(args.seed)
-    net, embed, opt = T.setup_model_and_optimizer(cfg)
-    for _ in range(max(3, args.warmup)):
-        T.train_single_epoch(ds, net, opt, embed, cfg)
-    torch.cuda.synchronize()
+    # reference semantics need an fp32-grade path: 'bf16x3' (tensor cores, exact integer features x split W1) is the
+    # headline; the default bench precision 'bf16' maps to it here.  fp32 (CUDA cores) and tf32 are timed beside it.
+    precision = "bf16x3" if args.precision == "bf16" else args.precision
+    steps = max(1, args.steps if steps is None else steps)
+    warmup = max(3, args.warmup if warmup is None else warmup)
+
+    def run(prec, k):
+        cfg = T.TrainingConfig(n_nodes=1000, dim_embedding=1000, hidden_dim=500, learning_rate=1e-3, gemm_precision=prec)
+        torch.manual_seed(args.seed)
+        net, embed, opt = T.setup_model_and_optimizer(cfg)
+        for _ in range(warmup):
+            T.train_single_epoch(ds, net, opt, embed, cfg)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            loss = T.train_single_epoch(ds, net, opt, embed, cfg)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, loss, T._engine_for(net, opt, cfg)
+
     sampler = ClockSampler(0)
     sampler.start()
-    steps = max(1, args.steps)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        loss = T.train_single_epoch(ds, net, opt, embed, cfg)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt, loss, eng = run(precision, steps)
     sampler.stop()
-    eng = T._engine_for(net, opt, cfg)
+    others = {}
+    for prec in ("fp32", "tf32", "bf16x3"):
+        if prec != precision:
+            d2, l2, _e = run(prec, steps)
+            others[prec] = {"value": n_graphs * steps / d2, "unit": UNIT, "ms_per_graph_step": 1000.0 * d2 / (steps * n_graphs),
+                            "loss_last_epoch": l2}
 
     from oracle import ref_step as rs
     port = rs.FaithfulPort(1000, 500, 3, lr=1e-3, seed=args.seed, pad=1000)
@@ -718,9 +855,9 @@ def run_config1(args):
     dt_cpu = time.perf_counter() - t0
     line = {
         "metric": "GCN train graph-epochs/s, reference pipeline (n=500, one Adam step per graph)",
-        "value": n_graphs * steps / dt, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
+        "value": n_graphs * steps / dt, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
         "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if precision == "fp32" else precision, "data": "synthetic",
+        "dtype": "f32" if precision == "fp32" else precision, "data": "synthetic", "precisions": others,
         "config": {"workload": "config 1: 20 random regular graphs n=500 (d in 6..8), 3 terminals, extended to 1000 "
                                "features, hidden 500, 3 classes, Adam lr=1e-3, sequential per-graph steps",
                    "api": "DataGenerator.graphExtender.process_graphs_from_folder -> Training.TrainingNeural.train_single_epoch",
@@ -736,11 +873,15 @@ def run_config1(args):
         "clocks": sampler.summary(),
         "loss_last_epoch": loss,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ----------------------------------------------------------------------------- config 2
 def run_config2(args):
+    print(json.dumps(config2_line(args)), flush=True)
+
+
+def config2_line(args, steps=None, warmup=None):
     """BASELINE.json configs[1]: inference + 200-iteration post-processing on test graphs n=50/100/200/300/500
     (10 each, d in 6..8, 3 terminals), single B200.  One step = one pass over the 50 graphs through the
     reference-facing API: forward, argmax assignment + integer cut, best-of-200 categorical sampling (the
@@ -792,7 +933,8 @@ def run_config2(args):
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / steps, out
 
-    steps, warmup = max(1, min(args.steps, 20)), max(3, args.warmup)
+    steps = max(1, min(args.steps if steps is None else steps, 20))
+    warmup = max(3, args.warmup if warmup is None else warmup)
     sampler = ClockSampler(0)
     sampler.start()
     dt_batched, (res_b, _) = timed(lambda: one_pass(True), steps, warmup)
@@ -842,7 +984,7 @@ def run_config2(args):
                     "sampled": float(np.mean([r["post_cut"] for r in res_b])),
                     "greedy": float(np.mean([r["greedy_cut"] for r in res_b]))},
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():

@@ -199,6 +199,9 @@ struct Params {
     int64_t b_split_rows;
     // fp32 epilogue (direct, non split-K outputs): C[m, n] = act(row_scale[m] * acc + bias[n]); each nullable / 0
     const float* row_scale;
+    // fp32 epilogue + proj_w: every (row, n-tile) writes its partial projection sum_n C[m, n] projW[n][0..3] to
+    // proj_part[n_tile][m] (one float4, written exactly once: deterministic); proj_reduce_kernel adds the n-tiles up
+    float4* proj_part;
 };
 
 // Thread-block cluster of CLM x CLN CTAs (rank = rm + CLM * rn) that owns CLM consecutive m-tiles x CLN consecutive
@@ -474,6 +477,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (k < p.proj_k) atomicAdd(po + k, pj[k]);
                 }
             } else {
+            float pj[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int c = 0; c < RN / 32; ++c) {
                 const int n = n0 + 32 * c;
@@ -514,6 +518,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
                 }
+                if (p.proj_part) {                                 // this row's 32 values against projW[n .. n+31][0..3]
+                    const float4* w4 = p.proj_w + n;               // same address in every lane: broadcast, L1-resident;
+#pragma unroll                                                     // rows >= N of projW are zero padding (up to N rounded to 64)
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = __uint_as_float(r[i]);
+                        const float4 w = __ldg(w4 + i);
+                        pj[0] = fmaf(v, w.x, pj[0]); pj[1] = fmaf(v, w.y, pj[1]); pj[2] = fmaf(v, w.z, pj[2]); pj[3] = fmaf(v, w.w, pj[3]);
+                    }
+                }
                 if (p.tma_store) {
                     // registers -> 128B-swizzled staging block (lane = row, 16-byte chunk i at i ^ (row & 7): conflict-free
                     // STS.128) -> one TMA store of 32 full 128-byte row segments; rows / columns beyond M / N are clipped
@@ -551,6 +564,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
+            if (p.proj_part && m < p.M && m0 < p.M && n0 < p.N)
+                p.proj_part[(int64_t)(n0 / RN) * p.M + m] = make_float4(pj[0], pj[1], pj[2], pj[3]);
             }
             tc_fence_before();
             __syncwarp();
@@ -776,6 +791,23 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
+// T[m, k] = sum over the n-tiles of their partial projections, in tile order (deterministic)
+__global__ void __launch_bounds__(256)
+proj_reduce_kernel(const float4* __restrict__ part, int n_tiles, int64_t M, float* __restrict__ out, int64_t ldp, int k) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float4 s = __ldg(part + m);
+    for (int t = 1; t < n_tiles; ++t) {
+        const float4 v = __ldg(part + (int64_t)t * M + m);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = out + m * ldp;
+    o[0] = s.x;
+    if (k > 1) o[1] = s.y;
+    if (k > 2) o[2] = s.z;
+    if (k > 3) o[3] = s.w;
+}
+
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t MN, int64_t N,
                                         float* __restrict__ C, int64_t ldc, int accumulate) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -929,7 +961,7 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     p.mg_tiles = ceil_div(p.m_tiles, CLM);
     p.ng_tiles = ceil_div(p.n_tiles, CLN);
     const int64_t ctiles = (int64_t)p.mg_tiles * p.ng_tiles;
-    const bool fused_epilogue = c_bf16 || row_scale || bias || relu;   // these leave straight from the accumulators
+    const bool fused_epilogue = c_bf16 || row_scale || bias || relu || proj_w;   // these leave straight from the accumulators
     int splits = fused_epilogue ? 1 : pick_splits_cl(ctiles, K, slots);
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
@@ -988,6 +1020,18 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
             p.bias = bias;
             p.relu = relu;
         }
+        if (proj_w) {
+            const size_t need = (size_t)p.n_tiles * (size_t)M * sizeof(float4);
+            if (splits != 1 || accumulate || !proj_out || proj_k < 1 || proj_k > 4 || ldp < proj_k || !aligned16(proj_w) ||
+                !workspace || workspace_bytes < need || !aligned16(workspace)) {
+                set_error("gmc_gemm: the fused fp32 projection needs a direct (non split-K, non accumulating) output, "
+                          "1 <= n_proj <= 4, ldp >= n_proj, a 16-byte aligned padded weight matrix and a workspace of "
+                          "n_tiles * M * 16 bytes (%zu)", need);
+                return GMC_ERR_INVALID_ARG;
+            }
+            p.proj_w = reinterpret_cast<const float4*>(proj_w);
+            p.proj_part = reinterpret_cast<float4*>(workspace);
+        }
         if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
             rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
             if (rc) return rc;
@@ -1001,6 +1045,10 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     if (splits > 1) {
         const int64_t MN = M * N;
         tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
+        GMC_LAUNCH_CHECK();
+    }
+    if (p.proj_part) {
+        proj_reduce_kernel<<<(unsigned)ceil_div<int64_t>(M, 256), 256, 0, s>>>(p.proj_part, p.n_tiles, M, proj_out, ldp, proj_k);
         GMC_LAUNCH_CHECK();
     }
     return GMC_OK;
@@ -1259,11 +1307,16 @@ int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64
 // accumulated in fp32 TMEM and added up in the epilogue.  op 0 (nn) and 2 (tn): B is MN-major in both.
 namespace tc {
 static void split_cluster(int ns, int* clm) {
-    // NS = 2: four 64-column chunks per stage -> 2x1 clusters share them (the plain bf16 default); NS = 3: three chunks,
-    // no even share -> single CTAs (the bf16 nn kernel is insensitive to the cluster shape, profiles/r01_gemm_notes.md)
-    *clm = ns == 2 ? 2 : 1;
+    // The B stage of a split GEMM is NS x as wide per real output column as a plain one, so sharing it pays (unlike the
+    // plain bf16 nn kernel): every CTA of a CLM x 1 cluster loads 1 / CLM of the stage's 64-column chunks and multicasts
+    // them.  NS = 2: four chunks -> CLM 1 | 2 | 4; NS = 3: three chunks -> CLM 1 | 3.  GMC_GEMM_SPLIT_CLUSTER overrides.
+    *clm = ns == 2 ? 2 : 3;
     const char* e = getenv("GMC_GEMM_SPLIT_CLUSTER");
-    if (e && e[0] == '1') *clm = 1;
+    if (e && e[0] >= '1' && e[0] <= '4') {
+        const int c = e[0] - '0';
+        if (ns == 2 && (c == 1 || c == 2 || c == 4)) *clm = c;
+        if (ns == 3 && (c == 1 || c == 3)) *clm = c;
+    }
 }
 
 static int64_t split_tiles(int ns, int64_t M, int64_t N, int clm) {
@@ -1272,9 +1325,13 @@ static int64_t split_tiles(int ns, int64_t M, int64_t N, int clm) {
 }
 }  // namespace tc
 
-size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int n_split) {
+size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int n_split, int with_projection) {
     (void)op;
     if (n_split < 2 || n_split > 3) return 0;
+    if (with_projection) {                                           // partial projections [n_tiles][M] float4, no split-K
+        const int rn = (n_split == 3 ? 192 : tc::BLOCK_N) / n_split;
+        return (size_t)ceil_div<int64_t>(N, rn) * (size_t)M * sizeof(float4);
+    }
     int clm;
     tc::split_cluster(n_split, &clm);
     const int splits = tc::pick_splits_cl(tc::split_tiles(n_split, M, N, clm), K, sm_count() / clm);
@@ -1283,7 +1340,8 @@ size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, in
 
 int tc_gemm_bf16_split(int op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                        int64_t ldb, int64_t ldc, int n_split, int64_t b_split_rows, const float* row_scale,
-                       const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                       const float* bias, int relu, const float* proj_w, float* proj_out, int64_t ldp, int proj_k,
+                       int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
     GMC_REQUIRE(op == 0 || op == 2, "gmc_gemm_bf16_split: op must be 0 (nn) or 2 (tn): the split operand is MN-major");
     GMC_REQUIRE(n_split == 2 || n_split == 3, "gmc_gemm_bf16_split: n_split must be 2 or 3");
     GMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B),
@@ -1302,13 +1360,15 @@ int tc_gemm_bf16_split(int op, const void* A, const void* B, float* C, int64_t M
     tc::split_cluster(n_split, &clm);
 #define GMC_SPLIT_CASE(AMN, CM, NSV)                                                                                  \
     return tc::launch<AMN, true, CM, 1, true, NSV>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, 0, \
-                                                   bias, relu, nullptr, nullptr, 0, 0, b_split_rows, row_scale);
-    if (op == 0) {
-        if (n_split == 2) { if (clm == 2) { GMC_SPLIT_CASE(false, 2, 2) } else { GMC_SPLIT_CASE(false, 1, 2) } }
-        GMC_SPLIT_CASE(false, 1, 3)
-    }
-    if (n_split == 2) { if (clm == 2) { GMC_SPLIT_CASE(true, 2, 2) } else { GMC_SPLIT_CASE(true, 1, 2) } }
-    GMC_SPLIT_CASE(true, 1, 3)
+                                                   bias, relu, proj_w, proj_out, ldp, proj_k, b_split_rows, row_scale);
+#define GMC_SPLIT_OP(AMN)                                                                                             \
+    if (n_split == 2) {                                                                                               \
+        if (clm == 4) { GMC_SPLIT_CASE(AMN, 4, 2) } else if (clm == 2) { GMC_SPLIT_CASE(AMN, 2, 2) } else { GMC_SPLIT_CASE(AMN, 1, 2) } \
+    }                                                                                                                 \
+    if (clm == 3) { GMC_SPLIT_CASE(AMN, 3, 3) } else { GMC_SPLIT_CASE(AMN, 1, 3) }
+    if (op == 0) { GMC_SPLIT_OP(false) }
+    GMC_SPLIT_OP(true)
+#undef GMC_SPLIT_OP
 #undef GMC_SPLIT_CASE
 }
 

@@ -19,10 +19,11 @@
 
 namespace gmc {
 
-size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int n_split);
+size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, int n_split, int with_projection);
 int tc_gemm_bf16_split(int op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                        int64_t ldb, int64_t ldc, int n_split, int64_t b_split_rows, const float* row_scale,
-                       const float* bias, int relu, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s);
+                       const float* bias, int relu, const float* proj_w, float* proj_out, int64_t ldp, int proj_k,
+                       int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
@@ -105,21 +106,22 @@ int gmc_row_scale_f32(const int32_t* rowptr, const float* coef, int64_t n_rows, 
     return GMC_OK;
 }
 
-size_t gmc_gemm_bf16_split_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t n_split) {
-    return gmc::tc_bf16_split_workspace_bytes(op, M, N, K, n_split);
+size_t gmc_gemm_bf16_split_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t n_split,
+                                           int32_t with_projection) {
+    return gmc::tc_bf16_split_workspace_bytes(op, M, N, K, n_split, with_projection);
 }
 
 int gmc_gemm_bf16_split(int32_t op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                         int64_t ldb, int64_t ldc, int32_t n_split, int64_t b_split_rows, const float* row_scale,
-                        const float* bias, int32_t relu, int32_t accumulate, void* workspace, size_t workspace_bytes,
-                        void* stream) {
+                        const float* bias, int32_t relu, const float* proj_w, float* proj_out, int64_t ldp, int32_t n_proj,
+                        int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace gmc;
     GMC_REQUIRE(A && B && C, "gmc_gemm_bf16_split: null pointer");
     GMC_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gmc_gemm_bf16_split: negative dimension");
     const int64_t a_min = (op == 2) ? M : K;
     GMC_REQUIRE(lda >= a_min && ldb >= N && ldc >= N, "gmc_gemm_bf16_split: leading dimension too small (op %d)", op);
-    return tc_gemm_bf16_split(op, A, B, C, M, N, K, lda, ldb, ldc, n_split, b_split_rows, row_scale, bias, relu, accumulate,
-                              workspace, workspace_bytes, as_stream(stream));
+    return tc_gemm_bf16_split(op, A, B, C, M, N, K, lda, ldb, ldc, n_split, b_split_rows, row_scale, bias, relu, proj_w,
+                              proj_out, ldp, n_proj, accumulate, workspace, workspace_bytes, as_stream(stream));
 }
 
 }  // extern "C"

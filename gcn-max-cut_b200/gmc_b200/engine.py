@@ -353,9 +353,18 @@ class GCNEngine:
             if self.W1s is None:
                 self.W1s = ops.split_empty(self.F, self.H, self.split_fwd, self.device)
             ops.f32_split_bf16(W1.data, self.split_fwd, out=self.W1s)
-            self._op("gemm_nn_layer1", 1, ops.gemm_bf16_split, "nn", XI.tensor, self.W1s, self.split_fwd, self.F, out=Bf,
-                     row_scale=XI.scale, bias=b1.data, relu=True, workspace=self.ws)
-            self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
+            if _FUSE_PROJ:
+                # ... and T2 = H1 W2 from the fp32 rows while they are in registers (per-tile partials + ordered reduce)
+                if self._w2p is None:
+                    self._w2p = torch.zeros(((self.H + 63) // 64 * 64, 4), dtype=torch.float32, device=self.device)
+                ops.pad_proj_weights(W2.data, out=self._w2p)
+                self._op("gemm_nn_layer1", 2, ops.gemm_bf16_split, "nn", XI.tensor, self.W1s, self.split_fwd, self.F, out=Bf,
+                         row_scale=XI.scale, bias=b1.data, relu=True, workspace=self.ws, proj_w=self._w2p,
+                         proj_out=self.T2[:N], n_proj=self.K)
+            else:
+                self._op("gemm_nn_layer1", 1, ops.gemm_bf16_split, "nn", XI.tensor, self.W1s, self.split_fwd, self.F, out=Bf,
+                         row_scale=XI.scale, bias=b1.data, relu=True, workspace=self.ws)
+                self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
             self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
             return self.Z[:N]
         X = self._features(batch, X)
@@ -475,7 +484,9 @@ class GCNEngine:
         """Data-parallel exchange: ONE NCCL all-reduce of the 502 003-float gradient buffer."""
         import torch.distributed as dist
         if self.pg is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            dist.all_reduce(self.grads_flat, op=dist.ReduceOp.SUM, group=self.pg)
+            # timed as its own op: the interval ends when the LAST rank's gradients have arrived, so it contains the
+            # wait for slower ranks (bench.py reports it per rank)
+            self._op("allreduce", 0, dist.all_reduce, self.grads_flat, op=dist.ReduceOp.SUM, group=self.pg)
 
     def apply_adam(self, feature_param: Optional[torch.Tensor] = None,
                    feature_grad: Optional[torch.Tensor] = None) -> None:

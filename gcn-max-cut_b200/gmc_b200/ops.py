@@ -433,10 +433,12 @@ class IntegerFeatures:
 def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: int, k: int,
                     out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
                     bias: Optional[torch.Tensor] = None, relu: bool = False, accumulate: bool = False,
-                    workspace: Optional[Workspace] = None) -> torch.Tensor:
+                    workspace: Optional[Workspace] = None, proj_w: Optional[torch.Tensor] = None,
+                    proj_out: Optional[torch.Tensor] = None, n_proj: int = 0) -> torch.Tensor:
     """C = op(A) (B_0 + ... + B_{n_split-1}) with bf16 A (exact) and the stacked bf16 parts of an fp32 B [k, N]
     (f32_split_bf16 / skinny_bwd_split); fp32 accumulation and output.  op 'nn': A [M, k]; 'tn': A [k, M].
-    Optional fp32 epilogue C[m, n] = act(row_scale[m] * acc + bias[n])."""
+    Optional fp32 epilogue C[m, n] = act(row_scale[m] * acc + bias[n]) and fused projection proj_out = C @ W for a
+    padded weight matrix from pad_proj_weights (deterministic: per-tile partials in the workspace, added in order)."""
     A, lda = _bf16_rowmajor(A, "A")
     B_split, ldb = _bf16_rowmajor(B_split, "B_split")
     if op == "nn":
@@ -460,11 +462,22 @@ def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: in
         raise ValueError(f"row_scale must be a contiguous fp32 vector of {M} elements")
     if bias is not None and (_f32(bias, "bias").numel() != N or not bias.is_contiguous()):
         raise ValueError(f"bias must be a contiguous fp32 vector of {N} elements")
+    ldp = 0
+    if proj_w is not None:
+        rows = (N + 63) // 64 * 64
+        if proj_w.shape != (rows, 4) or proj_w.dtype != torch.float32 or not proj_w.is_contiguous():
+            raise ValueError(f"proj_w must come from pad_proj_weights: contiguous fp32 [{rows}, 4]")
+        if proj_out is None or not 1 <= n_proj <= 4:
+            raise ValueError("the fused projection needs proj_out and 1 <= n_proj <= 4")
+        proj_out, ldp = _rowmajor(proj_out, "proj_out")
+        if proj_out.shape[0] != M or proj_out.shape[1] < n_proj:
+            raise ValueError(f"proj_out must be [{M}, >= {n_proj}]")
     ws = workspace or _default_ws
-    wptr, wbytes = ws.get(lib().gmc_gemm_bf16_split_workspace_bytes(_OPS[op], M, N, K, n_split), A.device)
+    wptr, wbytes = ws.get(lib().gmc_gemm_bf16_split_workspace_bytes(_OPS[op], M, N, K, n_split, int(proj_w is not None)),
+                          A.device)
     check(lib().gmc_gemm_bf16_split(_OPS[op], A.data_ptr(), B_split.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
-                                    n_split, sr, _ptr(row_scale), _ptr(bias), int(relu), int(accumulate), wptr, wbytes,
-                                    _stream()), "gmc_gemm_bf16_split")
+                                    n_split, sr, _ptr(row_scale), _ptr(bias), int(relu), _ptr(proj_w), _ptr(proj_out), ldp,
+                                    int(n_proj), int(accumulate), wptr, wbytes, _stream()), "gmc_gemm_bf16_split")
     return out
 
 

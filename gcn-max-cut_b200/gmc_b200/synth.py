@@ -104,3 +104,53 @@ def regular_batch(B: int, n: int, d, seed: int = 0, device=None):
     from .graph import GraphBatch
     rowptr, colidx, graph_ptr = regular_batch_arrays(B, n, d, seed)
     return GraphBatch.from_arrays(rowptr, colidx, graph_ptr, device=device)
+
+
+class RegularGraphDataset(dict):
+    """A graphExtender-format dataset `{key: [graph, X, nx.Graph, [0, 1, 2]]}` (graphExtender.py:114) over the graphs of
+    a block-diagonal CSR (`regular_batch_arrays`), materialised item by item on first access.
+
+    Keys are `first_key .. first_key + B - 1` of a dataset with `total` keys: under data parallelism every rank holds
+    the dataset with only ITS shard backed by arrays (train_single_epoch dereferences nothing else); asking for another
+    rank's item raises KeyError.  X is the AdjacencyFeatures stand-in (the dense [n, width] tensor is 4 MB per graph)."""
+
+    def __init__(self, rowptr, colidx, graph_ptr, width: int, first_key: int = 0, total: Optional[int] = None,
+                 with_networkx: bool = True):
+        n_local = len(graph_ptr) - 1
+        total = n_local + first_key if total is None else int(total)
+        super().__init__((k, None) for k in range(total))
+        self._arrays = (np.asarray(rowptr), np.asarray(colidx), np.asarray(graph_ptr))
+        self._first, self._n_local, self._width, self._nx = int(first_key), n_local, int(width), bool(with_networkx)
+
+    def _build(self, key: int):
+        from .graph import AdjacencyFeatures, CSRGraph
+        g = key - self._first
+        if not 0 <= g < self._n_local:
+            raise KeyError(f"graph {key} belongs to another rank's shard")
+        rowptr, colidx, gp = self._arrays
+        lo, hi = int(gp[g]), int(gp[g + 1])
+        rp = (rowptr[lo: hi + 1] - rowptr[lo]).astype(np.int32)
+        ci = (colidx[rowptr[lo]: rowptr[hi]] - lo).astype(np.int32)
+        handle = CSRGraph(rp, ci, None, hi - lo)
+        nx_graph = None
+        if self._nx:
+            import networkx as nx
+            rows = np.repeat(np.arange(hi - lo), np.diff(rp))
+            keep = rows < ci
+            nx_graph = nx.Graph()
+            nx_graph.add_nodes_from(range(hi - lo))
+            nx_graph.add_edges_from(zip(rows[keep].tolist(), ci[keep].tolist()), weight=1, capacity=1)
+        return [handle, AdjacencyFeatures(handle, self._width), nx_graph, [0, 1, 2]]
+
+    def __getitem__(self, key):
+        item = super().__getitem__(key)
+        if item is None:
+            item = self._build(key)
+            super().__setitem__(key, item)
+        return item
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]

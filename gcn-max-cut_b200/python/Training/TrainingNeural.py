@@ -337,14 +337,14 @@ def _prepare(dataset: Dict, batch_graphs: int, device, engine: Optional[GCNEngin
     sig = (keys, batch_graphs, mode, rank, world, bool(stream))
     if cache is not None and cache[0] is dataset and cache[1] == sig:
         return cache[2]
-    items = [dataset[k] for k in keys]
     steps: List[_PreparedItem] = []
     bg = max(1, batch_graphs)
-    for lo in range(0, len(items), bg):
-        chunk = items[lo: lo + bg]
+    for lo in range(0, len(keys), bg):
+        chunk_keys = keys[lo: lo + bg]
         if world > 1:
-            a, b = gdist.shard_bounds(len(chunk), rank, world)
-            chunk = chunk[a:b]
+            a, b = gdist.shard_bounds(len(chunk_keys), rank, world)
+            chunk_keys = chunk_keys[a:b]
+        chunk = [dataset[k] for k in chunk_keys]          # only this rank's items are ever dereferenced
         if not chunk:
             steps.append(_PreparedItem(None, None, n_graphs=0))        # this rank only joins the step's all-reduce
             continue
@@ -414,6 +414,8 @@ class _Streamer:
         self.ones = None
         self.feat = None
         self.loss_host = None
+        self.prefetched = None      # (host batch, step index whose slot holds it): upload begun by the previous epoch
+        self.speculative = True
         self.stats = {"h2d_bytes": 0, "d2h_bytes": 0, "steps": 0}
 
     def _slot(self, i: int, hb: _HostBatch) -> dict:
@@ -489,16 +491,26 @@ def _train_epoch_streamed(engine: GCNEngine, steps: List[_PreparedItem], device)
     mode = _engine_mode(engine)
     live = [s for s in steps if s.host is not None]
     host_losses: List[torch.Tensor] = []
-    if live:
-        st.issue(0, live[0].host)
     j = 0
+    if live:
+        if st.prefetched is not None and st.prefetched[0] is live[0].host:
+            j = st.prefetched[1]                       # the previous epoch already started this upload (slot parity j & 1)
+        else:
+            st.issue(0, live[0].host)
+    st.prefetched = None
+    first = j
     for step in steps:
         if step.host is None:
             engine.train_step_empty()
             continue
         slot = j & 1
-        if j + 1 < len(live):
-            st.issue(slot ^ 1, live[j + 1].host)
+        if j - first + 1 < len(live):
+            st.issue(slot ^ 1, live[j - first + 1].host)
+        elif st.speculative:
+            # last step of the epoch: start uploading the first step of the NEXT epoch over the same dataset, so the
+            # copy overlaps this step and the epoch-end read-back (epochs revisit the dataset in the same order, :371)
+            st.issue(slot ^ 1, live[0].host)
+            st.prefetched = (live[0].host, j + 1)
         batch = st.batch(slot, step.host)
         feats = st.features(slot, step.host, batch, engine, mode)
         losses = engine.train_step(batch, feats)

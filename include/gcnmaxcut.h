@@ -329,16 +329,22 @@ int gmc_adj_features_bwd_f32(const void* plan, const int32_t* graph_ptr, int32_t
  *   op 0 (nn): C[M,N] = act(row_scale[m] * (A[M,K] (B_0 + B_1 [+ B_2])) + bias[n])      H1 = relu(s . (XI W1) + b1)
  *   op 2 (tn): C[M,N] (+)= A[K,M]^T (B_0 + B_1 [+ B_2]), split-K over the workspace      dW1 = XI^T (s . dH1pre)
  * row_scale / bias (N % 4 == 0) / relu are nullable / 0 and need accumulate == 0 (they disable split-K).
+ * proj_w (nullable; [N rounded up to 64][4] fp32 zero padded, as for gmc_gemm_bf16_bf16out): fused skinny projection
+ * proj_out[m, 0..n_proj) = sum_n C[m, n] proj_w[n][.] of the fp32 result (T2 = H1 W2, TrainingNeural.py:83) -- every
+ * (row, n-tile) writes one partial into the workspace (gmc_gemm_bf16_split_workspace_bytes with with_projection = 1) and
+ * a second launch adds the tiles in order: deterministic, no atomics.
  * gmc_skinny_bwd_split is gmc_skinny_bwd_f32 (fp32 H) whose dHpre leaves as those stacked parts, pre-scaled by s. */
 int gmc_f32_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t n_rows, int32_t n_cols,
                        int32_t n_split, int64_t split_rows, void* stream);
 int gmc_row_scale_f32(const int32_t* rowptr, const float* coef, int64_t n_rows, float* row_scale,
                       int32_t* nonuniform_count /* device, nullable, incremented */, void* stream);
-size_t gmc_gemm_bf16_split_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t n_split);
+size_t gmc_gemm_bf16_split_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t n_split,
+                                           int32_t with_projection);
 int gmc_gemm_bf16_split(int32_t op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K,
                         int64_t lda, int64_t ldb, int64_t ldc, int32_t n_split, int64_t b_split_rows,
-                        const float* row_scale, const float* bias, int32_t relu, int32_t accumulate, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        const float* row_scale, const float* bias, int32_t relu, const float* proj_w, float* proj_out,
+                        int64_t ldp, int32_t n_proj, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream);
 int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh,
                          const float* row_scale, void* dH_split, int64_t lddh, int64_t split_rows, int32_t n_split,
                          float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace,

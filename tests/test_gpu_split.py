@@ -59,8 +59,46 @@ def test_split_gemm_nn_matches_float64(M, N, K, n_split):
     W = torch.randn(K, N) * 0.05
     want = A.double() @ W.double()
     got = ops.gemm_bf16_split("nn", ops.to_bf16(A.to(DEV)), ops.f32_split_bf16(W.to(DEV), n_split), n_split, K)
-    tol = (3e-6 if n_split == 2 else 4e-7) * max(1.0, math.sqrt(K) / 16)
+    tol = (2.0 ** -17 if n_split == 2 else 4e-7) * max(1.0, math.sqrt(K) / 16)     # 2 parts: 2^-17 per weight, worst case
     assert relerr(got.cpu(), want) < tol
+
+
+@pytest.mark.parametrize("op", ["nn", "tn"])
+@pytest.mark.parametrize("n_split,cluster", [(2, "1"), (2, "2"), (2, "4"), (3, "1"), (3, "3")])
+def test_split_gemm_cluster_shapes(op, n_split, cluster, monkeypatch):
+    """Every CLM x 1 cluster shape of the split kernels (B chunks shared out by multicast) gives the same product."""
+    monkeypatch.setenv("GMC_GEMM_SPLIT_CLUSTER", cluster)
+    M, N, K = (3000, 500, 1000) if op == "nn" else (1000, 500, 30000)
+    A = bf16_exact_ints(M, K, 7, 17) if op == "nn" else bf16_exact_ints(K, M, 7, 17)
+    torch.manual_seed(1)
+    B = torch.randn(K, N) * 0.02
+    want = (A.double() if op == "nn" else A.double().t()) @ B.double()
+    got = ops.gemm_bf16_split(op, ops.to_bf16(A.to(DEV)), ops.f32_split_bf16(B.to(DEV), n_split), n_split, K)
+    assert relerr(got.cpu(), want) < (2.0 ** -17 if n_split == 2 else 4e-7) * max(1.0, math.sqrt(K) / 16)
+
+
+@pytest.mark.parametrize("n_split", [2, 3])
+@pytest.mark.parametrize("M,N,n_proj", [(1000, 500, 3), (130, 260, 4), (4097, 96, 2), (70, 12, 3)])
+def test_split_gemm_fused_projection_is_deterministic_and_exact(M, N, n_proj, n_split):
+    K = 256
+    A = bf16_exact_ints(M, K, 6, M)
+    torch.manual_seed(N)
+    W, b, W2 = torch.randn(K, N) * 0.05, torch.randn(N) * 0.2, torch.randn(N, n_proj) * 0.3
+    s = torch.rand(M) * 0.2 + 0.05
+    Ws = ops.f32_split_bf16(W.to(DEV), n_split)
+    Ab, w2p = ops.to_bf16(A.to(DEV)), ops.pad_proj_weights(W2.to(DEV))
+    outs = []
+    for _ in range(2):
+        C = ops.padded_empty(M, N, DEV)
+        T = torch.full((M, n_proj), float("nan"), device=DEV)
+        ops.gemm_bf16_split("nn", Ab, Ws, n_split, K, out=C, row_scale=s.to(DEV), bias=b.to(DEV), relu=True, proj_w=w2p,
+                            proj_out=T, n_proj=n_proj)
+        outs.append((C.clone(), T.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    C, T = outs[0]
+    assert relerr(T.cpu(), C.cpu().double() @ W2.double()) < 2e-6        # the projection of the rows it wrote
+    C_plain = ops.gemm_bf16_split("nn", Ab, Ws, n_split, K, row_scale=s.to(DEV), bias=b.to(DEV), relu=True)
+    assert torch.equal(C, C_plain)
 
 
 @pytest.mark.parametrize("n_split", [2, 3])
@@ -74,7 +112,7 @@ def test_split_gemm_nn_epilogue_scale_bias_relu(M, N, K, n_split):
     out = ops.padded_empty(M, N, DEV)
     got = ops.gemm_bf16_split("nn", ops.to_bf16(A.to(DEV)), ops.f32_split_bf16(W.to(DEV), n_split), n_split, K, out=out,
                               row_scale=s.to(DEV), bias=b.to(DEV), relu=True)
-    assert relerr(got.cpu(), want) < (3e-6 if n_split == 2 else 5e-7)
+    assert relerr(got.cpu(), want) < (2.0 ** -17 if n_split == 2 else 5e-7)
     assert float(got.min()) >= 0.0
 
 
@@ -88,7 +126,7 @@ def test_split_gemm_tn_matches_float64(M, N, K, n_split):
     B = torch.randn(K, N) * 0.01
     want = A.double().t() @ B.double()
     got = ops.gemm_bf16_split("tn", ops.to_bf16(A.to(DEV)), ops.f32_split_bf16(B.to(DEV), n_split), n_split, K)
-    tol = (3e-6 if n_split == 2 else 5e-7) * max(1.0, math.sqrt(K) / 16)
+    tol = (2.0 ** -17 if n_split == 2 else 5e-7) * max(1.0, math.sqrt(K) / 16)
     assert relerr(got.cpu(), want) < tol
 
 
