@@ -380,9 +380,12 @@ class _HostBatch:
         np.cumsum(nnzs, out=ep[1:])
         if gp[-1] >= 2 ** 31 - 1 or ep[-1] >= 2 ** 31 - 1:
             raise ValueError("batch too large for int32 CSR indices; lower batch_graphs")
-        self.rowptr = torch.empty(int(gp[-1]) + 1, dtype=torch.int32).pin_memory()
-        self.colidx = torch.empty(int(ep[-1]), dtype=torch.int32).pin_memory()
-        self.graph_ptr = torch.from_numpy(gp.astype(np.int32)).pin_memory()
+        pin = torch.cuda.is_available()              # (host-only unit tests build the same batches unpinned)
+        self.rowptr = torch.empty(int(gp[-1]) + 1, dtype=torch.int32, pin_memory=pin)
+        self.colidx = torch.empty(int(ep[-1]), dtype=torch.int32, pin_memory=pin)
+        self.graph_ptr = torch.from_numpy(gp.astype(np.int32))
+        if pin:
+            self.graph_ptr = self.graph_ptr.pin_memory()
         rp, ci = self.rowptr.numpy(), self.colidx.numpy()
         rp[0] = 0
         uniform = True

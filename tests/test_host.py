@@ -397,6 +397,58 @@ def test_data_parallel_allreduce_world2_gloo():
         assert flat == want and loss == float(sum(range(11))) and mx == 1.0
 
 
+def _shard_worker(rank, world, port, q):
+    """world-size-2 gloo: train_single_epoch's step preparation shards every global batch contiguously over the ranks."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from Training import TrainingNeural as T
+    from gmc_b200 import synth
+    rp, ci, gp = synth.regular_batch_arrays(11, 16, 3, seed=4)
+    ds = synth.RegularGraphDataset(rp, ci, gp, 16, with_networkx=False)
+    steps = T._prepare(ds, 4, "cpu", None, stream=True)          # global batches of 4, 4, 3 graphs
+    out = []
+    for st in steps:
+        hb = st.host
+        out.append(None if hb is None else (st.n_graphs, hb.rowptr.tolist(), hb.colidx.tolist(), hb.graph_ptr.tolist(), hb.regular))
+    touched = sorted(k for k in ds.keys() if dict.__getitem__(ds, k) is not None)
+    q.put((rank, out, touched))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_train_steps_are_sharded_by_rank_world2_gloo():
+    import torch.multiprocessing as mp
+    from gmc_b200 import synth
+    from gmc_b200.dist import shard_bounds
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30000 + os.getpid() % 1000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((r, (out, touched)) for r, out, touched in (q.get(timeout=180) for _ in procs))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    rp, ci, gp = synth.regular_batch_arrays(11, 16, 3, seed=4)
+    chunks = [(0, 4), (4, 8), (8, 11)]
+    seen = {0: [], 1: []}
+    for step, (lo, hi) in enumerate(chunks):
+        for rank in (0, 1):
+            a, b = shard_bounds(hi - lo, rank, 2)
+            got = res[rank][0][step]
+            assert got[0] == b - a
+            g0, g1 = lo + a, lo + b
+            want_rp = (rp[g0 * 16: g1 * 16 + 1] - rp[g0 * 16]).tolist()
+            want_ci = (ci[rp[g0 * 16]: rp[g1 * 16]] - g0 * 16).tolist()
+            assert got[1] == want_rp and got[2] == want_ci and got[3] == [16 * i for i in range(b - a + 1)] and got[4]
+            seen[rank] += list(range(g0, g1))
+    # every graph belongs to exactly one rank, and a rank never dereferenced another rank's items
+    assert sorted(seen[0] + seen[1]) == list(range(11))
+    assert res[0][1] == sorted(seen[0]) and res[1][1] == sorted(seen[1])
+
+
 # ------------------------------------------------------------------ bench.py argument rules / config fields
 def _bench_args(argv, monkeypatch):
     import importlib
