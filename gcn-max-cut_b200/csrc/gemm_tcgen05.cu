@@ -204,6 +204,185 @@ struct Params {
     float4* proj_part;
 };
 
+// One accumulator tile (this warp's 32 rows x RN real columns) from TMEM to C: the epilogue shared by the cluster kernel and
+// the cta_group::2 kernel.  m0 = first row of this CTA's 128-row block, n0 = first real column, t_row = TMEM address of
+// the warp's lane quarter in the accumulator stage, epi = the CTA's staging block, ebuf = the warp's buffer toggle.
+template <int NS>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmC_ptr, uint32_t epi, int warp, int lane,
+                                              int q, int64_t m0, int n0, uint32_t t_row, float* Cs, int& ebuf) {
+    constexpr int BN = NS == 3 ? 192 : BLOCK_N;
+    constexpr int RN = BN / NS;
+    const CUtensorMap& tmC = *tmC_ptr;
+    const int64_t m = m0 + 32 * q + lane;
+        if (NS == 1 && p.c_bf16) {
+            // bf16 output: 64 accumulator columns -> 32 packed words = one 128-byte staging row per lane, same swizzle
+            // and the same 32-row TMA store as the fp32 path (box 64 x 32 bf16); half the store traffic of the tile
+            float pj[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 64; ++c) {
+                const int n = n0 + 64 * c;
+                if (n >= p.N || m0 >= p.M) break;              // warp-uniform
+                uint32_t ra[32], rb[32], wv[32];
+                tmem_ld32(t_row + 64 * c, ra);
+                tmem_ld32(t_row + 64 * c + 32, rb);
+                if (p.bias) {                                  // same address in every lane: broadcast loads, L1-resident
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (n + 4 * i < p.N) {                 // N % 4 == 0 (checked by the launcher)
+                            const float4 b = __ldg(b4 + i);
+                            ra[4 * i] = __float_as_uint(__uint_as_float(ra[4 * i]) + b.x);
+                            ra[4 * i + 1] = __float_as_uint(__uint_as_float(ra[4 * i + 1]) + b.y);
+                            ra[4 * i + 2] = __float_as_uint(__uint_as_float(ra[4 * i + 2]) + b.z);
+                            ra[4 * i + 3] = __float_as_uint(__uint_as_float(ra[4 * i + 3]) + b.w);
+                        }
+                        if (n + 32 + 4 * i < p.N) {
+                            const float4 b = __ldg(b4 + 8 + i);
+                            rb[4 * i] = __float_as_uint(__uint_as_float(rb[4 * i]) + b.x);
+                            rb[4 * i + 1] = __float_as_uint(__uint_as_float(rb[4 * i + 1]) + b.y);
+                            rb[4 * i + 2] = __float_as_uint(__uint_as_float(rb[4 * i + 2]) + b.z);
+                            rb[4 * i + 3] = __float_as_uint(__uint_as_float(rb[4 * i + 3]) + b.w);
+                        }
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        ra[i] = __float_as_uint(fmaxf(__uint_as_float(ra[i]), 0.f));
+                        rb[i] = __float_as_uint(fmaxf(__uint_as_float(rb[i]), 0.f));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    wv[i] = pack_bf16x2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
+                    wv[16 + i] = pack_bf16x2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+                }
+                if (p.proj_w) {                                // this row's 64 rounded values against projW[n .. n+63][0..3]
+                    const float4* w4 = p.proj_w + n;           // same address in every lane: broadcast, L1-resident
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float lo = __uint_as_float(wv[i] << 16), hi = __uint_as_float(wv[i] & 0xffff0000u);
+                        const float4 wa = __ldg(w4 + 2 * i), wb = __ldg(w4 + 2 * i + 1);
+                        pj[0] = fmaf(lo, wa.x, pj[0]); pj[1] = fmaf(lo, wa.y, pj[1]); pj[2] = fmaf(lo, wa.z, pj[2]); pj[3] = fmaf(lo, wa.w, pj[3]);
+                        pj[0] = fmaf(hi, wb.x, pj[0]); pj[1] = fmaf(hi, wb.y, pj[1]); pj[2] = fmaf(hi, wb.z, pj[2]); pj[3] = fmaf(hi, wb.w, pj[3]);
+                    }
+                }
+                const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+                const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((i ^ (lane & 7)) << 4)),
+                                 "r"(wv[4 * i]), "r"(wv[4 * i + 1]), "r"(wv[4 * i + 2]), "r"(wv[4 * i + 3]) : "memory");
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, buf, n, (int)(m0 + 32 * q));
+                    bulk_commit();
+                }
+                ebuf ^= 1;
+            }
+            if (p.proj_w && m < p.M && m0 < p.M && n0 < p.N) {
+                float* po = p.proj_out + m * p.ldp;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < p.proj_k) atomicAdd(po + k, pj[k]);
+            }
+        } else {
+        float pj[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int c = 0; c < RN / 32; ++c) {
+            const int n = n0 + 32 * c;
+            if (n >= p.N || m0 >= p.M) break;                  // warp-uniform
+            uint32_t r[32];
+            if (NS == 1) {
+                tmem_ld32(t_row + 32 * c, r);
+            } else {
+                // split operand: column n of the product = sum of the NS accumulator groups (low-order parts first)
+                uint32_t r2[32];
+                tmem_ld32(t_row + (NS - 1) * RN + 32 * c, r);
+#pragma unroll
+                for (int sp = NS - 2; sp >= 0; --sp) {
+                    tmem_ld32(t_row + sp * RN + 32 * c, r2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                }
+            }
+            if (p.row_scale) {
+                const float rs = m < p.M ? __ldg(p.row_scale + m) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
+            }
+            if (p.bias) {                                      // same address in every lane: broadcast loads
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (n + 4 * i < p.N) {                     // N % 4 == 0 (checked by the launcher)
+                        const float4 b = __ldg(b4 + i);
+                        r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + b.x);
+                        r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b.y);
+                        r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b.z);
+                        r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b.w);
+                    }
+                }
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
+            }
+            if (p.proj_part) {                                 // this row's 32 values against projW[n .. n+31][0..3]
+                const float4* w4 = p.proj_w + n;               // same address in every lane: broadcast, L1-resident;
+#pragma unroll                                                     // rows >= N of projW are zero padding (up to N rounded to 64)
+                for (int i = 0; i < 32; ++i) {
+                    const float v = __uint_as_float(r[i]);
+                    const float4 w = __ldg(w4 + i);
+                    pj[0] = fmaf(v, w.x, pj[0]); pj[1] = fmaf(v, w.y, pj[1]); pj[2] = fmaf(v, w.z, pj[2]); pj[3] = fmaf(v, w.w, pj[3]);
+                }
+            }
+            if (p.tma_store) {
+                // registers -> 128B-swizzled staging block (lane = row, 16-byte chunk i at i ^ (row & 7): conflict-free
+                // STS.128) -> one TMA store of 32 full 128-byte row segments; rows / columns beyond M / N are clipped
+                const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
+                if (lane == 0) bulk_wait_read<1>();            // the store that last read this buffer has drained it
+                __syncwarp();
+                const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((i ^ (lane & 7)) << 4)),
+                                 "r"(r[4 * i]), "r"(r[4 * i + 1]), "r"(r[4 * i + 2]), "r"(r[4 * i + 3]) : "memory");
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, buf, n, (int)(m0 + 32 * q));
+                    bulk_commit();
+                }
+                ebuf ^= 1;
+            } else if (m < p.M) {
+                float* dst = Cs + m * p.ldc + n;
+                if (p.vec_ok && n + 32 <= p.N) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                        float4* d4 = reinterpret_cast<float4*>(dst) + i;
+                        if (p.accumulate) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *d4 = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (n + i < p.N) dst[i] = p.accumulate ? dst[i] + __uint_as_float(r[i]) : __uint_as_float(r[i]);
+                }
+            }
+        }
+        if (p.proj_part && m < p.M && m0 < p.M && n0 < p.N)
+            p.proj_part[(int64_t)(n0 / RN) * p.M + m] = make_float4(pj[0], pj[1], pj[2], pj[3]);
+        }
+}
+
 // Thread-block cluster of CLM x CLN CTAs (rank = rm + CLM * rn) that owns CLM consecutive m-tiles x CLN consecutive
 // n-tiles of one k-range.  The A tile of m-tile rm is needed by the CLN CTAs of that row: each loads 1/CLN of it and
 // multicasts it to the row; the B tile of n-tile rn is needed by the CLM CTAs of that column: each loads 1/CLM and
@@ -398,175 +577,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float* Cs = p.C + (int64_t)split * p.split_stride;
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
-            const int64_t m = m0 + 32 * q + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BLOCK_N;
-            if (NS == 1 && p.c_bf16) {
-                // bf16 output: 64 accumulator columns -> 32 packed words = one 128-byte staging row per lane, same swizzle
-                // and the same 32-row TMA store as the fp32 path (box 64 x 32 bf16); half the store traffic of the tile
-                float pj[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 64; ++c) {
-                    const int n = n0 + 64 * c;
-                    if (n >= p.N || m0 >= p.M) break;              // warp-uniform
-                    uint32_t ra[32], rb[32], wv[32];
-                    tmem_ld32(t_row + 64 * c, ra);
-                    tmem_ld32(t_row + 64 * c + 32, rb);
-                    if (p.bias) {                                  // same address in every lane: broadcast loads, L1-resident
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (n + 4 * i < p.N) {                 // N % 4 == 0 (checked by the launcher)
-                                const float4 b = __ldg(b4 + i);
-                                ra[4 * i] = __float_as_uint(__uint_as_float(ra[4 * i]) + b.x);
-                                ra[4 * i + 1] = __float_as_uint(__uint_as_float(ra[4 * i + 1]) + b.y);
-                                ra[4 * i + 2] = __float_as_uint(__uint_as_float(ra[4 * i + 2]) + b.z);
-                                ra[4 * i + 3] = __float_as_uint(__uint_as_float(ra[4 * i + 3]) + b.w);
-                            }
-                            if (n + 32 + 4 * i < p.N) {
-                                const float4 b = __ldg(b4 + 8 + i);
-                                rb[4 * i] = __float_as_uint(__uint_as_float(rb[4 * i]) + b.x);
-                                rb[4 * i + 1] = __float_as_uint(__uint_as_float(rb[4 * i + 1]) + b.y);
-                                rb[4 * i + 2] = __float_as_uint(__uint_as_float(rb[4 * i + 2]) + b.z);
-                                rb[4 * i + 3] = __float_as_uint(__uint_as_float(rb[4 * i + 3]) + b.w);
-                            }
-                        }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            ra[i] = __float_as_uint(fmaxf(__uint_as_float(ra[i]), 0.f));
-                            rb[i] = __float_as_uint(fmaxf(__uint_as_float(rb[i]), 0.f));
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        wv[i] = pack_bf16x2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
-                        wv[16 + i] = pack_bf16x2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
-                    }
-                    if (p.proj_w) {                                // this row's 64 rounded values against projW[n .. n+63][0..3]
-                        const float4* w4 = p.proj_w + n;           // same address in every lane: broadcast, L1-resident
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float lo = __uint_as_float(wv[i] << 16), hi = __uint_as_float(wv[i] & 0xffff0000u);
-                            const float4 wa = __ldg(w4 + 2 * i), wb = __ldg(w4 + 2 * i + 1);
-                            pj[0] = fmaf(lo, wa.x, pj[0]); pj[1] = fmaf(lo, wa.y, pj[1]); pj[2] = fmaf(lo, wa.z, pj[2]); pj[3] = fmaf(lo, wa.w, pj[3]);
-                            pj[0] = fmaf(hi, wb.x, pj[0]); pj[1] = fmaf(hi, wb.y, pj[1]); pj[2] = fmaf(hi, wb.z, pj[2]); pj[3] = fmaf(hi, wb.w, pj[3]);
-                        }
-                    }
-                    const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
-                    if (lane == 0) bulk_wait_read<1>();
-                    __syncwarp();
-                    const uint32_t rowaddr = buf + lane * 128;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((i ^ (lane & 7)) << 4)),
-                                     "r"(wv[4 * i]), "r"(wv[4 * i + 1]), "r"(wv[4 * i + 2]), "r"(wv[4 * i + 3]) : "memory");
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC, buf, n, (int)(m0 + 32 * q));
-                        bulk_commit();
-                    }
-                    ebuf ^= 1;
-                }
-                if (p.proj_w && m < p.M && m0 < p.M && n0 < p.N) {
-                    float* po = p.proj_out + m * p.ldp;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k < p.proj_k) atomicAdd(po + k, pj[k]);
-                }
-            } else {
-            float pj[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int c = 0; c < RN / 32; ++c) {
-                const int n = n0 + 32 * c;
-                if (n >= p.N || m0 >= p.M) break;                  // warp-uniform
-                uint32_t r[32];
-                if (NS == 1) {
-                    tmem_ld32(t_row + 32 * c, r);
-                } else {
-                    // split operand: column n of the product = sum of the NS accumulator groups (low-order parts first)
-                    uint32_t r2[32];
-                    tmem_ld32(t_row + (NS - 1) * RN + 32 * c, r);
-#pragma unroll
-                    for (int sp = NS - 2; sp >= 0; --sp) {
-                        tmem_ld32(t_row + sp * RN + 32 * c, r2);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
-                    }
-                }
-                if (p.row_scale) {
-                    const float rs = m < p.M ? __ldg(p.row_scale + m) : 0.f;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
-                }
-                if (p.bias) {                                      // same address in every lane: broadcast loads
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (n + 4 * i < p.N) {                     // N % 4 == 0 (checked by the launcher)
-                            const float4 b = __ldg(b4 + i);
-                            r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + b.x);
-                            r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b.y);
-                            r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b.z);
-                            r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b.w);
-                        }
-                    }
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
-                }
-                if (p.proj_part) {                                 // this row's 32 values against projW[n .. n+31][0..3]
-                    const float4* w4 = p.proj_w + n;               // same address in every lane: broadcast, L1-resident;
-#pragma unroll                                                     // rows >= N of projW are zero padding (up to N rounded to 64)
-                    for (int i = 0; i < 32; ++i) {
-                        const float v = __uint_as_float(r[i]);
-                        const float4 w = __ldg(w4 + i);
-                        pj[0] = fmaf(v, w.x, pj[0]); pj[1] = fmaf(v, w.y, pj[1]); pj[2] = fmaf(v, w.z, pj[2]); pj[3] = fmaf(v, w.w, pj[3]);
-                    }
-                }
-                if (p.tma_store) {
-                    // registers -> 128B-swizzled staging block (lane = row, 16-byte chunk i at i ^ (row & 7): conflict-free
-                    // STS.128) -> one TMA store of 32 full 128-byte row segments; rows / columns beyond M / N are clipped
-                    const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
-                    if (lane == 0) bulk_wait_read<1>();            // the store that last read this buffer has drained it
-                    __syncwarp();
-                    const uint32_t rowaddr = buf + lane * 128;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((i ^ (lane & 7)) << 4)),
-                                     "r"(r[4 * i]), "r"(r[4 * i + 1]), "r"(r[4 * i + 2]), "r"(r[4 * i + 3]) : "memory");
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC, buf, n, (int)(m0 + 32 * q));
-                        bulk_commit();
-                    }
-                    ebuf ^= 1;
-                } else if (m < p.M) {
-                    float* dst = Cs + m * p.ldc + n;
-                    if (p.vec_ok && n + 32 <= p.N) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                            float4* d4 = reinterpret_cast<float4*>(dst) + i;
-                            if (p.accumulate) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                            *d4 = v;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (n + i < p.N) dst[i] = p.accumulate ? dst[i] + __uint_as_float(r[i]) : __uint_as_float(r[i]);
-                    }
-                }
-            }
-            if (p.proj_part && m < p.M && m0 < p.M && n0 < p.N)
-                p.proj_part[(int64_t)(n0 / RN) * p.M + m] = make_float4(pj[0], pj[1], pj[2], pj[3]);
-            }
+            epilogue_tile<NS>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
@@ -879,12 +891,20 @@ static void cluster_shape(bool a_mn, int64_t n_tiles, int* clm, int* cln, bool b
     *cln = 1;
 }
 
-static int pick_splits_cl(int64_t cluster_tiles, int64_t K, int slots) {
-    if (cluster_tiles >= slots || K < 8 * BLOCK_K) return 1;
-    int64_t s = slots / cluster_tiles;
-    const int64_t max_by_k = K / (4 * BLOCK_K);
-    if (s > max_by_k) s = max_by_k;
-    return (int)(s < 1 ? 1 : s);
+// max_chain > 0 (fp32-grade split GEMMs): no accumulator sums more than ~max_chain k-rows -- the fp32 TMEM accumulation
+// of a 10^6-term chain costs accuracy the split operands were meant to buy -- so a long K is cut into a multiple of the
+// slot-filling split count; the partials (2 MB each at config 3) are added by the deterministic reduce kernel.
+constexpr int64_t kSplitChain = 32768;
+static int pick_splits_cl(int64_t cluster_tiles, int64_t K, int slots, int64_t max_chain = 0) {
+    int64_t s = 1;
+    if (cluster_tiles < slots && K >= 8 * BLOCK_K) {
+        s = slots / cluster_tiles;
+        const int64_t max_by_k = K / (4 * BLOCK_K);
+        if (s > max_by_k) s = max_by_k;
+        if (s < 1) s = 1;
+    }
+    if (max_chain > 0 && K > s * max_chain) s *= ceil_div<int64_t>(K, s * max_chain);
+    return (int)s;
 }
 
 static bool no_tma_store() {
@@ -962,7 +982,7 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     p.ng_tiles = ceil_div(p.n_tiles, CLN);
     const int64_t ctiles = (int64_t)p.mg_tiles * p.ng_tiles;
     const bool fused_epilogue = c_bf16 || row_scale || bias || relu || proj_w;   // these leave straight from the accumulators
-    int splits = fused_epilogue ? 1 : pick_splits_cl(ctiles, K, slots);
+    int splits = fused_epilogue ? 1 : pick_splits_cl(ctiles, K, slots, NS > 1 ? kSplitChain : 0);
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
         if (splits < 1) splits = 1;
@@ -1306,11 +1326,14 @@ int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64
 // matrix split into NS bf16 parts by gmc_f32_split_bf16 (NS = 2: 16 mantissa bits, NS = 3: 24 = all of fp32), products
 // accumulated in fp32 TMEM and added up in the epilogue.  op 0 (nn) and 2 (tn): B is MN-major in both.
 namespace tc {
-static void split_cluster(int ns, int* clm) {
+static void split_cluster(int ns, int* clm, bool a_mn = false) {
     // The B stage of a split GEMM is NS x as wide per real output column as a plain one, so sharing it pays (unlike the
     // plain bf16 nn kernel): every CTA of a CLM x 1 cluster loads 1 / CLM of the stage's 64-column chunks and multicasts
     // them.  NS = 2: four chunks -> CLM 1 | 2 | 4; NS = 3: three chunks -> CLM 1 | 3.  GMC_GEMM_SPLIT_CLUSTER overrides.
-    *clm = ns == 2 ? 2 : 3;
+    // Measured at config 3 (profiles/r02_split_gemm.json): NS = 2 nn 8.6 / 6.3-7.0 / 7.5 ms for CLM 1 / 2 / 4, tn 10.6 /
+    // 7.0-7.5 / 7.7; NS = 3 nn 12.9 / 11.6-11.8 for CLM 1 / 3, tn 17.8 / 21.2 (48 co-resident clusters of 3 against 8
+    // m-tiles: idle CTAs) -> 2, 3 for nn, 2, 1 for tn.
+    *clm = ns == 2 ? 2 : (a_mn ? 1 : 3);
     const char* e = getenv("GMC_GEMM_SPLIT_CLUSTER");
     if (e && e[0] >= '1' && e[0] <= '4') {
         const int c = e[0] - '0';
@@ -1333,8 +1356,8 @@ size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, in
         return (size_t)ceil_div<int64_t>(N, rn) * (size_t)M * sizeof(float4);
     }
     int clm;
-    tc::split_cluster(n_split, &clm);
-    const int splits = tc::pick_splits_cl(tc::split_tiles(n_split, M, N, clm), K, sm_count() / clm);
+    tc::split_cluster(n_split, &clm, op == 2);
+    const int splits = tc::pick_splits_cl(tc::split_tiles(n_split, M, N, clm), K, sm_count() / clm, tc::kSplitChain);
     return splits > 1 ? (((size_t)splits * M * N * sizeof(float) + 255) & ~(size_t)255) : 0;
 }
 
@@ -1357,7 +1380,7 @@ int tc_gemm_bf16_split(int op, const void* A, const void* B, float* C, int64_t M
         return GMC_OK;
     }
     int clm;
-    tc::split_cluster(n_split, &clm);
+    tc::split_cluster(n_split, &clm, op == 2);
 #define GMC_SPLIT_CASE(AMN, CM, NSV)                                                                                  \
     return tc::launch<AMN, true, CM, 1, true, NSV>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, 0, \
                                                    bias, relu, proj_w, proj_out, ldp, proj_k, b_split_rows, row_scale);

@@ -66,7 +66,8 @@ def test_split_gemm_nn_matches_float64(M, N, K, n_split):
 @pytest.mark.parametrize("op", ["nn", "tn"])
 @pytest.mark.parametrize("n_split,cluster", [(2, "1"), (2, "2"), (2, "4"), (3, "1"), (3, "3")])
 def test_split_gemm_cluster_shapes(op, n_split, cluster, monkeypatch):
-    """Every CLM x 1 cluster shape of the split kernels (B chunks shared out by multicast) gives the same product."""
+    """Every CLM x 1 cluster shape of the split kernels (B chunks shared out by multicast) gives the same product
+    (tolerance: the split error bound plus fp32 accumulation over K terms in TMEM)."""
     monkeypatch.setenv("GMC_GEMM_SPLIT_CLUSTER", cluster)
     M, N, K = (3000, 500, 1000) if op == "nn" else (1000, 500, 30000)
     A = bf16_exact_ints(M, K, 7, 17) if op == "nn" else bf16_exact_ints(K, M, 7, 17)
@@ -74,7 +75,7 @@ def test_split_gemm_cluster_shapes(op, n_split, cluster, monkeypatch):
     B = torch.randn(K, N) * 0.02
     want = (A.double() if op == "nn" else A.double().t()) @ B.double()
     got = ops.gemm_bf16_split(op, ops.to_bf16(A.to(DEV)), ops.f32_split_bf16(B.to(DEV), n_split), n_split, K)
-    assert relerr(got.cpu(), want) < (2.0 ** -17 if n_split == 2 else 4e-7) * max(1.0, math.sqrt(K) / 16)
+    assert relerr(got.cpu(), want) < (2.0 ** -17 if n_split == 2 else 1e-6) * max(1.0, math.sqrt(K) / 16)
 
 
 @pytest.mark.parametrize("n_split", [2, 3])
