@@ -606,7 +606,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 constexpr int STAGES2 = 6;
 constexpr int HALF = 128;                                   // rows of A / columns of B staged per CTA
 constexpr int A2_BYTES = HALF * BLOCK_K * 4, B2_BYTES = HALF * BLOCK_K * 4, STAGE2_BYTES = A2_BYTES + B2_BYTES;
-constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + EPI_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -639,13 +639,34 @@ __host__ __device__ constexpr uint32_t make_idesc2(bool a_mn, bool b_mn) {
          | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);          // N = 256, M = 256 (pair)
 }
 
-template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc2x(bool a_mn, bool b_mn, bool bf16) {
+    return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
+         | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);          // N = 256, M = 256 (pair)
+}
+
+// fp32 (kind::tf32) or bf16 (kind::f16) operands; the epilogue is the cluster kernel's (epilogue_tile: fp32 / bf16 C, TMA
+// stores through the swizzled staging block, bias / ReLU / row scale / fused projection), run by both CTAs on their own
+// 128 rows.  Six 32 KB stages + the 32 KB staging block.
+template <bool A_MN, bool B_MN, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const Params p) {
+    constexpr int ELT = BF16 ? 2 : 4;
+    constexpr int BK = 128 / ELT;                                  // k elements per stage
+    constexpr int MNC = 128 / ELT;                                 // m/n elements per MN-major chunk
+    constexpr int UK = 32 / ELT;                                   // k elements per MMA
+    constexpr int CHUNK = BK * 128;                                // bytes of one MN-major chunk
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;
-    const uint32_t bars = tiles + STAGES2 * STAGE2_BYTES;
+    const uint32_t epi = tiles + STAGES2 * STAGE2_BYTES;           // 4 warps x 2 x 4 KB, 1024-aligned
+    const uint32_t bars = epi + EPI_BYTES;
     const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES2;
     const uint32_t tfull_bar = bars + 16 * STAGES2, tempty_bar = tfull_bar + 8 * ACC_STAGES;
     const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
@@ -687,20 +708,20 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const int n0 = (int)(rem % p.n_tiles) * 256 + HALF * (int)rank;
                 const int64_t kb = (int64_t)split * p.k_per_split;
                 const int64_t ke = min(p.K, kb + p.k_per_split);
-                for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+                for (int64_t k0 = kb; k0 < ke; k0 += BK) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A2_BYTES;
                     const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);          // the LEADER's full barrier
                     if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * STAGE2_BYTES);
                     if (A_MN) {
 #pragma unroll
-                        for (int j = 0; j < HALF / 32; ++j) tma_load_2d_2sm(sa + j * CHUNK_BYTES, &tmA, m0 + 32 * j, (int)k0, fb);
+                        for (int j = 0; j < HALF / MNC; ++j) tma_load_2d_2sm(sa + j * CHUNK, &tmA, m0 + MNC * j, (int)k0, fb);
                     } else {
                         tma_load_2d_2sm(sa, &tmA, (int)k0, m0, fb);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < HALF / 32; ++j) tma_load_2d_2sm(sb + j * CHUNK_BYTES, &tmB, n0 + 32 * j, (int)k0, fb);
+                        for (int j = 0; j < HALF / MNC; ++j) tma_load_2d_2sm(sb + j * CHUNK, &tmB, n0 + MNC * j, (int)k0, fb);
                     } else {
                         tma_load_2d_2sm(sb, &tmB, (int)k0, n0, fb);
                     }
@@ -711,11 +732,12 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc2(A_MN, B_MN);
-            const uint32_t a_lbo = A_MN ? CHUNK_BYTES : 16, b_lbo = B_MN ? CHUNK_BYTES : 16;
-            const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
-            const uint32_t a_lay = A_MN ? 1 : 2, b_lay = B_MN ? 1 : 2;
-            const uint32_t a_step = A_MN ? 1024 : UMMA_K * 4, b_step = B_MN ? 1024 : UMMA_K * 4;
+            constexpr uint32_t idesc = make_idesc2x(A_MN, B_MN, BF16);
+            constexpr uint32_t MN_SBO = BF16 ? 1024 : 512, MN_LAY = BF16 ? 2 : 1, MN_STEP = UK * 128;
+            const uint32_t a_lbo = A_MN ? CHUNK : 16, b_lbo = B_MN ? CHUNK : 16;
+            const uint32_t a_sbo = A_MN ? MN_SBO : 1024, b_sbo = B_MN ? MN_SBO : 1024;
+            const uint32_t a_lay = A_MN ? MN_LAY : 2, b_lay = B_MN ? MN_LAY : 2;
+            const uint32_t a_step = A_MN ? MN_STEP : 32, b_step = B_MN ? MN_STEP : 32;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int64_t w = pair; w < n_work; w += n_pairs) {
@@ -726,21 +748,22 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 uint32_t first = 1;
-                for (int64_t k0 = kb; k0 < ke; k0 += BLOCK_K) {
+                for (int64_t k0 = kb; k0 < ke; k0 += BK) {
                     mbar_wait(full_bar + 8 * stage, phase);
                     tc_fence_after();
                     __syncwarp();
                     if (elect_one()) {
                         const uint32_t sa = tiles + stage * STAGE2_BYTES, sb = sa + A2_BYTES;
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        for (int k = 0; k < BK / UK; ++k) {
                             const uint64_t ad = make_desc(sa + k * a_step, a_lbo, a_sbo, a_lay);
                             const uint64_t bd = make_desc(sb + k * b_step, b_lbo, b_sbo, b_lay);
-                            umma_tf32_2sm(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                            if (BF16) umma_bf16_2sm(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                            else umma_tf32_2sm(d_tmem, ad, bd, idesc, first ? 0u : 1u);
                             first = 0;
                         }
                         umma_commit_2sm(empty_bar + 8 * stage, 3);      // frees the stage in BOTH CTAs
-                        if (k0 + BLOCK_K >= ke) umma_commit_2sm(tfull_bar + 8 * acc, 3);
+                        if (k0 + BK >= ke) umma_commit_2sm(tfull_bar + 8 * acc, 3);
                     }
                     __syncwarp();
                     first = 0;
@@ -753,6 +776,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ===================== epilogue (warps 2..5, both CTAs: own 128 rows) =====================
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        int ebuf = 0;
         for (int64_t w = pair; w < n_work; w += n_pairs) {
             const int split = (int)(w / tiles_mn);
             const int64_t rem = w - (int64_t)split * tiles_mn;
@@ -761,37 +785,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float* Cs = p.C + (int64_t)split * p.split_stride;
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
-            const int64_t m = m0 + 32 * q + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
-#pragma unroll 1
-            for (int c = 0; c < 256 / 32; ++c) {
-                const int n = n0 + 32 * c;
-                if (n >= p.N) break;                               // warp-uniform
-                uint32_t r[32];
-                tmem_ld32(t_row + 32 * c, r);
-                if (m < p.M) {
-                    float* dst = Cs + m * p.ldc + n;
-                    if (p.vec_ok && n + 32 <= p.N) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                            float4* d4 = reinterpret_cast<float4*>(dst) + i;
-                            if (p.accumulate) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                            *d4 = v;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (n + i < p.N) dst[i] = p.accumulate ? dst[i] + __uint_as_float(r[i]) : __uint_as_float(r[i]);
-                    }
-                }
-            }
+            epilogue_tile<1>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty_bar + 8 * acc, 0));   // leader's barrier, 8 arrivals
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait_all();                            // outstanding TMA stores complete before the CTA exits
     }
 
     __syncwarp();                                                 // reconverge before the .aligned cluster barrier
@@ -943,6 +944,82 @@ static int cluster_slots() {
     return cached;
 }
 
+// Output side of a launch, shared by the cluster kernel and the cta_group::2 kernel: where the accumulators go (C or the
+// split-K workspace), the epilogue options and the TMA-store map.  p.n_tiles must be set (fused fp32 projection).
+static int setup_output(Params& p, CUtensorMap* tmC_out, float* C, int64_t M, int64_t N, int64_t ldc, int accumulate, int splits,
+                        void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16, const float* bias, int relu,
+                        const float* proj_w, float* proj_out, int64_t ldp, int proj_k, const float* row_scale) {
+    if (splits == 1) {
+        p.C = C; p.ldc = ldc; p.split_stride = 0; p.accumulate = accumulate;
+        p.vec_ok = (ldc % (c_bf16 ? 8 : 4) == 0) && aligned16(C);
+    } else {
+        p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
+        p.vec_ok = (N % 4 == 0) && aligned16(workspace);
+    }
+    // direct (non split-K, non accumulating) outputs leave through a 128B-swizzled staging block and TMA stores
+    CUtensorMap& tmC = *tmC_out;
+    memset(&tmC, 0, sizeof(tmC));
+    int rc;
+    p.tma_store = 0;
+    if (c_bf16) {
+        if (accumulate || !p.vec_ok) {
+            set_error("gmc_gemm_bf16_bf16out: needs accumulate = 0, a 16-byte aligned C and ldc %% 8 == 0");
+            return GMC_ERR_INVALID_ARG;
+        }
+        rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 64, 32, false, 2);
+        if (rc) return rc;
+        p.tma_store = 1;
+        p.c_bf16 = 1;
+        if (bias && (N % 4 != 0 || !aligned16(bias))) {
+            set_error("gmc_gemm_bf16_bf16out: a bias needs N %% 4 == 0 and a 16-byte aligned pointer");
+            return GMC_ERR_INVALID_ARG;
+        }
+        p.bias = bias;
+        p.relu = relu;
+        if (proj_w) {
+            if (!proj_out || proj_k < 1 || proj_k > 4 || ldp < proj_k || N > 2 * BLOCK_N || !aligned16(proj_w)) {
+                set_error("gmc_gemm_bf16_bf16out: the fused projection needs 1 <= n_proj <= 4, ldp >= n_proj, N <= 512 and a "
+                          "16-byte aligned padded weight matrix");
+                return GMC_ERR_INVALID_ARG;
+            }
+            GMC_CUDA(cudaMemset2DAsync(proj_out, (size_t)ldp * sizeof(float), 0, (size_t)proj_k * sizeof(float), (size_t)M, s));
+            p.proj_w = reinterpret_cast<const float4*>(proj_w);
+            p.proj_out = proj_out;
+            p.ldp = ldp;
+            p.proj_k = proj_k;
+        }
+    } else {
+        if (row_scale || bias || relu || proj_w) {
+            if (accumulate || (bias && (N % 4 != 0 || !aligned16(bias)))) {
+                set_error("gmc_gemm: an fp32 epilogue (row scale / bias / ReLU) needs accumulate = 0 and, with a bias, "
+                          "N %% 4 == 0 and a 16-byte aligned bias");
+                return GMC_ERR_INVALID_ARG;
+            }
+            p.row_scale = row_scale;
+            p.bias = bias;
+            p.relu = relu;
+        }
+        if (proj_w) {
+            const size_t need = (size_t)p.n_tiles * (size_t)M * sizeof(float4);
+            if (splits != 1 || accumulate || !proj_out || proj_k < 1 || proj_k > 4 || ldp < proj_k || !aligned16(proj_w) ||
+                !workspace || workspace_bytes < need || !aligned16(workspace)) {
+                set_error("gmc_gemm: the fused fp32 projection needs a direct (non split-K, non accumulating) output, "
+                          "1 <= n_proj <= 4, ldp >= n_proj, a 16-byte aligned padded weight matrix and a workspace of "
+                          "n_tiles * M * 16 bytes (%zu)", need);
+                return GMC_ERR_INVALID_ARG;
+            }
+            p.proj_w = reinterpret_cast<const float4*>(proj_w);
+            p.proj_part = reinterpret_cast<float4*>(workspace);
+        }
+        if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
+            rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
+            if (rc) return rc;
+            p.tma_store = 1;
+        }
+    }
+    return GMC_OK;
+}
+
 template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16, int NS = 1>
 static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
@@ -991,73 +1068,10 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     splits = (int)ceil_div<int64_t>(K, k_per);
     p.k_splits = splits;
     p.k_per_split = k_per;
-    if (splits == 1) {
-        p.C = C; p.ldc = ldc; p.split_stride = 0; p.accumulate = accumulate;
-        p.vec_ok = (ldc % (c_bf16 ? 8 : 4) == 0) && aligned16(C);
-    } else {
-        p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
-        p.vec_ok = (N % 4 == 0) && aligned16(workspace);
-    }
-    // direct (non split-K, non accumulating) outputs leave through a 128B-swizzled staging block and TMA stores
     CUtensorMap tmC;
-    memset(&tmC, 0, sizeof(tmC));
-    p.tma_store = 0;
-    if (c_bf16) {
-        if (accumulate || !p.vec_ok) {
-            set_error("gmc_gemm_bf16_bf16out: needs accumulate = 0, a 16-byte aligned C and ldc %% 8 == 0");
-            return GMC_ERR_INVALID_ARG;
-        }
-        rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 64, 32, false, 2);
-        if (rc) return rc;
-        p.tma_store = 1;
-        p.c_bf16 = 1;
-        if (bias && (N % 4 != 0 || !aligned16(bias))) {
-            set_error("gmc_gemm_bf16_bf16out: a bias needs N %% 4 == 0 and a 16-byte aligned pointer");
-            return GMC_ERR_INVALID_ARG;
-        }
-        p.bias = bias;
-        p.relu = relu;
-        if (proj_w) {
-            if (!proj_out || proj_k < 1 || proj_k > 4 || ldp < proj_k || N > 2 * BLOCK_N || !aligned16(proj_w)) {
-                set_error("gmc_gemm_bf16_bf16out: the fused projection needs 1 <= n_proj <= 4, ldp >= n_proj, N <= 512 and a "
-                          "16-byte aligned padded weight matrix");
-                return GMC_ERR_INVALID_ARG;
-            }
-            GMC_CUDA(cudaMemset2DAsync(proj_out, (size_t)ldp * sizeof(float), 0, (size_t)proj_k * sizeof(float), (size_t)M, s));
-            p.proj_w = reinterpret_cast<const float4*>(proj_w);
-            p.proj_out = proj_out;
-            p.ldp = ldp;
-            p.proj_k = proj_k;
-        }
-    } else {
-        if (fused_epilogue) {
-            if (accumulate || (bias && (N % 4 != 0 || !aligned16(bias)))) {
-                set_error("gmc_gemm: an fp32 epilogue (row scale / bias / ReLU) needs accumulate = 0 and, with a bias, "
-                          "N %% 4 == 0 and a 16-byte aligned bias");
-                return GMC_ERR_INVALID_ARG;
-            }
-            p.row_scale = row_scale;
-            p.bias = bias;
-            p.relu = relu;
-        }
-        if (proj_w) {
-            const size_t need = (size_t)p.n_tiles * (size_t)M * sizeof(float4);
-            if (splits != 1 || accumulate || !proj_out || proj_k < 1 || proj_k > 4 || ldp < proj_k || !aligned16(proj_w) ||
-                !workspace || workspace_bytes < need || !aligned16(workspace)) {
-                set_error("gmc_gemm: the fused fp32 projection needs a direct (non split-K, non accumulating) output, "
-                          "1 <= n_proj <= 4, ldp >= n_proj, a 16-byte aligned padded weight matrix and a workspace of "
-                          "n_tiles * M * 16 bytes (%zu)", need);
-                return GMC_ERR_INVALID_ARG;
-            }
-            p.proj_w = reinterpret_cast<const float4*>(proj_w);
-            p.proj_part = reinterpret_cast<float4*>(workspace);
-        }
-        if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
-            rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
-            if (rc) return rc;
-            p.tma_store = 1;
-        }
-    }
+    rc = setup_output(p, &tmC, C, M, N, ldc, accumulate, splits, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w,
+                      proj_out, ldp, proj_k, row_scale);
+    if (rc) return rc;
     const int64_t n_work = ctiles * splits;
     const int grid = (int)(n_work < slots ? n_work : slots) * CL;
     cfg.gridDim = dim3(grid);
@@ -1101,6 +1115,20 @@ static bool use_two_cta() {
     return cached == 1;
 }
 
+// bf16 operands through the cta_group::2 kernel: GMC_GEMM_BF16_2CTA = "1" (all ops) | "nn" | "tn" | "0"
+static int two_cta_bf16_mode() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("GMC_GEMM_BF16_2CTA");
+        cached = 0;
+        if (e && e[0] == '1') cached = 7;
+        else if (e && e[0] == 'n' && e[1] == 'n') cached = 1;
+        else if (e && e[0] == 't' && e[1] == 'n') cached = 4;
+    }
+    return cached;
+}
+static bool use_two_cta_bf16(int op) { return (two_cta_bf16_mode() >> op) & 1; }
+
 static int pick_splits2(int64_t tiles, int64_t K) {
     const int pairs = sm_count() / 2;
     if (tiles >= pairs || K < 8 * BLOCK_K) return 1;
@@ -1110,22 +1138,26 @@ static int pick_splits2(int64_t tiles, int64_t K) {
     return (int)(s < 1 ? 1 : s);
 }
 
-template <bool A_MN, bool B_MN>
-static int launch2(const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+template <bool A_MN, bool B_MN, bool BF16>
+static int launch2(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
+                   const float* bias = nullptr, int relu = 0, const float* proj_w = nullptr, float* proj_out = nullptr,
+                   int64_t ldp = 0, int proj_k = 0) {
+    constexpr int ELT = BF16 ? 2 : 4;
+    constexpr int BK = 128 / ELT, MNC = 128 / ELT;
     static bool attr_set = false;
     if (!attr_set) {
-        GMC_CUDA(cudaFuncSetAttribute(gemm_tf32_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GMC_CUDA(cudaFuncSetAttribute(gemm_umma2_kernel<A_MN, B_MN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SMEM2_BYTES));
         attr_set = true;
     }
     CUtensorMap tmA, tmB;
     int rc;
-    if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BLOCK_K, true);
-    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, HALF, false);
+    if (A_MN) rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, MNC, BK, true, ELT);
+    else      rc = make_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, HALF, false, ELT);
     if (rc) return rc;
-    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BLOCK_K, true);
-    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, HALF, false);
+    if (B_MN) rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, MNC, BK, true, ELT);
+    else      rc = make_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, HALF, false, ELT);
     if (rc) return rc;
 
     Params p = {};
@@ -1133,26 +1165,24 @@ static int launch2(const float* A, const float* B, float* C, int64_t M, int64_t 
     p.m_tiles = (int)ceil_div<int64_t>(M, 256);
     p.n_tiles = (int)ceil_div<int64_t>(N, 256);
     const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-    int splits = pick_splits2(tiles, K);
+    const bool fused_epilogue = c_bf16 || bias || relu || proj_w;
+    int splits = fused_epilogue ? 1 : pick_splits2(tiles, K);
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * M * N * sizeof(float))) {
         splits = workspace ? (int)(workspace_bytes / ((size_t)M * N * sizeof(float))) : 1;
         if (splits < 1) splits = 1;
     }
-    int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(K, splits), BLOCK_K) * BLOCK_K;
+    int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(K, splits), BK) * BK;
     splits = (int)ceil_div<int64_t>(K, k_per);
     p.k_splits = splits;
     p.k_per_split = k_per;
-    if (splits == 1) {
-        p.C = C; p.ldc = ldc; p.split_stride = 0; p.accumulate = accumulate;
-        p.vec_ok = (ldc % 4 == 0) && aligned16(C);
-    } else {
-        p.C = reinterpret_cast<float*>(workspace); p.ldc = N; p.split_stride = M * N; p.accumulate = 0;
-        p.vec_ok = (N % 4 == 0) && aligned16(workspace);
-    }
+    CUtensorMap tmC;
+    rc = setup_output(p, &tmC, C, M, N, ldc, accumulate, splits, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w,
+                      proj_out, ldp, proj_k, nullptr);
+    if (rc) return rc;
     const int64_t n_work = tiles * splits;
     const int pairs = sm_count() / 2;
     const int grid = 2 * (int)(n_work < pairs ? n_work : pairs);
-    gemm_tf32_2cta_kernel<A_MN, B_MN><<<grid, THREADS, SMEM2_BYTES, s>>>(tmA, tmB, p);
+    gemm_umma2_kernel<A_MN, B_MN, BF16><<<grid, THREADS, SMEM2_BYTES, s>>>(tmA, tmB, tmC, p);
     GMC_LAUNCH_CHECK();
     if (splits > 1) {
         const int64_t MN = M * N;
@@ -1198,7 +1228,7 @@ static int make_lo(const float* X, int64_t ldx, float* L, int64_t rows, int64_t 
 
 static size_t tc_splitk_bytes(int op, int64_t M, int64_t N, int64_t K, bool bf16 = false) {
     int splits;
-    if (tc::use_two_cta() && !bf16) {
+    if ((tc::use_two_cta() && !bf16) || (bf16 && tc::use_two_cta_bf16(op))) {
         const int64_t tiles = ceil_div<int64_t>(M, 256) * ceil_div<int64_t>(N, 256);
         splits = tc::pick_splits2(tiles, K);
     } else {
@@ -1242,9 +1272,9 @@ static int tc_gemm_pass(int op, const float* A, const float* B, float* C, int64_
     }
     if (tc::use_two_cta()) {
         switch (op) {
-            case 0: return tc::launch2<false, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-            case 1: return tc::launch2<false, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
-            case 2: return tc::launch2<true, true>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+            case 0: return tc::launch2<false, true, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+            case 1: return tc::launch2<false, false, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
+            case 2: return tc::launch2<true, true, false>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s);
         }
     }
     switch (op) {
@@ -1312,6 +1342,13 @@ int tc_gemm_bf16(int op, const void* A, const void* B, void* C, int64_t M, int64
         return GMC_OK;
     }
     float* Cf = reinterpret_cast<float*>(C);                       // reinterpreted by the kernel when c_bf16 is set
+    if (tc::use_two_cta_bf16(op)) {
+        switch (op) {
+            case 0: return tc::launch2<false, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
+            case 1: return tc::launch2<false, false, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
+            case 2: return tc::launch2<true, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
+        }
+    }
     switch (op) {
         case 0: return tc::launch_cl<false, true, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
         case 1: return tc::launch_cl<false, false, true>(A, B, Cf, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, c_bf16, bias, relu, proj_w, proj_out, ldp, proj_k);
