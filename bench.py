@@ -630,6 +630,8 @@ def run_b200_arm(args):
         "spmm_h_fused": ("hbm", spmm_bytes_fused), "spmm_h_fwd": ("hbm", spmm_bytes_h_bwd),
         "skinny_fwd": ("hbm", (2.0 if act16 else 4.0) * N * H + 4.0 * N * K), "skinny_bwd": ("hbm", skinny_bwd_bytes),
         "cut_loss": ("hbm", 12.0 * N * K + 4.0 * nnz + 4.0 * (N + 1)), "colsum_db2": ("hbm", 4.0 * N * K),
+        # fused second layer + loss + backward: read T2 and the CSR (ids + A_hat coefficients) once, write Z, P, dZ, dT2
+        "layer2_loss": ("hbm", 20.0 * N * K + 8.0 * nnz + 4.0 * (N + 1)),
         "adam": ("hbm", 28.0 * (F * H + H + H * K + K)),
         "gemm_nt_dx": ("tensor", gemm_flops), "adam_features": ("hbm", 28.0 * N * ldx),
         # aggregation form of layer 1: write T1 / read dT1 once + the 16-byte neighbour-id row per node

@@ -42,6 +42,9 @@ _FWD_SLAB = os.environ.get("GMC_FWD_SLAB", "0") == "1"
 _FWD16_SLAB = os.environ.get("GMC_FWD16", "slab") == "slab"
 # pre-aggregated layer 1: T2 = H1 W2 folded into the GEMM epilogue (GMC_FUSE_PROJ=0: separate skinny_fwd pass over H1)
 _FUSE_PROJ = os.environ.get("GMC_FUSE_PROJ", "1") == "1"
+# second layer + loss + its backward in one launch per batch (csrc/tail_fused.cu, one CTA per graph); GMC_FUSED_TAIL=0
+# keeps the separate spmm_k / cut_loss / colsum / spmm_k kernels
+_FUSED_TAIL = os.environ.get("GMC_FUSED_TAIL", "1") == "1"
 
 
 def _pad4(n: int) -> int:
@@ -323,6 +326,13 @@ class GCNEngine:
     def forward_logits(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
         """Z (pre-softmax) for the batch; leaves H1 in bufB."""
         N = batch.num_nodes
+        _, b2 = self._forward_t2(batch, X), self.params()[3]
+        self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
+        return self.Z[:N]
+
+    def _forward_t2(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
+        """Layer 1 and the projection of layer 2: T2 = relu(A_hat X W1 + b1) W2 in self.T2; leaves H1 in bufB / bufB16."""
+        N = batch.num_nodes
         W1, b1, W2, b2 = self.params()
         if self.preaggregate:
             if self.K > 4 or self.H > 512 or self.H % 4:
@@ -343,8 +353,7 @@ class GCNEngine:
                 # the whole first layer: H1 = relu(XA W1 + b1), bias and ReLU in the GEMM epilogue, bf16 out
                 self._op("gemm_nn_layer1", 1, ops.gemm_bf16_bf16out, "nn", XA, self.W1b, out=B16, bias=b1.data, relu=True)
                 self._op("skinny_fwd", 1, ops.skinny_fwd_bf16, B16, W2.data, out=self.T2[:N])
-            self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
-            return self.Z[:N]
+            return self.T2[:N]
         XI = self._integer_features(batch, X)
         if XI is not None:
             # fp32-grade layer 1 on the tensor cores: H1 = relu(s . (XI (W1_hi + W1_lo + W1_lo2)) + b1), fp32 out
@@ -365,8 +374,7 @@ class GCNEngine:
                 self._op("gemm_nn_layer1", 1, ops.gemm_bf16_split, "nn", XI.tensor, self.W1s, self.split_fwd, self.F, out=Bf,
                          row_scale=XI.scale, bias=b1.data, relu=True, workspace=self.ws)
                 self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
-            self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
-            return self.Z[:N]
+            return self.T2[:N]
         X = self._features(batch, X)
         if self._b16_activations(batch):
             self._ensure(N, batch.num_graphs, b16=True)
@@ -380,8 +388,7 @@ class GCNEngine:
             else:
                 self._op("spmm_h_fused", 1, ops.spmm_fused_skinny_bf16, batch, A16, W2.data, out=B16, proj=self.T2[:N],
                          bias=b1.data, relu=True)                                                               # H1 bf16, T2
-            self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
-            return self.Z[:N]
+            return self.T2[:N]
         self._ensure(N, batch.num_graphs)
         A, Bf = self.bufA[:N], self.bufB[:N]
         ops.copy2d(self.W1p, W1.data)
@@ -399,13 +406,20 @@ class GCNEngine:
         else:
             self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf, bias=b1.data, relu=True)
             self._op("skinny_fwd", 1, ops.skinny_fwd, Bf, W2.data, out=self.T2[:N])
-        self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
-        return self.Z[:N]
+        return self.T2[:N]
+
+    def _fused_tail(self, batch: GraphBatch) -> bool:
+        return _FUSED_TAIL and ops.layer2_loss_fused_applies(batch, self.K)
 
     def forward(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
         """Softmax probabilities P [N,K] (a view into engine memory; clone to keep)."""
-        Z = self.forward_logits(batch, X)
         N = batch.num_nodes
+        if self._fused_tail(batch):
+            self._forward_t2(batch, X)
+            self._op("layer2_loss", 1, ops.layer2_loss_fused, batch, self.T2[:N], self.params()[3].data, self.loss_mode,
+                     self.override, self.penalty, self.C, P=self.P[:N], loss=self.loss[: batch.num_graphs], Z=self.Z[:N])
+            return self.P[:N]
+        Z = self.forward_logits(batch, X)
         self._op("cut_loss", 1, ops.cut_loss, batch, Z, self.loss_mode, self.override, self.penalty, self.C,
                  need_P=True, need_dZ=False, P=self.P[:N], loss=self.loss[: batch.num_graphs])
         return self.P[:N]
@@ -428,13 +442,21 @@ class GCNEngine:
         if dX is not None and self._sparse_layer1(batch):
             raise ValueError("adjacency_kernels promises fixed adjacency features; trainable features need the dense path")
         N, B = batch.num_nodes, batch.num_graphs
-        Z = self.forward_logits(batch, X)
         W1, b1, W2, b2 = self.params()
-        loss = self.loss[:B]
-        self._op("cut_loss", 1, ops.cut_loss, batch, Z, self.loss_mode, self.override, self.penalty, self.C,
-                 need_P=True, need_dZ=True, P=self.P[:N], dZ=self.dZ[:N], loss=loss)
-        self._op("colsum_db2", 2, ops.colsum, self.dZ[:N], out=self.gb2, workspace=self.ws)
-        self._op("spmm_k", 1, ops.spmm, batch, self.dZ[:N], out=self.dT2[:N])
+        if self._fused_tail(batch):
+            # Z = A_hat T2 + b2, softmax / override / STE / loss, dZ, db2, dT2 = A_hat dZ: one launch (+ the db2 reduce)
+            self._forward_t2(batch, X)
+            loss = self.loss[:B]
+            self._op("layer2_loss", 2, ops.layer2_loss_fused, batch, self.T2[:N], b2.data, self.loss_mode, self.override,
+                     self.penalty, self.C, P=self.P[:N], loss=loss, dT2=self.dT2[:N], db2=self.gb2, Z=self.Z[:N],
+                     dZ=self.dZ[:N], workspace=self.ws)
+        else:
+            Z = self.forward_logits(batch, X)
+            loss = self.loss[:B]
+            self._op("cut_loss", 1, ops.cut_loss, batch, Z, self.loss_mode, self.override, self.penalty, self.C,
+                     need_P=True, need_dZ=True, P=self.P[:N], dZ=self.dZ[:N], loss=loss)
+            self._op("colsum_db2", 2, ops.colsum, self.dZ[:N], out=self.gb2, workspace=self.ws)
+            self._op("spmm_k", 1, ops.spmm, batch, self.dZ[:N], out=self.dT2[:N])
         if self.preaggregate:
             XA = self._preaggregated(batch, X)
             A16, B16 = self.bufA16[:N], self.bufB16[:N]

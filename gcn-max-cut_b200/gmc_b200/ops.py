@@ -756,6 +756,44 @@ def cut_loss(batch, Z: torch.Tensor, mode: str = "ste", override_terminals: bool
     return loss, (P if need_P else None), (dZ if need_dZ else None)
 
 
+def layer2_loss_fused_applies(batch, n_classes: int) -> bool:
+    """One CTA per graph with 3 * n * K floats of shared memory: graphs of up to 6000 nodes at 3 classes."""
+    return 0 < batch.max_nodes and 3 * batch.max_nodes * n_classes * 4 <= 216 * 1024
+
+
+def layer2_loss_fused(batch, T2: torch.Tensor, bias2: Optional[torch.Tensor], mode: str = "ste", override_terminals: bool = True,
+                      penalty: float = 0.0, C: float = 1.0, P: Optional[torch.Tensor] = None,
+                      dZ: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None,
+                      dT2: Optional[torch.Tensor] = None, db2: Optional[torch.Tensor] = None,
+                      Z: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """Z = A_hat T2 + b2, softmax / override / STE / max-cut loss, dZ, db2 = colsum(dZ), dT2 = A_hat dZ in one launch
+    (one CTA per graph).  P / dZ / Z (contiguous [N, K]), dT2 ([N, >= K]) and db2 ([K]) are optional outputs; returns the
+    per-graph loss (float64 [B])."""
+    T2, ldt = _rowmajor(T2, "T2")
+    n, K = T2.shape
+    if n != batch.num_nodes:
+        raise ValueError(f"T2 has {n} rows, batch has {batch.num_nodes} nodes")
+    if loss is None:
+        loss = torch.empty(batch.num_graphs, dtype=torch.float64, device=T2.device)
+    for t, nm in ((P, "P"), (dZ, "dZ"), (Z, "Z")):
+        if t is not None and (not t.is_contiguous() or t.shape != (n, K) or t.dtype != torch.float32):
+            raise ValueError(f"{nm} must be a contiguous fp32 [N, K] tensor")
+    lddt = 0
+    if dT2 is not None:
+        dT2, lddt = _rowmajor(dT2, "dT2")
+    wptr, wbytes = None, 0
+    if db2 is not None:
+        ws = workspace or _default_ws
+        wptr, wbytes = ws.get(lib().gmc_layer2_loss_fused_workspace_bytes(batch.num_graphs, K), T2.device)
+    check(lib().gmc_layer2_loss_fused(T2.data_ptr(), ldt, batch.rowptr.data_ptr(), batch.colidx.data_ptr(),
+                                      batch.coef.data_ptr(), _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(),
+                                      batch.num_graphs, batch.max_nodes, n, K, _ptr(bias2), _lib.LOSS_MODES[mode],
+                                      int(override_terminals), float(penalty), float(C), _ptr(Z), _ptr(P),
+                                      loss.data_ptr(), _ptr(dZ), _ptr(dT2), lddt, _ptr(db2), wptr, wbytes, _stream()),
+          "gmc_layer2_loss_fused")
+    return loss
+
+
 def softmax_fwd(Z: torch.Tensor) -> torch.Tensor:
     Z, ldz = _rowmajor(Z, "Z")
     n, K = Z.shape

@@ -192,6 +192,23 @@ int gmc_softmax_fwd_f32(const float* Z, int64_t ldz, int64_t n_rows, int32_t n_c
 int gmc_softmax_bwd_f32(const float* P, const float* dP, int64_t n_rows, int32_t n_classes, float* dZ,
                         void* stream);
 
+/* (c') The whole second layer + loss + its backward for a block-diagonal batch of small graphs, ONE CTA per graph:
+ *   Z = A_hat T2 + b2 (TrainingNeural.py:83), softmax / terminal override / STE / max-cut loss and dZ as
+ *   gmc_softmax_cut_loss_fwd_bwd, db2 = colsum(dZ), dT2 = A_hat dZ -- the work of two gmc_spmm_* launches, the loss kernel
+ *   and gmc_colsum_f32 with every node's label computed once and all [n, n_classes] intermediates in shared memory.
+ * `coef` = gmc_edge_coef_f32 values (A_hat), `vals` = loss edge weights (nullable = 1).  Z_out / P_out / dZ_out (dense
+ * [n_rows, n_classes]), dT2 ([n_rows, lddt]) and db2 ([n_classes]) are each nullable (inference passes dT2 = db2 = NULL).
+ * Per-graph losses and db2 are sums in a fixed order: bitwise reproducible, no atomics.  Needs 3 * max_nodes * n_classes
+ * floats of shared memory (max_nodes <= 6000 at 3 classes): GMC_ERR_UNSUPPORTED beyond that -- use the separate kernels.
+ * workspace >= gmc_layer2_loss_fused_workspace_bytes when db2 is requested. */
+size_t gmc_layer2_loss_fused_workspace_bytes(int32_t n_graphs, int32_t n_classes);
+int gmc_layer2_loss_fused(const float* T2, int64_t ldt, const int32_t* rowptr, const int32_t* colidx, const float* coef,
+                          const float* vals, const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes,
+                          int64_t n_rows, int32_t n_classes, const float* bias2, int32_t mode,
+                          int32_t override_terminals, float penalty, float C, float* Z_out, float* P_out,
+                          double* loss_per_graph, float* dZ_out, float* dT2, int64_t lddt, float* db2, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- (d) fused multi-tensor Adam ----------------------------------------------------- */
 
 /* torch.optim.Adam defaults (amsgrad=False, weight_decay=0): for each of n_tensors (<= 16)

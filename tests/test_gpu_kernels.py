@@ -284,6 +284,44 @@ def test_cut_loss_matches_oracle(mode, override, penalty, weighted):
             assert torch.equal((loss / -1.5).round().long().cpu(), cuts.cpu())
 
 
+@pytest.mark.parametrize("mode,override,penalty", [("ste", True, 0.0), ("ste", False, 0.0), ("soft", True, 0.0),
+                                                   ("soft", False, 7.0), ("ste", True, 5.0), ("soft", True, 3.0)])
+@pytest.mark.parametrize("weighted,K", [(False, 3), (True, 3), (False, 5), (False, 2)])
+def test_layer2_loss_fused_equals_the_separate_kernels(mode, override, penalty, weighted, K):
+    """One launch (one CTA per graph) == spmm + cut_loss + colsum + spmm: Z, P, dZ, per-graph loss, db2, dT2."""
+    if K == 2 and override:
+        pytest.skip("terminal override needs >= 3 classes")
+    specs = [(40, 5, 1), (64, 7, 2), (50, 8, 4), (300, 6, 9)] if weighted else [(40, 5, 1), (64, 7, 2), (4, 3, 3), (34, 8, 4), (1000, 7, 5)]
+    graphs, csrs, batch = make_batch(specs, weights=weighted)
+    torch.manual_seed(7)
+    T2 = (torch.randn(batch.num_nodes, K) * 1.5).to(DEV)
+    b2 = (torch.randn(K) * 0.3).to(DEV)
+    Z = ops.spmm(batch, T2, bias=b2)
+    loss, P, dZ = ops.cut_loss(batch, Z, mode=mode, override_terminals=override, penalty=penalty, C=1.5)
+    db2 = ops.colsum(dZ)
+    dT2 = ops.spmm(batch, dZ)
+    N = batch.num_nodes
+    outs = []
+    for _ in range(2):
+        P2, dZ2, Z2 = (torch.empty(N, K, device=DEV) for _ in range(3))
+        dT2b, db2b = torch.empty(N, K, device=DEV), torch.empty(K, device=DEV)
+        loss2 = ops.layer2_loss_fused(batch, T2, b2, mode=mode, override_terminals=override, penalty=penalty, C=1.5, P=P2,
+                                      dZ=dZ2, dT2=dT2b, db2=db2b, Z=Z2)
+        outs.append((loss2.clone(), P2, dZ2, Z2, dT2b, db2b))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)                                   # no atomics: bitwise reproducible
+    loss2, P2, dZ2, Z2, dT2b, db2b = outs[0]
+    assert relerr(Z2.cpu(), Z.cpu()) < 1e-6 and relerr(P2.cpu(), P.cpu()) < 1e-6
+    np.testing.assert_allclose(loss2.cpu().numpy(), loss.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert float((dZ2 - dZ).abs().max()) < 2e-5 * (1 + penalty)
+    assert float((dT2b - dT2).abs().max()) < 2e-5 * (1 + penalty)
+    assert float((db2b - db2).abs().max()) < 1e-4 * (1 + penalty) * max(1.0, float(db2.abs().max()))
+    # inference form: only P and the loss
+    P3 = torch.empty(N, K, device=DEV)
+    loss3 = ops.layer2_loss_fused(batch, T2, b2, mode=mode, override_terminals=override, penalty=penalty, C=1.5, P=P3)
+    assert torch.equal(P3, P2) and torch.equal(loss3, loss2)
+
+
 def test_cut_loss_two_class_and_eight_class():
     _, csrs, batch = make_batch([(30, 4, 1)])
     for K in (2, 8):
