@@ -1117,15 +1117,12 @@ static bool use_two_cta() {
 
 // bf16 operands through the cta_group::2 kernel: GMC_GEMM_BF16_2CTA = "1" (all ops) | "nn" | "tn" | "0"
 static int two_cta_bf16_mode() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char* e = getenv("GMC_GEMM_BF16_2CTA");
-        cached = 0;
-        if (e && e[0] == '1') cached = 7;
-        else if (e && e[0] == 'n' && e[1] == 'n') cached = 1;
-        else if (e && e[0] == 't' && e[1] == 'n') cached = 4;
-    }
-    return cached;
+    const char* e = getenv("GMC_GEMM_BF16_2CTA");                  // read per call: benchmarks toggle it in-process
+    if (!e) return 0;
+    if (e[0] == '1') return 7;
+    if (e[0] == 'n' && e[1] == 'n') return 1;
+    if (e[0] == 't' && e[1] == 'n') return 4;
+    return 0;
 }
 static bool use_two_cta_bf16(int op) { return (two_cta_bf16_mode() >> op) & 1; }
 
