@@ -1115,10 +1115,15 @@ static bool use_two_cta() {
     return cached == 1;
 }
 
-// bf16 operands through the cta_group::2 kernel: GMC_GEMM_BF16_2CTA = "1" (all ops) | "nn" | "tn" | "0"
+// bf16 operands through the cta_group::2 kernel: GMC_GEMM_BF16_2CTA = "1" (all ops) | "nn" | "tn" | "0".  Default "nn":
+// interleaved A/B at config 3 under the power cap (profiles/r02_gemm_2cta.json): layer-1 GEMM with its full epilogue
+// 3.6-5.3 ms (cluster kernel) vs 3.6-4.3 ms (pairs), plain bf16-out 3.4-4.6 vs 3.3-3.4 -- each CTA stages 32 KB per
+// k-block instead of 48 KB, fewer shared-memory and L2 transactions per flop, so the pair kernel also holds its clocks
+// under the 1 kW cap; tn (both operands MN-major, split-K) is slower in pairs (4.3-4.5 vs 3.2-3.3 ms) and keeps the
+// 2x1 multicast clusters.
 static int two_cta_bf16_mode() {
     const char* e = getenv("GMC_GEMM_BF16_2CTA");                  // read per call: benchmarks toggle it in-process
-    if (!e) return 0;
+    if (!e) return 1;
     if (e[0] == '1') return 7;
     if (e[0] == 'n' && e[1] == 'n') return 1;
     if (e[0] == 't' && e[1] == 'n') return 4;

@@ -138,9 +138,19 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     //               unordered shared-memory atomics and still reproduce bit for bit (equal addends commute exactly);
     //   other rows = neighbours one after the other in CSR order, lanes over N(u) (distinct columns): fixed order.
     // Config 3 (4.1 M rows, 8.4 GB written): 3.0 ms.
+    // ncu (round 2, profiles/r02_preagg_ncu.txt): the shared-memory pipe was the limiter at 70 % -- per row 40 store + 85
+    // load + 23 atomic wavefronts: full zeroing of the 4 KB row buffer, float4 reads at a 32-byte lane stride (two-way
+    // bank conflicts) and atomicAdd(float) on shared memory, which is a compare-and-swap loop (ATOMS.CAST.SPIN).  Now:
+    //  * fast rows COUNT with native integer atomics into the mantissa of the float 2^23 (bits 0x4B000000 + k is the
+    //    float 2^23 + k), so an entry is read back as fmaf(f, c, -2^23 c) = k c with one rounding;
+    //  * the buffer is initialised once and a fast row restores only the <= 64 entries it touched;
+    //  * the read-out uses a 16-byte lane stride (conflict-free LDS.128) and 8-byte stores.
+    constexpr uint32_t kMagicBits = 0x4B000000u;                       // 8388608.0f
+    const float magic = __uint_as_float(kMagicBits);
+    for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(magic, magic, magic, magic);
+    __syncwarp();
     for (int64_t row = (int64_t)blockIdx.x * kPreaggWarps + warp; row < n_rows; row += stride) {
         if (only && !__ldg(only + row)) continue;                      // second pass: rows the counting kernel left
-        for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
         const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
         int g = (int)(((float)row + 0.5f) * inv_n0);
         if (g >= n_graphs) g = n_graphs - 1;
@@ -162,7 +172,10 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
         const float c0 = __shfl_sync(0xffffffffu, my_c, 0);
         const bool same = __all_sync(0xffffffffu, lane >= cnt || (my_deg == D0 && my_c == c0));
         const bool fast = same && !vals && cnt > 0 && cnt <= 32 && D0 > 0 && cnt * D0 <= 64;
-        __syncwarp();                                                  // the row buffer is zero
+        int touched[2] = {-1, -1};
+        if (!fast)                                                     // general rows accumulate floats from zero
+            for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
         if (fast) {
             const int total = cnt * D0;
             const float inv_d = 1.0f / (float)D0;
@@ -173,7 +186,7 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
                 const int o_f0 = __shfl_sync(0xffffffffu, my_f0, owner);
                 if (p < total) {
                     const int local = __ldg(colidx + o_f0 + (p - owner * D0)) - base;
-                    if (local >= 0 && local < n_cols) atomicAdd(buf + local, c0);
+                    if (local >= 0 && local < n_cols) { atomicAdd(reinterpret_cast<unsigned int*>(buf) + local, 1u); touched[j] = local; }
                 }
             }
         } else {
@@ -201,11 +214,20 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
         }
         __syncwarp();
         __nv_bfloat16* xr = X + row * ldx;
-        for (int c8 = lane; c8 * 8 < ncp; c8 += 32) {
-            const float4 a = *reinterpret_cast<const float4*>(buf + c8 * 8), b = *reinterpret_cast<const float4*>(buf + c8 * 8 + 4);
-            __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
-                                   __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
-            *reinterpret_cast<uint4*>(xr + c8 * 8) = *reinterpret_cast<const uint4*>(o);
+        // lane l reads float4 number l + 32 i (16-byte stride: conflict-free LDS.128) and stores its four bf16 as 8 bytes
+        const float sc = fast ? c0 : 1.0f, off = fast ? -magic * c0 : 0.0f;   // 2^23 c0 is exact: one rounding of k c0
+        for (int c4 = lane; c4 * 4 < ncp; c4 += 32) {
+            const float4 a = *reinterpret_cast<const float4*>(buf + c4 * 4);
+            __nv_bfloat162 o[2] = {__floats2bfloat162_rn(fmaf(a.x, sc, off), fmaf(a.y, sc, off)),
+                                   __floats2bfloat162_rn(fmaf(a.z, sc, off), fmaf(a.w, sc, off))};
+            *reinterpret_cast<uint2*>(xr + c4 * 4) = *reinterpret_cast<const uint2*>(o);
+        }
+        __syncwarp();                                                  // everyone has read the row
+        if (fast) {
+            if (touched[0] >= 0) buf[touched[0]] = magic;
+            if (touched[1] >= 0) buf[touched[1]] = magic;
+        } else {
+            for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(magic, magic, magic, magic);
         }
         __syncwarp();
     }
