@@ -161,6 +161,9 @@ class GCNEngine:
         # (written directly by the slab SpMM) feed gmc_gemm_bf16; everything else stays fp32
         self.W1b = ops.padded_empty_bf16(self.F, self.H, self.device, zero=True) if precision == "bf16" else None
         self._xb_cache: Dict[tuple, torch.Tensor] = {}
+        self._trainable_features = False      # set for the duration of a loss_and_grads call that asks for dX
+        self._x16 = None                      # per-step bf16 copy of trainable features
+        self._x16_fresh = False
         self._xa_cache: Dict[tuple, torch.Tensor] = {}
         self._w2p = None
         self.bufB16 = None
@@ -304,9 +307,21 @@ class GCNEngine:
         return X
 
     def _bf16_features(self, X: torch.Tensor) -> torch.Tensor:
-        """bf16 copy of a (static) fp32 feature tensor, converted once and cached on its identity and version."""
+        """bf16 copy of a (static) fp32 feature tensor, converted once and cached on its identity and version.  Trainable
+        features (a dX was asked for: they change every step, through raw pointers) are converted afresh per step into
+        one reused buffer, once per step (the forward converts, the backward reuses)."""
         if X.dtype == torch.bfloat16:
             return X
+        if self._trainable_features:
+            if self._x16 is None or self._x16.shape[0] < X.shape[0] or self._x16.shape[1] != X.shape[1]:
+                self._x16 = ops.padded_empty_bf16(X.shape[0], X.shape[1], X.device, zero=True)
+                self._buffer_generation += 1
+                self._x16_fresh = False
+            view = self._x16[: X.shape[0]]
+            if not self._x16_fresh:
+                ops.to_bf16(X, out=view)
+                self._x16_fresh = True
+            return view
         key = (X.data_ptr(), tuple(X.shape), X.stride(0), X._version)
         hit = self._xb_cache.get(key)
         if hit is None or hit[0] is not X:                  # identity, not address: see _preaggregated
@@ -443,6 +458,14 @@ class GCNEngine:
             raise ValueError("adjacency_kernels promises fixed adjacency features; trainable features need the dense path")
         N, B = batch.num_nodes, batch.num_graphs
         W1, b1, W2, b2 = self.params()
+        self._trainable_features, self._x16_fresh = dX is not None, False
+        try:
+            return self._loss_and_grads(batch, X, dX, N, B)
+        finally:
+            self._trainable_features = False
+
+    def _loss_and_grads(self, batch: GraphBatch, X, dX, N: int, B: int) -> torch.Tensor:
+        W1, b1, W2, b2 = self.params()
         if self._fused_tail(batch):
             # Z = A_hat T2 + b2, softmax / override / STE / loss, dZ, db2, dT2 = A_hat dZ: one launch (+ the db2 reduce)
             self._forward_t2(batch, X)
@@ -475,22 +498,22 @@ class GCNEngine:
             self._op("gemm_tn_dw1", 2, ops.gemm_bf16_split, "tn", XI.tensor, S, ns, N, out=self.gW1, workspace=self.ws)
             return loss
         if self._b16_activations(batch):
-            if dX is not None:
-                raise NotImplementedError("trainable features (dX) are not wired to the bf16 GEMM path; use tf32")
             A16, B16 = self.bufA16[:N], self.bufB16[:N]
             self._op("skinny_bwd", 2, ops.skinny_bwd_bf16, self.dT2[:N], W2.data, B16, dH=A16, dW=self.gW2,
                      dbias=self.gb1, workspace=self.ws)                                              # dH1pre, bf16
             self._op("spmm_h", 1, ops.spmm_bf16, batch, A16, out=B16)                                # dT1, bf16
             self._op("gemm_tn_dw1", 2, ops.gemm_bf16, "tn", self._bf16_features(X), B16, out=self.gW1, workspace=self.ws)
+            if dX is not None:                                                                       # dX = dT1 W1^T, fp32 out
+                self._op("gemm_nt_dx", 1, ops.gemm_bf16, "nt", B16, self.W1b, out=dX, workspace=self.ws)
             return loss
         A, Bf = self.bufA[:N], self.bufB[:N]
         self._op("skinny_bwd", 2, ops.skinny_bwd, self.dT2[:N], W2.data, Bf, dH=A, dW=self.gW2, dbias=self.gb1,
                  workspace=self.ws)
         if self.precision == "bf16" and not self._sparse_layer1(batch):
-            if dX is not None:
-                raise NotImplementedError("trainable features (dX) are not wired to the bf16 GEMM path; use tf32")
             dT1b = self._op("spmm_h", 1, ops.spmm_bf16out, batch, A, out=self.bufB16[:N])            # dT1, bf16
             self._op("gemm_tn_dw1", 2, ops.gemm_bf16, "tn", self._bf16_features(X), dT1b, out=self.gW1, workspace=self.ws)
+            if dX is not None:
+                self._op("gemm_nt_dx", 1, ops.gemm_bf16, "nt", dT1b, self.W1b, out=dX, workspace=self.ws)
             return loss
         self._op("spmm_h", 1, ops.spmm, batch, A, out=Bf)                                   # dT1
         if self._sparse_layer1(batch):
@@ -594,6 +617,16 @@ class GCNEngine:
         for st in states:
             st["step"] += 1
         return entry["loss"]
+
+    def train_step_features(self, batch: GraphBatch, X: torch.Tensor, dX: torch.Tensor, update) -> torch.Tensor:
+        """One optimiser step with trainable features owned by the caller: dL/dX lands in `dX`, the shared weights take
+        their (all-reduced) Adam step, then `update()` runs the caller's update of the rows X views (per-graph embedding
+        tables never leave the rank: no all-reduce for them)."""
+        loss = self.loss_and_grads(batch, X, dX=dX)
+        self.allreduce_grads()
+        self.apply_adam()
+        self._op("adam_features", 1, update)
+        return loss
 
     def train_step_empty(self) -> None:
         """The optimiser step of a rank whose shard of the step's graphs is empty (data parallel, fewer graphs than

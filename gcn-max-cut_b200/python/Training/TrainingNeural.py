@@ -95,6 +95,9 @@ class TrainingConfig:
     stream_dataset: bool = False             # keep the dataset in pinned host memory and upload every step's graphs (H2D on a
                                              # copy stream, one step ahead) instead of caching device-resident batches
     eval_batch_graphs: int = 64              # evaluate_model: graphs per block-diagonal forward pass
+    per_graph_embeddings: bool = False       # feature_source='embedding': every dataset graph owns its [n_g, dim_embedding]
+                                             # table (initialised from embed.weight[:n_g]) with its own Adam state, so
+                                             # batch_graphs > 1 works; False = the legacy single shared table (utils.py:184)
 
     def __post_init__(self):
         if self.feature_source not in ("adjacency", "embedding"):
@@ -320,7 +323,7 @@ def _dist_world() -> Tuple[int, int]:
 
 
 def _prepare(dataset: Dict, batch_graphs: int, device, engine: Optional[GCNEngine] = None,
-             stream: bool = False) -> List[_PreparedItem]:
+             stream: bool = False, build_features: bool = True) -> List[_PreparedItem]:
     """One (GraphBatch, features) pair per optimiser step, cached on the dataset dict's identity.
 
     * every item's features are verified to be the adjacency rows of its graph (host-side, O(nnz) gather + one
@@ -334,7 +337,7 @@ def _prepare(dataset: Dict, batch_graphs: int, device, engine: Optional[GCNEngin
     mode = _engine_mode(engine)
     cache = _PREPARED.get(id(dataset))
     keys = list(dataset.keys())
-    sig = (keys, batch_graphs, mode, rank, world, bool(stream))
+    sig = (keys, batch_graphs, mode, rank, world, bool(stream), bool(build_features))
     if cache is not None and cache[0] is dataset and cache[1] == sig:
         return cache[2]
     steps: List[_PreparedItem] = []
@@ -349,6 +352,9 @@ def _prepare(dataset: Dict, batch_graphs: int, device, engine: Optional[GCNEngin
             steps.append(_PreparedItem(None, None, n_graphs=0))        # this rank only joins the step's all-reduce
             continue
         handles = [_graph_handle(it) for it in chunk]
+        if not build_features:                             # learned embeddings are the input: item[1] is not read
+            steps.append(_PreparedItem(GraphBatch(handles, device=device), None))
+            continue
         widths = {_check_item_features(h, it[1]) for h, it in zip(handles, chunk)}
         if len(widths) != 1:
             raise ValueError(f"items of one step have different feature widths: {sorted(widths)}")
@@ -548,13 +554,16 @@ def train_single_epoch(dataset: Dict, net, optimizer, embed, config: TrainingCon
     total = torch.zeros((), dtype=torch.float64, device=device)
     for dataset_file in dataset_files:
         current = dataset if isinstance(dataset, dict) else open_file(dataset_file)
-        steps = _prepare(current, int(getattr(config, "batch_graphs", 1)), device, engine, stream=streamed)
+        steps = _prepare(current, int(getattr(config, "batch_graphs", 1)), device, engine, stream=streamed,
+                         build_features=not embedding_mode)
         if streamed:
             total += _train_epoch_streamed(engine, steps, device)
             continue
-        for step in steps:
+        for i_step, step in enumerate(steps):
             if step.batch is None:
                 engine.train_step_empty()
+            elif embedding_mode and getattr(config, "per_graph_embeddings", False):
+                total += _graph_embeddings(embed, steps, current, config).step(engine, i_step, step).sum()
             elif embedding_mode:
                 total += _embedding_step(engine, step, embed).sum()
             elif _USE_CUDA_GRAPHS:
@@ -567,12 +576,87 @@ def train_single_epoch(dataset: Dict, net, optimizer, embed, config: TrainingCon
     return float(total.item())
 
 
+class GraphEmbeddings:
+    """Per-graph learned node embeddings (the north-star's input: "embeddings are per-graph, so they stay local").
+    One fp32 table row per dataset node of THIS rank's shard, rows of a step's graphs contiguous, 128-byte row pitch;
+    every graph starts from embed.weight[:n_g] (so a one-graph dataset reproduces the legacy `inputs = embed.weight`,
+    python/utils.py:184) and owns its Adam moments and step count.  Nothing here is ever all-reduced."""
+
+    def __init__(self, embed, steps: List[_PreparedItem], lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
+        from gmc_b200 import ops
+        weight = embed.weight.data
+        self.F = int(weight.shape[1])
+        ld = ops.pad_cols(self.F)
+        self.offsets, total, biggest = [], 0, 0
+        for st in steps:
+            n = st.batch.num_nodes if st.batch is not None else 0
+            self.offsets.append(total)
+            total += n
+            biggest = max(biggest, n)
+        dev = weight.device
+        self.param = torch.zeros((total, ld), dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.param)
+        self.exp_avg_sq = torch.zeros_like(self.param)
+        self.grad = torch.zeros((biggest, ld), dtype=torch.float32, device=dev)
+        self.steps_taken = [0] * len(steps)
+        self.lr, self.betas, self.eps = float(lr), tuple(betas), float(eps)
+        for st, off in zip(steps, self.offsets):
+            if st.batch is None:
+                continue
+            gp = st.batch.graph_ptr_host
+            for g in range(st.batch.num_graphs):
+                lo, hi = int(gp[g]), int(gp[g + 1])
+                if hi - lo > weight.shape[0]:
+                    raise ValueError(f"graph has {hi - lo} nodes but the embedding table has {weight.shape[0]} rows")
+                self.param[off + lo: off + hi, : self.F] = weight[: hi - lo]
+
+    def table(self, i_step: int, n_nodes: int) -> torch.Tensor:
+        """[n_nodes, F] view of the rows of step `i_step`'s graphs (block-diagonal order)."""
+        off = self.offsets[i_step]
+        return self.param[off: off + n_nodes, : self.F]
+
+    def step(self, engine: GCNEngine, i_step: int, prepared: _PreparedItem) -> torch.Tensor:
+        from gmc_b200 import ops
+        n = prepared.batch.num_nodes
+        off = self.offsets[i_step]
+        X = self.param[off: off + n, : self.F]
+        dX = self.grad[:n, : self.F]
+        rows = (self.param[off: off + n], self.grad[:n], self.exp_avg[off: off + n], self.exp_avg_sq[off: off + n])
+        self.steps_taken[i_step] += 1
+        count = self.steps_taken[i_step]
+
+        def update():
+            ops.adam_multi([rows[0]], [rows[1]], [rows[2]], [rows[3]], lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+                           eps=self.eps, step=count)
+
+        return engine.train_step_features(prepared.batch, X, dX, update)
+
+
+def _graph_embeddings(embed, steps, dataset, config) -> GraphEmbeddings:
+    hit = _GRAPH_EMBEDDINGS.get(embed)
+    sig = (id(dataset), len(steps), tuple(st.n_graphs for st in steps))
+    if hit is None or hit[0] != sig or hit[1] is not dataset:
+        hit = (sig, dataset, GraphEmbeddings(embed, steps, config.learning_rate))
+        _GRAPH_EMBEDDINGS[embed] = hit
+    return hit[2]
+
+
+def graph_embeddings(embed) -> Optional[GraphEmbeddings]:
+    """The per-graph embedding store a per_graph_embeddings=True run trained for `embed` (None before the first step)."""
+    hit = _GRAPH_EMBEDDINGS.get(embed)
+    return hit[2] if hit is not None else None
+
+
+_GRAPH_EMBEDDINGS = weakref.WeakKeyDictionary()       # nn.Embedding -> (signature, dataset, GraphEmbeddings)
+
+
 def _embedding_features(batch: GraphBatch, embed) -> torch.Tensor:
     """inputs = embed.weight[:n] (python/utils.py:184 generalised to the multi-graph loop): one graph per step, its
     node i reads embedding row i."""
     if batch.num_graphs != 1:
-        raise NotImplementedError("feature_source='embedding' trains one graph per step (batch_graphs=1): the "
-                                  "embedding table is indexed by node id, which a block-diagonal batch would alias")
+        raise NotImplementedError("feature_source='embedding' with the single shared table trains one graph per step "
+                                  "(batch_graphs=1): the table is indexed by node id, which a block-diagonal batch "
+                                  "would alias; set per_graph_embeddings=True for per-graph tables")
     weight = embed.weight
     if batch.num_nodes > weight.shape[0]:
         raise ValueError(f"graph has {batch.num_nodes} nodes but the embedding table has {weight.shape[0]} rows")
@@ -645,8 +729,12 @@ def _run_training_loop(config: TrainingConfig, epoch_fn: Callable[[], float], ne
 
 
 def _checkpoint(net, optimizer, embed, epoch, loss_history, config) -> Dict:
-    return {"epoch": epoch, "model": net.state_dict(), "optimizer": optimizer.state_dict(),
-            "loss_history": loss_history, "inputs": embed.weight, "config": config}
+    out = {"epoch": epoch, "model": net.state_dict(), "optimizer": optimizer.state_dict(),
+           "loss_history": loss_history, "inputs": embed.weight, "config": config}
+    store = graph_embeddings(embed)
+    if store is not None:                              # extension key, only when per-graph tables were trained
+        out["graph_inputs"] = {"param": store.param, "offsets": list(store.offsets), "dim": store.F}
+    return out
 
 
 def train_model(dataset: Dict, config: TrainingConfig, dataset_files: Optional[List[str]] = None) -> Tuple:
