@@ -90,18 +90,19 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the short config 1 / config 2 runs of the default line")
+    ap.add_argument("--no-embedding-alt", action="store_true", help="skip alt_paths.embedding (needs ~85 GB more HBM)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(--steps, 10)")
     args = ap.parse_args()
     if args.workload == "config5":
         args.graphs_per_gpu, args.nodes, args.degree, args.features, args.hidden = 1, 1000000, 7, 256, 128
         args.feature_source = "embedding"
         args.no_cpu_baseline = True          # the per-graph reference step at n = 1M is not a bounded sample
-    if args.feature_source == "embedding" and args.precision == "bf16":
-        args.precision = "tf32"              # trainable features need dL/dX = dT1 W1^T, which has no bf16-operand path
-    if args.precision != "bf16" or args.feature_source != "adjacency":
+    if args.workload == "config5" and args.precision == "bf16":
+        args.precision = "tf32"              # one graph, no ELL plan: fp32 activations; TF32 GEMMs as in round 1's numbers
+    if args.precision != "bf16" or args.feature_source == "adjacency-sparse":
         args.activations = "fp32"
-    if args.activations != "bf16":
-        args.layer1 = "standard"
+    if args.activations != "bf16" or args.feature_source != "adjacency":
+        args.layer1 = "standard"             # trainable features change every step: nothing to pre-aggregate
     return args
 
 
@@ -470,6 +471,60 @@ def run_b200_arm(args):
                 what="the same dense step with fp32 features and one-pass TF32 GEMMs (bench.py --precision tf32); "
                      "--precision tf32x3 / fp32 are the fp32-grade parity paths (profiles/)")
             del eng_t, X32
+            torch.cuda.empty_cache()
+        if args.precision == "bf16" and not args.no_embedding_alt and batch.plan is not None:
+            # north-star input: LEARNED per-graph node embeddings (X ~ N(0,1) [N, F] fp32 parameter + gradient + Adam
+            # moments, rows never leave the rank), bf16 GEMM operands and layer-1 activations, dL/dX = dT1 W1^T through the
+            # bf16 nt GEMM, own fused Adam pass.  All three feature GEMMs are dense here: the tensor-pipe fractions SURVEY
+            # 8(d) asks for are reported on this path.
+            import copy
+            ld = ops.pad_cols(F)
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(args.seed + 17 + rank)
+            E = torch.zeros((N, ld), dtype=torch.float32, device=dev)
+            E[:, :F].normal_(generator=gen)
+            E_g, E_m, E_v = torch.zeros_like(E), torch.zeros_like(E), torch.zeros_like(E)
+            net_e = copy.deepcopy(net)
+            net_e.load_state_dict(init_state)
+            eng_e = GCNEngine(net_e, type(opt)(net_e.parameters(), lr=1e-3), precision="bf16", activations="bf16")
+            cnt_e = [0]
+
+            def emb_update():
+                cnt_e[0] += 1
+                ops.adam_multi([E], [E_g], [E_m], [E_v], lr=1e-3, step=cnt_e[0])
+
+            def emb_step():
+                return eng_e.train_step_features(batch, E[:, :F], E_g[:, :F], emb_update)
+
+            k_emb = min(args.steps, 5)
+            for _ in range(3):
+                emb_step()
+            sync_all()
+            eng_e.timer = OpTimer()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(k_emb):
+                emb_step()
+            a1.record()
+            torch.cuda.synchronize()
+            eng_e.timer.collect()
+            t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+            gdist.all_reduce_max_(t)
+            t_e = eng_e.timer
+            peak_bf16 = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+            gemm_tf = {k: 2.0 * N * F * H / (t_e.total_ms[k] / t_e.calls[k] * 1e-3) / 1e12
+                       for k in ("gemm_nn_xw1", "gemm_tn_dw1", "gemm_nt_dx") if k in t_e.total_ms}
+            alt["embedding"] = {
+                "value": total_graphs * k_emb / (float(t.item()) / 1000.0), "unit": UNIT, "ms_per_step": float(t.item()) / k_emb,
+                "steps": k_emb, "dtype": "bf16",
+                "what": "learned per-graph node embeddings as the input (north-star mode; bench.py --feature-source embedding): "
+                        f"parameter + gradient + Adam moments {4 * N * ld * 4 / 1e9:.0f} GB/GPU, standard layer 1 (bf16 slab SpMM "
+                        "forward and backward), dL/dX through the bf16 nt GEMM, fused Adam over the table (28 B per element)",
+                "ops_ms": {k: t_e.total_ms[k] / t_e.calls[k] for k in t_e.total_ms},
+                "tensor_pipe": {k: {"achieved_tflops": v, "peak_tflops": peak_bf16, "frac": v / peak_bf16} for k, v in gemm_tf.items()},
+                "adam_features_GBps": 28.0 * N * ld / (t_e.total_ms["adam_features"] / t_e.calls["adam_features"] * 1e-3) / 1e9
+                if "adam_features" in t_e.total_ms else None}
+            del eng_e, net_e, E, E_g, E_m, E_v
             torch.cuda.empty_cache()
 
     # ---- parity-grade path + label agreement ------------------------------------------------------------------------

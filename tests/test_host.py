@@ -471,7 +471,7 @@ def test_bench_defaults_name_the_throughput_configuration(monkeypatch):
     (["--precision", "tf32"], ("tf32", "fp32", "standard")),            # bf16 storage needs bf16 GEMM operands
     (["--activations", "fp32"], ("bf16", "fp32", "standard")),          # pre-aggregation is built on the bf16 chain
     (["--layer1", "standard"], ("bf16", "bf16", "standard")),
-    (["--feature-source", "embedding"], ("tf32", "fp32", "standard")),  # trainable features: TF32 GEMMs (dX), no pre-aggregation
+    (["--feature-source", "embedding"], ("bf16", "bf16", "standard")),  # trainable features: nothing to pre-aggregate
     (["--precision", "fp32", "--layer1", "preaggregated"], ("fp32", "fp32", "standard")),
     (["--workload", "config5"], ("tf32", "fp32", "standard")),         # config 5 trains embeddings
 ])
