@@ -432,8 +432,8 @@ def run_b200_arm(args):
 
     alt = None
     spmm_from_alt = None
-    if args.workload == "config3" and not embedding and not sparse_adj and not split:
-        alt = {}
+    if args.workload == "config3" and not embedding and not sparse_adj and not split and world == 1:
+        alt = {}                                             # single-GPU analyses; the N > 1 line carries dp_check instead
         k_alt = min(args.steps, 10)
         if ops.adjacency_kernels_apply(batch, F):
             eng_s = GCNEngine(net, opt, precision="fp32", adjacency_kernels=True)
@@ -443,7 +443,7 @@ def run_b200_arm(args):
                      "zero-padded adjacency rows; bench.py --feature-source adjacency-sparse gives the full line")
             del eng_s
             torch.cuda.empty_cache()
-        if preagg:
+        if preagg and batch.plan is not None:
             eng_std = GCNEngine(net, opt, precision="bf16", activations="bf16")
             eng_std.timer = OpTimer()
             r_std = timed_alt(eng_std, X, k_alt)
@@ -535,7 +535,7 @@ def run_b200_arm(args):
     # number of optimiser steps to compare the hard labels they end up with.
     parity_grade = None
     label_agreement = None
-    if args.workload == "config3" and not embedding and not sparse_adj and args.precision == "bf16":
+    if args.workload == "config3" and not embedding and not sparse_adj and args.precision == "bf16" and world == 1:
         import copy
         k_pg = min(args.steps, 10)
         xi = ops.IntegerFeatures.from_batch(batch, F)
