@@ -462,16 +462,21 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
 
     const int j0 = tid * 4;
     const bool owner = j0 < n_in;
-    float w[4][NOUT], dw[4][NOUT], db[4];
+    // The kernel is issue-bound (ncu r01c: 71 % issue slots), and 24 of its ~40 instructions per row and thread were
+    // scalar FMAs.  Columns are held in PAIRS and multiplied with packed fp32x2 FMAs (fma.rn.f32x2, sm_100): each lane
+    // of a pair is an IEEE fma, so the results are bit-identical to the scalar form at half the FMA instructions.
+    float2 wp[2][NOUT], dwp[2][NOUT];                      // columns (4j, 4j+1) and (4j+2, 4j+3)
+    float db[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        db[i] = 0.f;
+    for (int i = 0; i < 4; ++i) db[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int k = 0; k < NOUT; ++k) {
-            w[i][k] = (j0 + i < n_in) ? __ldg(W + (int64_t)(j0 + i) * NOUT + k) : 0.f;
-            dw[i][k] = 0.f;
+            wp[q][k].x = (j0 + 2 * q < n_in) ? __ldg(W + (int64_t)(j0 + 2 * q) * NOUT + k) : 0.f;
+            wp[q][k].y = (j0 + 2 * q + 1 < n_in) ? __ldg(W + (int64_t)(j0 + 2 * q + 1) * NOUT + k) : 0.f;
+            dwp[q][k] = make_float2(0.f, 0.f);
         }
-    }
     const uint32_t my_off = (uint32_t)(tid >> 6) * BOX_BYTES + (uint32_t)(tid & 63) * 8;   // box, then 8 bytes per thread
     __syncthreads();
     int st = 0;
@@ -488,20 +493,23 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
                 const int64_t v = vb + r;
                 if (v < r1) {                              // CTA-uniform
                     const uint2 h2 = *reinterpret_cast<const uint2*>(stage + r * 512);
-                    const float h[4] = {__uint_as_float(h2.x << 16), __uint_as_float(h2.x & 0xffff0000u),
-                                        __uint_as_float(h2.y << 16), __uint_as_float(h2.y & 0xffff0000u)};
-                    float tk[NOUT];
+                    const float2 hp[2] = {make_float2(__uint_as_float(h2.x << 16), __uint_as_float(h2.x & 0xffff0000u)),
+                                          make_float2(__uint_as_float(h2.y << 16), __uint_as_float(h2.y & 0xffff0000u))};
+                    float2 sp[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-                    for (int k = 0; k < NOUT; ++k) tk[k] = ts[r * NOUT + k];
-                    float o[4];
+                    for (int k = 0; k < NOUT; ++k) {
+                        const float tk = ts[r * NOUT + k];
+                        const float2 tt = make_float2(tk, tk);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int k = 0; k < NOUT; ++k) { s = fmaf(tk[k], w[i][k], s); dw[i][k] = fmaf(h[i], tk[k], dw[i][k]); }
-                        o[i] = h[i] > 0.f ? s : 0.f;
-                        db[i] += o[i];
+                        for (int q = 0; q < 2; ++q) {
+                            sp[q] = __ffma2_rn(tt, wp[q][k], sp[q]);
+                            dwp[q][k] = __ffma2_rn(hp[q], tt, dwp[q][k]);
+                        }
                     }
+                    const float o[4] = {hp[0].x > 0.f ? sp[0].x : 0.f, hp[0].y > 0.f ? sp[0].y : 0.f,
+                                        hp[1].x > 0.f ? sp[1].x : 0.f, hp[1].y > 0.f ? sp[1].y : 0.f};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) db[i] += o[i];
                     uint2 pk;
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
@@ -520,7 +528,8 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
         for (int i = 0; i < 4; ++i) {
             if (j0 + i < n_in) {
 #pragma unroll
-                for (int k = 0; k < NOUT; ++k) my_ws[(int64_t)(j0 + i) * (NOUT + 1) + k] = dw[i][k];
+                for (int k = 0; k < NOUT; ++k)
+                    my_ws[(int64_t)(j0 + i) * (NOUT + 1) + k] = (i & 1) ? dwp[i >> 1][k].y : dwp[i >> 1][k].x;
                 my_ws[(int64_t)(j0 + i) * (NOUT + 1) + NOUT] = db[i];
             }
         }
