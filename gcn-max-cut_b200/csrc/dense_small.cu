@@ -536,6 +536,129 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
     }
 }
 
+// TMA-streamed form of skinny_bwd_split_kernel (fp32 H in, NS stacked bf16 parts of row_scale . dHpre out): the same
+// 4-stage ring of 8-row tiles as skinny_bwd_b16_tma_kernel with fp32 boxes of 128 columns (512-byte rows), thread j owns
+// columns 4j .. 4j+3 (one LDS.128 per row), packed fp32x2 FMAs.  16 KB per stage at n_in = 512: three CTAs per SM.
+template <int NB, int NOUT, int NS>
+__global__ void __launch_bounds__(128)
+skinny_bwd_split_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* __restrict__ dT, int64_t lddt,
+                            const float* __restrict__ W, const float* __restrict__ row_scale, uint2* __restrict__ dH,
+                            int64_t lddh4, int64_t split_rows, int64_t n_rows, int n_in, int64_t rows_per,
+                            float* __restrict__ ws) {
+    constexpr int TR = kBwdTileRows, NST = kStreamStages;
+    constexpr uint32_t BOX_BYTES = TR * 512, STAGE_BYTES = NB * BOX_BYTES;
+    extern __shared__ __align__(128) uint8_t stream_smem[];
+    __shared__ float tsm[2][TR * (NOUT + 1)];              // dT rows + the row scale of the tile
+    const uint32_t sbase = tma::smem_u32(stream_smem);
+    const uint32_t bar0 = sbase + NST * STAGE_BYTES;
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per;
+    const int64_t r1 = min(n_rows, r0 + rows_per);
+    const int n_tiles = r1 > r0 ? (int)ceil_div<int64_t>(r1 - r0, TR) : 0;
+    if (tid == 0) {
+        tma::prefetch_map(&tmH);
+        for (int s = 0; s < NST; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+        tma::mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t, int st) {
+        const uint32_t bar = bar0 + 8 * st;
+        tma::mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+            tma::load_2d(sbase + st * STAGE_BYTES + q * BOX_BYTES, &tmH, q * 128, (int)(r0 + (int64_t)t * TR), bar);
+    };
+    if (tid == 0)
+        for (int s = 0; s < NST && s < n_tiles; ++s) issue(s, s);
+    auto fetch_t = [&](int t) -> float {                   // thread tid < TR * (NOUT + 1): element (row, k) of tile t
+        const int row = tid / (NOUT + 1), k = tid % (NOUT + 1);
+        const int64_t v = r0 + (int64_t)t * TR + row;
+        if (tid >= TR * (NOUT + 1) || t >= n_tiles || v >= r1) return 0.f;
+        if (k < NOUT) return __ldg(dT + v * lddt + k);
+        return row_scale ? __ldg(row_scale + v) : 1.f;
+    };
+    if (tid < TR * (NOUT + 1)) tsm[0][tid] = fetch_t(0);
+
+    const int j0 = tid * 4;
+    const bool owner = j0 < n_in;
+    float2 wp[2][NOUT], dwp[2][NOUT];
+    float db[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) db[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+            wp[q][k].x = (j0 + 2 * q < n_in) ? __ldg(W + (int64_t)(j0 + 2 * q) * NOUT + k) : 0.f;
+            wp[q][k].y = (j0 + 2 * q + 1 < n_in) ? __ldg(W + (int64_t)(j0 + 2 * q + 1) * NOUT + k) : 0.f;
+            dwp[q][k] = make_float2(0.f, 0.f);
+        }
+    const uint32_t my_off = (uint32_t)(tid >> 5) * BOX_BYTES + (uint32_t)(tid & 31) * 16;   // box, then 16 bytes per thread
+    __syncthreads();
+    int st = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        const float t_next = fetch_t(t + 1);               // in flight during this tile
+        tma::mbar_wait(bar0 + 8 * st, phase);
+        const uint8_t* stage = stream_smem + st * STAGE_BYTES + my_off;
+        const float* ts = tsm[t & 1];
+        const int64_t vb = r0 + (int64_t)t * TR;
+        if (owner) {
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+                const int64_t v = vb + r;
+                if (v < r1) {                              // CTA-uniform
+                    const float4 h4 = *reinterpret_cast<const float4*>(stage + r * 512);
+                    const float2 hp[2] = {make_float2(h4.x, h4.y), make_float2(h4.z, h4.w)};
+                    float2 sp[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                    for (int k = 0; k < NOUT; ++k) {
+                        const float tk = ts[r * (NOUT + 1) + k];
+                        const float2 tt = make_float2(tk, tk);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            sp[q] = __ffma2_rn(tt, wp[q][k], sp[q]);
+                            dwp[q][k] = __ffma2_rn(hp[q], tt, dwp[q][k]);
+                        }
+                    }
+                    const float rs = ts[r * (NOUT + 1) + NOUT];
+                    float o[4] = {hp[0].x > 0.f ? sp[0].x : 0.f, hp[0].y > 0.f ? sp[0].y : 0.f,
+                                  hp[1].x > 0.f ? sp[1].x : 0.f, hp[1].y > 0.f ? sp[1].y : 0.f};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { db[i] += o[i]; o[i] *= rs; }
+#pragma unroll
+                    for (int sp_i = 0; sp_i < NS; ++sp_i) {
+                        uint2 pk;
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
+                        dH[((int64_t)sp_i * split_rows + v) * lddh4 + tid] = pk;
+                        if (sp_i + 1 < NS) {
+                            o[0] -= __uint_as_float(pk.x << 16); o[1] -= __uint_as_float(pk.x & 0xffff0000u);
+                            o[2] -= __uint_as_float(pk.y << 16); o[3] -= __uint_as_float(pk.y & 0xffff0000u);
+                        }
+                    }
+                }
+            }
+        }
+        if (tid < TR * (NOUT + 1)) tsm[(t + 1) & 1][tid] = t_next;
+        __syncthreads();                                   // stage and tsm[t & 1] are free, tsm[(t + 1) & 1] is published
+        if (tid == 0 && t + NST < n_tiles) issue(t + NST, st);
+        if (++st == NST) { st = 0; phase ^= 1; }
+    }
+    if (owner) {
+        float* my_ws = ws + (int64_t)blockIdx.x * n_in * (NOUT + 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (j0 + i < n_in) {
+#pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                    my_ws[(int64_t)(j0 + i) * (NOUT + 1) + k] = (i & 1) ? dwp[i >> 1][k].y : dwp[i >> 1][k].x;
+                my_ws[(int64_t)(j0 + i) * (NOUT + 1) + NOUT] = db[i];
+            }
+        }
+    }
+}
+
 static bool stream_kernels_enabled() {
     static int cached = -1;
     if (cached < 0) { const char* e = getenv("GMC_SKINNY_TMA"); cached = (e && e[0] == '0') ? 0 : 1; }
@@ -841,6 +964,45 @@ int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const fl
         return GMC_OK;
     }
     uint2* dH2 = reinterpret_cast<uint2*>(dH_split);
+    if (stream_kernels_enabled() && n_rows >= 65536 && n_rows < (1ll << 31) - 64 && n_in <= 512 && n_out <= 4) {
+        // TMA-streamed kernel: 16 KB stages, three CTAs per SM, one wave; row ranges in multiples of the 8-row tile
+        CUtensorMap tm;
+        int rc = tma::make_f32_map(&tm, H, (uint64_t)n_in, (uint64_t)n_rows, (uint64_t)ldh, 128, kBwdTileRows, "gmc_skinny_bwd_split");
+        if (rc != GMC_OK) return rc;
+        const int nb = (n_in + 127) / 128;
+        int nc = sm_count() * (nb <= 2 ? 6 : 3);
+        if (nc > n_ctas) nc = n_ctas;
+        const int64_t rows_per = ceil_div<int64_t>(ceil_div<int64_t>(n_rows, nc), kBwdTileRows) * kBwdTileRows;
+        nc = (int)ceil_div<int64_t>(n_rows, rows_per);
+        const size_t smem = (size_t)kStreamStages * nb * kBwdTileRows * 512 + 64;
+#define GMC_CASE(NB, K, NSV)                                                                                           \
+        {                                                                                                              \
+            static bool attr = false;                                                                                  \
+            if (!attr) {                                                                                               \
+                GMC_CUDA(cudaFuncSetAttribute(skinny_bwd_split_tma_kernel<NB, K, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              kStreamStages * NB * kBwdTileRows * 512 + 64));                          \
+                GMC_CUDA(cudaFuncSetAttribute(skinny_bwd_split_tma_kernel<NB, K, NSV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+                attr = true;                                                                                           \
+            }                                                                                                          \
+            skinny_bwd_split_tma_kernel<NB, K, NSV><<<nc, 128, smem, s>>>(tm, dT, lddt, W, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, rows_per, ws); \
+        }
+#define GMC_NS(NB, K) if (n_split == 2) GMC_CASE(NB, K, 2) else GMC_CASE(NB, K, 3)
+#define GMC_NB(K) switch (nb) { case 1: GMC_NS(1, K); break; case 2: GMC_NS(2, K); break; case 3: GMC_NS(3, K); break; default: GMC_NS(4, K); break; }
+        switch (n_out) {
+            case 1: GMC_NB(1); break;
+            case 2: GMC_NB(2); break;
+            case 3: GMC_NB(3); break;
+            default: GMC_NB(4); break;
+        }
+#undef GMC_NB
+#undef GMC_NS
+#undef GMC_CASE
+        GMC_LAUNCH_CHECK();
+        const int total = n_in * (n_out + 1);
+        skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, nc, n_in, n_out, dW, dbias);
+        GMC_LAUNCH_CHECK();
+        return GMC_OK;
+    }
 #define GMC_CASE(K)                                                                                                           \
     case K:                                                                                                                   \
         if (n_split == 2) skinny_bwd_split_kernel<K, 2><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws); \

@@ -78,5 +78,22 @@ static inline int make_bf16_map(CUtensorMap* map, const void* base, uint64_t col
     return GMC_OK;
 }
 
+// the same for a row-major fp32 matrix
+static inline int make_f32_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                               uint32_t box_cols, uint32_t box_rows, const char* who) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point not available", who); return GMC_ERR_UNSUPPORTED; }
+    memset(map, 0, sizeof(*map));
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r); return GMC_ERR_INVALID_ARG; }
+    return GMC_OK;
+}
+
 }  // namespace tma
 }  // namespace gmc

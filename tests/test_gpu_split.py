@@ -143,7 +143,8 @@ def test_split_gemm_rejects_bad_arguments():
 
 
 @pytest.mark.parametrize("n_split", [2, 3])
-@pytest.mark.parametrize("n,n_in,n_out", [(1000, 500, 3), (70, 16, 3), (4097, 128, 4), (333, 24, 2)])
+@pytest.mark.parametrize("n,n_in,n_out", [(1000, 500, 3), (70, 16, 3), (4097, 128, 4), (333, 24, 2), (70003, 500, 3),
+                                          (66000, 128, 2), (65540, 260, 4)])
 def test_skinny_bwd_split_equals_the_fp32_kernel(n, n_in, n_out, n_split):
     torch.manual_seed(n + n_in)
     H = torch.relu(torch.randn(n, n_in, device=DEV))
@@ -158,7 +159,11 @@ def test_skinny_bwd_split_equals_the_fp32_kernel(n, n_in, n_out, n_split):
     want = (s[:, None] * dH).double()
     scale = want.abs().max().item()
     assert (total - want).abs().max().item() <= scale * 2.0 ** -(8 * n_split) * 1.01
-    assert torch.equal(dW, dW2) and torch.equal(db, db2)          # unscaled fp32 sums, same reduction order
+    if n < 65536:
+        assert torch.equal(dW, dW2) and torch.equal(db, db2)      # unscaled fp32 sums, same reduction order
+    else:                                                          # TMA-streamed kernel: its own row partition
+        assert relerr(dW2.cpu(), dW.cpu()) < 1e-5 and relerr(db2.cpu(), db.cpu()) < 1e-5
+    assert int(torch.count_nonzero(S[n: sr])) == 0                 # pad rows of part 0 untouched
 
 
 def regular_batch(n_graphs, n, degs, seed):
