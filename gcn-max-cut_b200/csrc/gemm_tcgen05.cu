@@ -199,6 +199,11 @@ struct Params {
     int64_t b_split_rows;
     // fp32 epilogue (direct, non split-K outputs): C[m, n] = act(row_scale[m] * acc + bias[n]); each nullable / 0
     const float* row_scale;
+    // split operands stored as fp16 (b_f16 = 1: B format F16 in the instruction descriptor, A stays bf16) with the low-order
+    // parts scaled up by 1 / part_scale per level (they would be fp16 subnormals otherwise); the epilogue multiplies part s
+    // by part_scale^s before adding.  part_scale = 1 for bf16 parts.
+    int b_f16;
+    float part_scale;
     // fp32 epilogue + proj_w: every (row, n-tile) writes its partial projection sum_n C[m, n] projW[n][0..3] to
     // proj_part[n_tile][m] (one float4, written exactly once: deterministic); proj_reduce_kernel adds the n-tiles up
     float4* proj_part;
@@ -310,11 +315,12 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
                 // split operand: column n of the product = sum of the NS accumulator groups (low-order parts first)
                 uint32_t r2[32];
                 tmem_ld32(t_row + (NS - 1) * RN + 32 * c, r);
+                const float ps = p.part_scale;                     // Horner: ((p_{NS-1} ps + p_{NS-2}) ps + ...) + p_0
 #pragma unroll
                 for (int sp = NS - 2; sp >= 0; --sp) {
                     tmem_ld32(t_row + sp * RN + 32 * c, r2);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaf(__uint_as_float(r[i]), ps, __uint_as_float(r2[i])));
                 }
             }
             if (p.row_scale) {
@@ -530,7 +536,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BF16, BN);
+        // B format field (bits 10-12): BF16 = 1 -> F16 = 0 for fp16 split parts (kind::f16 takes either 16-bit type per operand)
+        const uint32_t idesc = make_idesc(A_MN, B_MN, BF16, BN) & ~((NS > 1 && p.b_f16) ? (1u << 10) : 0u);
         // K-major : SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1 = CUTLASS convention)
         // MN-major: SWIZZLE_128B_BASE32B, 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart (SBO)
         // 16-bit MN-major: plain SWIZZLE_128B, 64-element chunks CHUNK apart (LBO), 8-k-row atoms 1024 B apart (SBO)
@@ -1033,7 +1040,7 @@ template <bool A_MN, bool B_MN, int CLM, int CLN, bool BF16, int NS = 1>
 static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                   int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s, int c_bf16 = 0,
                   const float* bias = nullptr, int relu = 0, const float* proj_w = nullptr, float* proj_out = nullptr,
-                  int64_t ldp = 0, int proj_k = 0, int64_t b_split_rows = 0, const float* row_scale = nullptr) {
+                  int64_t ldp = 0, int proj_k = 0, int64_t b_split_rows = 0, const float* row_scale = nullptr, int lo_shift = 0) {
     constexpr int CL = CLM * CLN;
     constexpr int ELT = BF16 ? 2 : 4;
     constexpr int BK = 128 / ELT, MNC = 128 / ELT;                 // k elements per stage, m/n elements per MN-major chunk
@@ -1062,6 +1069,8 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     Params p = {};
     p.M = M; p.N = N; p.K = K;
     p.b_split_rows = b_split_rows;
+    p.b_f16 = lo_shift > 0 ? 1 : 0;
+    p.part_scale = lo_shift > 0 ? 1.0f / (float)(1u << lo_shift) : 1.0f;
     p.m_tiles = (int)ceil_div<int64_t>(M, BLOCK_M);
     p.n_tiles = (int)ceil_div<int64_t>(N, RN);
     p.mg_tiles = ceil_div(p.m_tiles, CLM);
@@ -1412,7 +1421,8 @@ size_t tc_bf16_split_workspace_bytes(int op, int64_t M, int64_t N, int64_t K, in
 int tc_gemm_bf16_split(int op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                        int64_t ldb, int64_t ldc, int n_split, int64_t b_split_rows, const float* row_scale,
                        const float* bias, int relu, const float* proj_w, float* proj_out, int64_t ldp, int proj_k,
-                       int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                       int accumulate, int lo_shift, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    GMC_REQUIRE(lo_shift >= 0 && lo_shift <= 24, "gmc_gemm_bf16_split: lo_shift must be 0 (bf16 parts) or 1..24 (fp16 parts)");
     GMC_REQUIRE(op == 0 || op == 2, "gmc_gemm_bf16_split: op must be 0 (nn) or 2 (tn): the split operand is MN-major");
     GMC_REQUIRE(n_split == 2 || n_split == 3, "gmc_gemm_bf16_split: n_split must be 2 or 3");
     GMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && aligned16(A) && aligned16(B),
@@ -1431,7 +1441,7 @@ int tc_gemm_bf16_split(int op, const void* A, const void* B, float* C, int64_t M
     tc::split_cluster(n_split, &clm, op == 2);
 #define GMC_SPLIT_CASE(AMN, CM, NSV)                                                                                  \
     return tc::launch<AMN, true, CM, 1, true, NSV>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, workspace, workspace_bytes, s, 0, \
-                                                   bias, relu, proj_w, proj_out, ldp, proj_k, b_split_rows, row_scale);
+                                                   bias, relu, proj_w, proj_out, ldp, proj_k, b_split_rows, row_scale, lo_shift);
 #define GMC_SPLIT_OP(AMN)                                                                                             \
     if (n_split == 2) {                                                                                               \
         if (clm == 4) { GMC_SPLIT_CASE(AMN, 4, 2) } else if (clm == 2) { GMC_SPLIT_CASE(AMN, 2, 2) } else { GMC_SPLIT_CASE(AMN, 1, 2) } \

@@ -20,7 +20,8 @@ PRECISIONS = {"fp32": GMC_GEMM_FP32, "tf32": GMC_GEMM_TF32, "tf32x3": GMC_GEMM_T
 # engine-level precision (GCNEngine / TrainingConfig.gemm_precision): the three above plus "bf16" (bf16 operands
 # through gmc_gemm_bf16; not a gmc_gemm_* precision code because its operands are a different type)
 # and "bf16x2" / "bf16x3" (fp32-grade: exact integer features x an fp32 operand split into 2 / 3 bf16 parts, csrc/split.cu)
-ENGINE_PRECISIONS = tuple(PRECISIONS) + ("bf16", "bf16x2", "bf16x3")
+# "f16x2": the same with W1 split into two fp16 parts (22 mantissa bits) -- fp32-grade at the cost of bf16x2
+ENGINE_PRECISIONS = tuple(PRECISIONS) + ("bf16", "bf16x2", "bf16x3", "f16x2")
 LOSS_MODES = {"ste": GMC_LOSS_STE, "soft": GMC_LOSS_SOFT}
 
 
@@ -72,7 +73,8 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_row_scale_f32": (c_int, [P, P, c_int64, P, P, P]),
     "gmc_gemm_bf16_split_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int32, c_int32]),
     "gmc_gemm_bf16_split": (c_int, [c_int32, P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_int64,
-                                    P, P, c_int32, P, P, c_int64, c_int32, c_int32, P, c_size_t, P]),
+                                    P, P, c_int32, P, P, c_int64, c_int32, c_int32, c_int32, P, c_size_t, P]),
+    "gmc_f32_split_f16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int64, c_int32, P]),
     "gmc_skinny_bwd_split": (c_int, [P, c_int64, P, P, c_int64, P, P, c_int64, c_int64, c_int32, P, P, c_int64, c_int32,
                                      c_int32, P, c_size_t, P]),
     "gmc_gemm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int32]),

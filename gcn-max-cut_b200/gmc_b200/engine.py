@@ -103,7 +103,10 @@ class GCNEngine:
         # Needs adjacency features (IntegerFeatures, or adjacency_features=True: the caller guarantees that the
         # features are the zero-padded 0/1 adjacency rows, as _prepare verifies) and one A_hat coefficient per row
         # (regular graphs); other batches take the standard layer 1 with tf32x3 GEMMs (also fp32-grade).
-        self.split_fwd = {"bf16x2": 2, "bf16x3": 3}.get(precision, 0)
+        # 'f16x2': W1 as TWO fp16 parts (11 significant bits each = 22 of fp32's 24; the low part stored scaled by 2^12 and
+        # scaled back in the epilogue) against the same bf16 integer features -- fp32-grade at the cost of 'bf16x2'.
+        self.split_fwd = {"bf16x2": 2, "bf16x3": 3, "f16x2": 2}.get(precision, 0)
+        self.split_f16 = precision == "f16x2"
         self.split_bwd = int(os.environ.get("GMC_SPLIT_BWD", "2")) if self.split_fwd else 0
         if self.split_bwd not in (0, 2, 3):
             raise ValueError("GMC_SPLIT_BWD must be 2 or 3")
@@ -376,7 +379,12 @@ class GCNEngine:
             Bf = self.bufB[:N]
             if self.W1s is None:
                 self.W1s = ops.split_empty(self.F, self.H, self.split_fwd, self.device)
-            ops.f32_split_bf16(W1.data, self.split_fwd, out=self.W1s)
+                if self.split_f16:
+                    self.W1s = self.W1s.view(torch.float16)
+            if self.split_f16:
+                ops.f32_split_f16(W1.data, self.split_fwd, out=self.W1s)
+            else:
+                ops.f32_split_bf16(W1.data, self.split_fwd, out=self.W1s)
             if _FUSE_PROJ:
                 # ... and T2 = H1 W2 from the fp32 rows while they are in registers (per-tile partials + ordered reduce)
                 if self._w2p is None:

@@ -188,7 +188,7 @@ class GCNSoftmax(nn.Module):
         # 'bf16' is an engine (training-step) mode with resident bf16 operands; this generic autograd path keeps fp32
         # operands and runs them through the one-pass TF32 kernel instead
         # ('bf16x3' / 'bf16x2' are fp32-grade engine modes on integer features: the generic path uses tf32x3 for them)
-        generic = {"bf16": "tf32", "bf16x3": "tf32x3", "bf16x2": "tf32x3"}.get(precision, precision)
+        generic = {"bf16": "tf32", "bf16x3": "tf32x3", "bf16x2": "tf32x3", "f16x2": "tf32x3"}.get(precision, precision)
         self.conv1.gemm_precision = generic
         self.conv2.gemm_precision = generic
 

@@ -375,6 +375,24 @@ def f32_split_bf16(src: torch.Tensor, n_split: int, out: Optional[torch.Tensor] 
     return out
 
 
+F16_LO_SHIFT = 12       # fp16 parts: part p is stored multiplied by 2^(12 p)
+
+
+def f32_split_f16(src: torch.Tensor, n_split: int = 2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [K, N] -> n_split stacked fp16 parts (11 significant bits each; part p scaled by 2^(12 p)), held in a
+    2-byte tensor of dtype float16; same stacking as f32_split_bf16."""
+    src, lds = _rowmajor(src, "src")
+    k, n = src.shape
+    sr = split_rows_for(k)
+    if out is None:
+        out = torch.zeros((n_split * sr, (n + 63) // 64 * 64), dtype=torch.float16, device=src.device)[:, :n]
+    if out.dtype != torch.float16 or not out.is_cuda or out.stride(1) != 1 or out.shape != (n_split * sr, n):
+        raise ValueError(f"out must be a row-major CUDA float16 [{n_split * sr}, {n}] matrix")
+    check(lib().gmc_f32_split_f16(src.data_ptr(), lds, out.data_ptr(), out.stride(0), k, n, n_split, sr, F16_LO_SHIFT,
+                                  _stream()), "gmc_f32_split_f16")
+    return out
+
+
 def row_scale(batch, count_nonuniform: bool = True, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[int]]:
     """(s, nonuniform): s[v] = the A_hat coefficient of row v's edges, nonuniform = rows whose edges differ (such a
     batch cannot take the integer-feature path).  count_nonuniform=False skips the count and its host read-back."""
@@ -440,7 +458,13 @@ def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: in
     Optional fp32 epilogue C[m, n] = act(row_scale[m] * acc + bias[n]) and fused projection proj_out = C @ W for a
     padded weight matrix from pad_proj_weights (deterministic: per-tile partials in the workspace, added in order)."""
     A, lda = _bf16_rowmajor(A, "A")
-    B_split, ldb = _bf16_rowmajor(B_split, "B_split")
+    lo_shift = 0
+    if B_split.dtype == torch.float16:                 # fp16 parts from f32_split_f16 (A stays bf16)
+        if not B_split.is_cuda or B_split.dim() != 2 or B_split.stride(1) != 1:
+            raise TypeError("B_split: expected a row-major CUDA float16 matrix")
+        ldb, lo_shift = B_split.stride(0), F16_LO_SHIFT
+    else:
+        B_split, ldb = _bf16_rowmajor(B_split, "B_split")
     if op == "nn":
         M, K = A.shape
     elif op == "tn":
@@ -477,7 +501,7 @@ def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: in
                           A.device)
     check(lib().gmc_gemm_bf16_split(_OPS[op], A.data_ptr(), B_split.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
                                     n_split, sr, _ptr(row_scale), _ptr(bias), int(relu), _ptr(proj_w), _ptr(proj_out), ldp,
-                                    int(n_proj), int(accumulate), wptr, wbytes, _stream()), "gmc_gemm_bf16_split")
+                                    int(n_proj), int(accumulate), lo_shift, wptr, wbytes, _stream()), "gmc_gemm_bf16_split")
     return out
 
 

@@ -353,6 +353,12 @@ int gmc_adj_features_bwd_f32(const void* plan, const int32_t* graph_ptr, int32_t
  * gmc_skinny_bwd_split is gmc_skinny_bwd_f32 (fp32 H) whose dHpre leaves as those stacked parts, pre-scaled by s. */
 int gmc_f32_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t n_rows, int32_t n_cols,
                        int32_t n_split, int64_t split_rows, void* stream);
+/* fp16 parts (11 significant bits each: TWO parts carry 22 of fp32's 24 bits -- fp32-grade at the cost of the two-part
+ * bf16 GEMM).  Part p is stored multiplied by 2^(lo_shift * p) (the residuals would be fp16 subnormals otherwise);
+ * gmc_gemm_bf16_split with the same lo_shift > 0 reads B as fp16 (A stays bf16: kind::f16 takes either 16-bit format per
+ * operand) and scales the parts back in its epilogue.  |src| must stay below 65504. */
+int gmc_f32_split_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t n_rows, int32_t n_cols,
+                      int32_t n_split, int64_t split_rows, int32_t lo_shift, void* stream);
 int gmc_row_scale_f32(const int32_t* rowptr, const float* coef, int64_t n_rows, float* row_scale,
                       int32_t* nonuniform_count /* device, nullable, incremented */, void* stream);
 size_t gmc_gemm_bf16_split_workspace_bytes(int32_t op, int64_t M, int64_t N, int64_t K, int32_t n_split,
@@ -360,8 +366,8 @@ size_t gmc_gemm_bf16_split_workspace_bytes(int32_t op, int64_t M, int64_t N, int
 int gmc_gemm_bf16_split(int32_t op, const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K,
                         int64_t lda, int64_t ldb, int64_t ldc, int32_t n_split, int64_t b_split_rows,
                         const float* row_scale, const float* bias, int32_t relu, const float* proj_w, float* proj_out,
-                        int64_t ldp, int32_t n_proj, int32_t accumulate, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        int64_t ldp, int32_t n_proj, int32_t accumulate, int32_t lo_shift, void* workspace,
+                        size_t workspace_bytes, void* stream);
 int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh,
                          const float* row_scale, void* dH_split, int64_t lddh, int64_t split_rows, int32_t n_split,
                          float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace,

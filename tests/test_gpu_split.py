@@ -78,6 +78,42 @@ def test_split_gemm_cluster_shapes(op, n_split, cluster, monkeypatch):
     assert relerr(got.cpu(), want) < (2.0 ** -17 if n_split == 2 else 1e-6) * max(1.0, math.sqrt(K) / 16)
 
 
+@pytest.mark.parametrize("n_split", [1, 2])
+@pytest.mark.parametrize("rows,cols", [(1000, 500), (37, 12), (64, 8)])
+def test_fp16_split_parts_add_up(rows, cols, n_split):
+    """fp16 parts (11 significant bits each, part p stored scaled by 2^(12 p)): two parts reproduce an fp32 weight to
+    2^-22 relative (its residual to one fp16 ulp of the scaled residual), also for weights whose residual would be an
+    fp16 subnormal unscaled."""
+    torch.manual_seed(rows)
+    W = (torch.randn(rows, cols) * torch.logspace(-4, 0, cols)).to(DEV)
+    parts = ops.f32_split_f16(W, n_split)
+    sr = ops.split_rows_for(rows)
+    assert parts.dtype == torch.float16 and parts.shape == (n_split * sr, cols)
+    total = sum(parts[p * sr: p * sr + rows].double() * 2.0 ** (-ops.F16_LO_SHIFT * p) for p in range(n_split))
+    err = ((total - W.double()).abs() / W.double().abs().clamp_min(2.0 ** -14)).max().item()
+    assert err <= 2.0 ** -(11 * n_split) * 1.01
+    assert int(torch.count_nonzero(parts[rows: sr])) == 0
+
+
+@pytest.mark.parametrize("op,M,N,K", [("nn", 1000, 500, 1000), ("nn", 130, 260, 40), ("nn", 40000, 500, 1000), ("nn", 5, 12, 8),
+                                      ("tn", 1000, 500, 30000), ("tn", 100, 64, 128)])
+def test_f16_split_gemm_matches_float64(op, M, N, K):
+    """bf16 integer A x two fp16 parts of an fp32 B (mixed 16-bit formats in one tcgen05.mma kind::f16): 22 mantissa bits
+    of B, i.e. 2^-23 per weight + fp32 accumulation noise."""
+    A = bf16_exact_ints(M, K, 7, M + K) if op == "nn" else bf16_exact_ints(K, M, 7, M + K)
+    torch.manual_seed(N)
+    B = torch.randn(K, N) * 0.05
+    want = (A.double() if op == "nn" else A.double().t()) @ B.double()
+    got = ops.gemm_bf16_split(op, ops.to_bf16(A.to(DEV)), ops.f32_split_f16(B.to(DEV), 2), 2, K)
+    assert relerr(got.cpu(), want) < 5e-7 * max(1.0, math.sqrt(K) / 16)
+    s, b = torch.rand(M) * 0.2 + 0.05, torch.randn(N) * 0.3
+    if op == "nn":
+        out = ops.padded_empty(M, N, DEV)
+        got = ops.gemm_bf16_split("nn", ops.to_bf16(A.to(DEV)), ops.f32_split_f16(B.to(DEV), 2), 2, K, out=out,
+                                  row_scale=s.to(DEV), bias=b.to(DEV), relu=True)
+        assert relerr(got.cpu(), torch.relu(s.double()[:, None] * want + b.double())) < 6e-7
+
+
 @pytest.mark.parametrize("n_split", [2, 3])
 @pytest.mark.parametrize("M,N,n_proj", [(1000, 500, 3), (130, 260, 4), (4097, 96, 2), (70, 12, 3)])
 def test_split_gemm_fused_projection_is_deterministic_and_exact(M, N, n_proj, n_split):
@@ -194,7 +230,7 @@ def test_integer_features_times_scale_is_ahat_x():
     assert torch.equal(vals, vals.round()) and float(vals.max()) <= 8.0
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x2"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x2", "f16x2"])
 @pytest.mark.parametrize("mode", ["ste", "soft"])
 def test_split_engine_step_matches_the_oracle(precision, mode):
     """Batched loss and all four gradients at fixed weights == the float32 oracle (sum over graphs), rel 1e-4 -- the same
@@ -219,7 +255,7 @@ def test_split_engine_step_matches_the_oracle(precision, mode):
         assert relerr(gten.cpu(), grads[k]) < 1e-4, k
     # probabilities: 3 parts reproduce fp32 to accumulation noise
     P_ref = torch.cat([rs.gcn_forward(csr, X, p)["P"] for csr, X in oracle_items(arrays, B, F)])
-    assert float((eng.P[: batch.num_nodes].cpu() - P_ref).abs().max()) < (2e-6 if precision == "bf16x3" else 2e-5)
+    assert float((eng.P[: batch.num_nodes].cpu() - P_ref).abs().max()) < (2e-5 if precision == "bf16x2" else 2e-6)
 
 
 def test_split_engine_falls_back_on_irregular_graphs():
@@ -255,7 +291,7 @@ def _dataset_from(z, prefix_fmt, count, n):
     return ds
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "bf16x3", "bf16x2"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "bf16x3", "bf16x2", "f16x2"])
 def test_single_step_at_baseline_shapes(precision):
     """Config 1's real shapes (n = 500, F = 1000, H = 500): P, loss and gradients of the engine == the reference's own
     run (baseline_shapes.npz part a), rel 1e-4, on every fp32-grade path."""
@@ -277,7 +313,7 @@ def test_single_step_at_baseline_shapes(precision):
         assert relerr(gten.cpu(), z[f"a_grad_{k}"]) < 1e-4, k
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16x2"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16x2", "f16x2"])
 def test_two_epochs_at_baseline_shapes(precision, monkeypatch, capsys):
     """The 20-graph reference pipeline (complete_training_pipeline.ipynb cell 15) for two epochs through train_model:
     loss history, final weights and evaluate_model == the reference's own run (baseline_shapes.npz part b)."""
@@ -360,7 +396,9 @@ def test_config3_shape_ste_labels_of_headline_and_parity_grade_paths():
     eng3 = GCNEngine(net, opt, precision="bf16x3", adjacency_features=True)
     headline = GCNEngine(net, opt, precision="bf16", activations="bf16", preaggregate=True)
     XA = ops.PreaggregatedFeatures(ops.preaggregate_features_bf16(batch, F))
-    for name, engine, feats, bound in (("bf16x3", eng3, None, 2e-6), ("bf16_preaggregated", headline, XA, 3 * 2.0 ** -8)):
+    eng_h = GCNEngine(net, opt, precision="f16x2", adjacency_features=True)
+    for name, engine, feats, bound in (("bf16x3", eng3, None, 2e-6), ("f16x2", eng_h, None, 2e-6),
+                                       ("bf16_preaggregated", headline, XA, 3 * 2.0 ** -8)):
         loss, err, labels = run(engine, feats)
         scale = float((Z64 - Z64.mean(1, keepdim=True)).abs().max())
         assert err <= bound * max(scale, 1.0), (name, err, scale)
@@ -381,7 +419,7 @@ def test_config3_shape_ste_labels_of_headline_and_parity_grade_paths():
                             undecided_nodes=int((~decided).sum()), graphs_compared=len(same_loss),
                             loss_sum=float(loss.sum()), loss_sum_f64=float(sum(loss64)))
     print("config3-shape label agreement:", report)
-    assert report["bf16x3"]["flip_rate"] <= 1e-4
+    assert report["bf16x3"]["flip_rate"] <= 1e-4 and report["f16x2"]["flip_rate"] <= 1e-4
     assert report["bf16_preaggregated"]["flip_rate"] <= 0.05
     rel = abs(report["bf16_preaggregated"]["loss_sum"] - report["bf16_preaggregated"]["loss_sum_f64"]) / abs(report["bf16_preaggregated"]["loss_sum_f64"])
     assert rel < 5e-3
