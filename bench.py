@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--hidden", type=int, default=500)
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("GMC_BENCH_PRECISION", "bf16"),
-                    choices=["fp32", "tf32", "tf32x3", "bf16", "bf16x3", "bf16x2"])
+                    choices=["fp32", "tf32", "tf32x3", "bf16", "bf16x3", "bf16x2", "f16x2"])
     ap.add_argument("--activations", default=os.environ.get("GMC_BENCH_ACTIVATIONS", "bf16"), choices=["fp32", "bf16"],
                     help="storage type of the four [nodes, hidden] layer-1 tensors (T1, H1, dH1pre, dT1); bf16 needs "
                          "--precision bf16.  Arithmetic is fp32 either way")
@@ -284,7 +284,7 @@ def run_b200_arm(args):
     N, nnz = batch.num_nodes, batch.nnz
     embedding = args.feature_source == "embedding"
     sparse_adj = args.feature_source == "adjacency-sparse"
-    split = args.precision in ("bf16x3", "bf16x2") and not embedding and not sparse_adj
+    split = args.precision in ("bf16x3", "bf16x2", "f16x2") and not embedding and not sparse_adj
     torch.manual_seed(args.seed)                        # identical initial weights on every rank
     cfg = T.TrainingConfig(n_nodes=n, dim_embedding=F, hidden_dim=H, number_classes=K, learning_rate=1e-3,
                            gemm_precision=args.precision, batch_graphs=B)
@@ -657,7 +657,7 @@ def run_b200_arm(args):
 
     # ---- rooflines ----------------------------------------------------------------------------
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0 if "bf16_tflops_sustained" in peaks else peaks["bf16_tflops"] / 2.0
-    if args.precision in ("bf16", "bf16x3", "bf16x2"):   # bf16 operands: the measured bf16 figure itself (a split GEMM
+    if args.precision in ("bf16", "bf16x3", "bf16x2", "f16x2"):   # bf16 operands: the measured bf16 figure itself (a split GEMM
         tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])   # issues 2-3 MMAs per algorithmic flop)
     # compulsory form while one graph's source rows stay L2-resident (n*C*4 <= 32 MiB), else gather form
     def spmm_bytes(C):
@@ -812,7 +812,7 @@ def run_b200_arm(args):
                              "scale per row, resident in HBM; W1 / s . dH1pre split into bf16 parts (fp32-grade)"
                              if split else
                              f"dense zero-padded adjacency rows [{N},{F}] {'bf16' if args.precision == 'bf16' else 'fp32'} "
-                             f"resident in HBM ({N * F * (2 if args.precision.startswith('bf16') else 4) / 1e9:.1f} GB/GPU)"),
+                             f"resident in HBM ({N * F * (2 if (args.precision.startswith('bf16') or args.precision == 'f16x2') else 4) / 1e9:.1f} GB/GPU)"),
                 "layer1": ("preaggregated: H1 = relu((A_hat X) W1 + b1) -- one tcgen05 GEMM with bias / ReLU epilogue; "
                            "dW1 = (A_hat X)^T dH1pre -- one GEMM; identical to the reference's relu(A_hat (X W1) + b1), with the "
                            "aggregation moved from the activations (every step) to the features (once per graph; every step "
@@ -826,7 +826,7 @@ def run_b200_arm(args):
                 "activations": ("bf16 storage of T1 / H1 / dH1pre / dT1 (fp32 arithmetic, logits, loss, gradients, Adam)"
                                 if act16 else "fp32"),
                 "l2": (f"inputs larger than L2 (activations {2 * N * H * 4 / 1e9:.1f} GB)" if sparse_adj else
-                       f"inputs larger than L2 (X {N * F * (2 if args.precision.startswith('bf16') else 4) / 1e9:.1f} GB, "
+                       f"inputs larger than L2 (X {N * F * (2 if (args.precision.startswith('bf16') or args.precision == 'f16x2') else 4) / 1e9:.1f} GB, "
                        f"activations {2 * N * H * (2 if act16 else 4) / 1e9:.1f} GB)"),
                 "graph_generation_s": t_gen,
             },
