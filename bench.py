@@ -322,7 +322,7 @@ def run_b200_arm(args):
     act16 = args.activations == "bf16" and (preagg or eng._b16_activations(batch))
     XA = None
     if split:
-        feats = ops.IntegerFeatures.from_batch(batch, F)
+        feats = ops.IntegerFeatures.from_batch(batch, F, f16=args.precision == "f16x2")
     elif preagg:
         # A_hat X straight from the graph (49 entries per row at d = 7), bf16, 128-byte pitch: the resident input of the step
         XA = ops.preaggregate_features_bf16(batch, F)

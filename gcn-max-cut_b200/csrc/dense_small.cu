@@ -8,6 +8,7 @@
 //                        in ONE pass over H (autograd of TrainingNeural.py:81-83)
 //   gmc_colsum_f32     : bias gradients
 // All reductions over nodes are two-stage with a fixed order -> bitwise reproducible.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -256,11 +257,34 @@ skinny_bwd_b16_kernel(const float* __restrict__ dT, int64_t lddt, const float* _
 // fp32-grade form for the split-operand weight-gradient GEMM (split.cu): H stays fp32, and dHpre leaves as NS stacked
 // bf16 parts (hi, lo [, lo2]) of row_scale[v] * dHpre[v, :] -- part s at rows [s * split_rows, s * split_rows + n_rows)
 // of dH -- the B operand of dW1 = XI^T (s . dH1pre).  dW and dbias are sums of the UNSCALED fp32 values.
-template <int NOUT, int NS>
+// two fp32 -> one word of two 16-bit floats (round to nearest even; fp16 saturates instead of overflowing to inf), and
+// what that word holds as fp32 again -- the exact residual o - parts drives the next part
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_part(float lo, float hi) {
+    uint32_t w;
+    if (F16) {
+        lo = fminf(fmaxf(lo, -65504.f), 65504.f); hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+    } else {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+    }
+    return w;
+}
+template <bool F16>
+__device__ __forceinline__ void unpack_part(uint32_t w, float& lo, float& hi) {
+    if (F16) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&w);
+        lo = __low2float(h); hi = __high2float(h);
+    } else {
+        lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+    }
+}
+
+template <int NOUT, int NS, bool F16 = false>
 __global__ void __launch_bounds__(128)
 skinny_bwd_split_kernel(const float* __restrict__ dT, int64_t lddt, const float* __restrict__ W, const float* __restrict__ H,
                         int64_t ldh, const float* __restrict__ row_scale, uint2* __restrict__ dH, int64_t lddh4,
-                        int64_t split_rows, int64_t n_rows, int n_in, float* __restrict__ ws) {
+                        int64_t split_rows, int64_t n_rows, int n_in, float* __restrict__ ws, float lo_up) {
     const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
     const int64_t r0 = (int64_t)blockIdx.x * rows_per;
     const int64_t r1 = min(n_rows, r0 + rows_per);
@@ -292,12 +316,14 @@ skinny_bwd_split_kernel(const float* __restrict__ dT, int64_t lddt, const float*
 #pragma unroll
             for (int sp = 0; sp < NS; ++sp) {
                 uint2 pk;
-                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
-                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
+                pk.x = pack_part<F16>(o[0], o[1]);
+                pk.y = pack_part<F16>(o[2], o[3]);
                 dH[((int64_t)sp * split_rows + v) * lddh4 + j4] = pk;
-                if (sp + 1 < NS) {                                 // exact residuals: what the next part has to carry
-                    o[0] -= __uint_as_float(pk.x << 16); o[1] -= __uint_as_float(pk.x & 0xffff0000u);
-                    o[2] -= __uint_as_float(pk.y << 16); o[3] -= __uint_as_float(pk.y & 0xffff0000u);
+                if (sp + 1 < NS) {                                 // exact residuals (scaled up for fp16 parts): the next part
+                    float p0, p1, p2, p3;
+                    unpack_part<F16>(pk.x, p0, p1); unpack_part<F16>(pk.y, p2, p3);
+                    o[0] = (o[0] - p0) * lo_up; o[1] = (o[1] - p1) * lo_up;
+                    o[2] = (o[2] - p2) * lo_up; o[3] = (o[3] - p3) * lo_up;
                 }
             }
         };
@@ -539,12 +565,12 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
 // TMA-streamed form of skinny_bwd_split_kernel (fp32 H in, NS stacked bf16 parts of row_scale . dHpre out): the same
 // 4-stage ring of 8-row tiles as skinny_bwd_b16_tma_kernel with fp32 boxes of 128 columns (512-byte rows), thread j owns
 // columns 4j .. 4j+3 (one LDS.128 per row), packed fp32x2 FMAs.  16 KB per stage at n_in = 512: three CTAs per SM.
-template <int NB, int NOUT, int NS>
+template <int NB, int NOUT, int NS, bool F16 = false>
 __global__ void __launch_bounds__(128)
 skinny_bwd_split_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* __restrict__ dT, int64_t lddt,
                             const float* __restrict__ W, const float* __restrict__ row_scale, uint2* __restrict__ dH,
                             int64_t lddh4, int64_t split_rows, int64_t n_rows, int n_in, int64_t rows_per,
-                            float* __restrict__ ws) {
+                            float* __restrict__ ws, float lo_up) {
     constexpr int TR = kBwdTileRows, NST = kStreamStages;
     constexpr uint32_t BOX_BYTES = TR * 512, STAGE_BYTES = NB * BOX_BYTES;
     extern __shared__ __align__(128) uint8_t stream_smem[];
@@ -629,12 +655,14 @@ skinny_bwd_split_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float
 #pragma unroll
                     for (int sp_i = 0; sp_i < NS; ++sp_i) {
                         uint2 pk;
-                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
-                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
+                        pk.x = pack_part<F16>(o[0], o[1]);
+                        pk.y = pack_part<F16>(o[2], o[3]);
                         dH[((int64_t)sp_i * split_rows + v) * lddh4 + tid] = pk;
                         if (sp_i + 1 < NS) {
-                            o[0] -= __uint_as_float(pk.x << 16); o[1] -= __uint_as_float(pk.x & 0xffff0000u);
-                            o[2] -= __uint_as_float(pk.y << 16); o[3] -= __uint_as_float(pk.y & 0xffff0000u);
+                            float p0, p1, p2, p3;
+                            unpack_part<F16>(pk.x, p0, p1); unpack_part<F16>(pk.y, p2, p3);
+                            o[0] = (o[0] - p0) * lo_up; o[1] = (o[1] - p1) * lo_up;
+                            o[2] = (o[2] - p2) * lo_up; o[3] = (o[3] - p3) * lo_up;
                         }
                     }
                 }
@@ -940,9 +968,13 @@ int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const voi
 // elements, multiple of 4).  H is fp32.  Feeds gmc_gemm_bf16_split (op tn) -- autograd of TrainingNeural.py:80-83 at fp32
 // grade on bf16 tensor cores.  Same workspace as gmc_skinny_bwd_f32.
 int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh, const float* row_scale,
-                         void* dH_split, int64_t lddh, int64_t split_rows, int32_t n_split, float* dW, float* dbias,
-                         int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes, void* stream) {
+                         void* dH_split, int64_t lddh, int64_t split_rows, int32_t n_split, int32_t lo_shift, float* dW,
+                         float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
     using namespace gmc;
+    GMC_REQUIRE(lo_shift >= 0 && lo_shift <= 24, "gmc_skinny_bwd_split: lo_shift must be 0 (bf16 parts) or 1..24 (fp16 parts)");
+    const bool f16 = lo_shift > 0;
+    const float lo_up = f16 ? (float)(1u << lo_shift) : 1.0f;
     GMC_REQUIRE(dT && W && H && dH_split && dW, "gmc_skinny_bwd_split: null pointer");
     GMC_REQUIRE(n_rows >= 0 && n_in > 0 && n_out >= 1 && n_out <= 4 && ldh >= n_in && lddh >= n_in && lddt >= n_out,
                 "gmc_skinny_bwd_split: bad sizes (n_out must be 1..4)");
@@ -984,7 +1016,12 @@ int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const fl
                 GMC_CUDA(cudaFuncSetAttribute(skinny_bwd_split_tma_kernel<NB, K, NSV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
                 attr = true;                                                                                           \
             }                                                                                                          \
-            skinny_bwd_split_tma_kernel<NB, K, NSV><<<nc, 128, smem, s>>>(tm, dT, lddt, W, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, rows_per, ws); \
+            if (f16) {                                                                                                 \
+                GMC_CUDA(cudaFuncSetAttribute(skinny_bwd_split_tma_kernel<NB, K, NSV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              kStreamStages * NB * kBwdTileRows * 512 + 64));                          \
+                skinny_bwd_split_tma_kernel<NB, K, NSV, true><<<nc, 128, smem, s>>>(tm, dT, lddt, W, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, rows_per, ws, lo_up); \
+            } else                                                                                                     \
+            skinny_bwd_split_tma_kernel<NB, K, NSV><<<nc, 128, smem, s>>>(tm, dT, lddt, W, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, rows_per, ws, lo_up); \
         }
 #define GMC_NS(NB, K) if (n_split == 2) GMC_CASE(NB, K, 2) else GMC_CASE(NB, K, 3)
 #define GMC_NB(K) switch (nb) { case 1: GMC_NS(1, K); break; case 2: GMC_NS(2, K); break; case 3: GMC_NS(3, K); break; default: GMC_NS(4, K); break; }
@@ -1005,8 +1042,10 @@ int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const fl
     }
 #define GMC_CASE(K)                                                                                                           \
     case K:                                                                                                                   \
-        if (n_split == 2) skinny_bwd_split_kernel<K, 2><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws); \
-        else skinny_bwd_split_kernel<K, 3><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws); \
+        if (f16 && n_split == 2) skinny_bwd_split_kernel<K, 2, true><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
+        else if (f16) skinny_bwd_split_kernel<K, 3, true><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
+        else if (n_split == 2) skinny_bwd_split_kernel<K, 2><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
+        else skinny_bwd_split_kernel<K, 3><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
         break;
     switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) }
 #undef GMC_CASE

@@ -199,9 +199,10 @@ struct Params {
     int64_t b_split_rows;
     // fp32 epilogue (direct, non split-K outputs): C[m, n] = act(row_scale[m] * acc + bias[n]); each nullable / 0
     const float* row_scale;
-    // split operands stored as fp16 (b_f16 = 1: B format F16 in the instruction descriptor, A stays bf16) with the low-order
-    // parts scaled up by 1 / part_scale per level (they would be fp16 subnormals otherwise); the epilogue multiplies part s
-    // by part_scale^s before adding.  part_scale = 1 for bf16 parts.
+    // split operands stored as fp16 (b_f16 = 1: A AND B are IEEE fp16 -- kind::f16 wants one 16-bit format for both operands,
+    // a bf16 A with an fp16 B raises an illegal-instruction fault on B200) with the low-order parts scaled up by
+    // 1 / part_scale per level (they would be fp16 subnormals otherwise); the epilogue multiplies part s by part_scale^s
+    // before adding.  part_scale = 1 for bf16 parts.
     int b_f16;
     float part_scale;
     // fp32 epilogue + proj_w: every (row, n-tile) writes its partial projection sum_n C[m, n] projW[n][0..3] to
@@ -536,8 +537,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // B format field (bits 10-12): BF16 = 1 -> F16 = 0 for fp16 split parts (kind::f16 takes either 16-bit type per operand)
-        const uint32_t idesc = make_idesc(A_MN, B_MN, BF16, BN) & ~((NS > 1 && p.b_f16) ? (1u << 10) : 0u);
+        // A / B format fields (bits 7-9, 10-12): BF16 = 1 -> F16 = 0 for fp16 operands
+        const uint32_t idesc = make_idesc(A_MN, B_MN, BF16, BN) & ~((NS > 1 && p.b_f16) ? ((1u << 7) | (1u << 10)) : 0u);
         // K-major : SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1 = CUTLASS convention)
         // MN-major: SWIZZLE_128B_BASE32B, 32-element chunks 4096 B apart (LBO), 4-k-row atoms 512 B apart (SBO)
         // 16-bit MN-major: plain SWIZZLE_128B, 64-element chunks CHUNK apart (LBO), 8-k-row atoms 1024 B apart (SBO)

@@ -1,6 +1,7 @@
 // graph_ops.cu -- per-batch graph preparation: degree norms, A_hat edge coefficients,
 // dense padded adjacency rows (device-side graphExtender).  HBM-bound integer/float work.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -114,6 +115,9 @@ __global__ void scatter_bf16_kernel(const int32_t* __restrict__ rowptr, const in
 // bf16 (zeros included: no memset of the [N, n_cols] matrix).
 constexpr int kPreaggWarps = 8;
 
+// F16OUT: the row is written as IEEE fp16 instead of bf16 (the integer features of the 'f16x2' GEMM path: small integers
+// are exact in both, the MMA needs both operands in ONE 16-bit format)
+template <bool F16OUT>
 __global__ void __launch_bounds__(kPreaggWarps * 32)
 preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                          const float* __restrict__ coef, const float* __restrict__ vals,
@@ -218,9 +222,16 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
         const float sc = fast ? c0 : 1.0f, off = fast ? -magic * c0 : 0.0f;   // 2^23 c0 is exact: one rounding of k c0
         for (int c4 = lane; c4 * 4 < ncp; c4 += 32) {
             const float4 a = *reinterpret_cast<const float4*>(buf + c4 * 4);
-            __nv_bfloat162 o[2] = {__floats2bfloat162_rn(fmaf(a.x, sc, off), fmaf(a.y, sc, off)),
-                                   __floats2bfloat162_rn(fmaf(a.z, sc, off), fmaf(a.w, sc, off))};
-            *reinterpret_cast<uint2*>(xr + c4 * 4) = *reinterpret_cast<const uint2*>(o);
+            const float v0 = fmaf(a.x, sc, off), v1 = fmaf(a.y, sc, off), v2 = fmaf(a.z, sc, off), v3 = fmaf(a.w, sc, off);
+            uint2 o;
+            if (F16OUT) {
+                const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
+                o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+            } else {
+                const __nv_bfloat162 b0 = __floats2bfloat162_rn(v0, v1), b1 = __floats2bfloat162_rn(v2, v3);
+                o.x = *reinterpret_cast<const uint32_t*>(&b0); o.y = *reinterpret_cast<const uint32_t*>(&b1);
+            }
+            *reinterpret_cast<uint2*>(xr + c4 * 4) = o;
         }
         __syncwarp();                                                  // everyone has read the row
         if (fast) {
@@ -414,9 +425,9 @@ int gmc_csr_scatter_bf16(const int32_t* rowptr, const int32_t* colidx, const flo
 // 16-byte aligned base); rows are built in a fixed order, so the result is bitwise reproducible.
 size_t gmc_csr_preaggregate_workspace_bytes(int64_t n_rows) { return n_rows > 0 ? (size_t)n_rows : 0; }
 
-int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
-                              const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
-                              int64_t ldx, void* workspace, size_t workspace_bytes, void* stream) {
+static int preaggregate_impl(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                             const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                             int64_t ldx, void* workspace, size_t workspace_bytes, void* stream, bool f16) {
     GMC_REQUIRE(rowptr && colidx && coef && graph_ptr && X, "gmc_csr_preaggregate_bf16: null pointer");
     GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0 && n_cols > 0 && ldx >= n_cols, "gmc_csr_preaggregate_bf16: bad sizes");
     const int ncp = (n_cols + 7) & ~7;
@@ -433,7 +444,7 @@ int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, cons
     const uint8_t* only = nullptr;
     const int wstride = ((ncp >> 2) + 3) & ~3;
     const size_t pc_smem = (size_t)gmc::kPcRows * wstride * 4 + (size_t)gmc::kPcRows * gmc::kPcLut * 2;
-    if (!vals && workspace && workspace_bytes >= (size_t)n_rows && pc_smem <= 100 * 1024) {
+    if (!f16 && !vals && workspace && workspace_bytes >= (size_t)n_rows && pc_smem <= 100 * 1024) {
         static bool attr2 = false;
         if (!attr2) {
             GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -453,7 +464,8 @@ int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, cons
     const size_t smem = (size_t)gmc::kPreaggWarps * ncp * sizeof(float);
     static bool attr = false;
     if (!attr) {
-        GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 6144 * 4));
+        GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 6144 * 4));
+        GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 6144 * 4));
         attr = true;
     }
     int per_sm = (int)((200 * 1024) / (smem + 1024));
@@ -462,10 +474,28 @@ int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, cons
     int64_t blocks = gmc::ceil_div<int64_t>(n_rows, gmc::kPreaggWarps);
     const int64_t cap = (int64_t)gmc::sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
-    gmc::preaggregate_bf16_kernel<<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, s>>>(
-        rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only);
+    if (f16)
+        gmc::preaggregate_bf16_kernel<true><<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, s>>>(
+            rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only);
+    else
+        gmc::preaggregate_bf16_kernel<false><<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, s>>>(
+            rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
+}
+
+int gmc_csr_preaggregate_bf16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                              const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                              int64_t ldx, void* workspace, size_t workspace_bytes, void* stream) {
+    return preaggregate_impl(rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, X, ldx, workspace,
+                             workspace_bytes, stream, false);
+}
+
+// the same rows written as IEEE fp16 (the 'f16x2' GEMM path needs both MMA operands in one 16-bit format)
+int gmc_csr_preaggregate_f16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                             const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                             int64_t ldx, void* stream) {
+    return preaggregate_impl(rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, X, ldx, nullptr, 0, stream, true);
 }
 
 // dst[r, c] = bf16(src[r, c]), round to nearest even; leading dimensions in elements

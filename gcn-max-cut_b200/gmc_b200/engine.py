@@ -104,7 +104,10 @@ class GCNEngine:
         # features are the zero-padded 0/1 adjacency rows, as _prepare verifies) and one A_hat coefficient per row
         # (regular graphs); other batches take the standard layer 1 with tf32x3 GEMMs (also fp32-grade).
         # 'f16x2': W1 as TWO fp16 parts (11 significant bits each = 22 of fp32's 24; the low part stored scaled by 2^12 and
-        # scaled back in the epilogue) against the same bf16 integer features -- fp32-grade at the cost of 'bf16x2'.
+        # scaled back in the epilogue) against the integer features held as fp16 (one 16-bit format per tcgen05.mma; a
+        # bf16 A with an fp16 B faults on B200) -- fp32-grade at the cost of 'bf16x2'.  Backward: s . dH1pre as two fp16
+        # parts as well (22 bits; values saturate at +-65504 and lose relative accuracy below 2^-14 -- the max-cut
+        # gradients sit at 1e-4 .. 1).
         self.split_fwd = {"bf16x2": 2, "bf16x3": 3, "f16x2": 2}.get(precision, 0)
         self.split_f16 = precision == "f16x2"
         self.split_bwd = int(os.environ.get("GMC_SPLIT_BWD", "2")) if self.split_fwd else 0
@@ -222,7 +225,8 @@ class GCNEngine:
                 self._buffer_generation += 1
             need = self.split_bwd * ops.split_rows_for(n_nodes)
             if self.bufS is None or self.bufS.shape[0] < need:
-                self.bufS = ops.padded_empty_bf16(need, self.H, dev, zero=True)
+                self.bufS = ops.padded_empty_bf16(need, self.H, dev, zero=True,
+                                                  dtype=torch.float16 if self.split_f16 else torch.bfloat16)
                 self._buffer_generation += 1
         elif not b16 and (self.bufA is None or self.bufA.shape[0] < n_nodes):
             # row pitch padded to 128 B: TMA boxes / 128-bit gathers never straddle cache lines
@@ -250,17 +254,22 @@ class GCNEngine:
         if isinstance(X, ops.IntegerFeatures):
             if X.tensor.shape[0] != batch.num_nodes or X.tensor.shape[1] != self.F:
                 raise ValueError(f"integer features must be [{batch.num_nodes}, {self.F}], got {tuple(X.tensor.shape)}")
+            want = torch.float16 if self.split_f16 else torch.bfloat16
+            if X.tensor.dtype != want:
+                raise ValueError(f"precision {self.precision!r} takes {want} integer features, got {X.tensor.dtype} "
+                                 "(IntegerFeatures.from_batch(..., f16=True) for 'f16x2')")
             return X
         if not (X is None or self.adjacency_features):
             return None
+        key = (self.F, self.split_f16)
         hit = getattr(batch, "_xi", None)
-        if hit is None or hit[0] != self.F:
+        if hit is None or hit[0] != key:
             xi = None
             if batch.unit_weights and batch.max_nodes <= self.F and self.H % 4 == 0 and self.K <= 4:
                 scale, bad = ops.row_scale(batch)
                 if bad == 0:
-                    xi = ops.IntegerFeatures(ops.integer_features_bf16(batch, self.F), scale)
-            hit = (self.F, xi)
+                    xi = ops.IntegerFeatures(ops.integer_features_bf16(batch, self.F, f16=self.split_f16), scale)
+            hit = (key, xi)
             batch._xi = hit
         return hit[1]
 

@@ -237,10 +237,17 @@ def _bf16_rowmajor(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
     return t, t.stride(0)
 
 
-def padded_empty_bf16(rows: int, cols: int, device, zero: bool = False) -> torch.Tensor:
-    """[rows, cols] bf16 view whose row pitch is a multiple of 128 bytes (64 elements)."""
+def _b16_rowmajor(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """bf16 or IEEE fp16 (the operand format of the 'f16x2' GEMMs)"""
+    if t.dtype not in (torch.bfloat16, torch.float16) or not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+        raise TypeError(f"{name}: expected a row-major CUDA bfloat16 / float16 matrix")
+    return t, t.stride(0)
+
+
+def padded_empty_bf16(rows: int, cols: int, device, zero: bool = False, dtype=torch.bfloat16) -> torch.Tensor:
+    """[rows, cols] bf16 (or fp16) view whose row pitch is a multiple of 128 bytes (64 elements)."""
     make = torch.zeros if zero else torch.empty
-    return make((rows, (cols + 63) // 64 * 64), dtype=torch.bfloat16, device=device)[:, :cols]
+    return make((rows, (cols + 63) // 64 * 64), dtype=dtype, device=device)[:, :cols]
 
 
 def to_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -408,10 +415,11 @@ def row_scale(batch, count_nonuniform: bool = True, out: Optional[torch.Tensor] 
 
 
 def integer_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None,
-                          ones: Optional[torch.Tensor] = None) -> torch.Tensor:
+                          ones: Optional[torch.Tensor] = None, f16: bool = False) -> torch.Tensor:
     """XI = sum over neighbours of the zero-padded 0/1 adjacency rows (2-step path counts): (A_hat X) = s . XI for a
-    batch with one coefficient per row; small integers, exact in bf16.  Unit edge weights only.  `ones` is an optional
-    caller-owned fp32 vector of >= nnz ones (streamed batches reuse one instead of allocating per step)."""
+    batch with one coefficient per row; small integers, exact in bf16 and in fp16 (f16=True, or an fp16 `out`: the
+    operand of the 'f16x2' GEMMs).  Unit edge weights only.  `ones` is an optional caller-owned fp32 vector of >= nnz ones
+    (streamed batches reuse one instead of allocating per step)."""
     if not batch.unit_weights:
         raise ValueError("integer features need unit edge weights")
     if ones is None:
@@ -422,8 +430,14 @@ def integer_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None
     elif ones.numel() < batch.nnz or ones.dtype != torch.float32:
         raise ValueError("ones must be an fp32 vector with at least nnz entries")
     if out is None:
-        out = padded_empty_bf16(batch.num_nodes, n_cols, batch.device, zero=True)
-    out, ld = _bf16_rowmajor(out, "out")
+        out = padded_empty_bf16(batch.num_nodes, n_cols, batch.device, zero=True,
+                                dtype=torch.float16 if f16 else torch.bfloat16)
+    out, ld = _b16_rowmajor(out, "out")
+    if out.dtype == torch.float16:
+        check(lib().gmc_csr_preaggregate_f16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), ones.data_ptr(), None,
+                                             batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
+                                             out.data_ptr(), ld, _stream()), "gmc_csr_preaggregate_f16")
+        return out
     check(lib().gmc_csr_preaggregate_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), ones.data_ptr(), None,
                                           batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
                                           out.data_ptr(), ld, None, 0, _stream()), "gmc_csr_preaggregate_bf16")
@@ -431,21 +445,22 @@ def integer_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None
 
 
 class IntegerFeatures:
-    """XI (bf16 integers) + the per-row scale s with A_hat X = s . XI, for GCNEngine(precision='bf16x2' | 'bf16x3')."""
+    """XI (bf16 integers; fp16 for 'f16x2') + the per-row scale s with A_hat X = s . XI, for
+    GCNEngine(precision='bf16x2' | 'bf16x3' | 'f16x2')."""
     __slots__ = ("tensor", "scale")
 
     def __init__(self, tensor: torch.Tensor, scale: torch.Tensor):
-        _bf16_rowmajor(tensor, "XI")
+        _b16_rowmajor(tensor, "XI")
         if scale.dtype != torch.float32 or scale.numel() != tensor.shape[0] or not scale.is_contiguous():
             raise ValueError("scale must be a contiguous fp32 vector with one entry per row")
         self.tensor, self.scale = tensor, scale
 
     @classmethod
-    def from_batch(cls, batch, n_cols: int) -> "IntegerFeatures":
+    def from_batch(cls, batch, n_cols: int, f16: bool = False) -> "IntegerFeatures":
         s, bad = row_scale(batch)
         if bad:
             raise ValueError(f"{bad} rows have neighbours of different degrees: no single A_hat coefficient per row")
-        return cls(integer_features_bf16(batch, n_cols), s)
+        return cls(integer_features_bf16(batch, n_cols, f16=f16), s)
 
 
 def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: int, k: int,
@@ -455,16 +470,16 @@ def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: in
                     proj_out: Optional[torch.Tensor] = None, n_proj: int = 0) -> torch.Tensor:
     """C = op(A) (B_0 + ... + B_{n_split-1}) with bf16 A (exact) and the stacked bf16 parts of an fp32 B [k, N]
     (f32_split_bf16 / skinny_bwd_split); fp32 accumulation and output.  op 'nn': A [M, k]; 'tn': A [k, M].
+    fp16 parts (f32_split_f16, or skinny_bwd_split into an fp16 buffer) need an fp16 A: tcgen05.mma kind::f16 takes ONE
+    16-bit format for both operands.
     Optional fp32 epilogue C[m, n] = act(row_scale[m] * acc + bias[n]) and fused projection proj_out = C @ W for a
     padded weight matrix from pad_proj_weights (deterministic: per-tile partials in the workspace, added in order)."""
-    A, lda = _bf16_rowmajor(A, "A")
-    lo_shift = 0
-    if B_split.dtype == torch.float16:                 # fp16 parts from f32_split_f16 (A stays bf16)
-        if not B_split.is_cuda or B_split.dim() != 2 or B_split.stride(1) != 1:
-            raise TypeError("B_split: expected a row-major CUDA float16 matrix")
-        ldb, lo_shift = B_split.stride(0), F16_LO_SHIFT
-    else:
-        B_split, ldb = _bf16_rowmajor(B_split, "B_split")
+    A, lda = _b16_rowmajor(A, "A")
+    B_split, ldb = _b16_rowmajor(B_split, "B_split")
+    if A.dtype != B_split.dtype:
+        raise TypeError(f"gemm_bf16_split: A is {A.dtype} and the parts are {B_split.dtype}; both operands of one "
+                        "tcgen05.mma must share a 16-bit format")
+    lo_shift = F16_LO_SHIFT if B_split.dtype == torch.float16 else 0
     if op == "nn":
         M, K = A.shape
     elif op == "tn":
@@ -508,13 +523,15 @@ def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: in
 def skinny_bwd_split(dT: torch.Tensor, W: torch.Tensor, H: torch.Tensor, n_split: int, dH_split: torch.Tensor,
                      row_scale: Optional[torch.Tensor] = None, dW: Optional[torch.Tensor] = None,
                      dbias: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None):
-    """skinny_bwd with an fp32 H whose dHpre leaves as n_split stacked bf16 parts of row_scale . dHpre."""
+    """skinny_bwd with an fp32 H whose dHpre leaves as n_split stacked bf16 parts of row_scale . dHpre -- or fp16 parts
+    when dH_split is a float16 buffer (part p scaled by 2^(F16_LO_SHIFT p), values saturate at +-65504)."""
     dT, lddt = _rowmajor(dT, "dT")
     H, ldh = _rowmajor(H, "H")
     W = _f32(W, "W").contiguous()
     n, n_in = H.shape
     n_out = W.shape[1]
-    dH_split, lddh = _bf16_rowmajor(dH_split, "dH_split")
+    dH_split, lddh = _b16_rowmajor(dH_split, "dH_split")
+    lo_shift = F16_LO_SHIFT if dH_split.dtype == torch.float16 else 0
     sr = split_rows_for(n)
     if dH_split.shape[0] < n_split * sr or dH_split.shape[1] != n_in:
         raise ValueError(f"dH_split must be [>= {n_split * sr}, {n_in}]")
@@ -525,7 +542,7 @@ def skinny_bwd_split(dT: torch.Tensor, W: torch.Tensor, H: torch.Tensor, n_split
     ws = workspace or _default_ws
     wptr, wbytes = ws.get(lib().gmc_skinny_bwd_workspace_bytes(n_in, n_out), H.device)
     check(lib().gmc_skinny_bwd_split(dT.data_ptr(), lddt, W.data_ptr(), H.data_ptr(), ldh, _ptr(row_scale),
-                                     dH_split.data_ptr(), lddh, sr, n_split, dW.data_ptr(), dbias.data_ptr(), n, n_in,
+                                     dH_split.data_ptr(), lddh, sr, n_split, lo_shift, dW.data_ptr(), dbias.data_ptr(), n, n_in,
                                      n_out, wptr, wbytes, _stream()), "gmc_skinny_bwd_split")
     return dH_split, dW, dbias
 

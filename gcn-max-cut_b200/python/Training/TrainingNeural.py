@@ -461,8 +461,10 @@ class _Streamer:
         from gmc_b200 import ops
         kind = mode[0]
         if kind in ("integer", "preaggregated"):
-            if self.feat is None or self.feat.shape[0] < hb.num_nodes or self.feat.shape[1] != hb.width:
-                self.feat = ops.padded_empty_bf16(hb.num_nodes, hb.width, self.device, zero=True)
+            want = torch.float16 if (kind == "integer" and engine.split_f16) else torch.bfloat16
+            if (self.feat is None or self.feat.dtype != want or self.feat.shape[0] < hb.num_nodes
+                    or self.feat.shape[1] != hb.width):
+                self.feat = ops.padded_empty_bf16(hb.num_nodes, hb.width, self.device, zero=True, dtype=want)
         if kind == "integer" and hb.regular and hb.max_nodes <= hb.width and engine.H % 4 == 0 and engine.K <= 4:
             if self.ones is None or self.ones.numel() < hb.nnz:
                 self.ones = torch.ones(hb.nnz, dtype=torch.float32, device=self.device)

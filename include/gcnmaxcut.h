@@ -355,8 +355,9 @@ int gmc_f32_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, in
                        int32_t n_split, int64_t split_rows, void* stream);
 /* fp16 parts (11 significant bits each: TWO parts carry 22 of fp32's 24 bits -- fp32-grade at the cost of the two-part
  * bf16 GEMM).  Part p is stored multiplied by 2^(lo_shift * p) (the residuals would be fp16 subnormals otherwise);
- * gmc_gemm_bf16_split with the same lo_shift > 0 reads B as fp16 (A stays bf16: kind::f16 takes either 16-bit format per
- * operand) and scales the parts back in its epilogue.  |src| must stay below 65504. */
+ * gmc_gemm_bf16_split with the same lo_shift > 0 reads A AND B as fp16 (one 16-bit format per tcgen05.mma kind::f16: the
+ * integer features come from gmc_csr_preaggregate_f16) and scales the parts back in its epilogue.  |src| must stay below
+ * 65504 (gmc_skinny_bwd_split saturates). */
 int gmc_f32_split_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t n_rows, int32_t n_cols,
                       int32_t n_split, int64_t split_rows, int32_t lo_shift, void* stream);
 int gmc_row_scale_f32(const int32_t* rowptr, const float* coef, int64_t n_rows, float* row_scale,
@@ -370,8 +371,14 @@ int gmc_gemm_bf16_split(int32_t op, const void* A, const void* B, float* C, int6
                         size_t workspace_bytes, void* stream);
 int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const float* H, int64_t ldh,
                          const float* row_scale, void* dH_split, int64_t lddh, int64_t split_rows, int32_t n_split,
+                         int32_t lo_shift /* 0: bf16 parts; > 0: fp16 parts, part p scaled by 2^(lo_shift p) */,
                          float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* gmc_csr_preaggregate_bf16 with the rows written as IEEE fp16: the A operand of the fp16-part GEMMs (both MMA operands
+ * must share one 16-bit format; small integers are exact in either). */
+int gmc_csr_preaggregate_f16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                             const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
+                             int64_t ldx, void* stream);
 
 /* ---- (e) integer post-processing ------------------------------------------------------ */
 

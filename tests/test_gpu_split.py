@@ -98,18 +98,22 @@ def test_fp16_split_parts_add_up(rows, cols, n_split):
 @pytest.mark.parametrize("op,M,N,K", [("nn", 1000, 500, 1000), ("nn", 130, 260, 40), ("nn", 40000, 500, 1000), ("nn", 5, 12, 8),
                                       ("tn", 1000, 500, 30000), ("tn", 100, 64, 128)])
 def test_f16_split_gemm_matches_float64(op, M, N, K):
-    """bf16 integer A x two fp16 parts of an fp32 B (mixed 16-bit formats in one tcgen05.mma kind::f16): 22 mantissa bits
-    of B, i.e. 2^-23 per weight + fp32 accumulation noise."""
+    """fp16 integer A x two fp16 parts of an fp32 B (tcgen05.mma kind::f16 takes one 16-bit format for both operands: a
+    bf16 A with fp16 parts is refused): 22 mantissa bits of B, i.e. 2^-23 per weight + fp32 accumulation noise."""
     A = bf16_exact_ints(M, K, 7, M + K) if op == "nn" else bf16_exact_ints(K, M, 7, M + K)
     torch.manual_seed(N)
     B = torch.randn(K, N) * 0.05
     want = (A.double() if op == "nn" else A.double().t()) @ B.double()
-    got = ops.gemm_bf16_split(op, ops.to_bf16(A.to(DEV)), ops.f32_split_f16(B.to(DEV), 2), 2, K)
+    A16 = ops.padded_empty_bf16(A.shape[0], A.shape[1], DEV, zero=True, dtype=torch.float16)
+    A16.copy_(A.to(DEV))
+    with pytest.raises(TypeError):
+        ops.gemm_bf16_split(op, ops.to_bf16(A.to(DEV)), ops.f32_split_f16(B.to(DEV), 2), 2, K)
+    got = ops.gemm_bf16_split(op, A16, ops.f32_split_f16(B.to(DEV), 2), 2, K)
     assert relerr(got.cpu(), want) < 5e-7 * max(1.0, math.sqrt(K) / 16)
     s, b = torch.rand(M) * 0.2 + 0.05, torch.randn(N) * 0.3
     if op == "nn":
         out = ops.padded_empty(M, N, DEV)
-        got = ops.gemm_bf16_split("nn", ops.to_bf16(A.to(DEV)), ops.f32_split_f16(B.to(DEV), 2), 2, K, out=out,
+        got = ops.gemm_bf16_split("nn", A16, ops.f32_split_f16(B.to(DEV), 2), 2, K, out=out,
                                   row_scale=s.to(DEV), bias=b.to(DEV), relu=True)
         assert relerr(got.cpu(), torch.relu(s.double()[:, None] * want + b.double())) < 6e-7
 
@@ -202,6 +206,28 @@ def test_skinny_bwd_split_equals_the_fp32_kernel(n, n_in, n_out, n_split):
     assert int(torch.count_nonzero(S[n: sr])) == 0                 # pad rows of part 0 untouched
 
 
+@pytest.mark.parametrize("n,n_in,n_out", [(1000, 500, 3), (70, 16, 3), (70003, 500, 3), (65540, 260, 4)])
+def test_skinny_bwd_split_fp16_parts(n, n_in, n_out):
+    """fp16 parts of s . dHpre (an fp16 buffer selects them): hi + 2^-12 lo carries 22 bits of every element in fp16's
+    normal range, elements below it keep an absolute error of one scaled subnormal quantum; huge values saturate."""
+    torch.manual_seed(n + n_in)
+    H = torch.relu(torch.randn(n, n_in, device=DEV))
+    dT = torch.randn(n, n_out, device=DEV)
+    W = torch.randn(n_in, n_out, device=DEV) * 0.2
+    s = torch.rand(n, device=DEV) * 0.3 + 0.05
+    dH, dW, db = ops.skinny_bwd(dT, W, H)
+    sr = ops.split_rows_for(n)
+    S = ops.padded_empty_bf16(2 * sr, n_in, DEV, zero=True, dtype=torch.float16)
+    _, dW2, db2 = ops.skinny_bwd_split(dT, W, H, 2, S, row_scale=s)
+    total = S[:n].double() + S[sr: sr + n].double() * 2.0 ** -ops.F16_LO_SHIFT
+    want = (s[:, None] * dH).double()
+    err = (total - want).abs()
+    assert (err <= want.abs() * 2.0 ** -21 + 2.0 ** -24).all()
+    assert relerr(dW2.cpu(), dW.cpu()) < 1e-5 and relerr(db2.cpu(), db.cpu()) < 1e-5
+    ops.skinny_bwd_split(dT * 1e7, W, H, 2, S, row_scale=s)                     # saturates, never inf / nan
+    assert bool(torch.isfinite(S[:n].float()).all()) and float(S[:n].float().abs().max()) == 65504.0
+
+
 def regular_batch(n_graphs, n, degs, seed):
     rowptr, colidx, gp = synth.regular_batch_arrays(n_graphs, n, degs, seed=seed)
     return GraphBatch.from_arrays(rowptr, colidx, gp, device=DEV), (rowptr, colidx, gp)
@@ -228,6 +254,8 @@ def test_integer_features_times_scale_is_ahat_x():
     assert relerr(got.cpu(), want.cpu()) < 1e-6
     vals = xi.tensor.float()
     assert torch.equal(vals, vals.round()) and float(vals.max()) <= 8.0
+    xi16 = ops.IntegerFeatures.from_batch(batch, 160, f16=True)                 # the 'f16x2' operand: same integers
+    assert xi16.tensor.dtype == torch.float16 and torch.equal(xi16.tensor.float(), vals)
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16x2", "f16x2"])
