@@ -43,6 +43,35 @@ int sm_count();                      // cached cudaDevAttrMultiProcessorCount of
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch ------------------------------------------------------
+// The reference trains one small graph per optimiser step (TrainingNeural.py:371-388): ~10 dependent launches of a few
+// microseconds each, so the gaps between kernels are a third of the step.  Kernels on that chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and begin with pdl_prologue(): `launch_dependents` lets the NEXT
+// kernel's CTAs be scheduled (and run their own prologue) as soon as every CTA of this grid is resident, `wait` blocks
+// until the PREVIOUS grid has completed and flushed -- executed by every thread before its first global access, so
+// completion stays transitive along the chain (C waits for B, which waited for A).  A kernel launched without the
+// attribute simply waits for full completion, so converted and unconverted kernels mix freely.  Opt-in (GMC_PDL=1):
+// without the attribute the device-side instructions are no-ops.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
@@ -50,6 +79,20 @@ __host__ __device__ constexpr inline T ceil_div(T a, T b) { return (a + b - 1) /
 
 // ---- device helpers -------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef GMC_PDL_EARLY
+#define GMC_PDL_EARLY 1
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if GMC_PDL_EARLY
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// wait FIRST: a kernel that triggers before it waits lets the whole chain behind it become resident at once (each early
+// CTA triggers its own dependents), and the spinning CTAs keep the 225 KB GEMM CTAs off their SMs -- measured 59 us per
+// 500-node step against 49 us without early launches
+__device__ __forceinline__ void pdl_prologue() { pdl_wait(); pdl_launch_dependents(); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

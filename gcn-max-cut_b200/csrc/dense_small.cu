@@ -127,6 +127,7 @@ template <int NOUT>
 __global__ void __launch_bounds__(128)
 skinny_bwd_kernel(const float* __restrict__ dT, int64_t lddt, const float* __restrict__ W, const float* __restrict__ H,
                   int64_t ldh, float* __restrict__ dH, int64_t lddh, int64_t n_rows, int n_in, float* __restrict__ ws) {
+    pdl_prologue();
     const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
     const int64_t r0 = (int64_t)blockIdx.x * rows_per;
     const int64_t r1 = min(n_rows, r0 + rows_per);
@@ -191,6 +192,7 @@ template <int NOUT>
 __global__ void __launch_bounds__(128)
 skinny_bwd_b16_kernel(const float* __restrict__ dT, int64_t lddt, const float* __restrict__ W, const uint2* __restrict__ H,
                       int64_t ldh4, uint2* __restrict__ dH, int64_t lddh4, int64_t n_rows, int n_in, float* __restrict__ ws) {
+    pdl_prologue();
     const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
     const int64_t r0 = (int64_t)blockIdx.x * rows_per;
     const int64_t r1 = min(n_rows, r0 + rows_per);
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(128)
 skinny_bwd_split_kernel(const float* __restrict__ dT, int64_t lddt, const float* __restrict__ W, const float* __restrict__ H,
                         int64_t ldh, const float* __restrict__ row_scale, uint2* __restrict__ dH, int64_t lddh4,
                         int64_t split_rows, int64_t n_rows, int n_in, float* __restrict__ ws, float lo_up) {
+    pdl_prologue();
     const int64_t rows_per = ceil_div<int64_t>(n_rows, gridDim.x);
     const int64_t r0 = (int64_t)blockIdx.x * rows_per;
     const int64_t r1 = min(n_rows, r0 + rows_per);
@@ -697,6 +700,7 @@ __global__ void skinny_bwd_reduce_kernel(const float* __restrict__ ws, int n_cta
                                          float* __restrict__ dW, float* __restrict__ dbias) {
     // block = 32 outputs (x) x 32 partial-groups (y): coalesced 128-byte reads, fixed summation order
     __shared__ float red[32][33];
+    pdl_prologue();
     const int total = n_in * (nout + 1);
     const int i = blockIdx.x * 32 + threadIdx.x;               // over n_in * (nout + 1)
     float s = 0.f;
@@ -757,6 +761,16 @@ __global__ void colsum_stage2(const float* __restrict__ ws, int n_ctas, int n_co
 }
 
 static int reduce_ctas() { return sm_count() * 4; }
+
+// CTAs of the (non-streamed) skinny_bwd kernels: two waves of four per SM for large inputs, but never fewer than 8 rows per
+// CTA -- every CTA leaves an [n_in, n_out + 1] partial for the reduce kernel, and a 500-node graph's step spent more time
+// writing and adding 500 one-row partials than on the rows themselves
+static int skinny_bwd_ctas(int64_t n_rows) {
+    int n_ctas = reduce_ctas() * 2;
+    const int64_t by_rows = n_rows > 8 ? (n_rows + 7) / 8 : 1;
+    if ((int64_t)n_ctas > by_rows) n_ctas = (int)by_rows;
+    return n_ctas;
+}
 
 }  // namespace gmc
 
@@ -859,8 +873,7 @@ int gmc_skinny_bwd_f32(const float* dT, int64_t lddt, const float* W, const floa
                 "gmc_skinny_bwd_f32: bad sizes (n_out must be 1..8)");
     GMC_REQUIRE(n_in % 4 == 0 && ldh % 4 == 0 && lddh % 4 == 0 && aligned16(H) && aligned16(dHpre),
                 "gmc_skinny_bwd_f32: n_in and leading dimensions must be multiples of 4 with 16-byte aligned bases");
-    int n_ctas = reduce_ctas() * 2;
-    if ((int64_t)n_ctas > n_rows) n_ctas = (int)(n_rows > 0 ? n_rows : 1);
+    const int n_ctas = skinny_bwd_ctas(n_rows);
     const size_t need = (size_t)n_ctas * n_in * (n_out + 1) * sizeof(float);
     if (!workspace || workspace_bytes < need) {
         set_error("gmc_skinny_bwd_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -873,13 +886,12 @@ int gmc_skinny_bwd_f32(const float* dT, int64_t lddt, const float* W, const floa
         if (dbias) GMC_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * n_in, s));
         return GMC_OK;
     }
-#define GMC_CASE(K) case K: skinny_bwd_kernel<K><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, dHpre, lddh, n_rows, n_in, ws); break;
+#define GMC_CASE(K) case K: GMC_CUDA(launch_pdl(skinny_bwd_kernel<K>, n_ctas, 128, 0, s, dT, lddt, W, H, ldh, dHpre, lddh, n_rows, n_in, ws)); break;
     switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();
     const int total = n_in * (n_out + 1);
-    skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
-    GMC_LAUNCH_CHECK();
+    GMC_CUDA(launch_pdl(skinny_bwd_reduce_kernel, ceil_div(total, 32), dim3(32, 32), 0, s, ws, n_ctas, n_in, n_out, dW, dbias));
     return GMC_OK;
 }
 
@@ -895,8 +907,7 @@ int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const voi
     GMC_REQUIRE(n_in % 4 == 0 && ldh % 4 == 0 && lddh % 4 == 0 && (reinterpret_cast<uintptr_t>(H) & 7u) == 0 &&
                     (reinterpret_cast<uintptr_t>(dHpre) & 7u) == 0,
                 "gmc_skinny_bwd_bf16: n_in and leading dimensions must be multiples of 4 with 8-byte aligned bases");
-    int n_ctas = reduce_ctas() * 2;
-    if ((int64_t)n_ctas > n_rows) n_ctas = (int)(n_rows > 0 ? n_rows : 1);
+    const int n_ctas = skinny_bwd_ctas(n_rows);
     const size_t need = (size_t)n_ctas * n_in * (n_out + 1) * sizeof(float);
     if (!workspace || workspace_bytes < need) {
         set_error("gmc_skinny_bwd_bf16: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -953,13 +964,12 @@ int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const voi
         GMC_LAUNCH_CHECK();
         return GMC_OK;
     }
-#define GMC_CASE(K) case K: skinny_bwd_b16_kernel<K><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H2, ldh / 4, dH2, lddh / 4, n_rows, n_in, ws); break;
+#define GMC_CASE(K) case K: GMC_CUDA(launch_pdl(skinny_bwd_b16_kernel<K>, n_ctas, 128, 0, s, dT, lddt, W, H2, ldh / 4, dH2, lddh / 4, n_rows, n_in, ws)); break;
     switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();
     const int total = n_in * (n_out + 1);
-    skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
-    GMC_LAUNCH_CHECK();
+    GMC_CUDA(launch_pdl(skinny_bwd_reduce_kernel, ceil_div(total, 32), dim3(32, 32), 0, s, ws, n_ctas, n_in, n_out, dW, dbias));
     return GMC_OK;
 }
 
@@ -981,8 +991,7 @@ int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const fl
     GMC_REQUIRE((n_split == 2 || n_split == 3) && split_rows >= n_rows, "gmc_skinny_bwd_split: n_split must be 2 or 3 and split_rows >= n_rows");
     GMC_REQUIRE(n_in % 4 == 0 && ldh % 4 == 0 && lddh % 4 == 0 && aligned16(H) && (reinterpret_cast<uintptr_t>(dH_split) & 7u) == 0,
                 "gmc_skinny_bwd_split: n_in and leading dimensions must be multiples of 4 with aligned bases");
-    int n_ctas = reduce_ctas() * 2;
-    if ((int64_t)n_ctas > n_rows) n_ctas = (int)(n_rows > 0 ? n_rows : 1);
+    const int n_ctas = skinny_bwd_ctas(n_rows);
     const size_t need = (size_t)n_ctas * n_in * (n_out + 1) * sizeof(float);
     if (!workspace || workspace_bytes < need) {
         set_error("gmc_skinny_bwd_split: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -1042,17 +1051,16 @@ int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const fl
     }
 #define GMC_CASE(K)                                                                                                           \
     case K:                                                                                                                   \
-        if (f16 && n_split == 2) skinny_bwd_split_kernel<K, 2, true><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
-        else if (f16) skinny_bwd_split_kernel<K, 3, true><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
-        else if (n_split == 2) skinny_bwd_split_kernel<K, 2><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
-        else skinny_bwd_split_kernel<K, 3><<<n_ctas, 128, 0, s>>>(dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up); \
+        if (f16 && n_split == 2) GMC_CUDA(launch_pdl(skinny_bwd_split_kernel<K, 2, true>, n_ctas, 128, 0, s, dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up)); \
+        else if (f16) GMC_CUDA(launch_pdl(skinny_bwd_split_kernel<K, 3, true>, n_ctas, 128, 0, s, dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up)); \
+        else if (n_split == 2) GMC_CUDA(launch_pdl(skinny_bwd_split_kernel<K, 2>, n_ctas, 128, 0, s, dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up)); \
+        else GMC_CUDA(launch_pdl(skinny_bwd_split_kernel<K, 3>, n_ctas, 128, 0, s, dT, lddt, W, H, ldh, row_scale, dH2, lddh / 4, split_rows, n_rows, n_in, ws, lo_up)); \
         break;
     switch (n_out) { GMC_CASE(1) GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) }
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();
     const int total = n_in * (n_out + 1);
-    skinny_bwd_reduce_kernel<<<ceil_div(total, 32), dim3(32, 32), 0, s>>>(ws, n_ctas, n_in, n_out, dW, dbias);
-    GMC_LAUNCH_CHECK();
+    GMC_CUDA(launch_pdl(skinny_bwd_reduce_kernel, ceil_div(total, 32), dim3(32, 32), 0, s, ws, n_ctas, n_in, n_out, dW, dbias));
     return GMC_OK;
 }
 

@@ -466,6 +466,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (CL > 1) cluster_sync_all(); else __syncthreads();          // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // programmatic dependent launch: barrier init, TMEM allocation and descriptor prefetch above overlap the previous
+    // kernel's tail; nothing before this line touches global memory
+    pdl_wait();
+    pdl_launch_dependents();
 
     // cluster-level work items: (split, m-group, n-group); every CTA of a cluster walks the same list
     const int64_t tiles_gn = (int64_t)p.mg_tiles * p.ng_tiles;
@@ -710,6 +714,8 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                                                    // see gemm_umma_kernel
+    pdl_launch_dependents();
 
     const int64_t tiles_mn = (int64_t)p.m_tiles * p.n_tiles;       // tiles of 256 x 256
     const int64_t n_work = tiles_mn * p.k_splits;
@@ -824,6 +830,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // T[m, k] = sum over the n-tiles of their partial projections, in tile order (deterministic)
 __global__ void __launch_bounds__(256)
 proj_reduce_kernel(const float4* __restrict__ part, int n_tiles, int64_t M, float* __restrict__ out, int64_t ldp, int k) {
+    pdl_prologue();
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     float4 s = __ldg(part + m);
@@ -840,6 +847,7 @@ proj_reduce_kernel(const float4* __restrict__ part, int n_tiles, int64_t M, floa
 
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t MN, int64_t N,
                                         float* __restrict__ C, int64_t ldc, int accumulate) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= MN) return;
     float s = 0.f;
@@ -915,9 +923,11 @@ static void cluster_shape(bool a_mn, int64_t n_tiles, int* clm, int* cln, bool b
 constexpr int64_t kSplitChain = 32768;
 static int pick_splits_cl(int64_t cluster_tiles, int64_t K, int slots, int64_t max_chain = 0) {
     int64_t s = 1;
-    if (cluster_tiles < slots && K >= 8 * BLOCK_K) {
+    // a split must be worth its reduce launch: >= 16 k-blocks each (a 500-node graph's dW1 GEMM, K = 500, ran as three
+    // splits of 170 k-rows plus a 6.5 us reduce kernel in a 70 us step)
+    if (cluster_tiles < slots && K >= 32 * BLOCK_K) {
         s = slots / cluster_tiles;
-        const int64_t max_by_k = K / (4 * BLOCK_K);
+        const int64_t max_by_k = K / (16 * BLOCK_K);
         if (s > max_by_k) s = max_by_k;
         if (s < 1) s = 1;
     }
@@ -1060,11 +1070,13 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     const int slots = cluster_slots<A_MN, B_MN, CLM, CLN, BF16, NS>();  // co-resident clusters (GPC geometry), <= SMs / CL
 
     Params p = {};
@@ -1097,12 +1109,12 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
     GMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_umma_kernel<A_MN, B_MN, CLM, CLN, BF16, NS>, tmA, tmB, tmC, p));
     if (splits > 1) {
         const int64_t MN = M * N;
-        tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
-        GMC_LAUNCH_CHECK();
+        GMC_CUDA(launch_pdl(tc_splitk_reduce_kernel, (unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s, p.C, splits, MN, N, C, ldc,
+                            accumulate));
     }
     if (p.proj_part) {
-        proj_reduce_kernel<<<(unsigned)ceil_div<int64_t>(M, 256), 256, 0, s>>>(p.proj_part, p.n_tiles, M, proj_out, ldp, proj_k);
-        GMC_LAUNCH_CHECK();
+        GMC_CUDA(launch_pdl(proj_reduce_kernel, (unsigned)ceil_div<int64_t>(M, 256), 256, 0, s, p.proj_part, p.n_tiles, M,
+                            proj_out, ldp, proj_k));
     }
     return GMC_OK;
 }
@@ -1152,9 +1164,9 @@ static bool use_two_cta_bf16(int op) { return (two_cta_bf16_mode() >> op) & 1; }
 
 static int pick_splits2(int64_t tiles, int64_t K) {
     const int pairs = sm_count() / 2;
-    if (tiles >= pairs || K < 8 * BLOCK_K) return 1;
+    if (tiles >= pairs || K < 32 * BLOCK_K) return 1;
     int64_t s = pairs / tiles;
-    const int64_t max_by_k = K / (4 * BLOCK_K);
+    const int64_t max_by_k = K / (16 * BLOCK_K);
     if (s > max_by_k) s = max_by_k;
     return (int)(s < 1 ? 1 : s);
 }
@@ -1203,12 +1215,23 @@ static int launch2(const void* A, const void* B, float* C, int64_t M, int64_t N,
     const int64_t n_work = tiles * splits;
     const int pairs = sm_count() / 2;
     const int grid = 2 * (int)(n_work < pairs ? n_work : pairs);
-    gemm_umma2_kernel<A_MN, B_MN, BF16><<<grid, THREADS, SMEM2_BYTES, s>>>(tmA, tmB, tmC, p);
-    GMC_LAUNCH_CHECK();
+    {
+        cudaLaunchConfig_t cfg2 = {};
+        cfg2.gridDim = dim3(grid);
+        cfg2.blockDim = dim3(THREADS);
+        cfg2.dynamicSmemBytes = SMEM2_BYTES;
+        cfg2.stream = s;
+        cudaLaunchAttribute attr2[1];
+        attr2[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr2[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+        cfg2.attrs = attr2;
+        cfg2.numAttrs = 1;
+        GMC_CUDA(cudaLaunchKernelEx(&cfg2, gemm_umma2_kernel<A_MN, B_MN, BF16>, tmA, tmB, tmC, p));
+    }
     if (splits > 1) {
         const int64_t MN = M * N;
-        tc_splitk_reduce_kernel<<<(unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s>>>(p.C, splits, MN, N, C, ldc, accumulate);
-        GMC_LAUNCH_CHECK();
+        GMC_CUDA(launch_pdl(tc_splitk_reduce_kernel, (unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s, p.C, splits, MN, N, C, ldc,
+                            accumulate));
     }
     return GMC_OK;
 }

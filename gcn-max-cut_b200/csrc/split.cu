@@ -33,6 +33,7 @@ template <int NS>
 __global__ void __launch_bounds__(256)
 f32_split_bf16_kernel(const float* __restrict__ src, int64_t lds, __nv_bfloat16* __restrict__ dst, int64_t ldd,
                       int64_t n_rows, int n_cols, int64_t split_rows, int units_per_row) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = i / units_per_row;
     const int c0 = (int)(i - r * units_per_row) * 8;
@@ -59,6 +60,7 @@ template <int NS>
 __global__ void __launch_bounds__(256)
 f32_split_f16_kernel(const float* __restrict__ src, int64_t lds, __half* __restrict__ dst, int64_t ldd, int64_t n_rows,
                      int n_cols, int64_t split_rows, int units_per_row, float up) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = i / units_per_row;
     const int c0 = (int)(i - r * units_per_row) * 8;
@@ -113,9 +115,9 @@ int gmc_f32_split_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, in
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
     cudaStream_t s = as_stream(stream);
     switch (n_split) {
-        case 1: f32_split_bf16_kernel<1><<<grid, 256, 0, s>>>(src, lds, d, ldd, n_rows, n_cols, split_rows, units); break;
-        case 2: f32_split_bf16_kernel<2><<<grid, 256, 0, s>>>(src, lds, d, ldd, n_rows, n_cols, split_rows, units); break;
-        default: f32_split_bf16_kernel<3><<<grid, 256, 0, s>>>(src, lds, d, ldd, n_rows, n_cols, split_rows, units); break;
+        case 1: GMC_CUDA(launch_pdl(f32_split_bf16_kernel<1>, grid, 256, 0, s, src, lds, d, ldd, n_rows, n_cols, split_rows, units)); break;
+        case 2: GMC_CUDA(launch_pdl(f32_split_bf16_kernel<2>, grid, 256, 0, s, src, lds, d, ldd, n_rows, n_cols, split_rows, units)); break;
+        default: GMC_CUDA(launch_pdl(f32_split_bf16_kernel<3>, grid, 256, 0, s, src, lds, d, ldd, n_rows, n_cols, split_rows, units)); break;
     }
     GMC_LAUNCH_CHECK();
     return GMC_OK;
@@ -138,9 +140,9 @@ int gmc_f32_split_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int
     const float up = (float)(1u << lo_shift);
     cudaStream_t s = as_stream(stream);
     switch (n_split) {
-        case 1: f32_split_f16_kernel<1><<<grid, 256, 0, s>>>(src, lds, d, ldd, n_rows, n_cols, split_rows, units, up); break;
-        case 2: f32_split_f16_kernel<2><<<grid, 256, 0, s>>>(src, lds, d, ldd, n_rows, n_cols, split_rows, units, up); break;
-        default: f32_split_f16_kernel<3><<<grid, 256, 0, s>>>(src, lds, d, ldd, n_rows, n_cols, split_rows, units, up); break;
+        case 1: GMC_CUDA(launch_pdl(f32_split_f16_kernel<1>, grid, 256, 0, s, src, lds, d, ldd, n_rows, n_cols, split_rows, units, up)); break;
+        case 2: GMC_CUDA(launch_pdl(f32_split_f16_kernel<2>, grid, 256, 0, s, src, lds, d, ldd, n_rows, n_cols, split_rows, units, up)); break;
+        default: GMC_CUDA(launch_pdl(f32_split_f16_kernel<3>, grid, 256, 0, s, src, lds, d, ldd, n_rows, n_cols, split_rows, units, up)); break;
     }
     GMC_LAUNCH_CHECK();
     return GMC_OK;

@@ -29,6 +29,7 @@ layer2_loss_fused_kernel(const float* __restrict__ T2, int64_t ldt, const int32_
     extern __shared__ __align__(16) float tail_smem[];
     __shared__ double red_loss[kTailThreads / 32];
     __shared__ float red_db[kTailThreads / 32][K];
+    pdl_prologue();
     const int g = blockIdx.x;
     const int base = __ldg(graph_ptr + g);
     const int n = __ldg(graph_ptr + g + 1) - base;
@@ -183,6 +184,7 @@ layer2_loss_fused_kernel(const float* __restrict__ T2, int64_t ldt, const int32_
 __global__ void __launch_bounds__(256)
 tail_db2_reduce_kernel(const float* __restrict__ part, int n_graphs, int K, float* __restrict__ db2) {
     __shared__ float red[256];
+    pdl_prologue();
     for (int k = 0; k < K; ++k) {
         // fixed assignment of graphs to threads and a fixed tree: deterministic
         float s = 0.f;
@@ -231,7 +233,8 @@ int gmc_layer2_loss_fused(const float* T2, int64_t ldt, const int32_t* rowptr, c
             set_error("gmc_layer2_loss_fused: workspace too small (%zu < %zu)", workspace_bytes, need);
             return GMC_ERR_WORKSPACE;
         }
-        part = reinterpret_cast<float*>(workspace);
+        // one graph: its partial IS db2 (the reduce of one term adds zeros: same bits), no second launch
+        part = n_graphs == 1 ? db2 : reinterpret_cast<float*>(workspace);
     }
     cudaStream_t s = as_stream(stream);
     if (n_graphs == 0 || n_rows == 0) {
@@ -246,17 +249,14 @@ int gmc_layer2_loss_fused(const float* T2, int64_t ldt, const int32_t* rowptr, c
             GMC_CUDA(cudaFuncSetAttribute(layer2_loss_fused_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailMaxSmem)); \
             attr = kTailMaxSmem;                                                                                          \
         }                                                                                                                 \
-        layer2_loss_fused_kernel<K><<<n_graphs, kTailThreads, smem, s>>>(T2, ldt, rowptr, colidx, coef, vals, graph_ptr, bias2, mode, \
-                                                                         override_terminals, penalty, C, Z_out, P_out,   \
-                                                                         loss_per_graph, dZ_out, dT2, lddt, part);        \
+        GMC_CUDA(launch_pdl(layer2_loss_fused_kernel<K>, n_graphs, kTailThreads, smem, s, T2, ldt, rowptr, colidx, coef, vals, \
+                            graph_ptr, bias2, mode, override_terminals, penalty, C, Z_out, P_out, loss_per_graph, dZ_out,  \
+                            dT2, lddt, part));                                                                            \
     } break;
     switch (n_classes) { GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();
-    if (db2) {
-        tail_db2_reduce_kernel<<<1, 256, 0, s>>>(part, n_graphs, n_classes, db2);
-        GMC_LAUNCH_CHECK();
-    }
+    if (db2 && n_graphs > 1) GMC_CUDA(launch_pdl(tail_db2_reduce_kernel, 1, 256, 0, s, part, n_graphs, n_classes, db2));
     return GMC_OK;
 }
 

@@ -99,6 +99,9 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_adam_multi_devstep": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                        POINTER(c_void_p), POINTER(c_int64), c_double, c_double, c_double, c_double,
                                        P, P]),
+    "gmc_adam_multi_devstate": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                        POINTER(c_void_p), POINTER(c_int64), c_double, c_double, c_double, c_double,
+                                        P, P]),
     "gmc_argmax_labels": (c_int, [P, c_int64, P, c_int32, c_int64, c_int32, c_int32, P, P]),
     "gmc_cut_value_i32": (c_int, [P, P, P, P, P, c_int32, c_int64, P, P]),
     "gmc_cut_value_multi_u8": (c_int, [P, P, P, P, c_int32, c_int32, P, P]),

@@ -864,7 +864,8 @@ def adam_multi(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], ex
                exp_avg_sq: Sequence[torch.Tensor], lr: float, beta1: float = 0.9, beta2: float = 0.999,
                eps: float = 1e-8, step: Optional[int] = None, step_dev: Optional[torch.Tensor] = None) -> None:
     """In-place Adam on up to 16 tensors per launch.  Pass either `step` (1-based host count) or
-    `step_dev` (int64 device scalar holding the number of steps taken; incremented on device)."""
+    `step_dev` (int64 device scalar holding the number of steps taken; incremented on device) -- or an 8-word int64
+    state whose word 0 is that count (gmc_adam_multi_devstate: no increment launch, bias corrections precomputed)."""
     n = len(params)
     for group in (params, grads, exp_avg, exp_avg_sq):
         if len(group) != n:
@@ -881,7 +882,12 @@ def adam_multi(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], ex
         if step_dev is not None:
             if hi < n:
                 raise ValueError("adam_multi with step_dev supports at most 16 tensors per call")
-            check(lib().gmc_adam_multi_devstep(*args, step_dev.data_ptr(), _stream()), "gmc_adam_multi_devstep")
+            if step_dev.dtype != torch.int64 or not step_dev.is_cuda or not step_dev.is_contiguous() or step_dev.numel() not in (1, 8):
+                raise ValueError("step_dev must be a contiguous CUDA int64 tensor of 1 (count) or 8 (state) elements")
+            if step_dev.numel() == 8:
+                check(lib().gmc_adam_multi_devstate(*args, step_dev.data_ptr(), _stream()), "gmc_adam_multi_devstate")
+            else:
+                check(lib().gmc_adam_multi_devstep(*args, step_dev.data_ptr(), _stream()), "gmc_adam_multi_devstep")
         else:
             if step is None or step < 1:
                 raise ValueError("adam_multi: step must be >= 1")

@@ -56,6 +56,7 @@ import os as _os
 # per-graph optimiser steps are replayed from captured CUDA graphs (GCNEngine.train_step_graphed); GMC_CUDA_GRAPHS=0
 # keeps the eager launch sequence
 _USE_CUDA_GRAPHS = _os.environ.get("GMC_CUDA_GRAPHS", "1") != "0"
+_EPOCH_GRAPH = _os.environ.get("GMC_EPOCH_GRAPH", "1") != "0"     # one captured graph per epoch instead of one per step
 
 TORCH_DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 TORCH_DTYPE = torch.float32
@@ -561,6 +562,13 @@ def train_single_epoch(dataset: Dict, net, optimizer, embed, config: TrainingCon
         if streamed:
             total += _train_epoch_streamed(engine, steps, device)
             continue
+        if (_USE_CUDA_GRAPHS and _EPOCH_GRAPH and not embedding_mode and world == 1
+                and all(st.batch is not None for st in steps)):
+            # the whole epoch as one captured CUDA graph (the dataset dict is revisited in the same order, :371)
+            epoch_total = engine.train_epoch_graphed([(st.batch, st.X) for st in steps])
+            if epoch_total is not None:
+                total += epoch_total
+                continue
         for i_step, step in enumerate(steps):
             if step.batch is None:
                 engine.train_step_empty()

@@ -227,6 +227,14 @@ int gmc_adam_multi_devstep(int32_t n_tensors, float* const* params, const float*
                            double lr, double beta1, double beta2, double eps, int64_t* step_dev,
                            void* stream);
 
+/* The same with an 8-word device state (zero-initialised; word 0 = steps already taken): the launch advances the count
+ * itself and leaves the bias-correction scalars of the NEXT step in the state, so a replayed per-graph training step
+ * (TrainingNeural.py:371-388) carries neither a one-thread increment launch nor a double-precision pow() in front of
+ * every CTA. */
+int gmc_adam_multi_devstate(int32_t n_tensors, float* const* params, const float* const* grads,
+                            float* const* exp_avg, float* const* exp_avg_sq, const int64_t* sizes,
+                            double lr, double beta1, double beta2, double eps, int64_t* state, void* stream);
+
 /* gmc_spmm_fused_skinny_f32 for a block-diagonal batch with an ELL plan: the TMA-staged slab kernel with the
  * skinny projection T = Y W (n_out <= 4) folded into its epilogue; per-slab partial sums go to `workspace`
  * (gmc_spmm_batched_fused_workspace_bytes) and are reduced in slab order, so T is deterministic.

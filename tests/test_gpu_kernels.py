@@ -435,9 +435,13 @@ def test_adam_matches_torch_adam_over_steps():
     v = [torch.zeros_like(p) for p in mine]
     opt = torch.optim.Adam(ref, lr=1e-3)
     step_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    state = torch.zeros(8, dtype=torch.int64, device=DEV)        # gmc_adam_multi_devstate: count + cached scalars
     mine2 = [p.clone() for p in mine]
     m2 = [torch.zeros_like(p) for p in mine]
     v2 = [torch.zeros_like(p) for p in mine]
+    mine3 = [p.clone() for p in mine]
+    m3 = [torch.zeros_like(p) for p in mine]
+    v3 = [torch.zeros_like(p) for p in mine]
     for t in range(1, 8):
         grads = [torch.randn(*s) * (10.0 if t % 2 else 0.01) for s in shapes]
         for p, g in zip(ref, grads):
@@ -446,10 +450,17 @@ def test_adam_matches_torch_adam_over_steps():
         gd = [g.to(DEV) for g in grads]
         ops.adam_multi(mine, gd, m, v, lr=1e-3, step=t)
         ops.adam_multi(mine2, gd, m2, v2, lr=1e-3, step_dev=step_dev)
-        for a, b, c in zip(mine, ref, mine2):
+        # the cached state survives a change of hyper-parameters (recomputed, not reused) and a host-side reset
+        lr3 = 1e-3 if t != 4 else 2e-3
+        if t == 4:
+            ops.adam_multi([q.clone() for q in mine3], gd, [q.clone() for q in m3], [q.clone() for q in v3], lr=lr3, step_dev=state)
+            state[:1].fill_(t - 1)
+        ops.adam_multi(mine3, gd, m3, v3, lr=1e-3, step_dev=state)
+        for a, b, c, d in zip(mine, ref, mine2, mine3):
             assert relerr(a.cpu(), b.detach()) < 2e-6
             assert relerr(c.cpu(), b.detach()) < 2e-6
-    assert int(step_dev.item()) == 7
+            assert torch.equal(c, d)                                  # same double-precision scalars either way
+    assert int(step_dev.item()) == 7 and int(state[0].item()) == 7 and int(state[3].item()) == 0
 
 
 # ------------------------------------------------------------------ integer post-processing
