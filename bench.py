@@ -209,6 +209,13 @@ def cpu_reference_run(args, steps: int, warmup: int, sample: int, budget_s: floa
         csr = rs.HostCSR(rp, ci, np.ones(len(ci), dtype=np.float32), args.nodes)
         X = rs.dense_adjacency(csr, args.features)
         items.append((csr, X))
+    # all the host threads the process may use: torchrun exports OMP_NUM_THREADS=1, which would halve the baseline at N > 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     threads = torch.get_num_threads()
     port = rs.FaithfulPort(args.features, args.hidden, args.classes, lr=1e-3, seed=args.seed, pad=args.features)
 
@@ -538,7 +545,6 @@ def run_b200_arm(args):
     if args.workload == "config3" and not embedding and not sparse_adj and args.precision == "bf16" and world == 1:
         import copy
         k_pg = min(args.steps, 10)
-        xi = ops.IntegerFeatures.from_batch(batch, F)
 
         def fresh(precision, **kw):
             net_c = copy.deepcopy(net)
@@ -546,20 +552,32 @@ def run_b200_arm(args):
             opt_c = type(opt)(net_c.parameters(), lr=1e-3)
             return net_c, GCNEngine(net_c, opt_c, precision=precision, **kw)
 
-        net_pg, eng_pg = fresh("bf16x3", adjacency_features=True)
-        eng_pg.timer = OpTimer()
-        r_pg = timed_alt(eng_pg, xi, k_pg)
-        eng_pg.timer.collect()
-        t_pg = eng_pg.timer
-        eng_pg.timer = None
-        parity_grade = dict(r_pg, dtype="bf16x3 (fp32-grade)",
-            what="the same step on the fp32-grade tensor-core path (bench.py --precision bf16x3): H1 = relu(s . (XI (W1_hi + "
-                 "W1_lo + W1_lo2)) + b1) with XI = the integer 2-step path counts (exact in bf16) and W1 split into three bf16 "
-                 "parts (24 mantissa bits), dW1 = XI^T (s . dH1pre) with two parts; fp32 H1, logits, loss, gradients, Adam",
+        def timed_pg(precision, feats_pg, k):
+            net_c, eng_c = fresh(precision, adjacency_features=True)
+            eng_c.timer = OpTimer()
+            r = timed_alt(eng_c, feats_pg, k)
+            eng_c.timer.collect()
+            t = eng_c.timer
+            eng_c.timer = None
+            return net_c, eng_c, dict(r, ops_ms={k_: t.total_ms[k_] / t.calls[k_] for k_ in t.total_ms})
+
+        # all 24 bits of W1 in three bf16 parts first (5 steps), then the default: two fp16 parts (22 bits)
+        xi3 = ops.IntegerFeatures.from_batch(batch, F)
+        net_3, eng_3, r_3 = timed_pg("bf16x3", xi3, min(k_pg, 5))
+        del net_3, eng_3, xi3
+        torch.cuda.empty_cache()
+        xi = ops.IntegerFeatures.from_batch(batch, F, f16=True)
+        net_pg, eng_pg, r_pg = timed_pg("f16x2", xi, k_pg)
+        parity_grade = dict(r_pg, dtype="f16x2 (fp32-grade)",
+            what="the same step on the fp32-grade tensor-core path (bench.py --precision f16x2): H1 = relu(s . (XI (W1_hi + "
+                 "2^-12 W1_lo)) + b1) with XI = the integer 2-step path counts (exact in fp16) and W1 split into two fp16 parts "
+                 "(22 mantissa bits), dW1 = XI^T (s . dH1pre) with two fp16 parts as well; fp32 H1, logits, loss, gradients, "
+                 "Adam.  bf16x3 (three bf16 parts = all 24 bits of W1) is timed beside it",
             parity="rel 1e-4 on loss / logits / gradients / weights against reference-generated fixtures "
-                   "(tests/test_gpu_api.py::test_step_matches_reference_fixture[*-bf16x3], tests/test_gpu_split.py::"
-                   "test_two_epochs_at_baseline_shapes[bf16x3])",
-            ops_ms={k: t_pg.total_ms[k] / t_pg.calls[k] for k in t_pg.total_ms})
+                   "(tests/test_gpu_api.py::test_step_matches_reference_fixture[*-f16x2|bf16x3], tests/test_gpu_split.py::"
+                   "test_two_epochs_at_baseline_shapes[f16x2|bf16x3]); hard labels at config-3 shape against the float64 "
+                   "oracle: test_config3_shape_ste_labels_of_headline_and_parity_grade_paths",
+            bf16x3=dict(r_3, dtype="bf16x3 (fp32-grade)"))
         # label agreement: both paths from the same initial weights, same batch, same number of steps
         net_a, eng_a = fresh("bf16", activations=args.activations, preaggregate=preagg)
         net_b, eng_b = net_pg, eng_pg
