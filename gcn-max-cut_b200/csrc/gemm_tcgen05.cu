@@ -213,9 +213,20 @@ struct Params {
 // One accumulator tile (this warp's 32 rows x RN real columns) from TMEM to C: the epilogue shared by the cluster kernel and
 // the cta_group::2 kernel.  m0 = first row of this CTA's 128-row block, n0 = first real column, t_row = TMEM address of
 // the warp's lane quarter in the accumulator stage, epi = the CTA's staging block, ebuf = the warp's buffer toggle.
-template <int NS>
+// SC: bias and projection weights are read from the CTA's shared-memory copy `sconst` (kEpiConstCols bias floats, then
+// kEpiConstCols float4 rows of projW, zero beyond N) instead of through __ldg.  The kernels run with ~225 KB of the SM's
+// 256 KB as shared memory, so the "L1-resident" broadcast loads were L2 round trips: ncu (profiles/r02g_nn_epilogue.md)
+// put 36 % of the epilogue warps' stall samples on the first use of those loads, and the epilogue -- one warp per
+// scheduler -- is what a tile of the fused layer-1 GEMM waits for (tensor pipe 69 % active against 85 % without it).
+constexpr int kEpiConstCols = 512;
+constexpr int kEpiConstBytes = kEpiConstCols * 4 + kEpiConstCols * 16;
+
+// EBUFS: staging buffers per epilogue warp (2 = the next chunk is staged while the TMA store of the previous one drains;
+// 1 where the 10 KB of constants need the space: the NS = 2 cluster kernel, whose four 48 KB stages fill the SM).
+template <int NS, bool SC = false, int EBUFS = 2>
 __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmC_ptr, uint32_t epi, int warp, int lane,
-                                              int q, int64_t m0, int n0, uint32_t t_row, float* Cs, int& ebuf) {
+                                              int q, int64_t m0, int n0, uint32_t t_row, float* Cs, int& ebuf,
+                                              const float* sconst = nullptr) {
     constexpr int BN = NS == 3 ? 192 : BLOCK_N;
     constexpr int RN = BN / NS;
     const CUtensorMap& tmC = *tmC_ptr;
@@ -235,18 +246,18 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
                 tmem_ld32(t_row + 64 * c, ra);
                 tmem_ld32(t_row + 64 * c + 32, rb);
                 if (p.bias) {                                  // same address in every lane: broadcast loads, L1-resident
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+                    const float4* b4 = reinterpret_cast<const float4*>((SC ? sconst : p.bias) + n);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (n + 4 * i < p.N) {                 // N % 4 == 0 (checked by the launcher)
-                            const float4 b = __ldg(b4 + i);
+                            const float4 b = SC ? b4[i] : __ldg(b4 + i);
                             ra[4 * i] = __float_as_uint(__uint_as_float(ra[4 * i]) + b.x);
                             ra[4 * i + 1] = __float_as_uint(__uint_as_float(ra[4 * i + 1]) + b.y);
                             ra[4 * i + 2] = __float_as_uint(__uint_as_float(ra[4 * i + 2]) + b.z);
                             ra[4 * i + 3] = __float_as_uint(__uint_as_float(ra[4 * i + 3]) + b.w);
                         }
                         if (n + 32 + 4 * i < p.N) {
-                            const float4 b = __ldg(b4 + 8 + i);
+                            const float4 b = SC ? b4[8 + i] : __ldg(b4 + 8 + i);
                             rb[4 * i] = __float_as_uint(__uint_as_float(rb[4 * i]) + b.x);
                             rb[4 * i + 1] = __float_as_uint(__uint_as_float(rb[4 * i + 1]) + b.y);
                             rb[4 * i + 2] = __float_as_uint(__uint_as_float(rb[4 * i + 2]) + b.z);
@@ -267,11 +278,12 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
                     wv[16 + i] = pack_bf16x2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
                 }
                 if (p.proj_w) {                                // this row's 64 rounded values against projW[n .. n+63][0..3]
-                    const float4* w4 = p.proj_w + n;           // same address in every lane: broadcast, L1-resident
+                    // same address in every lane: one broadcast wavefront (shared) / one sector (global)
+                    const float4* w4 = (SC ? reinterpret_cast<const float4*>(sconst + kEpiConstCols) : p.proj_w) + n;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float lo = __uint_as_float(wv[i] << 16), hi = __uint_as_float(wv[i] & 0xffff0000u);
-                        const float4 wa = __ldg(w4 + 2 * i), wb = __ldg(w4 + 2 * i + 1);
+                        const float4 wa = SC ? w4[2 * i] : __ldg(w4 + 2 * i), wb = SC ? w4[2 * i + 1] : __ldg(w4 + 2 * i + 1);
                         const float2 l2 = make_float2(lo, lo), h2 = make_float2(hi, hi);
                         pj01 = __ffma2_rn(l2, make_float2(wa.x, wa.y), pj01);
                         pj23 = __ffma2_rn(l2, make_float2(wa.z, wa.w), pj23);
@@ -279,8 +291,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
                         pj23 = __ffma2_rn(h2, make_float2(wb.z, wb.w), pj23);
                     }
                 }
-                const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
-                if (lane == 0) bulk_wait_read<1>();
+                const uint32_t buf = epi + (uint32_t)((warp - 2) * EBUFS + (EBUFS == 2 ? ebuf : 0)) * EPI_BUF_BYTES;
+                if (lane == 0) bulk_wait_read<EBUFS - 1>();
                 __syncwarp();
                 const uint32_t rowaddr = buf + lane * 128;
 #pragma unroll
@@ -330,11 +342,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
                 for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
             }
             if (p.bias) {                                      // same address in every lane: broadcast loads
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+                const float4* b4 = reinterpret_cast<const float4*>((SC ? sconst : p.bias) + n);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (n + 4 * i < p.N) {                     // N % 4 == 0 (checked by the launcher)
-                        const float4 b = __ldg(b4 + i);
+                        const float4 b = SC ? b4[i] : __ldg(b4 + i);
                         r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + b.x);
                         r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b.y);
                         r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b.z);
@@ -347,11 +359,12 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
                 for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
             }
             if (p.proj_part) {                                 // this row's 32 values against projW[n .. n+31][0..3]
-                const float4* w4 = p.proj_w + n;               // same address in every lane: broadcast, L1-resident;
-#pragma unroll                                                     // rows >= N of projW are zero padding (up to N rounded to 64)
+                // same address in every lane: broadcast; rows >= N of projW are zero padding (up to N rounded to 64)
+                const float4* w4 = (SC ? reinterpret_cast<const float4*>(sconst + kEpiConstCols) : p.proj_w) + n;
+#pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float v = __uint_as_float(r[i]);
-                    const float4 w = __ldg(w4 + i);
+                    const float4 w = SC ? w4[i] : __ldg(w4 + i);
                     const float2 v2 = make_float2(v, v);
                     pj01 = __ffma2_rn(v2, make_float2(w.x, w.y), pj01);
                     pj23 = __ffma2_rn(v2, make_float2(w.z, w.w), pj23);
@@ -360,8 +373,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
             if (p.tma_store) {
                 // registers -> 128B-swizzled staging block (lane = row, 16-byte chunk i at i ^ (row & 7): conflict-free
                 // STS.128) -> one TMA store of 32 full 128-byte row segments; rows / columns beyond M / N are clipped
-                const uint32_t buf = epi + (uint32_t)((warp - 2) * 2 + ebuf) * EPI_BUF_BYTES;
-                if (lane == 0) bulk_wait_read<1>();            // the store that last read this buffer has drained it
+                const uint32_t buf = epi + (uint32_t)((warp - 2) * EBUFS + (EBUFS == 2 ? ebuf : 0)) * EPI_BUF_BYTES;
+                if (lane == 0) bulk_wait_read<EBUFS - 1>();    // the store that last read this buffer has drained it
                 __syncwarp();
                 const uint32_t rowaddr = buf + lane * 128;
 #pragma unroll
@@ -433,8 +446,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
-    const uint32_t epi = tiles + STAGES * STAGE_T;                 // epilogue staging: 4 warps x 2 x 4 KB, 1024-aligned
-    const uint32_t bars = epi + EPI_BYTES;
+    // split-operand kernels (NS > 1) carry the fused layer-1 epilogue: their bias / projection weights live in shared
+    // memory behind the barriers (see epilogue_tile).  NS = 3 stages are 40 KB, so there is room; NS = 2 stages are 48 KB
+    // and the staging block drops to one buffer per warp instead.
+    constexpr bool kConsts = NS > 1;
+    constexpr int EBUFS = NS == 2 ? 1 : 2;
+    const uint32_t epi = tiles + STAGES * STAGE_T;                 // epilogue staging: 4 warps x EBUFS x 4 KB, 1024-aligned
+    const uint32_t bars = epi + 4 * EBUFS * EPI_BUF_BYTES;
+    static_assert(!kConsts || (size_t)STAGES * STAGE_T + 4 * EBUFS * EPI_BUF_BYTES + 256 + kEpiConstBytes + 1024 <= SMEM_BYTES,
+                  "no room for the epilogue constants");
     const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
     const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 8 * ACC_STAGES;
     const uint32_t tmem_slot = tempty_bar + 8 * ACC_STAGES;
@@ -470,6 +490,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // kernel's tail; nothing before this line touches global memory
     pdl_wait();
     pdl_launch_dependents();
+    const float* sconst = nullptr;
+    if (kConsts && (p.bias || p.proj_w) && p.N <= kEpiConstCols) {  // uniform over the grid
+        float* sb = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));
+        float4* sp = reinterpret_cast<float4*>(sb + kEpiConstCols);
+        const int prow = (int)((p.N + 63) / 64 * 64);              // rows of the padded projection matrix
+        for (int i = threadIdx.x; i < kEpiConstCols; i += THREADS) {
+            sb[i] = (p.bias && i < p.N) ? __ldg(p.bias + i) : 0.f;
+            sp[i] = (p.proj_w && i < prow) ? __ldg(p.proj_w + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        sconst = sb;
+        __syncthreads();
+    }
 
     // cluster-level work items: (split, m-group, n-group); every CTA of a cluster walks the same list
     const int64_t tiles_gn = (int64_t)p.mg_tiles * p.ng_tiles;
@@ -599,7 +631,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BLOCK_N;
-            epilogue_tile<NS>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf);
+            if (kConsts && sconst) epilogue_tile<NS, true, EBUFS>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf, sconst);
+            else epilogue_tile<NS, false, EBUFS>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
@@ -624,10 +657,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // kernel is L2->SM bandwidth bound (48 KB per 512 MMA cycles = the ~42 B/clk/SM LTS limit); pairing cuts the
 // operand traffic per SM by a third.
 // =================================================================================================
-constexpr int STAGES2 = 6;
+constexpr int STAGES2 = 5;                                  // 6 before the epilogue constants moved into shared memory
 constexpr int HALF = 128;                                   // rows of A / columns of B staged per CTA
 constexpr int A2_BYTES = HALF * BLOCK_K * 4, B2_BYTES = HALF * BLOCK_K * 4, STAGE2_BYTES = A2_BYTES + B2_BYTES;
-constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + EPI_BYTES + 1024 + 256;
+constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + EPI_BYTES + 1024 + 256 + kEpiConstBytes;
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -673,7 +706,7 @@ __host__ __device__ constexpr uint32_t make_idesc2x(bool a_mn, bool b_mn, bool b
 
 // fp32 (kind::tf32) or bf16 (kind::f16) operands; the epilogue is the cluster kernel's (epilogue_tile: fp32 / bf16 C, TMA
 // stores through the swizzled staging block, bias / ReLU / row scale / fused projection), run by both CTAs on their own
-// 128 rows.  Six 32 KB stages + the 32 KB staging block.
+// 128 rows.  Five 32 KB stages + the 32 KB staging block + 10 KB of epilogue constants (bias, projection weights).
 template <bool A_MN, bool B_MN, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -716,6 +749,20 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_wait();                                                    // see gemm_umma_kernel
     pdl_launch_dependents();
+
+    // bias / projection weights of all <= 512 columns into shared memory, once per CTA (see epilogue_tile)
+    const float* sconst = nullptr;
+    if ((p.bias || p.proj_w) && p.N <= kEpiConstCols) {            // uniform over the grid
+        float* sb = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));
+        float4* sp = reinterpret_cast<float4*>(sb + kEpiConstCols);
+        const int prow = (int)((p.N + 63) / 64 * 64);             // rows of the padded projection matrix
+        for (int i = threadIdx.x; i < kEpiConstCols; i += THREADS) {
+            sb[i] = (p.bias && i < p.N) ? __ldg(p.bias + i) : 0.f;
+            sp[i] = (p.proj_w && i < prow) ? __ldg(p.proj_w + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        sconst = sb;
+        __syncthreads();
+    }
 
     const int64_t tiles_mn = (int64_t)p.m_tiles * p.n_tiles;       // tiles of 256 x 256
     const int64_t n_work = tiles_mn * p.k_splits;
@@ -809,7 +856,8 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256;
-            epilogue_tile<1>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf);
+            if (sconst) epilogue_tile<1, true>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf, sconst);
+            else epilogue_tile<1>(p, &tmC, epi, warp, lane, q, m0, n0, t_row, Cs, ebuf);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty_bar + 8 * acc, 0));   // leader's barrier, 8 arrivals
