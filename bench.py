@@ -647,8 +647,7 @@ def run_b200_arm(args):
                 ops.densify_bf16(b_all, F) if args.precision == "bf16" else ops.densify(b_all, F, out=ops.padded_empty(b_all.num_nodes, F, dev)))
             net_1 = copy.deepcopy(net_d)
             eng_1 = GCNEngine(net_1, type(opt)(net_1.parameters(), lr=1e-3), precision=args.precision,
-                              activations=args.activations, preaggregate=preagg)
-            eng_1.pg = None
+                              activations=args.activations, preaggregate=preagg, data_parallel=False)
             loss_1 = eng_1.loss_and_grads(b_all, f_all).sum()
             rel = float(((g_dp - eng_1.grads_flat).abs().max() / eng_1.grads_flat.abs().max()).item())
             rel_loss = abs(float(loss_s.item()) - float(loss_1.item())) / max(abs(float(loss_1.item())), 1.0)
@@ -668,8 +667,9 @@ def run_b200_arm(args):
                   "per_rank_ms_per_step": [float(p[0]) for p in per_rank],
                   "per_rank_allreduce_ms": [float(p[1]) for p in per_rank],
                   "per_rank_compute_ms": [float(p[2]) for p in per_rank],
-                  "note": "the all-reduce interval ends when the slowest rank's gradients arrive: it is 2 MB of NCCL latency plus "
-                          "the wait for slower ranks (ranks power-cap differently)"}
+                  "allreduce": "peer-memory kernel (csrc/peer.cu)" if eng._peer is not None else "NCCL",
+                  "note": "the all-reduce interval ends when the slowest rank's gradients arrive: the exchange itself (2 MB: latency) "
+                          "plus the wait for slower ranks (ranks power-cap differently)"}
         del eng_d, net_d, b_s, f_s
         torch.cuda.empty_cache()
 

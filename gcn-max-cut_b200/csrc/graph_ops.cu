@@ -244,6 +244,138 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
     }
 }
 
+// Per-GRAPH form of preaggregate_bf16_kernel for batches of small graphs (every training / test set of the reference:
+// n <= 1000).  A row of A_hat X is a 2-hop walk -- row extent -> neighbours -> THEIR extents -> 2-hop columns -- and in the
+// row-parallel kernel above each of those four dependent levels is an L2 round trip (the kernel runs at 3.7 TB/s of a
+// 6.5 TB/s write roof with its warps waiting on them).  Here one CTA owns one graph: its CSR slice (local row pointers,
+// local 16-bit column ids: 4 (n + 1) + 2 nnz bytes = 18 KB at n = 1000, d = 7) is staged in shared memory with one
+// coalesced pass, and the whole walk runs on shared-memory latency; only the per-row coefficient (needed at read-out) and
+// the 2 KB row store touch global memory.  Row arithmetic, order and rounding are those of the row-parallel kernel, so the
+// two produce the same bits.  Graphs that do not fit the staging buffers are walked from global memory by the same code.
+constexpr int kPgWarps = 8;
+
+static bool graph_kernel_enabled() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("GMC_PREAGG_GRAPH"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached == 1;
+}
+
+template <bool F16OUT>
+__global__ void __launch_bounds__(kPgWarps * 32)
+preaggregate_graph_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                          const float* __restrict__ coef, const int32_t* __restrict__ graph_ptr, int n_graphs, int n_cols,
+                          int ncp, int cap_nodes, int cap_edges, __nv_bfloat16* __restrict__ X, int64_t ldx) {
+    extern __shared__ __align__(16) float pg_smem[];                   // kPgWarps x ncp row buffers, then the CSR slice
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* buf = pg_smem + warp * ncp;
+    int32_t* s_rp = reinterpret_cast<int32_t*>(pg_smem + kPgWarps * ncp);
+    uint16_t* s_ci = reinterpret_cast<uint16_t*>(s_rp + cap_nodes + 1);
+    constexpr uint32_t kMagicBits = 0x4B000000u;                       // 8388608.0f: counts live in its mantissa
+    const float magic = __uint_as_float(kMagicBits);
+    for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(magic, magic, magic, magic);
+    for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
+        const int base = __ldg(graph_ptr + g);
+        const int n = __ldg(graph_ptr + g + 1) - base;
+        const int e_base = __ldg(rowptr + base);
+        const int nnz = __ldg(rowptr + base + n) - e_base;
+        const bool staged = n <= cap_nodes && nnz <= cap_edges && n <= 65535;      // block-uniform
+        __syncthreads();                                               // the previous graph's slice is no longer read
+        if (staged) {
+            for (int i = threadIdx.x; i <= n; i += kPgWarps * 32) s_rp[i] = __ldg(rowptr + base + i) - e_base;
+            for (int e = threadIdx.x; e < nnz; e += kPgWarps * 32) {
+                const int local = __ldg(colidx + e_base + e) - base;   // a neighbour outside the graph cannot be staged
+                s_ci[e] = (local >= 0 && local < n) ? (uint16_t)local : (uint16_t)0xFFFF;
+            }
+        }
+        __syncthreads();
+        // local accessors: row pointer (relative to the graph's first edge) and local column id (-1 = outside)
+        auto rp = [&](int i) -> int { return staged ? s_rp[i] : __ldg(rowptr + base + i) - e_base; };
+        auto ci = [&](int e) -> int {
+            if (staged) { const int v = s_ci[e]; return v == 0xFFFF ? -1 : v; }
+            const int v = __ldg(colidx + e_base + e) - base;
+            return (v >= 0 && v < n) ? v : -1;
+        };
+        for (int v = warp; v < n; v += kPgWarps) {
+            const int e0 = rp(v), cnt = rp(v + 1) - e0;
+            int my_f0 = 0, my_deg = 0;
+            float my_c = 0.f;
+            if (lane < min(cnt, 32)) {
+                my_c = __ldg(coef + e_base + e0 + lane);
+                const int u = ci(e0 + lane);
+                if (u >= 0) { my_f0 = rp(u); my_deg = rp(u + 1) - my_f0; }
+            }
+            const int D0 = __shfl_sync(0xffffffffu, my_deg, 0);
+            const float c0 = __shfl_sync(0xffffffffu, my_c, 0);
+            const bool same = __all_sync(0xffffffffu, lane >= cnt || (my_deg == D0 && my_c == c0));
+            const bool fast = same && cnt > 0 && cnt <= 32 && D0 > 0 && cnt * D0 <= 64;
+            int touched[2] = {-1, -1};
+            if (!fast)
+                for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (fast) {
+                const int total = cnt * D0;
+                const float inv_d = 1.0f / (float)D0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int p = 32 * j + lane;
+                    const int owner = p < total ? (int)(((float)p + 0.5f) * inv_d) : 0;
+                    const int o_f0 = __shfl_sync(0xffffffffu, my_f0, owner);
+                    if (p < total) {
+                        const int local = ci(o_f0 + (p - owner * D0));
+                        if (local >= 0 && local < n_cols) { atomicAdd(reinterpret_cast<unsigned int*>(buf) + local, 1u); touched[j] = local; }
+                    }
+                }
+            } else {
+                // neighbours one after the other in CSR order, lanes over N(u) (distinct columns): fixed order
+                for (int eb = e0; eb < e0 + cnt; eb += 32) {
+                    const int n_here = min(32, e0 + cnt - eb);
+                    if (eb > e0) {
+                        my_f0 = 0; my_deg = 0; my_c = 0.f;
+                        if (lane < n_here) {
+                            my_c = __ldg(coef + e_base + eb + lane);
+                            const int u = ci(eb + lane);
+                            if (u >= 0) { my_f0 = rp(u); my_deg = rp(u + 1) - my_f0; }
+                        }
+                    }
+                    for (int q = 0; q < n_here; ++q) {
+                        const int f0 = __shfl_sync(0xffffffffu, my_f0, q), dg = __shfl_sync(0xffffffffu, my_deg, q);
+                        const float c = __shfl_sync(0xffffffffu, my_c, q);
+                        for (int f = f0 + lane; f < f0 + dg; f += 32) {
+                            const int local = ci(f);
+                            if (local >= 0 && local < n_cols) buf[local] += c;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncwarp();
+            __nv_bfloat16* xr = X + (int64_t)(base + v) * ldx;
+            const float sc = fast ? c0 : 1.0f, off = fast ? -magic * c0 : 0.0f;
+            for (int c4 = lane; c4 * 4 < ncp; c4 += 32) {
+                const float4 a = *reinterpret_cast<const float4*>(buf + c4 * 4);
+                const float v0 = fmaf(a.x, sc, off), v1 = fmaf(a.y, sc, off), v2 = fmaf(a.z, sc, off), v3 = fmaf(a.w, sc, off);
+                uint2 o;
+                if (F16OUT) {
+                    const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
+                    o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+                } else {
+                    const __nv_bfloat162 b0 = __floats2bfloat162_rn(v0, v1), b1 = __floats2bfloat162_rn(v2, v3);
+                    o.x = *reinterpret_cast<const uint32_t*>(&b0); o.y = *reinterpret_cast<const uint32_t*>(&b1);
+                }
+                *reinterpret_cast<uint2*>(xr + c4 * 4) = o;
+            }
+            __syncwarp();
+            if (fast) {
+                if (touched[0] >= 0) buf[touched[0]] = magic;
+                if (touched[1] >= 0) buf[touched[1]] = magic;
+            } else {
+                for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(magic, magic, magic, magic);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // Counting form of the fast rows (unit weights, <= 8 neighbours which all have one degree D <= 8 and one coefficient
 // c): every 2-hop addend is the same c, so a row of A_hat X is c x (number of 2-hop paths into each column).  Eight
 // lanes own a row and count the paths in BYTES (1 KB per row instead of a 4 KB fp32 buffer: 32 rows per CTA, ~190 rows
@@ -460,6 +592,32 @@ static int preaggregate_impl(const int32_t* rowptr, const int32_t* colidx, const
             rowptr, colidx, coef, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, slow);
         GMC_LAUNCH_CHECK();
         only = slow;
+    }
+    // batches of small graphs (on average no more nodes than feature columns, unit weights): one CTA per graph with its CSR
+    // slice in shared memory; graphs that exceed the staging buffers are walked from global memory by the same kernel
+    if (!only && !vals && n_graphs > 0 && n_rows / n_graphs <= (int64_t)ncp && ncp <= 2048 && gmc::graph_kernel_enabled()) {
+        const int cap_nodes = ncp, cap_edges = 8 * ncp + 64;
+        const size_t g_smem = (size_t)gmc::kPgWarps * ncp * sizeof(float) + (size_t)(cap_nodes + 1) * 4 + (size_t)cap_edges * 2 + 16;
+        static bool attr3 = false;
+        if (!attr3) {
+            GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_graph_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            GMC_CUDA(cudaFuncSetAttribute(gmc::preaggregate_graph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            attr3 = true;
+        }
+        int per_sm = (int)((220 * 1024) / (g_smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        int64_t blocks = n_graphs;
+        const int64_t cap = (int64_t)gmc::sm_count() * per_sm;
+        if (blocks > cap) blocks = cap;
+        if (f16)
+            gmc::preaggregate_graph_kernel<true><<<(unsigned)blocks, gmc::kPgWarps * 32, g_smem, s>>>(
+                rowptr, colidx, coef, graph_ptr, n_graphs, n_cols, ncp, cap_nodes, cap_edges, Xb, ldx);
+        else
+            gmc::preaggregate_graph_kernel<false><<<(unsigned)blocks, gmc::kPgWarps * 32, g_smem, s>>>(
+                rowptr, colidx, coef, graph_ptr, n_graphs, n_cols, ncp, cap_nodes, cap_edges, Xb, ldx);
+        GMC_LAUNCH_CHECK();
+        return GMC_OK;
     }
     const size_t smem = (size_t)gmc::kPreaggWarps * ncp * sizeof(float);
     static bool attr = false;

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 from typing import Dict, List
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -102,6 +102,14 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_adam_multi_devstate": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                         POINTER(c_void_p), POINTER(c_int64), c_double, c_double, c_double, c_double,
                                         P, P]),
+    "gmc_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "gmc_peer_free": (c_int, [P]),
+    "gmc_peer_flag_bytes": (c_size_t, []),
+    "gmc_ipc_handle_bytes": (c_int32, []),
+    "gmc_ipc_get_handle": (c_int, [P, P]),
+    "gmc_ipc_open_handle": (c_int, [P, POINTER(c_void_p)]),
+    "gmc_ipc_close_handle": (c_int, [P]),
+    "gmc_peer_allreduce_f32": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int32, c_int32, c_int64, c_uint32, P]),
     "gmc_argmax_labels": (c_int, [P, c_int64, P, c_int32, c_int64, c_int32, c_int32, P, P]),
     "gmc_cut_value_i32": (c_int, [P, P, P, P, P, c_int32, c_int64, P, P]),
     "gmc_cut_value_multi_u8": (c_int, [P, P, P, P, c_int32, c_int32, P, P]),

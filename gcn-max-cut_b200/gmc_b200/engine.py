@@ -85,7 +85,7 @@ class GCNEngine:
     def __init__(self, net, optimizer: Optional[FusedAdam] = None, *, C: float = 1.0, loss_mode: str = "ste",
                  override_terminals: bool = True, penalty: float = 0.0, precision: str = "fp32",
                  process_group=None, adjacency_kernels: bool = False, activations: str = "fp32",
-                 preaggregate: bool = False, adjacency_features: bool = False):
+                 preaggregate: bool = False, adjacency_features: bool = False, data_parallel: bool = True):
         self.device = _lib.require_cuda()
         self.net = net
         self.optimizer = optimizer
@@ -156,7 +156,15 @@ class GCNEngine:
         for s in sizes:
             offs.append(tot)
             tot += _pad4(s)
-        self.grads_flat = torch.zeros(tot, dtype=torch.float32, device=self.device)
+        # data parallel on one node: the buffer lives in memory every rank has mapped and the exchange is one kernel over
+        # NVLink (dist.PeerAllReduce, csrc/peer.cu); otherwise a torch tensor and NCCL
+        from . import dist as gdist
+        # (construction is a COLLECTIVE under torch.distributed -- every rank builds its engines in the same order;
+        # data_parallel=False builds a purely local engine, e.g. a one-rank reference inside a distributed job)
+        self.data_parallel = bool(data_parallel) and optimizer is not None      # inference engines exchange nothing
+        self._peer = gdist.make_peer_allreduce(tot, self.device, self.pg) if self.data_parallel else None
+        self.grads_flat = self._peer.tensor[:tot] if self._peer is not None else torch.zeros(tot, dtype=torch.float32,
+                                                                                             device=self.device)
         self.gW1 = self.grads_flat[offs[0]: offs[0] + sizes[0]].view_as(W1)
         self.gb1 = self.grads_flat[offs[1]: offs[1] + sizes[1]]
         self.gW2 = self.grads_flat[offs[2]: offs[2] + sizes[2]].view_as(W2)
@@ -547,10 +555,15 @@ class GCNEngine:
     def allreduce_grads(self) -> None:
         """Data-parallel exchange: ONE NCCL all-reduce of the 502 003-float gradient buffer."""
         import torch.distributed as dist
+        if not self.data_parallel:
+            return
         if self.pg is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             # timed as its own op: the interval ends when the LAST rank's gradients have arrived, so it contains the
             # wait for slower ranks (bench.py reports it per rank)
-            self._op("allreduce", 0, dist.all_reduce, self.grads_flat, op=dist.ReduceOp.SUM, group=self.pg)
+            if self._peer is not None:
+                self._op("allreduce", 1, self._peer.all_reduce_)
+            else:
+                self._op("allreduce", 0, dist.all_reduce, self.grads_flat, op=dist.ReduceOp.SUM, group=self.pg)
 
     def apply_adam(self, feature_param: Optional[torch.Tensor] = None,
                    feature_grad: Optional[torch.Tensor] = None) -> None:

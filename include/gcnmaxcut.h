@@ -388,6 +388,28 @@ int gmc_csr_preaggregate_f16(const int32_t* rowptr, const int32_t* colidx, const
                              const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
                              int64_t ldx, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (csrc/peer.cu) -------------- */
+/* The step's only collective -- all-reduce(sum) of the flat weight-gradient buffer between loss.backward() and
+ * optimizer.step() (TrainingNeural.py:380-386 under data parallelism; the reference itself is single-process) -- as ONE
+ * kernel: every rank's buffer is mapped into every other rank's address space (cudaIpc), rank r sums slice r of all
+ * buffers in rank order and writes it to all of them; two flag barriers in the same kernel.  2 MB is pure latency:
+ * 36.6 us per call on 8 B200s against 32.4 us for NCCL's all-reduce -- no gain, so the engine uses it only on request
+ * (GMC_PEER_ALLREDUCE=1) and NCCL by default.
+ *   gmc_peer_alloc / gmc_peer_free           cudaMalloc'ed, zero-filled memory whose cudaIpc handle may be exported
+ *   gmc_ipc_get_handle / open / close        gmc_ipc_handle_bytes() opaque bytes per allocation, exchanged by the host
+ *   gmc_peer_allreduce_f32                   bufs / flags: HOST arrays of `world` device pointers as mapped in THIS process
+ *                                            (entry `rank` = the local allocation; flags: gmc_peer_flag_bytes() zeroed
+ *                                            bytes each); `epoch` grows by one per call, identically on all ranks */
+int gmc_peer_alloc(size_t bytes, void** ptr);
+int gmc_peer_free(void* ptr);
+size_t gmc_peer_flag_bytes(void);
+int32_t gmc_ipc_handle_bytes(void);
+int gmc_ipc_get_handle(const void* ptr, void* handle);
+int gmc_ipc_open_handle(const void* handle, void** ptr);
+int gmc_ipc_close_handle(void* ptr);
+int gmc_peer_allreduce_f32(void* const* bufs, void* const* flags, int32_t world, int32_t rank, int64_t n, uint32_t epoch,
+                           void* stream);
+
 /* ---- (e) integer post-processing ------------------------------------------------------ */
 
 /* labels[v] = first argmax_k P[v,k]; the first min(3,n_g) nodes of each graph are forced to

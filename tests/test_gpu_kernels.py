@@ -567,3 +567,36 @@ def test_full_size_properties_n1000_d7():
     out3, cut3, moves3 = ops.greedy_node_move(batch, out, 3, 10**4, 3)
     out4, cut4, moves4 = ops.greedy_node_move(batch, out3, 3, 200, 3)
     assert int(moves4.sum()) == 0 and torch.equal(out3, out4) and torch.equal(cut3, cut4)
+
+
+# ------------------------------------------------------------------ gradient exchange over peer memory (csrc/peer.cu)
+@pytest.mark.parametrize("world,n", [(2, 502003), (4, 1003), (8, 70001), (3, 17)])
+def test_peer_allreduce_protocol_on_one_device(world, n):
+    """The one-kernel all-reduce with its two flag barriers, exercised with `world` ranks living on ONE device: every
+    rank's kernel runs on its own stream (they wait for each other inside the kernel, so they must be co-resident -- at
+    most 64 blocks each), buffers and flags are ordinary allocations of this process standing in for the cudaIpc mappings.
+    Result: every buffer holds the rank-ordered sum, bit for bit the same in all of them, over several epochs."""
+    import ctypes
+    from gmc_b200 import _lib
+    lib = _lib.lib()
+    pad = (n + 3) // 4 * 4
+    bufs = [torch.zeros(pad, device=DEV) for _ in range(world)]
+    flags = [torch.zeros(lib.gmc_peer_flag_bytes() // 4, dtype=torch.int32, device=DEV) for _ in range(world)]
+    bp = (ctypes.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    fp = (ctypes.c_void_p * world)(*[f.data_ptr() for f in flags])
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.manual_seed(world * 1000 + n)
+    for epoch in range(1, 5):
+        data = [torch.randn(n, device=DEV) * (10.0 ** (q % 3)) for q in range(world)]
+        for q in range(world):
+            bufs[q][:n].copy_(data[q])
+        torch.cuda.synchronize()
+        for q in range(world):
+            _lib.check(lib.gmc_peer_allreduce_f32(bp, fp, world, q, n, epoch, streams[q].cuda_stream), "gmc_peer_allreduce_f32")
+        torch.cuda.synchronize()
+        want = data[0].clone()
+        for q in range(1, world):
+            want += data[q]                                    # the kernel's order: ranks 0 .. W-1, one fp32 add each
+        for q in range(world):
+            assert torch.equal(bufs[q][:n], want), (epoch, q)
+        assert all(int(f[32].item()) == 0 for f in flags)      # block counters reset for the next launch
