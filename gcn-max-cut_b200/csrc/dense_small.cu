@@ -368,9 +368,15 @@ skinny_bwd_split_kernel(const float* __restrict__ dT, int64_t lddt, const float*
 // H rows arrive through cp.async.bulk.tensor boxes (256 columns x TR rows, out-of-range rows / pad columns zero-filled)
 // in a 4-stage shared-memory ring filled by one thread, so ~3 stages per CTA are always in flight and the compute reads
 // shared memory.  A tile is released with one __syncthreads, after which thread 0 refills its stage.
-constexpr int kStreamStages = 4;
+#ifndef GMC_STREAM_STAGES
+#define GMC_STREAM_STAGES 4
+#endif
+#ifndef GMC_BWD_TILE_ROWS
+#define GMC_BWD_TILE_ROWS 8
+#endif
+constexpr int kStreamStages = GMC_STREAM_STAGES;
 constexpr int kFwdTileRows = 32;
-constexpr int kBwdTileRows = 8;
+constexpr int kBwdTileRows = GMC_BWD_TILE_ROWS;
 
 template <int NB, int NOUT>
 __global__ void __launch_bounds__(512, 1)
@@ -928,12 +934,15 @@ int gmc_skinny_bwd_bf16(const float* dT, int64_t lddt, const float* W, const voi
         CUtensorMap tm;
         int rc = tma::make_bf16_map(&tm, H, (uint64_t)n_in, (uint64_t)n_rows, (uint64_t)ldh, 256, kBwdTileRows, "gmc_skinny_bwd_bf16");
         if (rc != GMC_OK) return rc;
-        int nc = sm_count() * 6;
+        const int nb = n_in > 256 ? 2 : 1;
+        const size_t smem = (size_t)kStreamStages * nb * kBwdTileRows * 512 + 64;
+        int per_sm = (int)((226 * 1024) / (smem + 1024 + 256));          // 1 KB reserved per CTA + static shared memory
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        int nc = sm_count() * per_sm;
         if (nc > n_ctas) nc = n_ctas;
         const int64_t rows_per = ceil_div<int64_t>(ceil_div<int64_t>(n_rows, nc), kBwdTileRows) * kBwdTileRows;
         nc = (int)ceil_div<int64_t>(n_rows, rows_per);
-        const int nb = n_in > 256 ? 2 : 1;
-        const size_t smem = (size_t)kStreamStages * nb * kBwdTileRows * 512 + 64;
 #define GMC_CASE(NB, K)                                                                                                \
         {                                                                                                              \
             static bool attr = false;                                                                                  \
