@@ -1076,7 +1076,8 @@ static int setup_output(Params& p, CUtensorMap* tmC_out, float* C, int64_t M, in
         }
         if (proj_w) {
             const size_t need = (size_t)p.n_tiles * (size_t)M * sizeof(float4);
-            if (splits != 1 || accumulate || !proj_out || proj_k < 1 || proj_k > 4 || ldp < proj_k || !aligned16(proj_w) ||
+            // proj_out may be NULL: the partials then stay in the workspace for gmc_layer2_loss_fused_parts (no reduce launch)
+            if (splits != 1 || accumulate || proj_k < 1 || proj_k > 4 || (proj_out && ldp < proj_k) || !aligned16(proj_w) ||
                 !workspace || workspace_bytes < need || !aligned16(workspace)) {
                 set_error("gmc_gemm: the fused fp32 projection needs a direct (non split-K, non accumulating) output, "
                           "1 <= n_proj <= 4, ldp >= n_proj, a 16-byte aligned padded weight matrix and a workspace of "
@@ -1160,7 +1161,7 @@ static int launch(const void* A, const void* B, float* C, int64_t M, int64_t N, 
         GMC_CUDA(launch_pdl(tc_splitk_reduce_kernel, (unsigned)ceil_div<int64_t>(MN, 256), 256, 0, s, p.C, splits, MN, N, C, ldc,
                             accumulate));
     }
-    if (p.proj_part) {
+    if (p.proj_part && proj_out) {
         GMC_CUDA(launch_pdl(proj_reduce_kernel, (unsigned)ceil_div<int64_t>(M, 256), 256, 0, s, p.proj_part, p.n_tiles, M,
                             proj_out, ldp, proj_k));
     }

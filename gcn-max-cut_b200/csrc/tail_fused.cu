@@ -25,7 +25,8 @@ layer2_loss_fused_kernel(const float* __restrict__ T2, int64_t ldt, const int32_
                          const int32_t* __restrict__ graph_ptr, const float* __restrict__ bias2, int mode, int override_t,
                          float penalty, float C, float* __restrict__ Z_out, float* __restrict__ P_out,
                          double* __restrict__ loss, float* __restrict__ dZ_out, float* __restrict__ dT2, int64_t lddt,
-                         float* __restrict__ db2_part) {
+                         float* __restrict__ db2_part, const float4* __restrict__ parts, int n_parts, int64_t part_stride,
+                         float* __restrict__ T2_out) {
     extern __shared__ __align__(16) float tail_smem[];
     __shared__ double red_loss[kTailThreads / 32];
     __shared__ float red_db[kTailThreads / 32][K];
@@ -38,9 +39,29 @@ layer2_loss_fused_kernel(const float* __restrict__ T2, int64_t ldt, const int32_
     float* sP = sS + (size_t)n * K;         // softmax probabilities
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < n * K; i += kTailThreads) {
-        const int v = i / K, k = i - v * K;
-        sX[i] = __ldg(T2 + (int64_t)(base + v) * ldt + k);
+    if (parts) {
+        // T2 rows straight from the layer-1 GEMM's per-n-tile projection partials, added in tile order -- the arithmetic of
+        // proj_reduce_kernel without its launch or the round trip of T2 through memory (K <= 4 here)
+        for (int v = tid; v < n; v += kTailThreads) {
+            float4 a = __ldg(parts + base + v);
+            for (int t = 1; t < n_parts; ++t) {
+                const float4 b = __ldg(parts + (int64_t)t * part_stride + base + v);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k < 4) {
+                    sX[v * K + k] = av[k];
+                    if (T2_out) T2_out[(int64_t)(base + v) * ldt + k] = av[k];
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < n * K; i += kTailThreads) {
+            const int v = i / K, k = i - v * K;
+            sX[i] = __ldg(T2 + (int64_t)(base + v) * ldt + k);
+        }
     }
     __syncthreads();
 
@@ -208,13 +229,16 @@ size_t gmc_layer2_loss_fused_workspace_bytes(int32_t n_graphs, int32_t n_classes
     return (size_t)(n_graphs > 0 ? n_graphs : 0) * (size_t)n_classes * sizeof(float);
 }
 
-int gmc_layer2_loss_fused(const float* T2, int64_t ldt, const int32_t* rowptr, const int32_t* colidx, const float* coef,
-                          const float* vals, const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t n_rows,
-                          int32_t n_classes, const float* bias2, int32_t mode, int32_t override_terminals, float penalty,
-                          float C, float* Z_out, float* P_out, double* loss_per_graph, float* dZ_out, float* dT2,
-                          int64_t lddt, float* db2, void* workspace, size_t workspace_bytes, void* stream) {
+static int layer2_loss_impl(const float* T2, int64_t ldt, const float4* parts, int32_t n_parts, int64_t part_stride, float* T2_out,
+                            const int32_t* rowptr, const int32_t* colidx, const float* coef,
+                            const float* vals, const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t n_rows,
+                            int32_t n_classes, const float* bias2, int32_t mode, int32_t override_terminals, float penalty,
+                            float C, float* Z_out, float* P_out, double* loss_per_graph, float* dZ_out, float* dT2,
+                            int64_t lddt, float* db2, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace gmc;
-    GMC_REQUIRE(T2 && rowptr && colidx && coef && graph_ptr && loss_per_graph, "gmc_layer2_loss_fused: null pointer");
+    GMC_REQUIRE((T2 || parts) && rowptr && colidx && coef && graph_ptr && loss_per_graph, "gmc_layer2_loss_fused: null pointer");
+    GMC_REQUIRE(!parts || (n_parts >= 1 && part_stride >= n_rows && n_classes <= 4 && aligned16(parts)),
+                "gmc_layer2_loss_fused_parts: needs n_parts >= 1, part_stride >= n_rows, n_classes <= 4, 16-byte aligned partials");
     GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0 && max_nodes >= 0 && ldt >= n_classes, "gmc_layer2_loss_fused: bad sizes");
     GMC_REQUIRE(n_classes >= 2 && n_classes <= kMaxClasses, "gmc_layer2_loss_fused: n_classes must be 2..8");
     GMC_REQUIRE(mode == GMC_LOSS_STE || mode == GMC_LOSS_SOFT, "gmc_layer2_loss_fused: bad mode %d", mode);
@@ -251,13 +275,41 @@ int gmc_layer2_loss_fused(const float* T2, int64_t ldt, const int32_t* rowptr, c
         }                                                                                                                 \
         GMC_CUDA(launch_pdl(layer2_loss_fused_kernel<K>, n_graphs, kTailThreads, smem, s, T2, ldt, rowptr, colidx, coef, vals, \
                             graph_ptr, bias2, mode, override_terminals, penalty, C, Z_out, P_out, loss_per_graph, dZ_out,  \
-                            dT2, lddt, part));                                                                            \
+                            dT2, lddt, part, parts, n_parts, part_stride, T2_out));                                       \
     } break;
     switch (n_classes) { GMC_CASE(2) GMC_CASE(3) GMC_CASE(4) GMC_CASE(5) GMC_CASE(6) GMC_CASE(7) GMC_CASE(8) }
 #undef GMC_CASE
     GMC_LAUNCH_CHECK();
     if (db2 && n_graphs > 1) GMC_CUDA(launch_pdl(tail_db2_reduce_kernel, 1, 256, 0, s, part, n_graphs, n_classes, db2));
     return GMC_OK;
+}
+
+int gmc_layer2_loss_fused(const float* T2, int64_t ldt, const int32_t* rowptr, const int32_t* colidx, const float* coef,
+                          const float* vals, const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t n_rows,
+                          int32_t n_classes, const float* bias2, int32_t mode, int32_t override_terminals, float penalty,
+                          float C, float* Z_out, float* P_out, double* loss_per_graph, float* dZ_out, float* dT2,
+                          int64_t lddt, float* db2, void* workspace, size_t workspace_bytes, void* stream) {
+    GMC_REQUIRE(T2, "gmc_layer2_loss_fused: null pointer");
+    return layer2_loss_impl(T2, ldt, nullptr, 0, 0, nullptr, rowptr, colidx, coef, vals, graph_ptr, n_graphs, max_nodes, n_rows,
+                            n_classes, bias2, mode, override_terminals, penalty, C, Z_out, P_out, loss_per_graph, dZ_out, dT2,
+                            lddt, db2, workspace, workspace_bytes, stream);
+}
+
+// The same with T2 given as the projection partials a gmc_gemm_bf16_split call left in ITS workspace (proj_w set,
+// proj_out = NULL): parts[t * part_stride + row] = float4 partial of n-tile t, n_parts = ceil(hidden / real columns per tile).
+// T2_out (nullable, leading dimension ldt) receives the reduced rows.
+int gmc_layer2_loss_fused_parts(const void* parts, int32_t n_parts, int64_t part_stride, float* T2_out, int64_t ldt,
+                                const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                                const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t n_rows,
+                                int32_t n_classes, const float* bias2, int32_t mode, int32_t override_terminals,
+                                float penalty, float C, float* Z_out, float* P_out, double* loss_per_graph, float* dZ_out,
+                                float* dT2, int64_t lddt, float* db2, void* workspace, size_t workspace_bytes, void* stream) {
+    GMC_REQUIRE(parts, "gmc_layer2_loss_fused_parts: null pointer");
+    GMC_REQUIRE(!T2_out || ldt >= n_classes, "gmc_layer2_loss_fused_parts: ldt too small");
+    return layer2_loss_impl(nullptr, T2_out ? ldt : n_classes, reinterpret_cast<const float4*>(parts), n_parts, part_stride, T2_out,
+                            rowptr, colidx, coef, vals, graph_ptr, n_graphs, max_nodes, n_rows, n_classes, bias2, mode,
+                            override_terminals, penalty, C, Z_out, P_out, loss_per_graph, dZ_out, dT2, lddt, db2, workspace,
+                            workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -45,6 +45,8 @@ _FUSE_PROJ = os.environ.get("GMC_FUSE_PROJ", "1") == "1"
 # second layer + loss + its backward in one launch per batch (csrc/tail_fused.cu, one CTA per graph); GMC_FUSED_TAIL=0
 # keeps the separate spmm_k / cut_loss / colsum / spmm_k kernels
 _FUSED_TAIL = os.environ.get("GMC_FUSED_TAIL", "1") == "1"
+# split-operand path: the layer-1 GEMM's projection partials are added by the tail kernel while it loads T2 (no reduce launch)
+_DEFER_PROJ = os.environ.get("GMC_DEFER_PROJ", "1") == "1"
 
 
 def _pad4(n: int) -> int:
@@ -195,6 +197,7 @@ class GCNEngine:
         self._graphs: Dict[tuple, dict] = {}
         self._epoch_graphs: Dict[tuple, dict] = {}
         self._loss_out = None                 # train_epoch_graphed: where the step being captured writes its losses
+        self._t2parts = None                  # projection partials of the split-operand layer-1 GEMM (deferred reduce)
         self._step_dev: Optional[torch.Tensor] = None      # device-side Adam step counter shared by all graphs
         self._step_dev_value = 0                           # what that counter holds, mirrored on the host
         self.graph_replays = 0
@@ -367,8 +370,10 @@ class GCNEngine:
         self._op("spmm_k", 1, ops.spmm, batch, self.T2[:N], out=self.Z[:N], bias=b2.data)
         return self.Z[:N]
 
-    def _forward_t2(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
-        """Layer 1 and the projection of layer 2: T2 = relu(A_hat X W1 + b1) W2 in self.T2; leaves H1 in bufB / bufB16."""
+    def _forward_t2(self, batch: GraphBatch, X: torch.Tensor, defer_proj: bool = False):
+        """Layer 1 and the projection of layer 2: T2 = relu(A_hat X W1 + b1) W2 in self.T2; leaves H1 in bufB / bufB16.
+        defer_proj (split-operand path): the GEMM's per-n-tile projection partials may stay un-reduced -- returns
+        (buffer, n_parts) for layer2_loss_fused(t2_parts=...), which adds them while it loads T2; None otherwise."""
         N = batch.num_nodes
         W1, b1, W2, b2 = self.params()
         if self.preaggregate:
@@ -409,6 +414,15 @@ class GCNEngine:
                 if self._w2p is None:
                     self._w2p = torch.zeros(((self.H + 63) // 64 * 64, 4), dtype=torch.float32, device=self.device)
                 ops.pad_proj_weights(W2.data, out=self._w2p)
+                if defer_proj and _DEFER_PROJ:
+                    tiles = ops.split_proj_tiles(self.H, self.split_fwd)
+                    if self._t2parts is None or self._t2parts.numel() < tiles * N * 4:
+                        self._t2parts = torch.empty(tiles * max(N, self._cap_nodes) * 4, dtype=torch.float32, device=self.device)
+                        self._buffer_generation += 1
+                    self._op("gemm_nn_layer1", 1, ops.gemm_bf16_split, "nn", XI.tensor, self.W1s, self.split_fwd, self.F,
+                             out=Bf, row_scale=XI.scale, bias=b1.data, relu=True, proj_w=self._w2p, n_proj=self.K,
+                             proj_parts=self._t2parts)
+                    return (self._t2parts, tiles)
                 self._op("gemm_nn_layer1", 2, ops.gemm_bf16_split, "nn", XI.tensor, self.W1s, self.split_fwd, self.F, out=Bf,
                          row_scale=XI.scale, bias=b1.data, relu=True, workspace=self.ws, proj_w=self._w2p,
                          proj_out=self.T2[:N], n_proj=self.K)
@@ -495,11 +509,12 @@ class GCNEngine:
         W1, b1, W2, b2 = self.params()
         if self._fused_tail(batch):
             # Z = A_hat T2 + b2, softmax / override / STE / loss, dZ, db2, dT2 = A_hat dZ: one launch (+ the db2 reduce)
-            self._forward_t2(batch, X)
+            parts = self._forward_t2(batch, X, defer_proj=True)
+            parts = parts if isinstance(parts, tuple) else None
             loss = self.loss[:B] if self._loss_out is None else self._loss_out
-            self._op("layer2_loss", 2, ops.layer2_loss_fused, batch, self.T2[:N], b2.data, self.loss_mode, self.override,
-                     self.penalty, self.C, P=self.P[:N], loss=loss, dT2=self.dT2[:N], db2=self.gb2, Z=self.Z[:N],
-                     dZ=self.dZ[:N], workspace=self.ws)
+            self._op("layer2_loss", 2 if B > 1 else 1, ops.layer2_loss_fused, batch, self.T2[:N], b2.data, self.loss_mode,
+                     self.override, self.penalty, self.C, P=self.P[:N], loss=loss, dT2=self.dT2[:N], db2=self.gb2, Z=self.Z[:N],
+                     dZ=self.dZ[:N], workspace=self.ws, t2_parts=parts)
         else:
             Z = self.forward_logits(batch, X)
             loss = self.loss[:B] if self._loss_out is None else self._loss_out

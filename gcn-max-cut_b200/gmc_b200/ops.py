@@ -467,7 +467,8 @@ def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: in
                     out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
                     bias: Optional[torch.Tensor] = None, relu: bool = False, accumulate: bool = False,
                     workspace: Optional[Workspace] = None, proj_w: Optional[torch.Tensor] = None,
-                    proj_out: Optional[torch.Tensor] = None, n_proj: int = 0) -> torch.Tensor:
+                    proj_out: Optional[torch.Tensor] = None, n_proj: int = 0,
+                    proj_parts: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C = op(A) (B_0 + ... + B_{n_split-1}) with bf16 A (exact) and the stacked bf16 parts of an fp32 B [k, N]
     (f32_split_bf16 / skinny_bwd_split); fp32 accumulation and output.  op 'nn': A [M, k]; 'tn': A [k, M].
     fp16 parts (f32_split_f16, or skinny_bwd_split into an fp16 buffer) need an fp16 A: tcgen05.mma kind::f16 takes ONE
@@ -506,18 +507,37 @@ def gemm_bf16_split(op: str, A: torch.Tensor, B_split: torch.Tensor, n_split: in
         rows = (N + 63) // 64 * 64
         if proj_w.shape != (rows, 4) or proj_w.dtype != torch.float32 or not proj_w.is_contiguous():
             raise ValueError(f"proj_w must come from pad_proj_weights: contiguous fp32 [{rows}, 4]")
-        if proj_out is None or not 1 <= n_proj <= 4:
-            raise ValueError("the fused projection needs proj_out and 1 <= n_proj <= 4")
-        proj_out, ldp = _rowmajor(proj_out, "proj_out")
-        if proj_out.shape[0] != M or proj_out.shape[1] < n_proj:
-            raise ValueError(f"proj_out must be [{M}, >= {n_proj}]")
-    ws = workspace or _default_ws
-    wptr, wbytes = ws.get(lib().gmc_gemm_bf16_split_workspace_bytes(_OPS[op], M, N, K, n_split, int(proj_w is not None)),
-                          A.device)
+        if not 1 <= n_proj <= 4:
+            raise ValueError("the fused projection needs 1 <= n_proj <= 4")
+        if proj_parts is not None:
+            # deferred: the per-n-tile partials stay in `proj_parts` (fp32 [split_proj_tiles(N, n_split) * M, 4]) for
+            # layer2_loss_fused(t2_parts=...) -- no reduce launch, no proj_out
+            tiles = split_proj_tiles(N, n_split)
+            if (proj_out is not None or proj_parts.dtype != torch.float32 or not proj_parts.is_contiguous()
+                    or proj_parts.numel() < tiles * M * 4):
+                raise ValueError(f"proj_parts must be a contiguous fp32 buffer of {tiles} x {M} float4 (and proj_out None)")
+        else:
+            if proj_out is None:
+                raise ValueError("the fused projection needs proj_out (or proj_parts)")
+            proj_out, ldp = _rowmajor(proj_out, "proj_out")
+            if proj_out.shape[0] != M or proj_out.shape[1] < n_proj:
+                raise ValueError(f"proj_out must be [{M}, >= {n_proj}]")
+    if proj_parts is not None and proj_w is not None:
+        wptr, wbytes = proj_parts.data_ptr(), proj_parts.numel() * 4
+    else:
+        ws = workspace or _default_ws
+        wptr, wbytes = ws.get(lib().gmc_gemm_bf16_split_workspace_bytes(_OPS[op], M, N, K, n_split, int(proj_w is not None)),
+                              A.device)
     check(lib().gmc_gemm_bf16_split(_OPS[op], A.data_ptr(), B_split.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
                                     n_split, sr, _ptr(row_scale), _ptr(bias), int(relu), _ptr(proj_w), _ptr(proj_out), ldp,
                                     int(n_proj), int(accumulate), lo_shift, wptr, wbytes, _stream()), "gmc_gemm_bf16_split")
     return out
+
+
+def split_proj_tiles(n_cols: int, n_split: int) -> int:
+    """n-tiles of a split-operand GEMM = projection partials per row (128 real columns per tile for two parts, 64 for three)."""
+    rn = 128 if n_split == 2 else 64
+    return (int(n_cols) + rn - 1) // rn
 
 
 def skinny_bwd_split(dT: torch.Tensor, W: torch.Tensor, H: torch.Tensor, n_split: int, dH_split: torch.Tensor,
@@ -806,10 +826,12 @@ def layer2_loss_fused(batch, T2: torch.Tensor, bias2: Optional[torch.Tensor], mo
                       penalty: float = 0.0, C: float = 1.0, P: Optional[torch.Tensor] = None,
                       dZ: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None,
                       dT2: Optional[torch.Tensor] = None, db2: Optional[torch.Tensor] = None,
-                      Z: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None) -> torch.Tensor:
+                      Z: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None,
+                      t2_parts: Optional[Tuple[torch.Tensor, int]] = None) -> torch.Tensor:
     """Z = A_hat T2 + b2, softmax / override / STE / max-cut loss, dZ, db2 = colsum(dZ), dT2 = A_hat dZ in one launch
     (one CTA per graph).  P / dZ / Z (contiguous [N, K]), dT2 ([N, >= K]) and db2 ([K]) are optional outputs; returns the
-    per-graph loss (float64 [B])."""
+    per-graph loss (float64 [B]).  t2_parts = (buffer, n_parts): T2 is READ from the projection partials a
+    gemm_bf16_split(..., proj_parts=buffer) call left behind (added in tile order) and only written to the T2 argument."""
     T2, ldt = _rowmajor(T2, "T2")
     n, K = T2.shape
     if n != batch.num_nodes:
@@ -826,6 +848,18 @@ def layer2_loss_fused(batch, T2: torch.Tensor, bias2: Optional[torch.Tensor], mo
     if db2 is not None:
         ws = workspace or _default_ws
         wptr, wbytes = ws.get(lib().gmc_layer2_loss_fused_workspace_bytes(batch.num_graphs, K), T2.device)
+    if t2_parts is not None:
+        parts, n_parts = t2_parts
+        if K > 4 or parts.dtype != torch.float32 or not parts.is_contiguous() or parts.numel() < n_parts * n * 4:
+            raise ValueError(f"t2_parts needs <= 4 classes and a contiguous fp32 buffer of {n_parts} x {n} float4")
+        check(lib().gmc_layer2_loss_fused_parts(parts.data_ptr(), int(n_parts), n, T2.data_ptr(), ldt,
+                                                batch.rowptr.data_ptr(), batch.colidx.data_ptr(),
+                                                batch.coef.data_ptr(), _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(),
+                                                batch.num_graphs, batch.max_nodes, n, K, _ptr(bias2), _lib.LOSS_MODES[mode],
+                                                int(override_terminals), float(penalty), float(C), _ptr(Z), _ptr(P),
+                                                loss.data_ptr(), _ptr(dZ), _ptr(dT2), lddt, _ptr(db2), wptr, wbytes, _stream()),
+              "gmc_layer2_loss_fused_parts")
+        return loss
     check(lib().gmc_layer2_loss_fused(T2.data_ptr(), ldt, batch.rowptr.data_ptr(), batch.colidx.data_ptr(),
                                       batch.coef.data_ptr(), _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(),
                                       batch.num_graphs, batch.max_nodes, n, K, _ptr(bias2), _lib.LOSS_MODES[mode],

@@ -208,6 +208,17 @@ int gmc_layer2_loss_fused(const float* T2, int64_t ldt, const int32_t* rowptr, c
                           int32_t override_terminals, float penalty, float C, float* Z_out, float* P_out,
                           double* loss_per_graph, float* dZ_out, float* dT2, int64_t lddt, float* db2, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* The same with T2 given as the per-n-tile projection partials that gmc_gemm_bf16_split leaves in its workspace when it is
+ * called with proj_w and proj_out = NULL: parts[t * part_stride + row] (float4), n_parts = ceil(hidden / real columns per
+ * tile: 128 for two parts, 64 for three).  Saves the reduce launch and T2's round trip through memory on the per-graph
+ * training path (TrainingNeural.py:371-388: ~9 launches of a few microseconds per step).  T2_out (nullable) receives the
+ * reduced rows. */
+int gmc_layer2_loss_fused_parts(const void* parts, int32_t n_parts, int64_t part_stride, float* T2_out, int64_t ldt,
+                                const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                                const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t n_rows,
+                                int32_t n_classes, const float* bias2, int32_t mode, int32_t override_terminals,
+                                float penalty, float C, float* Z_out, float* P_out, double* loss_per_graph, float* dZ_out,
+                                float* dT2, int64_t lddt, float* db2, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- (d) fused multi-tensor Adam ----------------------------------------------------- */
 
