@@ -25,6 +25,8 @@ struct AdamArgs {
     float* m[kAdamMaxTensors];
     float* v[kAdamMaxTensors];
     int64_t n[kAdamMaxTensors];
+    uint16_t* shadow[kAdamMaxTensors];     // nullable: bf16 copy of the updated parameter, same element index (the operand of
+                                           // next step's bf16 GEMMs: learned node embeddings, TrainingNeural.py:332 / utils.py:184)
     int block_start[kAdamMaxTensors + 1];  // first CTA of each tensor
     int n_tensors;
 };
@@ -107,7 +109,8 @@ adam_kernel(AdamArgs a, AdamScalars c, double lr, double b1, double b2, int64_t*
     const float* __restrict__ g = a.g[t];
     float* __restrict__ m = a.m[t];
     float* __restrict__ v = a.v[t];
-    const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15u) == 0;
+    uint16_t* __restrict__ sh = a.shadow[t];
+    const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15u) == 0 && (((uintptr_t)sh) & 7u) == 0;
 #pragma unroll
     for (int r = 0; r < ITER; ++r) {
         const int64_t i = base + ((int64_t)r * 256 + threadIdx.x) * 4;
@@ -122,11 +125,22 @@ adam_kernel(AdamArgs a, AdamScalars c, double lr, double b1, double b2, int64_t*
             *reinterpret_cast<float4*>(p + i) = pp;
             *reinterpret_cast<float4*>(m + i) = mm;
             *reinterpret_cast<float4*>(v + i) = vv;
+            if (sh) {
+                uint2 pk;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(pp.y), "f"(pp.x));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(pp.w), "f"(pp.z));
+                *reinterpret_cast<uint2*>(sh + i) = pk;
+            }
         } else {
             for (int64_t j = i; j < n && j < i + 4; ++j) {
                 float pp = p[j], mm = m[j], vv = v[j];
                 adam_elem(pp, g[j], mm, vv, c);
                 p[j] = pp; m[j] = mm; v[j] = vv;
+                if (sh) {
+                    uint32_t w;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(0.f), "f"(pp));
+                    sh[j] = (uint16_t)(w & 0xffffu);
+                }
             }
         }
     }
@@ -136,7 +150,8 @@ __global__ void adam_step_inc_kernel(int64_t* step_dev) { *step_dev += 1; }
 
 static int adam_launch(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                        float* const* exp_avg_sq, const int64_t* sizes, double lr, double beta1, double beta2,
-                       double eps, int64_t step, int64_t* step_dev, void* stream, int cached = 0) {
+                       double eps, int64_t step, int64_t* step_dev, void* stream, int cached = 0,
+                       void* const* shadows = nullptr) {
     GMC_REQUIRE(n_tensors >= 0 && n_tensors <= kAdamMaxTensors, "gmc_adam_multi: n_tensors must be 0..%d", kAdamMaxTensors);
     GMC_REQUIRE(n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && sizes), "gmc_adam_multi: null array");
     GMC_REQUIRE(step_dev || step >= 1, "gmc_adam_multi: step is 1-based");
@@ -153,6 +168,7 @@ static int adam_launch(int32_t n_tensors, float* const* params, const float* con
         GMC_REQUIRE(params[t] && grads[t] && exp_avg[t] && exp_avg_sq[t], "gmc_adam_multi: null tensor %d", t);
         const int k = a.n_tensors++;
         a.p[k] = params[t]; a.g[k] = grads[t]; a.m[k] = exp_avg[t]; a.v[k] = exp_avg_sq[t]; a.n[k] = sizes[t];
+        a.shadow[k] = shadows ? reinterpret_cast<uint16_t*>(shadows[t]) : nullptr;
         a.block_start[k] = blocks;
         blocks += (int)ceil_div<int64_t>(sizes[t], chunk);
     }
@@ -199,6 +215,16 @@ int gmc_adam_multi_devstep(int32_t n_tensors, float* const* params, const float*
                             stream);
 }
 
+
+// gmc_adam_multi that also leaves a bf16 copy of every updated parameter in shadows[t] (nullable per tensor; same element
+// index as the parameter): the next step's bf16 GEMM operand without a separate 6-bytes-per-element conversion pass.
+int gmc_adam_multi_shadow(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                          float* const* exp_avg_sq, void* const* shadows, const int64_t* sizes, double lr, double beta1,
+                          double beta2, double eps, int64_t step, void* stream) {
+    GMC_REQUIRE(n_tensors == 0 || shadows, "gmc_adam_multi_shadow: null shadow array");
+    return gmc::adam_launch(n_tensors, params, grads, exp_avg, exp_avg_sq, sizes, lr, beta1, beta2, eps, step, nullptr,
+                            stream, 0, shadows);
+}
 
 // step state of kAdamStateWords (8) int64 words, zero-initialised by the caller (word 0 may be preset to the number of
 // steps already taken); no separate increment launch, bias-correction scalars precomputed by the previous launch.

@@ -98,6 +98,8 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_softmax_bwd_f32": (c_int, [P, P, c_int64, c_int32, P, P]),
     "gmc_adam_multi": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                POINTER(c_int64), c_double, c_double, c_double, c_double, c_int64, P]),
+    "gmc_adam_multi_shadow": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                      POINTER(c_void_p), POINTER(c_int64), c_double, c_double, c_double, c_double, c_int64, P]),
     "gmc_adam_multi_devstep": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                        POINTER(c_void_p), POINTER(c_int64), c_double, c_double, c_double, c_double,
                                        P, P]),

@@ -180,6 +180,8 @@ class GCNEngine:
         self._trainable_features = False      # set for the duration of a loss_and_grads call that asks for dX
         self._x16 = None                      # per-step bf16 copy of trainable features
         self._x16_fresh = False
+        self._x16_shadow_of = None            # (ptr, version, shape) of the parameter whose bf16 copy Adam wrote into _x16
+        self._x16_use_shadow = False
         self._xa_cache: Dict[tuple, torch.Tensor] = {}
         self._w2p = None
         self.bufB16 = None
@@ -361,6 +363,7 @@ class GCNEngine:
         raw pointers (gmc_* kernels such as ops.densify(out=X) do not bump torch's version counter)."""
         self._xb_cache.clear()
         self._xa_cache.clear()
+        self._x16_shadow_of = None
 
     # ------------------------------------------------------------------ forward
     def forward_logits(self, batch: GraphBatch, X: torch.Tensor) -> torch.Tensor:
@@ -500,6 +503,10 @@ class GCNEngine:
         N, B = batch.num_nodes, batch.num_graphs
         W1, b1, W2, b2 = self.params()
         self._trainable_features, self._x16_fresh = dX is not None, False
+        if dX is not None and self._x16_use_shadow:
+            # train_step found the bf16 copy the previous step's feature Adam left behind still valid for this table
+            self._x16_fresh = self._x16 is not None and self._x16.shape[0] >= X.shape[0] and self._x16.shape[1] == X.shape[1]
+        self._x16_use_shadow = False
         try:
             return self._loss_and_grads(batch, X, dX, N, B)
         finally:
@@ -586,8 +593,23 @@ class GCNEngine:
             raise RuntimeError("GCNEngine was built without an optimizer")
         self._op("adam", 1, self.optimizer.fused_step, list(self.params()), self.grads())
         if feature_param is not None:
-            # per-graph / per-node embeddings never leave the rank: no all-reduce, their own Adam launch
-            self._op("adam_features", 1, self.optimizer.fused_step, [feature_param], [feature_grad])
+            # per-graph / per-node embeddings never leave the rank: no all-reduce, their own Adam launch.  With bf16 GEMM
+            # operands the same pass also writes the bf16 copy the next step's GEMMs read (30 instead of 28 bytes per
+            # element, against a separate 6-byte conversion pass over the table): valid for the next loss_and_grads as long
+            # as nobody else writes the parameter in between (its autograd version is unchanged).
+            shadow = None
+            x16 = self._x16
+            if (self.precision == "bf16" and x16 is not None and feature_param.dim() == 2 and feature_param.is_contiguous()
+                    and hasattr(self.optimizer, "fused_step")):
+                base = x16._base if x16._base is not None else x16
+                if base.is_contiguous() and base.shape == feature_param.shape:
+                    shadow = base
+            if shadow is not None:
+                self._op("adam_features", 1, self.optimizer.fused_step, [feature_param], [feature_grad], shadows=[shadow])
+                self._x16_shadow_of = (feature_param.data_ptr(), feature_param._version, tuple(feature_param.shape))
+            else:
+                self._op("adam_features", 1, self.optimizer.fused_step, [feature_param], [feature_grad])
+                self._x16_shadow_of = None
 
     # ------------------------------------------------------------------ CUDA-graph replay
     def _adam_state(self):
@@ -766,6 +788,10 @@ class GCNEngine:
                     or X.stride(0) != feature_param.stride(0):
                 raise ValueError("X must be a leading-rows / leading-columns view of feature_param")
             dX = feature_grad[: X.shape[0], : X.shape[1]]
+            # bf16 copy written by the previous step's feature Adam: still this table, untouched since (torch's version
+            # counter; writes through .data or raw pointers are invisible to it -- invalidate_feature_caches() after those)
+            self._x16_use_shadow = self._x16_shadow_of == (feature_param.data_ptr(), feature_param._version,
+                                                           tuple(feature_param.shape))
         loss = self.loss_and_grads(batch, X, dX=dX)
         self.allreduce_grads()
         self.apply_adam(feature_param, feature_grad)

@@ -896,7 +896,8 @@ def _ptr_array(ts: Sequence[torch.Tensor]):
 
 def adam_multi(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], exp_avg: Sequence[torch.Tensor],
                exp_avg_sq: Sequence[torch.Tensor], lr: float, beta1: float = 0.9, beta2: float = 0.999,
-               eps: float = 1e-8, step: Optional[int] = None, step_dev: Optional[torch.Tensor] = None) -> None:
+               eps: float = 1e-8, step: Optional[int] = None, step_dev: Optional[torch.Tensor] = None,
+               shadows: Optional[Sequence[Optional[torch.Tensor]]] = None) -> None:
     """In-place Adam on up to 16 tensors per launch.  Pass either `step` (1-based host count) or
     `step_dev` (int64 device scalar holding the number of steps taken; incremented on device) -- or an 8-word int64
     state whose word 0 is that count (gmc_adam_multi_devstate: no increment launch, bias corrections precomputed)."""
@@ -925,7 +926,19 @@ def adam_multi(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], ex
         else:
             if step is None or step < 1:
                 raise ValueError("adam_multi: step must be >= 1")
-            check(lib().gmc_adam_multi(*args, int(step), _stream()), "gmc_adam_multi")
+            if shadows is not None and any(sh is not None for sh in shadows[lo:hi]):
+                # bf16 copies of the updated parameters (same element index), written by the same pass
+                arr = (ctypes.c_void_p * (hi - lo))()
+                for i, (sh, p) in enumerate(zip(shadows[lo:hi], params[lo:hi])):
+                    if sh is None:
+                        continue
+                    if sh.dtype != torch.bfloat16 or not sh.is_contiguous() or sh.numel() != p.numel() or not sh.is_cuda:
+                        raise ValueError("adam_multi: a shadow must be a contiguous CUDA bf16 tensor with the parameter's numel")
+                    arr[i] = sh.data_ptr()
+                a = args[:5] + (arr,) + args[5:]
+                check(lib().gmc_adam_multi_shadow(*a, int(step), _stream()), "gmc_adam_multi_shadow")
+            else:
+                check(lib().gmc_adam_multi(*args, int(step), _stream()), "gmc_adam_multi")
 
 
 # ---------------------------------------------------------------- (e) post-processing

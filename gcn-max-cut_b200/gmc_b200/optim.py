@@ -36,24 +36,27 @@ class FusedAdam(torch.optim.Optimizer):
         return st
 
     @torch.no_grad()
-    def fused_step(self, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor]) -> None:
-        """One Adam step on `params` with explicit gradient tensors (engine-owned buffers)."""
+    def fused_step(self, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], shadows=None) -> None:
+        """One Adam step on `params` with explicit gradient tensors (engine-owned buffers).  shadows: optional list of
+        contiguous bf16 tensors (or None) that receive bf16 copies of the updated parameters in the same pass."""
         by_group = {}
         for group in self.param_groups:
             for p in group["params"]:
                 by_group[id(p)] = group
         buckets = {}
-        for p, g in zip(params, grads):
+        for i, (p, g) in enumerate(zip(params, grads)):
             group = by_group[id(p)]
             st = self._state_for(p)
             st["step"] += 1
             key = (id(group), int(st["step"].item()))
-            buckets.setdefault(key, (group, [], [], [], []))
-            _, ps, gs, ms, vs = buckets[key]
+            buckets.setdefault(key, (group, [], [], [], [], []))
+            _, ps, gs, ms, vs, shs = buckets[key]
             ps.append(p.data); gs.append(g); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
-        for (_, step), (group, ps, gs, ms, vs) in buckets.items():
+            shs.append(shadows[i] if shadows is not None else None)
+        for (_, step), (group, ps, gs, ms, vs, shs) in buckets.items():
             b1, b2 = group["betas"]
-            ops.adam_multi(ps, gs, ms, vs, lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], step=step)
+            ops.adam_multi(ps, gs, ms, vs, lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], step=step,
+                           shadows=shs if any(sh is not None for sh in shs) else None)
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -238,6 +238,13 @@ int gmc_adam_multi_devstep(int32_t n_tensors, float* const* params, const float*
                            double lr, double beta1, double beta2, double eps, int64_t* step_dev,
                            void* stream);
 
+/* gmc_adam_multi that also writes a bf16 copy of each updated parameter to shadows[t] (HOST array of device pointers,
+ * entries nullable; element i of the copy = bf16(element i of the parameter)): learned node embeddings feed the next
+ * step's bf16 GEMMs without a conversion pass (python/utils.py:184 `inputs = embed.weight`). */
+int gmc_adam_multi_shadow(int32_t n_tensors, float* const* params, const float* const* grads,
+                          float* const* exp_avg, float* const* exp_avg_sq, void* const* shadows, const int64_t* sizes,
+                          double lr, double beta1, double beta2, double eps, int64_t step, void* stream);
+
 /* The same with an 8-word device state (zero-initialised; word 0 = steps already taken): the launch advances the count
  * itself and leaves the bias-correction scalars of the NEXT step in the state, so a replayed per-graph training step
  * (TrainingNeural.py:371-388) carries neither a one-thread increment launch nor a double-precision pow() in front of
