@@ -497,8 +497,12 @@ def run_b200_arm(args):
             cnt_e = [0]
 
             def emb_update():
+                # the table's Adam pass also writes the bf16 GEMM operand of the next step (no conversion pass)
                 cnt_e[0] += 1
-                ops.adam_multi([E], [E_g], [E_m], [E_v], lr=1e-3, step=cnt_e[0])
+                sh = eng_e.feature_shadow(E[:, :F])
+                ops.adam_multi([E], [E_g], [E_m], [E_v], lr=1e-3, step=cnt_e[0], shadows=[sh] if sh is not None else None)
+                if sh is not None:
+                    eng_e.note_feature_shadow(E[:, :F])
 
             def emb_step():
                 return eng_e.train_step_features(batch, E[:, :F], E_g[:, :F], emb_update)
@@ -526,7 +530,8 @@ def run_b200_arm(args):
                 "steps": k_emb, "dtype": "bf16",
                 "what": "learned per-graph node embeddings as the input (north-star mode; bench.py --feature-source embedding): "
                         f"parameter + gradient + Adam moments {4 * N * ld * 4 / 1e9:.0f} GB/GPU, standard layer 1 (bf16 slab SpMM "
-                        "forward and backward), dL/dX through the bf16 nt GEMM, fused Adam over the table (28 B per element)",
+                        "forward and backward), dL/dX through the bf16 nt GEMM, fused Adam over the table (28 B per element + the bf16 copy "
+                        "the next step's GEMMs read)",
                 "ops_ms": {k: t_e.total_ms[k] / t_e.calls[k] for k in t_e.total_ms},
                 "tensor_pipe": {k: {"achieved_tflops": v, "peak_tflops": peak_bf16, "frac": v / peak_bf16} for k, v in gemm_tf.items()},
                 "adam_features_GBps": 28.0 * N * ld / (t_e.total_ms["adam_features"] / t_e.calls["adam_features"] * 1e-3) / 1e9

@@ -606,7 +606,7 @@ class GCNEngine:
                     shadow = base
             if shadow is not None:
                 self._op("adam_features", 1, self.optimizer.fused_step, [feature_param], [feature_grad], shadows=[shadow])
-                self._x16_shadow_of = (feature_param.data_ptr(), feature_param._version, tuple(feature_param.shape))
+                self._x16_shadow_of = self._shadow_key(feature_param)
             else:
                 self._op("adam_features", 1, self.optimizer.fused_step, [feature_param], [feature_grad])
                 self._x16_shadow_of = None
@@ -758,11 +758,31 @@ class GCNEngine:
         """One optimiser step with trainable features owned by the caller: dL/dX lands in `dX`, the shared weights take
         their (all-reduced) Adam step, then `update()` runs the caller's update of the rows X views (per-graph embedding
         tables never leave the rank: no all-reduce for them)."""
+        self._x16_use_shadow = self._x16_shadow_of == self._shadow_key(X)
         loss = self.loss_and_grads(batch, X, dX=dX)
         self.allreduce_grads()
         self.apply_adam()
         self._op("adam_features", 1, update)
         return loss
+
+    @staticmethod
+    def _shadow_key(X: torch.Tensor):
+        return (X.data_ptr(), X._version, (int(X.shape[0]), int(X.stride(0))))
+
+    def feature_shadow(self, X: torch.Tensor) -> Optional[torch.Tensor]:
+        """For callers that own the Adam update of trainable features (train_step_features): the bf16 buffer
+        [rows, row pitch] the engine's GEMMs read X from, or None (no bf16 operands, pitch mismatch, not allocated yet).
+        Fill it in the update -- ops.adam_multi(..., shadows=[buffer]) writes bf16(parameter) at the same element index --
+        and call note_feature_shadow(X): the next step over the same, untouched X skips its conversion pass."""
+        if self.precision != "bf16" or self._x16 is None or not torch.is_tensor(X) or X.dim() != 2:
+            return None
+        base = self._x16._base if self._x16._base is not None else self._x16
+        if base.dim() != 2 or not base.is_contiguous() or X.stride(0) != base.shape[1] or X.shape[0] > base.shape[0]:
+            return None
+        return base[: X.shape[0]]
+
+    def note_feature_shadow(self, X: torch.Tensor) -> None:
+        self._x16_shadow_of = self._shadow_key(X)
 
     def train_step_empty(self) -> None:
         """The optimiser step of a rank whose shard of the step's graphs is empty (data parallel, fewer graphs than
@@ -790,8 +810,7 @@ class GCNEngine:
             dX = feature_grad[: X.shape[0], : X.shape[1]]
             # bf16 copy written by the previous step's feature Adam: still this table, untouched since (torch's version
             # counter; writes through .data or raw pointers are invisible to it -- invalidate_feature_caches() after those)
-            self._x16_use_shadow = self._x16_shadow_of == (feature_param.data_ptr(), feature_param._version,
-                                                           tuple(feature_param.shape))
+            self._x16_use_shadow = self._x16_shadow_of == self._shadow_key(feature_param)
         loss = self.loss_and_grads(batch, X, dX=dX)
         self.allreduce_grads()
         self.apply_adam(feature_param, feature_grad)

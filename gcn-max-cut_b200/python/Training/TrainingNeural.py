@@ -636,8 +636,13 @@ class GraphEmbeddings:
         count = self.steps_taken[i_step]
 
         def update():
+            # with bf16 GEMM operands the same pass leaves the bf16 copy of the rows for the next visit (it survives only
+            # when the next step trains the same rows: single-step datasets)
+            sh = engine.feature_shadow(X)
             ops.adam_multi([rows[0]], [rows[1]], [rows[2]], [rows[3]], lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
-                           eps=self.eps, step=count)
+                           eps=self.eps, step=count, shadows=[sh] if sh is not None else None)
+            if sh is not None:
+                engine.note_feature_shadow(X)
 
         return engine.train_step_features(prepared.batch, X, dX, update)
 
