@@ -284,6 +284,19 @@ def test_bf16_activation_forward_variants_agree(monkeypatch):
         assert relerr(a, b) < 1e-2
 
 
+@pytest.mark.parametrize("N", [500, 512, 640])
+def test_gemm_bf16_bf16out_bias_relu_epilogue_wide(N):
+    """bias / ReLU epilogue of the pair kernel: <= 512 columns read the bias from its shared-memory copy, more columns from
+    global memory -- same results."""
+    torch.manual_seed(N)
+    M, K = 300, 192
+    A, B, bias = torch.randn(M, K), torch.randn(K, N) / K ** 0.5, torch.randn(N)
+    Ab, Bb = ops.to_bf16(A.to(DEV)), ops.to_bf16(B.to(DEV))
+    want = torch.relu(bf16_round(A) @ bf16_round(B) + bias.double())
+    got = ops.gemm_bf16_bf16out("nn", Ab, Bb, bias=bias.to(DEV), relu=True)
+    assert_bf16_close(got, want, extra=1e-4)
+
+
 def test_gemm_bf16_bf16out_bias_relu_epilogue():
     torch.manual_seed(8)
     M, N, K = 700, 500, 320

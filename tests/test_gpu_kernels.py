@@ -600,3 +600,56 @@ def test_peer_allreduce_protocol_on_one_device(world, n):
         for q in range(world):
             assert torch.equal(bufs[q][:n], want), (epoch, q)
         assert all(int(f[32].item()) == 0 for f in flags)      # block counters reset for the next launch
+
+
+def _peer_worker(rank, world, port, n, out_q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gmc_b200 import dist as gdist
+        torch.cuda.set_device(0)
+        peer = gdist.PeerAllReduce(n, torch.device("cuda", 0))
+        ok = True
+        for epoch in range(3):
+            torch.manual_seed(100 * epoch + rank)
+            mine = torch.randn(n, device="cuda")
+            peer.tensor[:n].copy_(mine)
+            torch.cuda.synchronize()
+            dist.barrier()
+            peer.all_reduce_()
+            torch.cuda.synchronize()
+            want = torch.zeros(n, device="cuda")
+            for q in range(world):
+                torch.manual_seed(100 * epoch + q)
+                want += torch.randn(n, device="cuda")
+            ok = ok and bool(torch.equal(peer.tensor[:n], want))
+            dist.barrier()
+        out_q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_allreduce_across_processes_through_cuda_ipc():
+    """dist.PeerAllReduce as the engine uses it: separate PROCESSES exchange cudaIpc handles through torch.distributed
+    (gloo here, both ranks on the one GPU of the test box -- NCCL refuses two ranks per device, cudaIpc does not) and run
+    the one-kernel exchange on each other's mapped buffers."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, n = 2, 50003
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, 29631, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    try:
+        for _ in range(world):
+            results.append(q.get(timeout=120))
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    assert sorted(results) == [(0, True), (1, True)]

@@ -143,8 +143,9 @@ def test_split_gemm_fused_projection_is_deterministic_and_exact(M, N, n_proj, n_
 
 
 @pytest.mark.parametrize("n_split", [2, 3])
-@pytest.mark.parametrize("M,N,K", [(1000, 500, 1000), (130, 260, 40), (2000, 500, 1000)])
+@pytest.mark.parametrize("M,N,K", [(1000, 500, 1000), (130, 260, 40), (2000, 500, 1000), (300, 640, 128), (200, 512, 64)])
 def test_split_gemm_nn_epilogue_scale_bias_relu(M, N, K, n_split):
+    # N = 500 / 260 / 512: bias staged in shared memory; N = 640 (> 512 columns): the global-load form of the same epilogue
     A = bf16_exact_ints(M, K, 8, 3 * M)
     torch.manual_seed(K)
     W, b = torch.randn(K, N) * 0.05, torch.randn(N) * 0.3
