@@ -559,7 +559,8 @@ size_t gmc_csr_preaggregate_workspace_bytes(int64_t n_rows) { return n_rows > 0 
 
 static int preaggregate_impl(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
                              const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
-                             int64_t ldx, void* workspace, size_t workspace_bytes, void* stream, bool f16) {
+                             int64_t ldx, void* workspace, size_t workspace_bytes, void* stream, bool f16,
+                             int32_t max_nodes = -1) {
     GMC_REQUIRE(rowptr && colidx && coef && graph_ptr && X, "gmc_csr_preaggregate_bf16: null pointer");
     GMC_REQUIRE(n_graphs >= 0 && n_rows >= 0 && n_cols > 0 && ldx >= n_cols, "gmc_csr_preaggregate_bf16: bad sizes");
     const int ncp = (n_cols + 7) & ~7;
@@ -593,9 +594,10 @@ static int preaggregate_impl(const int32_t* rowptr, const int32_t* colidx, const
         GMC_LAUNCH_CHECK();
         only = slow;
     }
-    // batches of small graphs (on average no more nodes than feature columns, unit weights): one CTA per graph with its CSR
-    // slice in shared memory; graphs that exceed the staging buffers are walked from global memory by the same kernel
-    if (!only && !vals && n_graphs > 0 && n_rows / n_graphs <= (int64_t)ncp && ncp <= 2048 && gmc::graph_kernel_enabled()) {
+    // batches of small graphs (the caller states the largest one: no more nodes than feature columns; unit weights): one
+    // CTA per graph with its CSR slice in shared memory.  A graph whose EDGES exceed the staging buffer (average degree
+    // above 8) is walked from global memory by its CTA -- bounded work, since it has at most ncp rows.
+    if (!only && !vals && n_graphs > 0 && max_nodes > 0 && max_nodes <= ncp && ncp <= 2048 && gmc::graph_kernel_enabled()) {
         const int cap_nodes = ncp, cap_edges = 8 * ncp + 64;
         const size_t g_smem = (size_t)gmc::kPgWarps * ncp * sizeof(float) + (size_t)(cap_nodes + 1) * 4 + (size_t)cap_edges * 2 + 16;
         static bool attr3 = false;
@@ -654,6 +656,16 @@ int gmc_csr_preaggregate_f16(const int32_t* rowptr, const int32_t* colidx, const
                              const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows, int32_t n_cols, void* X,
                              int64_t ldx, void* stream) {
     return preaggregate_impl(rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, X, ldx, nullptr, 0, stream, true);
+}
+
+// gmc_csr_preaggregate_bf16 / _f16 for a batch whose largest graph has max_nodes nodes (a host-side fact of every batch
+// the callers build): batches of small graphs (max_nodes <= n_cols rounded up to 8, <= 2048) take the per-graph kernel
+// with the graph's CSR slice in shared memory; everything else the row-parallel one.  out_f16 != 0 writes IEEE fp16.
+int gmc_csr_preaggregate_graphs(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                                const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t n_rows, int32_t n_cols,
+                                void* X, int64_t ldx, int32_t out_f16, void* stream) {
+    return preaggregate_impl(rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, X, ldx, nullptr, 0, stream,
+                             out_f16 != 0, max_nodes);
 }
 
 // dst[r, c] = bf16(src[r, c]), round to nearest even; leading dimensions in elements

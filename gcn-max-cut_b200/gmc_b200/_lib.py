@@ -77,6 +77,7 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_f32_split_f16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, c_int64, c_int32, P]),
     "gmc_skinny_bwd_split": (c_int, [P, c_int64, P, P, c_int64, P, P, c_int64, c_int64, c_int32, c_int32, P, P, c_int64, c_int32,
                                      c_int32, P, c_size_t, P]),
+    "gmc_csr_preaggregate_graphs": (c_int, [P, P, P, P, P, c_int32, c_int32, c_int64, c_int32, P, c_int64, c_int32, P]),
     "gmc_csr_preaggregate_f16": (c_int, [P, P, P, P, P, c_int32, c_int64, c_int32, P, c_int64, P]),
     "gmc_gemm_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int64, c_int64, c_int32]),
     "gmc_gemm_nn": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, P, c_size_t, P]),

@@ -306,6 +306,12 @@ def preaggregate_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] =
     if counting:        # byte-counting kernel for the regular rows + masked general kernel (no faster at config 3: opt-in)
         ws = workspace or _default_ws
         wptr, wbytes = ws.get(lib().gmc_csr_preaggregate_workspace_bytes(batch.num_nodes), batch.device)
+    if not counting:
+        check(lib().gmc_csr_preaggregate_graphs(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(),
+                                                _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(), batch.num_graphs,
+                                                int(batch.max_nodes), batch.num_nodes, n_cols, out.data_ptr(), ld, 0,
+                                                _stream()), "gmc_csr_preaggregate_graphs")
+        return out
     check(lib().gmc_csr_preaggregate_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(),
                                           _ptr(batch.wts_f32), batch.graph_ptr.data_ptr(), batch.num_graphs,
                                           batch.num_nodes, n_cols, out.data_ptr(), ld, wptr, wbytes, _stream()),
@@ -433,14 +439,10 @@ def integer_features_bf16(batch, n_cols: int, out: Optional[torch.Tensor] = None
         out = padded_empty_bf16(batch.num_nodes, n_cols, batch.device, zero=True,
                                 dtype=torch.float16 if f16 else torch.bfloat16)
     out, ld = _b16_rowmajor(out, "out")
-    if out.dtype == torch.float16:
-        check(lib().gmc_csr_preaggregate_f16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), ones.data_ptr(), None,
-                                             batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
-                                             out.data_ptr(), ld, _stream()), "gmc_csr_preaggregate_f16")
-        return out
-    check(lib().gmc_csr_preaggregate_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), ones.data_ptr(), None,
-                                          batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, n_cols,
-                                          out.data_ptr(), ld, None, 0, _stream()), "gmc_csr_preaggregate_bf16")
+    check(lib().gmc_csr_preaggregate_graphs(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), ones.data_ptr(), None,
+                                            batch.graph_ptr.data_ptr(), batch.num_graphs, int(batch.max_nodes),
+                                            batch.num_nodes, n_cols, out.data_ptr(), ld,
+                                            int(out.dtype == torch.float16), _stream()), "gmc_csr_preaggregate_graphs")
     return out
 
 

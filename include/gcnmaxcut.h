@@ -400,6 +400,13 @@ int gmc_skinny_bwd_split(const float* dT, int64_t lddt, const float* W, const fl
                          int32_t lo_shift /* 0: bf16 parts; > 0: fp16 parts, part p scaled by 2^(lo_shift p) */,
                          float* dW, float* dbias, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* Both of the above for a batch whose largest graph has max_nodes nodes (known to whoever built the batch): when
+ * max_nodes <= n_cols (rounded up to 8) <= 2048 one CTA owns one graph and walks its 2-hop neighbourhoods from a
+ * shared-memory copy of the graph's CSR slice (the row-parallel kernel pays an L2 round trip per level); out_f16 != 0
+ * writes IEEE fp16.  Same bits as the row-parallel kernels. */
+int gmc_csr_preaggregate_graphs(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,
+                                const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t n_rows,
+                                int32_t n_cols, void* X, int64_t ldx, int32_t out_f16, void* stream);
 /* gmc_csr_preaggregate_bf16 with the rows written as IEEE fp16: the A operand of the fp16-part GEMMs (both MMA operands
  * must share one 16-bit format; small integers are exact in either). */
 int gmc_csr_preaggregate_f16(const int32_t* rowptr, const int32_t* colidx, const float* coef, const float* vals,

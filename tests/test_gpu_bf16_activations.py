@@ -368,6 +368,45 @@ def test_preaggregated_features_equal_ahat_times_adjacency():
     assert float(full[:, F:].abs().max()) == 0.0 if full.shape[1] > F else True
 
 
+@pytest.mark.parametrize("f16", [False, True])
+def test_preaggregate_per_graph_kernel_equals_the_row_parallel_kernel(f16):
+    """Unit-weight batches of small graphs take the per-graph kernel (CSR slice staged in shared memory, chosen by the
+    caller-supplied max_nodes); it must write the very bits of the row-parallel kernel: regular graphs of several sizes and
+    degrees (fast rows), an irregular graph (ordered slow rows), and a dense one whose edges exceed the staging buffer (walked
+    from global memory by its CTA)."""
+    import ctypes
+    import networkx as nx
+    from gmc_b200 import _lib
+    from gmc_b200.graph import CSRGraph
+    graphs = []
+    for n, d, seed in [(130, 6, 1), (256, 7, 2), (60, 3, 3), (128, 8, 4), (256, 7, 5)]:
+        g = nx.random_regular_graph(d=d, n=n, seed=seed)
+        nx.set_edge_attributes(g, 1, "weight")
+        graphs.append(CSRGraph.from_networkx(g))
+    for g in (nx.barabasi_albert_graph(200, 3, seed=1), nx.random_regular_graph(d=20, n=250, seed=7)):
+        nx.set_edge_attributes(g, 1, "weight")
+        graphs.append(CSRGraph.from_networkx(g))
+    batch = GraphBatch(graphs, device=DEV)
+    F = 256                                                        # = max_nodes: the per-graph kernel applies
+    assert batch.max_nodes <= F and 250 * 20 > 8 * F + 64          # the d = 20 graph does not fit the edge buffer
+    dt = torch.float16 if f16 else torch.bfloat16
+    ones = torch.ones(batch.nnz, device=DEV)
+    got = ops.integer_features_bf16(batch, F, f16=f16)             # gmc_csr_preaggregate_graphs, unit coefficients
+    ref = ops.padded_empty_bf16(batch.num_nodes, F, DEV, zero=True, dtype=dt)
+    L, z = _lib.lib(), ctypes.c_void_p()
+    args = (batch.rowptr.data_ptr(), batch.colidx.data_ptr(), ones.data_ptr(), z, batch.graph_ptr.data_ptr(), batch.num_graphs,
+            batch.num_nodes, F, ref.data_ptr(), ref.stride(0))
+    rc = L.gmc_csr_preaggregate_f16(*args, z) if f16 else L.gmc_csr_preaggregate_bf16(*args, z, 0, z)   # row-parallel kernel
+    assert rc == 0
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    XA = ops.preaggregate_features_bf16(batch, F)                  # A_hat coefficients instead of ones
+    ref2 = ops.padded_empty_bf16(batch.num_nodes, F, DEV, zero=True)
+    assert L.gmc_csr_preaggregate_bf16(batch.rowptr.data_ptr(), batch.colidx.data_ptr(), batch.coef.data_ptr(), z,
+                                       batch.graph_ptr.data_ptr(), batch.num_graphs, batch.num_nodes, F, ref2.data_ptr(),
+                                       ref2.stride(0), z, 0, z) == 0
+    assert torch.equal(XA.view(torch.int16), ref2.view(torch.int16))
+
+
 def test_preaggregate_counting_kernel_and_masked_fallback():
     """Unit weights: rows with <= 8 neighbours of one degree take the byte-counting kernel, the irregular graph's rows
     (and a 12-regular graph's) are flagged and finished by the general kernel in the same call (counting=True; opt-in --
