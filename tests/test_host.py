@@ -412,6 +412,11 @@ def _shard_worker(rank, world, port, q):
         hb = st.host
         out.append(None if hb is None else (st.n_graphs, hb.rowptr.tolist(), hb.colidx.tolist(), hb.graph_ptr.tolist(), hb.regular))
     touched = sorted(k for k in ds.keys() if dict.__getitem__(ds, k) is not None)
+    # the peer-memory gradient exchange is an NCCL-on-GPU, opt-in affair: under gloo every rank agrees on "no" without a
+    # collective (an engine built here would use torch.distributed's all_reduce)
+    from gmc_b200 import dist as gdist
+    os.environ["GMC_PEER_ALLREDUCE"] = "1"
+    assert gdist.make_peer_allreduce(1024, "cpu") is None
     q.put((rank, out, touched))
     dist.barrier()
     dist.destroy_process_group()
