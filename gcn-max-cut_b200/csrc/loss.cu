@@ -222,6 +222,43 @@ extern "C" int gmc_softmax_bwd_f32(const float* P, const float* dP, int64_t n_ro
     return GMC_OK;
 }
 
+// dX[r, c] = Y[r, c] > 0 ? dY[r, c] : 0 -- backward of the ReLU between the two GraphConv layers (TrainingNeural.py:81)
+// for the generic autograd path; leading dimensions in elements, one thread per 4 columns when everything is 16-byte aligned.
+namespace gmc {
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ Y, int64_t ldy, float* __restrict__ dX,
+                int64_t lddx, int64_t n_rows, int n_cols, int vec) {
+    const int per = vec ? (n_cols + 3) / 4 : n_cols;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * per) return;
+    const int64_t r = i / per;
+    const int c = (int)(i - r * per);
+    if (vec) {
+        const float4 g = *reinterpret_cast<const float4*>(dY + r * lddy + 4 * c);
+        const float4 y = *reinterpret_cast<const float4*>(Y + r * ldy + 4 * c);
+        *reinterpret_cast<float4*>(dX + r * lddx + 4 * c) =
+            make_float4(y.x > 0.f ? g.x : 0.f, y.y > 0.f ? g.y : 0.f, y.z > 0.f ? g.z : 0.f, y.w > 0.f ? g.w : 0.f);
+    } else {
+        dX[r * lddx + c] = Y[r * ldy + c] > 0.f ? dY[r * lddy + c] : 0.f;
+    }
+}
+}  // namespace gmc
+
+extern "C" int gmc_relu_bwd_f32(const float* dY, int64_t lddy, const float* Y, int64_t ldy, float* dX, int64_t lddx,
+                                int64_t n_rows, int32_t n_cols, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(dY && Y && dX, "gmc_relu_bwd_f32: null pointer");
+    GMC_REQUIRE(n_rows >= 0 && n_cols > 0 && lddy >= n_cols && ldy >= n_cols && lddx >= n_cols, "gmc_relu_bwd_f32: bad sizes");
+    if (n_rows == 0) return GMC_OK;
+    const int vec = (n_cols % 4 == 0 && lddy % 4 == 0 && ldy % 4 == 0 && lddx % 4 == 0 && aligned16(dY) && aligned16(Y) &&
+                     aligned16(dX)) ? 1 : 0;
+    const int64_t total = n_rows * (vec ? n_cols / 4 : n_cols);
+    relu_bwd_kernel<<<(unsigned)ceil_div<int64_t>(total, 256), 256, 0, as_stream(stream)>>>(dY, lddy, Y, ldy, dX, lddx, n_rows,
+                                                                                            n_cols, vec);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
+
 extern "C" int gmc_softmax_cut_loss_fwd_bwd(const float* Z, int64_t ldz, const int32_t* rowptr, const int32_t* colidx,
                                             const float* vals, const int32_t* graph_ptr, int32_t n_graphs,
                                             int64_t n_rows, int32_t n_classes, int32_t mode,

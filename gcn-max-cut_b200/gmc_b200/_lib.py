@@ -96,6 +96,7 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_layer2_loss_fused_parts": (c_int, [P, c_int32, c_int64, P, c_int64, P, P, P, P, P, c_int32, c_int32, c_int64, c_int32, P, c_int32, c_int32,
                                       c_float, c_float, P, P, P, P, P, c_int64, P, P, c_size_t, P]),
     "gmc_softmax_fwd_f32": (c_int, [P, c_int64, c_int64, c_int32, P, P]),
+    "gmc_relu_bwd_f32": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, P]),
     "gmc_softmax_bwd_f32": (c_int, [P, P, c_int64, c_int32, P, P]),
     "gmc_adam_multi": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                POINTER(c_int64), c_double, c_double, c_double, c_double, c_int64, P]),

@@ -117,7 +117,7 @@ def _bias_act(Y, b, relu):
 
 
 def _relu_mask(dY, Y):
-    return dY * (Y > 0).to(dY.dtype)
+    return ops.relu_bwd(dY, Y)
 
 
 class _SoftmaxFn(torch.autograd.Function):

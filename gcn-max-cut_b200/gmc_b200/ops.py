@@ -879,6 +879,18 @@ def softmax_fwd(Z: torch.Tensor) -> torch.Tensor:
     return P
 
 
+def relu_bwd(dY: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
+    """dX = (Y > 0) ? dY : 0 in one launch (the autograd path's ReLU backward)."""
+    dY, lddy = _rowmajor(dY, "dY")
+    Y, ldy = _rowmajor(Y, "Y")
+    if dY.shape != Y.shape:
+        raise ValueError("relu_bwd: shapes differ")
+    out = padded_empty(dY.shape[0], dY.shape[1], dY.device)
+    check(lib().gmc_relu_bwd_f32(dY.data_ptr(), lddy, Y.data_ptr(), ldy, out.data_ptr(), out.stride(0), dY.shape[0],
+                                 dY.shape[1], _stream()), "gmc_relu_bwd_f32")
+    return out
+
+
 def softmax_bwd(P: torch.Tensor, dP: torch.Tensor) -> torch.Tensor:
     P = _f32(P, "P").contiguous()
     dP = _f32(dP, "dP").contiguous()

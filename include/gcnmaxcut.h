@@ -191,6 +191,10 @@ int gmc_softmax_fwd_f32(const float* Z, int64_t ldz, int64_t n_rows, int32_t n_c
                         void* stream);
 int gmc_softmax_bwd_f32(const float* P, const float* dP, int64_t n_rows, int32_t n_classes, float* dZ,
                         void* stream);
+/* dX = (Y > 0) ? dY : 0 -- backward of F.relu (TrainingNeural.py:81) on the generic autograd path; leading dimensions in
+ * elements. */
+int gmc_relu_bwd_f32(const float* dY, int64_t lddy, const float* Y, int64_t ldy, float* dX, int64_t lddx,
+                     int64_t n_rows, int32_t n_cols, void* stream);
 
 /* (c') The whole second layer + loss + its backward for a block-diagonal batch of small graphs, ONE CTA per graph:
  *   Z = A_hat T2 + b2 (TrainingNeural.py:83), softmax / terminal override / STE / max-cut loss and dZ as
