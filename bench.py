@@ -90,6 +90,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the short config 1 / config 2 runs of the default line")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config-5 subprocess of the default line's workloads block")
     ap.add_argument("--no-embedding-alt", action="store_true", help="skip alt_paths.embedding (needs ~85 GB more HBM)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(--steps, 10)")
     args = ap.parse_args()
@@ -833,6 +834,27 @@ def run_b200_arm(args):
             except Exception as exc:                                 # a secondary workload never takes the headline down
                 workloads[name] = {"error": f"{type(exc).__name__}: {exc}"}
             torch.cuda.empty_cache()
+        # BASELINE config 5 (one 7-regular graph of 10^6 nodes, F = 256, H = 128, learned embeddings) in its own process: a
+        # different problem shape end to end (run_b200_arm with the config-5 overrides), 5 timed steps
+        if not args.no_config5:
+            import subprocess
+            t0 = time.perf_counter()
+            try:
+                res5 = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "config5", "--steps", "5",
+                                       "--warmup", "3", "--no-workloads", "--seed", str(args.seed)],
+                                      capture_output=True, text=True, timeout=240)
+                lines5 = [ln for ln in res5.stdout.splitlines() if ln.startswith("{")]
+                w5 = json.loads(lines5[-1])
+                workloads["config5"] = {
+                    "metric": "GCN train graph-epochs/s (one graph, n=1e6, d=7, F=256, H=128, learned embeddings)",
+                    "value": w5["value"], "unit": w5["unit"], "steps": w5["steps"], "ms_per_step": w5["ms_per_step"],
+                    "dtype": w5["dtype"], "node_epochs_per_s": w5.get("node_epochs_per_s"),
+                    "config": w5["config"], "roofline": w5["roofline"], "spmm": w5["spmm"],
+                    "ops_ms": {k: v["avg_ms"] for k, v in (w5.get("ops") or {}).items()},
+                    "ops_frac": {k: v.get("frac") for k, v in (w5.get("ops") or {}).items()},
+                    "wall_s": time.perf_counter() - t0}
+            except Exception as exc:
+                workloads["config5"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         clocks = sampler.summary()
