@@ -640,7 +640,8 @@ def test_peer_allreduce_across_processes_through_cuda_ipc():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     world, n = 2, 50003
-    procs = [ctx.Process(target=_peer_worker, args=(r, world, 29631, n, q)) for r in range(world)]
+    port = 31000 + os.getpid() % 1000
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = []
