@@ -654,3 +654,51 @@ def test_peer_allreduce_across_processes_through_cuda_ipc():
             if p.is_alive():
                 p.kill()
     assert sorted(results) == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_integer_postprocessing_on_random_irregular_weighted_graphs(seed):
+    """Differential sweep against oracle/postproc.c on graphs the seeded cases do not cover: irregular degrees (a ring for
+    connectivity plus random chords), small integer weights (many tied gains for the greedy tie-break: lowest node, then
+    lowest class), sizes from 3 nodes up, K = 2 .. 5 -- cut evaluator, greedy node moves and best-of-N sampling, bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    graphs = []
+    for _ in range(6):
+        n = int(rng.integers(3, 90))
+        g = nx.cycle_graph(n)
+        for _ in range(int(rng.integers(0, 3 * n))):
+            u, v = int(rng.integers(0, n)), int(rng.integers(0, n))
+            if u != v:
+                g.add_edge(u, v)
+        for u, v in g.edges():
+            g[u][v]["weight"] = int(rng.integers(1, 4))
+        graphs.append(g)
+    csrs = [rs.csr_from_networkx(g) for g in graphs]
+    batch = GraphBatch([CSRGraph.from_networkx(g) for g in graphs])
+    gp = batch.graph_ptr_host
+    K = int(rng.integers(2, 6))
+    n_frozen = 3 if K >= 3 else 0
+    start = rng.integers(0, K, size=batch.num_nodes).astype(np.int32)
+    cuts = ops.cut_value(batch, torch.from_numpy(start).to(DEV)).cpu().numpy()
+    for iters in (1, 200):
+        out, cut, moves = ops.greedy_node_move(batch, torch.from_numpy(start).to(DEV), K, iters, n_frozen)
+        for i, csr in enumerate(csrs):
+            w = csr.weights.astype(np.int32)
+            assert int(cuts[i]) == pp.cut_value(csr.rowptr, csr.colidx, start[gp[i]: gp[i + 1]], w)
+            wl, wc, wm = pp.greedy_node_move(csr.rowptr, csr.colidx, start[gp[i]: gp[i + 1]], K, iters, n_frozen, w)
+            assert int(cut[i].item()) == wc and int(moves[i].item()) == wm
+            assert out[gp[i]: gp[i + 1]].cpu().tolist() == wl.tolist()
+    # best-of-N categorical sampling (3 classes: the reference's assign_partitions), both numpy comparison modes
+    P = torch.softmax(torch.from_numpy(rng.normal(0, 2.0, size=(batch.num_nodes, 3)).astype(np.float32)), 1)
+    iters = 23
+    counts = [iters * max(g.number_of_nodes() - 3, 0) for g in graphs]
+    u_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    U = rng.random(int(u_ptr[-1]))
+    for f32 in (True, False):
+        labels, best, best_it = ops.sample_best_cut(batch, P.to(DEV), torch.from_numpy(U).to(DEV),
+                                                    torch.from_numpy(u_ptr).to(DEV), iters, compare_f32=f32)
+        for i, csr in enumerate(csrs):
+            wl, wc, wi = pp.sample_best_cut(csr.rowptr, csr.colidx, P.numpy()[gp[i]: gp[i + 1]], U[u_ptr[i]: u_ptr[i + 1]],
+                                            iters, csr.weights.astype(np.int32), compare_f32=f32)
+            assert int(best[i].item()) == wc and int(best_it[i].item()) == wi
+            assert labels[gp[i]: gp[i + 1]].cpu().tolist() == wl.tolist()
