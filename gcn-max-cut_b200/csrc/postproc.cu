@@ -278,7 +278,102 @@ greedy_kernel(const int32_t* __restrict__ labels_in, const int32_t* __restrict__
 
 }  // namespace gmc
 
+// ---- numpy's legacy generator on the device -----------------------------------------------------
+// assign_partitions (TestingNeuralNetwork.py:18-46) draws one np.random.rand() per node and iteration: 2.27 M doubles
+// for one pass over BASELINE config 2's test graphs -- 10 ms of host time (MT19937 is sequential) plus an 18 MB upload,
+// half of the pass.  The same stream on the device: MT19937 as numpy's randomkit runs it (624-word state, regenerated
+// in place; a double = (a >> 5) * 2^26 + (b >> 6) over 2^53 from two consecutive tempered words), one CTA.  The
+// regeneration is three data-parallel sweeps (words [0, 227) from the old state, [227, 454) and [454, 623) from words
+// produced 227 places earlier) and one last word, so a block of 312 doubles costs eight barriers instead of 624
+// dependent steps.  The caller hands in np.random.get_state() and puts the returned state back: the host generator
+// ends exactly where the reference's own draws would have left it.
+namespace gmc {
+constexpr int kMtN = 624, kMtM = 397;
+
+__device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t nxt, uint32_t far_word) {
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return far_word ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+__device__ __forceinline__ double mt_double(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+__global__ void __launch_bounds__(256)
+mt19937_uniform_kernel(const uint32_t* __restrict__ state_in, int pos_in, int64_t n, double* __restrict__ out,
+                       uint32_t* __restrict__ state_out, int32_t* __restrict__ pos_out) {
+    __shared__ uint32_t mt[kMtN];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kMtN; i += 256) mt[i] = state_in[i];
+    __syncthreads();
+    // everything below is uniform over the CTA
+    int p = pos_in;
+    int64_t remaining = n, oi = 0;
+    bool carry = false;
+    uint32_t cw = 0;
+    while (remaining > 0) {
+        if (p == kMtN) {
+            uint32_t v = 0;
+            if (tid < kMtN - kMtM) v = mt_mix(mt[tid], mt[tid + 1], mt[tid + kMtM]);                       // [0, 227)
+            __syncthreads();
+            if (tid < kMtN - kMtM) mt[tid] = v;
+            __syncthreads();
+            if (tid < 227) v = mt_mix(mt[227 + tid], mt[228 + tid], mt[tid]);                              // [227, 454)
+            __syncthreads();
+            if (tid < 227) mt[227 + tid] = v;
+            __syncthreads();
+            if (tid < 169) v = mt_mix(mt[454 + tid], mt[455 + tid], mt[227 + tid]);                        // [454, 623)
+            __syncthreads();
+            if (tid < 169) mt[454 + tid] = v;
+            __syncthreads();
+            if (tid == 0) mt[kMtN - 1] = mt_mix(mt[kMtN - 1], mt[0], mt[kMtM - 1]);                        // 623
+            __syncthreads();
+            p = 0;
+        }
+        int start = p;
+        if (carry) {                                              // the first word of this block completes a double
+            if (tid == 0) out[oi] = mt_double(cw, mt_temper(mt[p]));
+            ++oi; --remaining; start = p + 1; carry = false;
+        }
+        if (remaining == 0) { p = start; break; }
+        const int64_t fit = (kMtN - start) / 2;
+        const int pairs = (int)(remaining < fit ? remaining : fit);
+        for (int t = tid; t < pairs; t += 256)
+            out[oi + t] = mt_double(mt_temper(mt[start + 2 * t]), mt_temper(mt[start + 2 * t + 1]));
+        oi += pairs; remaining -= pairs;
+        int used = start + 2 * pairs;
+        if (remaining > 0 && used < kMtN) {                       // one word left in the block: first half of the next double
+            cw = mt_temper(mt[kMtN - 1]);
+            carry = true;
+            used = kMtN;
+        }
+        p = used;
+        __syncthreads();                                          // the block has been read before it is regenerated
+    }
+    for (int i = tid; i < kMtN; i += 256) state_out[i] = mt[i];
+    if (tid == 0) *pos_out = p;
+}
+}  // namespace gmc
+
 extern "C" {
+
+// n doubles of numpy's legacy np.random.rand stream, continued from `state_in` (624 words, np.random.get_state()[1]) at
+// position `pos` (0..624): out[0..n) on the device, and the generator state after those draws in state_out / pos_out.
+int gmc_mt19937_uniform_f64(const uint32_t* state_in, int32_t pos, int64_t n, double* out, uint32_t* state_out,
+                            int32_t* pos_out, void* stream) {
+    using namespace gmc;
+    GMC_REQUIRE(state_in && state_out && pos_out && (out || n == 0), "gmc_mt19937_uniform_f64: null pointer");
+    GMC_REQUIRE(pos >= 0 && pos <= kMtN && n >= 0, "gmc_mt19937_uniform_f64: pos must be 0..624, n >= 0");
+    mt19937_uniform_kernel<<<1, 256, 0, as_stream(stream)>>>(state_in, pos, n, out, state_out, pos_out);
+    GMC_LAUNCH_CHECK();
+    return GMC_OK;
+}
 
 int gmc_argmax_labels(const float* P, int64_t ldp, const int32_t* graph_ptr, int32_t n_graphs, int64_t n_rows,
                       int32_t n_classes, int32_t force_terminals, int32_t* labels, void* stream) {

@@ -116,6 +116,7 @@ SIGNATURES: Dict[str, tuple] = {
     "gmc_ipc_open_handle": (c_int, [P, POINTER(c_void_p)]),
     "gmc_ipc_close_handle": (c_int, [P]),
     "gmc_peer_allreduce_f32": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int32, c_int32, c_int64, c_uint32, P]),
+    "gmc_mt19937_uniform_f64": (c_int, [P, c_int32, c_int64, P, P, P, P]),
     "gmc_argmax_labels": (c_int, [P, c_int64, P, c_int32, c_int64, c_int32, c_int32, P, P]),
     "gmc_cut_value_i32": (c_int, [P, P, P, P, P, c_int32, c_int64, P, P]),
     "gmc_cut_value_multi_u8": (c_int, [P, P, P, P, c_int32, c_int32, P, P]),

@@ -1000,6 +1000,25 @@ def cut_value_multi(batch, labels_u8: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def numpy_rand_on_device(n: int, device) -> Optional[torch.Tensor]:
+    """n doubles of the GLOBAL numpy generator's np.random.rand stream, produced on the device (gmc_mt19937_uniform_f64);
+    the host generator is advanced to exactly where n scalar draws would have left it.  None when the global generator is
+    not the legacy MT19937 (the caller then draws on the host)."""
+    import numpy as np
+    st = np.random.get_state()
+    if st[0] != "MT19937" or n <= 0:
+        return None
+    key = torch.from_numpy(np.ascontiguousarray(st[1], dtype=np.uint32).view(np.int32)).to(device)
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    new_key = torch.empty(624, dtype=torch.int32, device=device)
+    new_pos = torch.empty(1, dtype=torch.int32, device=device)
+    check(lib().gmc_mt19937_uniform_f64(key.data_ptr(), int(st[2]), int(n), out.data_ptr(), new_key.data_ptr(),
+                                        new_pos.data_ptr(), _stream()), "gmc_mt19937_uniform_f64")
+    host_key = new_key.cpu().numpy().view(np.uint32)              # synchronises: the state must be back before anyone draws
+    np.random.set_state((st[0], host_key, int(new_pos.item()), st[3], st[4]))
+    return out
+
+
 def sample_best_cut(batch, P: torch.Tensor, U: torch.Tensor, u_ptr: torch.Tensor, iters: int,
                     compare_f32: bool):
     """P1.  U float64 device uniforms, u_ptr int64 [B+1] offsets.  Returns (labels, cut, best_iter)."""

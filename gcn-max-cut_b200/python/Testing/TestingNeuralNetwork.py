@@ -89,6 +89,10 @@ def _device_probs(node_probabilities) -> torch.Tensor:
     return torch.as_tensor(np.asarray(node_probabilities), dtype=torch.float32).to(dev).contiguous()
 
 
+# draws per call from which the uniforms of the sampling post-processing come from the device generator (GMC_DEVICE_RNG=0: never)
+_DEVICE_RNG_MIN = 20000 if os.environ.get("GMC_DEVICE_RNG", "1") != "0" else (1 << 62)
+
+
 def _sample_best(batch: GraphBatch, probs: torch.Tensor, iterations: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """P1 on the device for every graph of `batch`; uniforms drawn per graph in dataset order with
     np.random.rand (same stream as the reference's scalar draws)."""
@@ -97,9 +101,15 @@ def _sample_best(batch: GraphBatch, probs: torch.Tensor, iterations: int) -> Tup
     u_ptr = np.zeros(len(counts) + 1, dtype=np.int64)
     np.cumsum(counts, out=u_ptr[1:])
     total = int(u_ptr[-1])
-    U = np.random.rand(total) if total else np.zeros(0, dtype=np.float64)
     dev = probs.device
-    U_d = torch.from_numpy(np.ascontiguousarray(U, dtype=np.float64)).to(dev)
+    U_d = None
+    if total >= _DEVICE_RNG_MIN:
+        # the same np.random.rand stream, generated on the device (MT19937 is 10 ms of host time per 2 M draws, plus the
+        # upload); the host generator is left where the scalar draws would have left it
+        U_d = _ops.numpy_rand_on_device(total, dev)
+    if U_d is None:
+        U = np.random.rand(total) if total else np.zeros(0, dtype=np.float64)
+        U_d = torch.from_numpy(np.ascontiguousarray(U, dtype=np.float64)).to(dev)
     if U_d.numel() == 0:
         U_d = torch.zeros(1, dtype=torch.float64, device=dev)
     labels, best, _ = _ops.sample_best_cut(batch, probs, U_d, torch.from_numpy(u_ptr).to(dev), iterations,

@@ -461,6 +461,12 @@ int gmc_cut_value_multi_u8(const uint8_t* labels, const int32_t* rowptr, const i
                            const int32_t* wts, int32_t n_nodes, int32_t n_labelings, int64_t* cut,
                            void* stream);
 
+/* numpy's legacy MT19937 stream on the device: n doubles exactly as n calls of np.random.rand() would return them
+ * (assign_partitions draws one per node and iteration, TestingNeuralNetwork.py:18-46), continued from the host generator's
+ * state (np.random.get_state(): 624 words + position) -- state_out / pos_out go back into np.random.set_state(), so the
+ * host generator ends where the reference's own draws would leave it.  All pointers are device pointers. */
+int gmc_mt19937_uniform_f64(const uint32_t* state_in, int32_t pos, int64_t n, double* out, uint32_t* state_out,
+                            int32_t* pos_out, void* stream);
 /* P1: `iters` categorical samplings per graph, keep the FIRST iteration with the maximal cut.
  * U: float64 uniforms, graph g uses U[u_ptr[g] + it*(n_g-3) + (i-3)] for local node i >= 3 --
  * the host draws them with np.random.rand in the reference's call order.  compare_f32 selects

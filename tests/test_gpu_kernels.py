@@ -702,3 +702,26 @@ def test_integer_postprocessing_on_random_irregular_weighted_graphs(seed):
                                             iters, csr.weights.astype(np.int32), compare_f32=f32)
             assert int(best[i].item()) == wc and int(best_it[i].item()) == wi
             assert labels[gp[i]: gp[i + 1]].cpu().tolist() == wl.tolist()
+
+
+@pytest.mark.parametrize("burn,n", [(0, 1), (0, 312), (1, 311), (3, 313), (623, 2), (624, 5), (17, 100001), (0, 0),
+                                     (1247, 625), (5, 2270000)])
+def test_numpy_rand_stream_on_the_device(burn, n):
+    """gmc_mt19937_uniform_f64 continues np.random's legacy MT19937 stream bit for bit from any position (pairs that straddle
+    a state regeneration, odd word counts, a position of exactly 624) and hands the generator back in the state n scalar
+    np.random.rand() calls would have left it in."""
+    np.random.seed(1234)
+    if burn:
+        np.random.randint(0, 2 ** 31, size=burn)              # moves the position by `burn` 32-bit words
+    st = np.random.get_state()
+    want = np.random.rand(n)
+    after = np.random.get_state()
+    np.random.set_state(st)
+    got = ops.numpy_rand_on_device(n, DEV)
+    if n == 0:
+        assert got is None
+    else:
+        assert np.array_equal(got.cpu().numpy(), want)
+    now = np.random.get_state()
+    assert now[0] == after[0] and np.array_equal(now[1], after[1]) and now[2] == after[2]
+    assert np.random.rand() == (np.random.set_state(after) or np.random.rand())
