@@ -22,7 +22,7 @@ import numpy as np
 class CSRGraph:
     """In-edge CSR of an undirected graph (both directions stored), host arrays."""
 
-    __slots__ = ("rowptr", "colidx", "weights", "n", "_device", "_batch", "_features_verified")
+    __slots__ = ("rowptr", "colidx", "weights", "n", "_device", "_batch", "_features_verified", "_nx_edges")
 
     def __init__(self, rowptr: np.ndarray, colidx: np.ndarray, weights: Optional[np.ndarray], n: int):
         self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
@@ -34,6 +34,7 @@ class CSRGraph:
         self._device = "cpu"
         self._batch = None           # lazily built one-graph GraphBatch (device), never pickled
         self._features_verified = None   # check_adjacency_features memo (weakref to the tensor, version, width), never pickled
+        self._nx_edges = None            # (id of the networkx graph, its undirected edge count), never pickled
         if self.rowptr.shape[0] != self.n + 1 or self.rowptr[-1] != self.colidx.shape[0]:
             raise ValueError("inconsistent CSR arrays")
 
@@ -45,6 +46,7 @@ class CSRGraph:
         self._device = "cpu"
         self._batch = None
         self._features_verified = None
+        self._nx_edges = None
 
     # ---- DGLGraph surface -------------------------------------------------------------
     def number_of_nodes(self) -> int:
