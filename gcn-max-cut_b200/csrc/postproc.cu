@@ -283,9 +283,9 @@ greedy_kernel(const int32_t* __restrict__ labels_in, const int32_t* __restrict__
 // for one pass over BASELINE config 2's test graphs -- 10 ms of host time (MT19937 is sequential) plus an 18 MB upload,
 // half of the pass.  The same stream on the device: MT19937 as numpy's randomkit runs it (624-word state, regenerated
 // in place; a double = (a >> 5) * 2^26 + (b >> 6) over 2^53 from two consecutive tempered words), one CTA.  The
-// regeneration is three data-parallel sweeps (words [0, 227) from the old state, [227, 454) and [454, 623) from words
-// produced 227 places earlier) and one last word, so a block of 312 doubles costs eight barriers instead of 624
-// dependent steps.  The caller hands in np.random.get_state() and puts the returned state back: the host generator
+// regeneration is a three-word chain per thread (word i from the old state, i + 227 and i + 454 from the word produced
+// 227 places earlier -- by the same thread) plus one last word, so a block of 312 doubles costs three barriers instead
+// of 624 dependent steps.  The caller hands in np.random.get_state() and puts the returned state back: the host generator
 // ends exactly where the reference's own draws would have left it.
 namespace gmc {
 constexpr int kMtN = 624, kMtM = 397;
@@ -319,20 +319,25 @@ mt19937_uniform_kernel(const uint32_t* __restrict__ state_in, int pos_in, int64_
     uint32_t cw = 0;
     while (remaining > 0) {
         if (p == kMtN) {
-            uint32_t v = 0;
-            if (tid < kMtN - kMtM) v = mt_mix(mt[tid], mt[tid + 1], mt[tid + kMtM]);                       // [0, 227)
+            // Thread i < 227 owns words i, i + 227 and (i < 169) i + 454: new[i] needs old words only, new[i + 227] needs
+            // new[i], new[i + 454] needs new[i + 227] -- a chain inside the thread once the OLD neighbours are in registers.
+            uint32_t o0 = 0, n0 = 0, far_w = 0, o1 = 0, n1 = 0, o2 = 0, n2 = 0, last = 0;
+            if (tid < 227) {
+                o0 = mt[tid]; n0 = mt[tid + 1]; far_w = mt[tid + kMtM];
+                o1 = mt[tid + 227]; n1 = mt[tid + 228];
+                if (tid < 169) { o2 = mt[tid + 454]; n2 = mt[tid + 455]; }
+            }
+            if (tid == 0) last = mt[kMtN - 1];
+            __syncthreads();                                      // every read of the old state (and of its outputs) is done
+            if (tid < 227) {
+                const uint32_t v0 = mt_mix(o0, n0, far_w);
+                const uint32_t v1 = mt_mix(o1, n1, v0);
+                mt[tid] = v0;
+                mt[tid + 227] = v1;
+                if (tid < 169) mt[tid + 454] = mt_mix(o2, n2, v1);
+            }
             __syncthreads();
-            if (tid < kMtN - kMtM) mt[tid] = v;
-            __syncthreads();
-            if (tid < 227) v = mt_mix(mt[227 + tid], mt[228 + tid], mt[tid]);                              // [227, 454)
-            __syncthreads();
-            if (tid < 227) mt[227 + tid] = v;
-            __syncthreads();
-            if (tid < 169) v = mt_mix(mt[454 + tid], mt[455 + tid], mt[227 + tid]);                        // [454, 623)
-            __syncthreads();
-            if (tid < 169) mt[454 + tid] = v;
-            __syncthreads();
-            if (tid == 0) mt[kMtN - 1] = mt_mix(mt[kMtN - 1], mt[0], mt[kMtM - 1]);                        // 623
+            if (tid == 0) mt[kMtN - 1] = mt_mix(last, mt[0], mt[kMtM - 1]);   // 623: new[0] and new[396]
             __syncthreads();
             p = 0;
         }
@@ -353,9 +358,9 @@ mt19937_uniform_kernel(const uint32_t* __restrict__ state_in, int pos_in, int64_
             carry = true;
             used = kMtN;
         }
-        p = used;
-        __syncthreads();                                          // the block has been read before it is regenerated
+        p = used;                                                 // (the regeneration's first barrier comes after these reads)
     }
+    __syncthreads();
     for (int i = tid; i < kMtN; i += 256) state_out[i] = mt[i];
     if (tid == 0) *pos_out = p;
 }
