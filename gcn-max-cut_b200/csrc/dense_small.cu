@@ -497,6 +497,7 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
 
     const int j0 = tid * 4;
     const bool owner = j0 < n_in;
+    const bool pad_owner = !owner && j0 < min((int)(lddh4 * 4), (n_in + 63) & ~63);   // zero-fills the row's pad columns
     // The kernel is issue-bound (ncu r01c: 71 % issue slots), and 24 of its ~40 instructions per row and thread were
     // scalar FMAs.  Columns are held in PAIRS and multiplied with packed fp32x2 FMAs (fma.rn.f32x2, sm_100): each lane
     // of a pair is an IEEE fma, so the results are bit-identical to the scalar form at half the FMA instructions.
@@ -551,6 +552,12 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
                     dH[v * lddh4 + tid] = pk;
                 }
             }
+        } else if (pad_owner) {
+            // columns n_in .. next 128-byte line as zeros: a 1000-byte row in a 1024-byte pitch would end inside a sector
+            // and turn the row's last write into a read-modify-write (scratch/wrows_probe.py: 3.9 vs 6.4 TB/s)
+#pragma unroll
+            for (int r = 0; r < TR; ++r)
+                if (vb + r < r1) dH[(vb + r) * lddh4 + tid] = make_uint2(0u, 0u);
         }
         if (tid < TR * NOUT) tsm[(t + 1) & 1][tid] = t_next;
         __syncthreads();                                   // stage and tsm[t & 1] are free, tsm[(t + 1) & 1] is published
@@ -616,6 +623,7 @@ skinny_bwd_split_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float
 
     const int j0 = tid * 4;
     const bool owner = j0 < n_in;
+    const bool pad_owner = !owner && j0 < min((int)(lddh4 * 4), (n_in + 63) & ~63);   // zero-fills the row's pad columns
     float2 wp[2][NOUT], dwp[2][NOUT];
     float db[4];
 #pragma unroll
@@ -676,6 +684,13 @@ skinny_bwd_split_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float
                     }
                 }
             }
+        }
+        if (pad_owner) {                                   // full 128-byte lines (see skinny_bwd_b16_tma_kernel)
+#pragma unroll
+            for (int r = 0; r < TR; ++r)
+                if (vb + r < r1)
+#pragma unroll
+                    for (int sp_i = 0; sp_i < NS; ++sp_i) dH[((int64_t)sp_i * split_rows + vb + r) * lddh4 + tid] = make_uint2(0u, 0u);
         }
         if (tid < TR * (NOUT + 1)) tsm[(t + 1) & 1][tid] = t_next;
         __syncthreads();                                   // stage and tsm[t & 1] are free, tsm[(t + 1) & 1] is published

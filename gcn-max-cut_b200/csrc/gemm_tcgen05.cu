@@ -1041,7 +1041,11 @@ static int setup_output(Params& p, CUtensorMap* tmC_out, float* C, int64_t M, in
             set_error("gmc_gemm_bf16_bf16out: needs accumulate = 0, a 16-byte aligned C and ldc %% 8 == 0");
             return GMC_ERR_INVALID_ARG;
         }
-        rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 64, 32, false, 2);
+        // the stored width runs to the end of the row's last 128-byte line when the pitch covers it: the columns past N
+        // hold exact zeros (their accumulators see zero-filled B columns, no bias), and a row that ends inside a line
+        // turns its last sector into a read-modify-write that costs a write stream 40 % of its bandwidth
+        rc = make_map(&tmC, C, (uint64_t)(((N + 63) & ~(int64_t)63) <= ldc ? ((N + 63) & ~(int64_t)63) : N), (uint64_t)M,
+                      (uint64_t)ldc, 64, 32, false, 2);
         if (rc) return rc;
         p.tma_store = 1;
         p.c_bf16 = 1;
@@ -1088,7 +1092,8 @@ static int setup_output(Params& p, CUtensorMap* tmC_out, float* C, int64_t M, in
             p.proj_part = reinterpret_cast<float4*>(workspace);
         }
         if (splits == 1 && !accumulate && p.vec_ok && !no_tma_store()) {
-            rc = make_map(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, false);
+            rc = make_map(&tmC, C, (uint64_t)(((N + 31) & ~(int64_t)31) <= ldc ? ((N + 31) & ~(int64_t)31) : N), (uint64_t)M,
+                          (uint64_t)ldc, 32, 32, false);                         // full 128-byte lines, as above
             if (rc) return rc;
             p.tma_store = 1;
         }

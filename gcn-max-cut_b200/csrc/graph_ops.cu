@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kPreaggWarps * 32)
 preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                          const float* __restrict__ coef, const float* __restrict__ vals,
                          const int32_t* __restrict__ graph_ptr, int n_graphs, int64_t n_rows, int n_cols, int ncp,
-                         __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ only) {
+                         __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ only, int pad_cols) {
     extern __shared__ __align__(16) float preagg_rows[];              // kPreaggWarps x ncp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* buf = preagg_rows + warp * ncp;
@@ -233,6 +233,9 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
             }
             *reinterpret_cast<uint2*>(xr + c4 * 4) = o;
         }
+        // pad columns up to the 128-byte line boundary as zeros: a row that ends inside a line (2000 of 2048 bytes) makes
+        // its last sector a read-modify-write and costs the whole stream 40 % of its bandwidth (scratch/wrows_probe.py)
+        for (int c = ncp + lane * 4; c < pad_cols; c += 128) *reinterpret_cast<uint2*>(xr + c) = make_uint2(0u, 0u);
         __syncwarp();                                                  // everyone has read the row
         if (fast) {
             if (touched[0] >= 0) buf[touched[0]] = magic;
@@ -260,18 +263,140 @@ static bool graph_kernel_enabled() {
     return cached == 1;
 }
 
+// Rows of one graph, one warp per row.  STAGED: the CSR slice is in shared memory (s_rp relative row pointers, s_ci 16-bit
+// local column ids, 0xFFFF = outside), else it is read from global memory.  Compile-time so that the accessors are plain
+// loads: as run-time selects inside lambdas they cost a third of the kernel's 358 instructions per row and put their
+// closure in local memory (ncu: 4 LDL + 3 STL per row).  The row's coefficients -- the only global load on the walk -- are
+// requested one row ahead (37 % of the stall samples sat on their first use).
+template <bool F16OUT, bool STAGED>
+__device__ __forceinline__ void pg_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                        const float* __restrict__ coef, const int32_t* __restrict__ s_rp,
+                                        const uint16_t* __restrict__ s_ci, float* __restrict__ buf, int base, int n,
+                                        int e_base, int n_cols, int ncp, __nv_bfloat16* __restrict__ X, int64_t ldx,
+                                        int lane, int warp, int pad_cols) {
+    constexpr uint32_t kMagicBits = 0x4B000000u;                       // 8388608.0f: counts live in its mantissa
+    const float magic = __uint_as_float(kMagicBits);
+#define PG_RP(i) (STAGED ? s_rp[(i)] : (__ldg(rowptr + base + (i)) - e_base))
+    auto ci = [=](int e) -> int {
+        if (STAGED) { const int v = s_ci[e]; return v == 0xFFFF ? -1 : v; }
+        const int v = __ldg(colidx + e_base + e) - base;
+        return (v >= 0 && v < n) ? v : -1;
+    };
+    int v = warp;
+    int e0 = 0, cnt = 0;
+    float my_c = 0.f;
+    if (v < n) {
+        e0 = PG_RP(v); cnt = PG_RP(v + 1) - e0;
+        if (lane < min(cnt, 32)) my_c = __ldg(coef + e_base + e0 + lane);
+    }
+    for (; v < n; v += kPgWarps) {
+        // next row's extent and coefficients: in flight while this row is built
+        const int vn = v + kPgWarps;
+        int e0_n = 0, cnt_n = 0;
+        float c_n = 0.f;
+        if (vn < n) {
+            e0_n = PG_RP(vn); cnt_n = PG_RP(vn + 1) - e0_n;
+            if (lane < min(cnt_n, 32)) c_n = __ldg(coef + e_base + e0_n + lane);
+        }
+        int my_f0 = 0, my_deg = 0;
+        if (lane < min(cnt, 32)) {
+            const int u = ci(e0 + lane);
+            if (u >= 0) { my_f0 = PG_RP(u); my_deg = PG_RP(u + 1) - my_f0; }
+        }
+        const int D0 = __shfl_sync(0xffffffffu, my_deg, 0);
+        const float c0 = __shfl_sync(0xffffffffu, my_c, 0);
+        const bool same = __all_sync(0xffffffffu, lane >= cnt || (my_deg == D0 && my_c == c0));
+        const bool fast = same && cnt > 0 && cnt <= 32 && D0 > 0 && cnt * D0 <= 64;
+        int touched0 = -1, touched1 = -1;
+        if (!fast)
+            for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        if (fast) {
+            const int total = cnt * D0;
+            const float inv_d = 1.0f / (float)D0;
+            {
+                const int p = lane;
+                const int owner = p < total ? (int)(((float)p + 0.5f) * inv_d) : 0;
+                const int o_f0 = __shfl_sync(0xffffffffu, my_f0, owner);
+                if (p < total) {
+                    const int local = ci(o_f0 + (p - owner * D0));
+                    if (local >= 0 && local < n_cols) { atomicAdd(reinterpret_cast<unsigned int*>(buf) + local, 1u); touched0 = local; }
+                }
+            }
+            {
+                const int p = 32 + lane;
+                const int owner = p < total ? (int)(((float)p + 0.5f) * inv_d) : 0;
+                const int o_f0 = __shfl_sync(0xffffffffu, my_f0, owner);
+                if (p < total) {
+                    const int local = ci(o_f0 + (p - owner * D0));
+                    if (local >= 0 && local < n_cols) { atomicAdd(reinterpret_cast<unsigned int*>(buf) + local, 1u); touched1 = local; }
+                }
+            }
+        } else {
+            // neighbours one after the other in CSR order, lanes over N(u) (distinct columns): fixed order
+            float cc = my_c;
+            for (int eb = e0; eb < e0 + cnt; eb += 32) {
+                const int n_here = min(32, e0 + cnt - eb);
+                if (eb > e0) {
+                    my_f0 = 0; my_deg = 0; cc = 0.f;
+                    if (lane < n_here) {
+                        cc = __ldg(coef + e_base + eb + lane);
+                        const int u = ci(eb + lane);
+                        if (u >= 0) { my_f0 = PG_RP(u); my_deg = PG_RP(u + 1) - my_f0; }
+                    }
+                }
+                for (int q = 0; q < n_here; ++q) {
+                    const int f0 = __shfl_sync(0xffffffffu, my_f0, q), dg = __shfl_sync(0xffffffffu, my_deg, q);
+                    const float c = __shfl_sync(0xffffffffu, cc, q);
+                    for (int f = f0 + lane; f < f0 + dg; f += 32) {
+                        const int local = ci(f);
+                        if (local >= 0 && local < n_cols) buf[local] += c;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+        __nv_bfloat16* xr = X + (int64_t)(base + v) * ldx;
+        const float sc = fast ? c0 : 1.0f, off = fast ? -magic * c0 : 0.0f;
+        for (int c4 = lane; c4 * 4 < ncp; c4 += 32) {
+            const float4 a = *reinterpret_cast<const float4*>(buf + c4 * 4);
+            const float v0 = fmaf(a.x, sc, off), v1 = fmaf(a.y, sc, off), v2 = fmaf(a.z, sc, off), v3 = fmaf(a.w, sc, off);
+            uint2 o;
+            if (F16OUT) {
+                const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
+                o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+            } else {
+                const __nv_bfloat162 b0 = __floats2bfloat162_rn(v0, v1), b1 = __floats2bfloat162_rn(v2, v3);
+                o.x = *reinterpret_cast<const uint32_t*>(&b0); o.y = *reinterpret_cast<const uint32_t*>(&b1);
+            }
+            *reinterpret_cast<uint2*>(xr + c4 * 4) = o;
+        }
+        for (int c = ncp + lane * 4; c < pad_cols; c += 128) *reinterpret_cast<uint2*>(xr + c) = make_uint2(0u, 0u);   // full lines
+        __syncwarp();
+        if (fast) {
+            if (touched0 >= 0) buf[touched0] = magic;
+            if (touched1 >= 0) buf[touched1] = magic;
+        } else {
+            for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(magic, magic, magic, magic);
+        }
+        __syncwarp();
+        e0 = e0_n; cnt = cnt_n; my_c = c_n;
+    }
+#undef PG_RP
+}
+
 template <bool F16OUT>
 __global__ void __launch_bounds__(kPgWarps * 32)
 preaggregate_graph_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                           const float* __restrict__ coef, const int32_t* __restrict__ graph_ptr, int n_graphs, int n_cols,
-                          int ncp, int cap_nodes, int cap_edges, __nv_bfloat16* __restrict__ X, int64_t ldx) {
+                          int ncp, int cap_nodes, int cap_edges, __nv_bfloat16* __restrict__ X, int64_t ldx, int pad_cols) {
     extern __shared__ __align__(16) float pg_smem[];                   // kPgWarps x ncp row buffers, then the CSR slice
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* buf = pg_smem + warp * ncp;
     int32_t* s_rp = reinterpret_cast<int32_t*>(pg_smem + kPgWarps * ncp);
     uint16_t* s_ci = reinterpret_cast<uint16_t*>(s_rp + cap_nodes + 1);
-    constexpr uint32_t kMagicBits = 0x4B000000u;                       // 8388608.0f: counts live in its mantissa
-    const float magic = __uint_as_float(kMagicBits);
+    const float magic = __uint_as_float(0x4B000000u);
     for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(magic, magic, magic, magic);
     for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
         const int base = __ldg(graph_ptr + g);
@@ -288,91 +413,8 @@ preaggregate_graph_kernel(const int32_t* __restrict__ rowptr, const int32_t* __r
             }
         }
         __syncthreads();
-        // local accessors: row pointer (relative to the graph's first edge) and local column id (-1 = outside)
-        auto rp = [&](int i) -> int { return staged ? s_rp[i] : __ldg(rowptr + base + i) - e_base; };
-        auto ci = [&](int e) -> int {
-            if (staged) { const int v = s_ci[e]; return v == 0xFFFF ? -1 : v; }
-            const int v = __ldg(colidx + e_base + e) - base;
-            return (v >= 0 && v < n) ? v : -1;
-        };
-        for (int v = warp; v < n; v += kPgWarps) {
-            const int e0 = rp(v), cnt = rp(v + 1) - e0;
-            int my_f0 = 0, my_deg = 0;
-            float my_c = 0.f;
-            if (lane < min(cnt, 32)) {
-                my_c = __ldg(coef + e_base + e0 + lane);
-                const int u = ci(e0 + lane);
-                if (u >= 0) { my_f0 = rp(u); my_deg = rp(u + 1) - my_f0; }
-            }
-            const int D0 = __shfl_sync(0xffffffffu, my_deg, 0);
-            const float c0 = __shfl_sync(0xffffffffu, my_c, 0);
-            const bool same = __all_sync(0xffffffffu, lane >= cnt || (my_deg == D0 && my_c == c0));
-            const bool fast = same && cnt > 0 && cnt <= 32 && D0 > 0 && cnt * D0 <= 64;
-            int touched[2] = {-1, -1};
-            if (!fast)
-                for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
-            if (fast) {
-                const int total = cnt * D0;
-                const float inv_d = 1.0f / (float)D0;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int p = 32 * j + lane;
-                    const int owner = p < total ? (int)(((float)p + 0.5f) * inv_d) : 0;
-                    const int o_f0 = __shfl_sync(0xffffffffu, my_f0, owner);
-                    if (p < total) {
-                        const int local = ci(o_f0 + (p - owner * D0));
-                        if (local >= 0 && local < n_cols) { atomicAdd(reinterpret_cast<unsigned int*>(buf) + local, 1u); touched[j] = local; }
-                    }
-                }
-            } else {
-                // neighbours one after the other in CSR order, lanes over N(u) (distinct columns): fixed order
-                for (int eb = e0; eb < e0 + cnt; eb += 32) {
-                    const int n_here = min(32, e0 + cnt - eb);
-                    if (eb > e0) {
-                        my_f0 = 0; my_deg = 0; my_c = 0.f;
-                        if (lane < n_here) {
-                            my_c = __ldg(coef + e_base + eb + lane);
-                            const int u = ci(eb + lane);
-                            if (u >= 0) { my_f0 = rp(u); my_deg = rp(u + 1) - my_f0; }
-                        }
-                    }
-                    for (int q = 0; q < n_here; ++q) {
-                        const int f0 = __shfl_sync(0xffffffffu, my_f0, q), dg = __shfl_sync(0xffffffffu, my_deg, q);
-                        const float c = __shfl_sync(0xffffffffu, my_c, q);
-                        for (int f = f0 + lane; f < f0 + dg; f += 32) {
-                            const int local = ci(f);
-                            if (local >= 0 && local < n_cols) buf[local] += c;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            __syncwarp();
-            __nv_bfloat16* xr = X + (int64_t)(base + v) * ldx;
-            const float sc = fast ? c0 : 1.0f, off = fast ? -magic * c0 : 0.0f;
-            for (int c4 = lane; c4 * 4 < ncp; c4 += 32) {
-                const float4 a = *reinterpret_cast<const float4*>(buf + c4 * 4);
-                const float v0 = fmaf(a.x, sc, off), v1 = fmaf(a.y, sc, off), v2 = fmaf(a.z, sc, off), v3 = fmaf(a.w, sc, off);
-                uint2 o;
-                if (F16OUT) {
-                    const __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
-                    o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
-                } else {
-                    const __nv_bfloat162 b0 = __floats2bfloat162_rn(v0, v1), b1 = __floats2bfloat162_rn(v2, v3);
-                    o.x = *reinterpret_cast<const uint32_t*>(&b0); o.y = *reinterpret_cast<const uint32_t*>(&b1);
-                }
-                *reinterpret_cast<uint2*>(xr + c4 * 4) = o;
-            }
-            __syncwarp();
-            if (fast) {
-                if (touched[0] >= 0) buf[touched[0]] = magic;
-                if (touched[1] >= 0) buf[touched[1]] = magic;
-            } else {
-                for (int c = lane * 4; c < ncp; c += 128) *reinterpret_cast<float4*>(buf + c) = make_float4(magic, magic, magic, magic);
-            }
-            __syncwarp();
-        }
+        if (staged) pg_rows<F16OUT, true>(rowptr, colidx, coef, s_rp, s_ci, buf, base, n, e_base, n_cols, ncp, X, ldx, lane, warp, pad_cols);
+        else pg_rows<F16OUT, false>(rowptr, colidx, coef, s_rp, s_ci, buf, base, n, e_base, n_cols, ncp, X, ldx, lane, warp, pad_cols);
     }
 }
 
@@ -570,6 +612,12 @@ static int preaggregate_impl(const int32_t* rowptr, const int32_t* colidx, const
     if (n_rows == 0) return GMC_OK;
     cudaStream_t s = gmc::as_stream(stream);
     __nv_bfloat16* Xb = reinterpret_cast<__nv_bfloat16*>(X);
+    // gmc_csr_preaggregate_graphs (max_nodes >= 0) also owns the pad columns of a row up to the next 128-byte line (zeros)
+    int pad_cols = ncp;
+    if (max_nodes >= 0) {
+        const int64_t line = ((int64_t)ncp + 63) & ~(int64_t)63;
+        pad_cols = (int)(line <= ldx ? line : ncp);
+    }
     // counting kernel first when the caller passes the row-mask workspace (unit weights and a count row that fits): it
     // flags the rows it leaves.  Measured at config 3: 3.24 ms for the pair of launches against 3.00 ms for the general
     // kernel alone -- byte counters lift the occupancy limit (160 rows in flight per SM instead of 48) without making
@@ -614,10 +662,10 @@ static int preaggregate_impl(const int32_t* rowptr, const int32_t* colidx, const
         if (blocks > cap) blocks = cap;
         if (f16)
             gmc::preaggregate_graph_kernel<true><<<(unsigned)blocks, gmc::kPgWarps * 32, g_smem, s>>>(
-                rowptr, colidx, coef, graph_ptr, n_graphs, n_cols, ncp, cap_nodes, cap_edges, Xb, ldx);
+                rowptr, colidx, coef, graph_ptr, n_graphs, n_cols, ncp, cap_nodes, cap_edges, Xb, ldx, pad_cols);
         else
             gmc::preaggregate_graph_kernel<false><<<(unsigned)blocks, gmc::kPgWarps * 32, g_smem, s>>>(
-                rowptr, colidx, coef, graph_ptr, n_graphs, n_cols, ncp, cap_nodes, cap_edges, Xb, ldx);
+                rowptr, colidx, coef, graph_ptr, n_graphs, n_cols, ncp, cap_nodes, cap_edges, Xb, ldx, pad_cols);
         GMC_LAUNCH_CHECK();
         return GMC_OK;
     }
@@ -636,10 +684,10 @@ static int preaggregate_impl(const int32_t* rowptr, const int32_t* colidx, const
     if (blocks > cap) blocks = cap;
     if (f16)
         gmc::preaggregate_bf16_kernel<true><<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, s>>>(
-            rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only);
+            rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only, pad_cols);
     else
         gmc::preaggregate_bf16_kernel<false><<<(unsigned)blocks, gmc::kPreaggWarps * 32, smem, s>>>(
-            rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only);
+            rowptr, colidx, coef, vals, graph_ptr, n_graphs, n_rows, n_cols, ncp, Xb, ldx, only, pad_cols);
     GMC_LAUNCH_CHECK();
     return GMC_OK;
 }
