@@ -592,8 +592,26 @@ int gmc_spmm_batched_bf16(const int32_t* graph_ptr, int32_t n_graphs, int32_t ma
         const SlabProj none{nullptr, nullptr, 0, 0};
         const float4* b4 = reinterpret_cast<const float4*>(bias);
         int rc = GMC_OK;
-        static int variant = -1;                          // GMC_SLAB16_VARIANT=C: one CTA of 1024 threads, two slab buffers
-        if (variant < 0) { const char* e = getenv("GMC_SLAB16_VARIANT"); variant = (e && e[0] == 'C') ? 1 : 0; }
+        static int variant = -1;                          // GMC_SLAB16_VARIANT = B | C (default) | D | E
+        if (variant < 0) {
+            const char* e = getenv("GMC_SLAB16_VARIANT");
+            // default C (one CTA of 1024 threads per SM, two 112-byte slab buffers): 2.12 ms = 0.60 of the HBM roofline
+            // inside the standard-layer-1 step against 2.37 ms = 0.54 for B (two CTAs of 512 threads), 1.90 vs 2.49 ms alone;
+            // D / E = 64-column slabs, whose row pieces are full 128-byte lines: 2.13 ms
+            variant = (e && e[0] == 'B') ? 0 : (e && e[0] == 'D') ? 2 : (e && e[0] == 'E') ? 3 : 1;
+        }
+        if (variant == 2) {                               // D: 64-column slabs (full 128-byte lines per row piece), one CTA per SM
+            rc = slab_launch_one<8, 8, 1024, 1, 2, true, 1, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows, c8,
+                                                                         ldx / 8, ldy / 8, b4, relu, as_stream(stream),
+                                                                         &launched, 1, none, n_cols);
+            if (rc != GMC_OK) return rc;
+        }
+        if (variant == 3) {                               // E: the same with 512 threads
+            rc = slab_launch_one<8, 8, 512, 1, 2, true, 1, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows, c8,
+                                                                        ldx / 8, ldy / 8, b4, relu, as_stream(stream),
+                                                                        &launched, 1, none, n_cols);
+            if (rc != GMC_OK) return rc;
+        }
         if (variant == 1) {
             rc = slab_launch_one<7, 8, 1024, 1, 2, true, 2, false, true>(plan, graph_ptr, n_graphs, max_nodes, X4, Y4, n_rows, c8,
                                                                          ldx / 8, ldy / 8, b4, relu, as_stream(stream),
