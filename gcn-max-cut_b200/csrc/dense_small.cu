@@ -554,7 +554,7 @@ skinny_bwd_b16_tma_kernel(const __grid_constant__ CUtensorMap tmH, const float* 
             }
         } else if (pad_owner) {
             // columns n_in .. next 128-byte line as zeros: a 1000-byte row in a 1024-byte pitch would end inside a sector
-            // and turn the row's last write into a read-modify-write (scratch/wrows_probe.py: 3.9 vs 6.4 TB/s)
+            // and turn the row's last write into a read-modify-write (profiles/r02r_write_pattern_probe: 3.9 vs 6.4 TB/s)
 #pragma unroll
             for (int r = 0; r < TR; ++r)
                 if (vb + r < r1) dH[(vb + r) * lddh4 + tid] = make_uint2(0u, 0u);

@@ -234,7 +234,7 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
             *reinterpret_cast<uint2*>(xr + c4 * 4) = o;
         }
         // pad columns up to the 128-byte line boundary as zeros: a row that ends inside a line (2000 of 2048 bytes) makes
-        // its last sector a read-modify-write and costs the whole stream 40 % of its bandwidth (scratch/wrows_probe.py)
+        // its last sector a read-modify-write and costs the whole stream 40 % of its bandwidth (profiles/r02r_write_pattern_probe)
         for (int c = ncp + lane * 4; c < pad_cols; c += 128) *reinterpret_cast<uint2*>(xr + c) = make_uint2(0u, 0u);
         __syncwarp();                                                  // everyone has read the row
         if (fast) {
@@ -249,8 +249,7 @@ preaggregate_bf16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
 
 // Per-GRAPH form of preaggregate_bf16_kernel for batches of small graphs (every training / test set of the reference:
 // n <= 1000).  A row of A_hat X is a 2-hop walk -- row extent -> neighbours -> THEIR extents -> 2-hop columns -- and in the
-// row-parallel kernel above each of those four dependent levels is an L2 round trip (the kernel runs at 3.7 TB/s of a
-// 6.5 TB/s write roof with its warps waiting on them).  Here one CTA owns one graph: its CSR slice (local row pointers,
+// row-parallel kernel above each of those four dependent levels is an L2 round trip.  Here one CTA owns one graph: its CSR slice (local row pointers,
 // local 16-bit column ids: 4 (n + 1) + 2 nnz bytes = 18 KB at n = 1000, d = 7) is staged in shared memory with one
 // coalesced pass, and the whole walk runs on shared-memory latency; only the per-row coefficient (needed at read-out) and
 // the 2 KB row store touch global memory.  Row arithmetic, order and rounding are those of the row-parallel kernel, so the
