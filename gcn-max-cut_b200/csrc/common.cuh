@@ -81,14 +81,7 @@ __host__ __device__ constexpr inline T ceil_div(T a, T b) { return (a + b - 1) /
 #ifdef __CUDACC__
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#ifndef GMC_PDL_EARLY
-#define GMC_PDL_EARLY 1
-#endif
-__device__ __forceinline__ void pdl_launch_dependents() {
-#if GMC_PDL_EARLY
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // wait FIRST: a kernel that triggers before it waits lets the whole chain behind it become resident at once (each early
 // CTA triggers its own dependents), and the spinning CTAs keep the 225 KB GEMM CTAs off their SMs -- measured 59 us per
 // 500-node step against 49 us without early launches
