@@ -493,3 +493,35 @@ def test_training_config_extension_fields_default_to_reference_behaviour():
     blob = pickle.dumps(T.TrainingConfig(activations="bf16", gemm_precision="bf16", preaggregate_features=True))
     back = pickle.loads(blob)
     assert back.activations == "bf16" and back.preaggregate_features is True
+
+
+def test_feature_verification_is_memoised_per_item_and_notices_writes():
+    """check_adjacency_features (host tensors stay on the host): a verified (graph, tensor) pair is not verified again while
+    the tensor is untouched -- a test harness revisits the same dataset items every pass -- and any write torch can see
+    (version counter) or another tensor object triggers the full check again; a pickled handle carries no memo."""
+    import pickle
+    import networkx as nx
+    import torch
+    from gmc_b200 import graph as G
+    g = nx.random_regular_graph(d=4, n=30, seed=1)
+    nx.set_edge_attributes(g, 1, "weight")
+    h = G.CSRGraph.from_networkx(g)
+    X = torch.zeros(30, 40)
+    for u, v in g.edges():
+        X[u, v] = X[v, u] = 1.0
+    assert G.check_adjacency_features(h, X) == 40
+    memo = h._features_verified
+    assert memo is not None and memo[0]() is X and memo[1] == X._version
+    assert G.check_adjacency_features(h, X) == 40 and h._features_verified is memo      # served from the memo
+    X[0, 39] = 5.0                                   # a write: version bumps, the entry is not an edge -> refused
+    with pytest.raises(NotImplementedError):
+        G.check_adjacency_features(h, X)
+    X[0, 39] = 0.0
+    assert G.check_adjacency_features(h, X) == 40    # verified afresh at the new version
+    assert h._features_verified[1] == X._version
+    Y = X.clone()
+    Y[3, 3] = 1.0                                    # another tensor object: its own check
+    with pytest.raises(NotImplementedError):
+        G.check_adjacency_features(h, Y)
+    h2 = pickle.loads(pickle.dumps(h))
+    assert h2._features_verified is None and h2._nx_edges is None and np.array_equal(h2.colidx, h.colidx)
