@@ -335,3 +335,20 @@ def test_bf16_storage_emulation_brackets_the_fp32_forward():
     assert 0 < float((std - exact).abs().max()) < 2e-2 * scale
     H = rs.gcn_forward_bf16_storage(csr, X, p)["H1"]
     assert torch.equal(H, H.to(torch.bfloat16).to(torch.float64))          # H1 is exactly representable in bf16
+
+
+@pytest.mark.parametrize("burn,n", [(0, 1), (0, 312), (1, 311), (3, 313), (623, 2), (624, 5), (17, 20001), (1247, 625)])
+def test_mt19937_restatement_is_numpys_generator(burn, n):
+    """oracle/mt19937.py (the device generator's algorithm: three-sweep regeneration, carry across blocks) against np.random
+    itself: same doubles, same state and position afterwards."""
+    from oracle import mt19937 as mt
+    np.random.seed(4321)
+    if burn:
+        np.random.randint(0, 2 ** 31, size=burn)
+    st = np.random.get_state()
+    want = np.random.rand(n)
+    after = np.random.get_state()
+    got, key, pos = mt.uniform(st[1], int(st[2]), n)
+    assert np.array_equal(got, want)
+    assert np.array_equal(key, after[1]) and pos == after[2]
+    np.random.set_state(st)
